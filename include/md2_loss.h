@@ -1,0 +1,144 @@
+/*
+ * md2_loss.h - C ABI of the B200-native view-synthesis loss path of monodepth2.
+ *
+ * The reference (GenkiK/monodepth2) is pure Python and has no FFI; the boundary a
+ * maintainer would bind is the Python API of layers.py plus the two Trainer methods
+ * that drive it.  Every entry point below names the reference interface it replaces
+ * (file:line under /root/reference).  All pointers are CUDA *device* pointers to
+ * contiguous fp32 NCHW tensors unless stated otherwise; `stream` is a cudaStream_t
+ * passed as void*.  No torch types cross this boundary.  Every function returns
+ * MD2_OK (0) or a negative md2_status; md2_status_string() names it.  All work is
+ * enqueued asynchronously on `stream`; nothing synchronises the device.
+ *
+ * The shared library is libmd2loss.so (built by monodepth2_b200/build.py for sm_100a).
+ */
+#ifndef MD2_LOSS_H_
+#define MD2_LOSS_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MD2_MAX_SCALES 4
+#define MD2_MAX_SRC 4
+
+typedef enum md2_status {
+  MD2_OK = 0,
+  MD2_ERR_INVALID_ARGUMENT = -1,
+  MD2_ERR_UNSUPPORTED = -2,
+  MD2_ERR_WORKSPACE_TOO_SMALL = -3,
+  MD2_ERR_CUDA = -4
+} md2_status;
+
+/* Shape and flags of one loss evaluation: the subset of options.py that changes the
+ * path (options.py:52-119) plus two tuning knobs. */
+typedef struct md2_problem {
+  int batch;                  /* opt.batch_size                        options.py:87  */
+  int height, width;          /* opt.height / opt.width                options.py:52  */
+  int num_scales;             /* len(opt.scales), scales 0..n-1        options.py:64  */
+  int num_src;                /* len(opt.frame_ids) - 1 (incl. "s")    options.py:80  */
+  int automask;               /* !opt.disable_automasking              options.py:111 */
+  int avg_reprojection;       /* opt.avg_reprojection                  options.py:108 */
+  int align_corners;          /* grid_sample align_corners; the reference leaves it
+                                 unspecified = 0 on torch>=1.3       trainer.py:384 */
+  float min_depth, max_depth; /* opt.min_depth / opt.max_depth         options.py:69  */
+  float disparity_smoothness; /* opt.disparity_smoothness              options.py:60  */
+  int want_grad;              /* 0: forward only (Trainer.val under no_grad, trainer.py:330) */
+  int rows_per_segment;       /* tuning: rows marched per warp job (0 = default) */
+  int reserved;
+} md2_problem;
+
+/* Tensors of one evaluation.  Names follow the reference's dict keys. */
+typedef struct md2_tensors {
+  /* ---- inputs ---- */
+  const float *target;                  /* inputs[("color",0,0)]         (B,3,H,W)      */
+  const float *source[MD2_MAX_SRC];     /* inputs[("color",f,0)]         (B,3,H,W)      */
+  const float *T[MD2_MAX_SRC];          /* outputs[("cam_T_cam",0,f)] or inputs["stereo_T"], (B,4,4) */
+  int pose_requires_grad[MD2_MAX_SRC];  /* 0 for the constant stereo_T                   */
+  const float *K;                       /* inputs[("K",0)]               (B,4,4)        */
+  const float *inv_K;                   /* inputs[("inv_K",0)]           (B,4,4)        */
+  const float *disp[MD2_MAX_SCALES];    /* outputs[("disp",s)]           (B,1,H>>s,W>>s) */
+  const float *color[MD2_MAX_SCALES];   /* inputs[("color",0,s)]         (B,3,H>>s,W>>s) */
+  const float *noise[MD2_MAX_SCALES];   /* tie-break draws of trainer.py:468-469, standard normal,
+                                           (B,n_id,H,W), n_id = num_src | 1 (avg) ; NULL if !automask */
+  /* ---- outputs ---- */
+  float *losses;                        /* [0]=losses["loss"], [1+s]=losses["loss/s"]    */
+  float *grad_disp[MD2_MAX_SCALES];     /* d loss / d disp_s             (B,1,H>>s,W>>s) */
+  float *grad_T[MD2_MAX_SRC];           /* d loss / d cam_T_cam          (B,4,4); NULL allowed */
+  /* ---- optional side outputs (NULL = skip), SURVEY.md 3.3 ---- */
+  float *depth[MD2_MAX_SCALES];               /* outputs[("depth",0,s)]    (B,1,H,W)     */
+  float *warped[MD2_MAX_SRC][MD2_MAX_SCALES]; /* outputs[("color",f,s)]    (B,3,H,W)     */
+  float *identity_selection[MD2_MAX_SCALES];  /* outputs["identity_selection/s"] (B,H,W) */
+  float *grad_depth_dbg[MD2_MAX_SCALES];      /* test hook: d loss / d upsampled disp_s (B,1,H,W) */
+} md2_tensors;
+
+int md2_version(void);
+const char *md2_status_string(int status);
+
+/* Bytes of device scratch the fused call needs for `p`. */
+int md2_loss_workspace_bytes(const md2_problem *p, size_t *bytes);
+
+/* Fused replacement for Trainer.generate_images_pred (trainer.py:341-391) followed by
+ * Trainer.compute_losses (trainer.py:407-496) and, when want_grad, the adjoint that
+ * losses["loss"].backward() (trainer.py:208) propagates to disp_s and cam_T_cam. */
+int md2_view_synthesis_loss(const md2_problem *p, const md2_tensors *t,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- per-layer entry points: one per layers.py symbol on the path ---- */
+
+/* layers.py:16-25 disp_to_depth -> scaled_disp, depth (either output may be NULL). n elements. */
+int md2_disp_to_depth(const float *disp, float min_depth, float max_depth,
+                      float *scaled_disp, float *depth, long long n, void *stream);
+int md2_disp_to_depth_backward(const float *disp, float min_depth, float max_depth,
+                               const float *grad_scaled, const float *grad_depth,
+                               float *grad_disp, long long n, void *stream);
+
+/* layers.py:139-168 BackprojectDepth.forward: depth (B,1,H,W), inv_K (B,4,4) -> (B,4,H*W). */
+int md2_backproject_depth(const float *depth, const float *inv_K, float *cam_points,
+                          int batch, int height, int width, void *stream);
+int md2_backproject_depth_backward(const float *grad_cam_points, const float *inv_K,
+                                   float *grad_depth, int batch, int height, int width, void *stream);
+
+/* layers.py:171-193 Project3D.forward: points (B,4,H*W), K, T (B,4,4) -> grid (B,H,W,2). */
+int md2_project3d(const float *points, const float *K, const float *T, float eps, float *pix_coords,
+                  int batch, int height, int width, void *stream);
+/* grad_points (B,4,H*W) and grad_T (B,4,4, accumulated from zero) may each be NULL. */
+int md2_project3d_backward(const float *grad_pix, const float *points, const float *K, const float *T,
+                           float eps, float *grad_points, float *grad_T,
+                           int batch, int height, int width, void *stream);
+
+/* trainer.py:384-387 F.grid_sample(img, grid, padding_mode="border"), bilinear. */
+int md2_grid_sample_border(const float *img, const float *grid, float *out, int batch, int channels,
+                           int in_h, int in_w, int out_h, int out_w, int align_corners, void *stream);
+int md2_grid_sample_border_backward(const float *grad_out, const float *img, const float *grid,
+                                    float *grad_grid, int batch, int channels, int in_h, int in_w,
+                                    int out_h, int out_w, int align_corners, void *stream);
+
+/* layers.py:218-248 SSIM.forward(x, y) -> clamp((1-SSIM)/2,0,1), (B,C,H,W). */
+int md2_ssim(const float *x, const float *y, float *out, int batch, int channels, int height,
+             int width, void *stream);
+/* grad_x and grad_y may each be NULL. */
+int md2_ssim_backward(const float *grad_out, const float *x, const float *y, float *grad_x,
+                      float *grad_y, int batch, int channels, int height, int width, void *stream);
+
+/* layers.py:202-215 get_smooth_loss(disp, img) -> scalar (loss[0]); scratch: 2 doubles. */
+int md2_smooth_loss(const float *disp, const float *img, float *loss, void *scratch16,
+                    int batch, int channels, int height, int width, void *stream);
+int md2_smooth_loss_backward(const float *grad_loss, const float *disp, const float *img,
+                             float *grad_disp, int batch, int channels, int height, int width,
+                             void *stream);
+
+/* layers.py:28-103 transformation_from_parameters(axisangle, translation, invert):
+ * axisangle, translation (B,3) -> T (B,4,4); backward maps grad_T to the two leaves. */
+int md2_pose_to_matrix(const float *axisangle, const float *translation, int invert, float *T,
+                       int batch, void *stream);
+int md2_pose_to_matrix_backward(const float *grad_T, const float *axisangle, const float *translation,
+                                int invert, float *grad_axisangle, float *grad_translation,
+                                int batch, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MD2_LOSS_H_ */

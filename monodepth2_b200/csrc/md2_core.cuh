@@ -1,0 +1,855 @@
+// md2_core.cuh - per-lane building blocks of the fused view-synthesis loss.
+//
+// Everything here is written as host/device functions of ONE lane's state so that
+// the identical arithmetic runs (a) inside the sm_100a kernels of md2_kernels.cu, one
+// lane per CUDA thread with warp shuffles between the stages, and (b) inside the
+// lock-step host emulator of tests/emu (32 lanes in an array), which lets the tile /
+// halo / reflection logic be checked against the oracle without a GPU.  The emulator
+// is test infrastructure; the product path is the CUDA build only.
+//
+// Algorithm (reference file:line under /root/reference, restated per pixel in
+// SURVEY.md Appendix A):
+//   disp_s --bilinear up (trainer.py:350)--> D --(layers.py:16-25)--> depth z
+//   cam = z * inv_K3 (x,y,1)          (layers.py:163-168)
+//   cc  = (K T)[:3] (cam,1), u=cc0/(cc2+eps), v=cc1/(cc2+eps)   (layers.py:182-193)
+//   border-clamped bilinear gather of the source at (u,v)        (trainer.py:384-387)
+//   0.85*SSIM_3x3_reflect + 0.15*L1                              (trainer.py:393-405, layers.py:218-248)
+//   per-pixel min over [identity+1e-5*noise, reprojection]       (trainer.py:426-484)
+// and its adjoint back to D (then disp_s) and to the 3x4 projection P (then cam_T_cam).
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MD2_HD __host__ __device__ __forceinline__
+#else
+#define MD2_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define MD2_LD(p) __ldg(p)
+#define MD2_FMUL(a, b) __fmul_rn(a, b)
+#define MD2_FADD(a, b) __fadd_rn(a, b)
+#define MD2_RCP(a) __frcp_rn(a)
+#define MD2_DIV(a, b) __fdiv_rn(a, b)
+#define MD2_FLOORF(a) floorf(a)
+#else
+#define MD2_LD(p) (*(p))
+#define MD2_FMUL(a, b) md2::host_fmul(a, b)
+#define MD2_FADD(a, b) md2::host_fadd(a, b)
+#define MD2_RCP(a) (1.0f / (a))
+#define MD2_DIV(a, b) ((a) / (b))
+#define MD2_FLOORF(a) floorf(a)
+#endif
+
+namespace md2 {
+
+#if !defined(__CUDA_ARCH__)
+// keep the host compiler from contracting these into an fma
+inline float host_fmul(float a, float b) { volatile float r = a * b; return r; }
+inline float host_fadd(float a, float b) { volatile float r = a + b; return r; }
+#endif
+
+constexpr int kMaxScales = 4;
+constexpr int kMaxSrc = 4;
+constexpr int kLanes = 32;
+constexpr int kOwnCols = 28;   // columns a marching warp owns (32 lanes - 2x2 halo)
+constexpr int kIdCols = 30;    // columns the identity pass owns (32 lanes - 2x1 halo)
+constexpr int kRing = 3;       // rows kept in the per-thread stash ring
+
+constexpr float kSsimC1 = 0.0001f;
+constexpr float kSsimC2 = 0.0009f;
+
+// Device-side view of one evaluation (filled by the host planner in md2_plan.h).
+struct Params {
+  int B, H, W, S, nsrc, nid;
+  int automask, avg, align_corners, want_grad;
+  float a_disp, c_disp;      // scaled_disp = a + c*disp            layers.py:21-23
+  float sx, ox, sy, oy;      // ix = u*sx + ox ; iy = v*sy + oy     (grid normalise o unnormalise)
+  float wmax, hmax;          // W-1, H-1
+  float eps;
+  float gscale;              // 1/(S*B*H*W) [* 1/nsrc under avg_reprojection]
+  float smooth_w[kMaxScales];  // disparity_smoothness / 2^s
+  int seg_rows, nseg, nband, nband_id;
+  const float* tgt;
+  const float* src[kMaxSrc];
+  const float* Tm[kMaxSrc];
+  int pose_grad[kMaxSrc];
+  const float* K;
+  const float* invK;
+  const float* disp[kMaxScales];
+  const float* color[kMaxScales];
+  const float* noise[kMaxScales];
+  // workspace
+  float* proj;     // (B,nsrc,12): M=P3*invK3 (row-major 3x3) then p4
+  float* idloss;   // (B,nsrc,H,W)
+  float* dD[kMaxScales];   // (B,H,W)   d loss / d upsampled disp_s
+  float* gn[kMaxScales];   // (B,Hs,Ws) smoothness numerator gradient
+  double* acc;     // accumulators, layout below
+  // outputs
+  float* losses;
+  float* grad_disp[kMaxScales];
+  float* grad_T[kMaxSrc];
+  float* depth[kMaxScales];
+  float* warped[kMaxSrc][kMaxScales];
+  float* idsel[kMaxScales];
+};
+
+// accumulator layout (doubles)
+MD2_HD int acc_photo(int s) { return s; }
+MD2_HD int acc_smx(int s) { return kMaxScales + s; }
+MD2_HD int acc_smy(int s) { return 2 * kMaxScales + s; }
+MD2_HD int acc_dispsum(const Params& P, int s, int b) { return 3 * kMaxScales + s * P.B + b; }
+MD2_HD int acc_dot(const Params& P, int s, int b) { return 3 * kMaxScales + kMaxScales * P.B + s * P.B + b; }
+MD2_HD int acc_dP(const Params& P, int b, int f, int k) {
+  return 3 * kMaxScales + 2 * kMaxScales * P.B + (b * P.nsrc + f) * 12 + k;
+}
+MD2_HD int acc_count(const Params& P) { return 3 * kMaxScales + 2 * kMaxScales * P.B + P.B * P.nsrc * 12; }
+
+struct WarpJob {
+  int s, b;
+  int x0;        // first owned column
+  int y0, y1;    // owned rows [y0, y1)
+};
+
+template <int NSRC_, bool AVG_, bool AUTOMASK_, bool GRAD_>
+struct Cfg {
+  static constexpr int NSRC = NSRC_;
+  static constexpr bool AVG = AVG_;
+  static constexpr bool AUTOMASK = AUTOMASK_;
+  static constexpr bool GRAD = GRAD_;
+  static constexpr int NCS = AVG_ ? NSRC_ : 1;                   // coefficient sets shipped per window
+  static constexpr int NID = AUTOMASK_ ? (AVG_ ? 1 : NSRC_) : 0; // identity candidates
+  static constexpr int STASH = 4 + 11 * NSRC_;                   // floats per ring row
+};
+
+// ------------------------------------------------------------------ SSIM pieces
+// Sums over the 3x3 window: sx=Σx, sxx=Σx², sxy=Σxy, sy=Σy, syy=Σy².
+// Returns clamp((1 - n/d)/2, 0, 1)  (layers.py:238-248).  The means and (co)variances are
+// kept multiplied by 9 / 81 (the factors cancel in n/d), which avoids the 1/9 constant
+// whose fp32 rounding would be amplified by the E[x^2]-mu^2 cancellation:
+//   81 n1 = 2 sx sy + 81 C1          81 n2 = 2 (9 sxy - sx sy) + 81 C2
+//   81 d1 = sx^2 + sy^2 + 81 C1      81 d2 = 9 (sxx + syy) - sx^2 - sy^2 + 81 C2
+// When `coef` is non-null it receives -0.5*live*(alpha, beta, gamma) with
+// d(n/d)/dx_j = alpha + beta*x_j + gamma*y_j for every x_j of the window.
+MD2_HD float ssim_window(float sx, float sxx, float sxy, float sy, float syy, float* coef) {
+  const float c1 = 81.0f * kSsimC1, c2 = 81.0f * kSsimC2;
+  const float pxy = sx * sy;
+  const float pp = fmaf(sx, sx, sy * sy);
+  const float n1 = fmaf(2.0f, pxy, c1);
+  const float n2 = fmaf(2.0f, fmaf(9.0f, sxy, -pxy), c2);
+  const float d1 = pp + c1;
+  const float d2 = fmaf(9.0f, sxx + syy, -pp) + c2;
+  const float N = n1 * n2, D = d1 * d2;
+  const float invD = MD2_RCP(D);
+  const float Q = N * invD;
+  const float raw = fmaf(-0.5f, Q, 0.5f);
+  const float S = fminf(fmaxf(raw, 0.0f), 1.0f);
+  if (coef) {
+    const bool live = (raw >= 0.0f) && (raw <= 1.0f);
+    const float k = live ? -0.5f : 0.0f;
+    const float QD = Q * invD;                       // N / D^2
+    const float alpha = 2.0f * (sy * (n2 - n1) * invD - sx * (d2 - d1) * QD);
+    const float beta = -18.0f * d1 * QD;
+    const float gamma = 18.0f * n1 * invD;
+    coef[0] = k * alpha;
+    coef[1] = k * beta;
+    coef[2] = k * gamma;
+  }
+  return S;
+}
+
+// ------------------------------------------------------------------ lane state
+template <class C>
+struct Lane {
+  // constants of the job
+  int x;            // column of this lane (may be outside the image)
+  int xi;           // x clamped into the image (safe for addressing)
+  bool colok;
+  float qa[C::NSRC][3];   // M[i][0]*x + M[i][2]
+  float qb[C::NSRC][3];   // M[i][1]
+  float p4[C::NSRC][3];   // (K T)[i][3]
+  int ux0, ux1;           // bilinear up-sampling taps of disp_s in x
+  float ul0, ul1;
+  // forward rolling state (horizontal 3-sums of the two previous rows)
+  float H1[C::NSRC][3][3], H2[C::NSRC][3][3];   // [f][c][x,xx,xy]
+  float HY1[3][2], HY2[3][2];                   // [c][y,yy]
+  float pr1[C::NSRC][3], tg1[3];                // own pred / target of the previous row
+  // exports of the current step
+  float pr[C::NSRC][3], tg[3];
+  float coef[C::NCS][9];                        // [set][c*3 + {alpha,beta,gamma}]
+  int tag;                                      // winner of the current window row
+  // backward rolling state
+  float B1[C::NSRC][9], B2[C::NSRC][9];
+  int tag1;                                     // winner one window row earlier
+  // accumulators
+  float loss;
+  float S1[C::NSRC][3], S2[C::NSRC][3], S3[C::NSRC][3];
+};
+
+template <class C>
+struct Xchg1 {   // what stage B needs from a horizontal neighbour
+  float pr[C::NSRC][3];
+  float tg[3];
+};
+template <class C>
+struct Xchg2 {   // what stage C needs from a horizontal neighbour
+  float coef[C::NCS][9];
+  int tag;
+};
+
+MD2_HD int ring_slot(int t) { return ((t % kRing) + kRing) % kRing; }
+
+// thread-private stash: element (slot, field) of lane `lane_off` with lane stride `stride`
+struct Stash {
+  float* base;
+  int stride;     // distance between consecutive fields of one lane (threads per CTA / lanes)
+  MD2_HD float& at(int slot, int field, int nfields) const {
+    return base[(slot * nfields + field) * stride];
+  }
+};
+
+template <class C>
+MD2_HD void lane_init(Lane<C>& L, const Params& P, const WarpJob& J, int lane) {
+  L.x = J.x0 - 2 + lane;
+  L.colok = (L.x >= 0) && (L.x < P.W);
+  L.xi = L.x < 0 ? 0 : (L.x >= P.W ? P.W - 1 : L.x);
+  const float xf = (float)L.xi;
+#pragma unroll
+  for (int f = 0; f < C::NSRC; ++f) {
+    const float* m = P.proj + (J.b * C::NSRC + f) * 12;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      L.qa[f][i] = fmaf(MD2_LD(m + i * 3 + 0), xf, MD2_LD(m + i * 3 + 2));
+      L.qb[f][i] = MD2_LD(m + i * 3 + 1);
+      L.p4[f][i] = MD2_LD(m + 9 + i);
+    }
+  }
+  if (J.s > 0) {
+    const int Ws = P.W >> J.s;
+    const float r = 1.0f / (float)(1 << J.s);
+    float sxr = fmaf(r, (float)L.xi + 0.5f, -0.5f);
+    sxr = sxr < 0.0f ? 0.0f : sxr;
+    L.ux0 = (int)sxr;
+    L.ux1 = L.ux0 + ((L.ux0 < Ws - 1) ? 1 : 0);
+    L.ul1 = sxr - (float)L.ux0;
+    L.ul0 = 1.0f - L.ul1;
+  } else {
+    L.ux0 = L.ux1 = L.xi;
+    L.ul0 = 1.0f; L.ul1 = 0.0f;
+  }
+#pragma unroll
+  for (int f = 0; f < C::NSRC; ++f) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { L.H1[f][c][k] = 0.f; L.H2[f][c][k] = 0.f; }
+      L.pr1[f][c] = 0.f; L.pr[f][c] = 0.f;
+      L.S1[f][c] = 0.f; L.S2[f][c] = 0.f; L.S3[f][c] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { L.B1[f][k] = 0.f; L.B2[f][k] = 0.f; }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    L.HY1[c][0] = L.HY1[c][1] = L.HY2[c][0] = L.HY2[c][1] = 0.f;
+    L.tg1[c] = 0.f; L.tg[c] = 0.f;
+  }
+#pragma unroll
+  for (int n = 0; n < C::NCS; ++n)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) L.coef[n][k] = 0.f;
+  L.tag = -1; L.tag1 = -1;
+  L.loss = 0.f;
+}
+
+// Up-sampled disparity D at (x, y) of the full-resolution grid (trainer.py:350-351,
+// torch upsample_bilinear2d, align_corners=False); scale 0 is the identity.
+template <class C>
+MD2_HD float sample_disp(const Lane<C>& L, const Params& P, const WarpJob& J, int y) {
+  const float* d = P.disp[J.s];
+  if (J.s == 0) return MD2_LD(d + ((size_t)J.b * P.H + y) * P.W + L.xi);
+  const int Hs = P.H >> J.s, Ws = P.W >> J.s;
+  const float r = 1.0f / (float)(1 << J.s);
+  float syr = fmaf(r, (float)y + 0.5f, -0.5f);
+  syr = syr < 0.0f ? 0.0f : syr;
+  const int y0 = (int)syr;
+  const int y1 = y0 + ((y0 < Hs - 1) ? 1 : 0);
+  const float l1 = syr - (float)y0, l0 = 1.0f - l1;
+  const float* r0 = d + ((size_t)J.b * Hs + y0) * Ws;
+  const float* r1 = d + ((size_t)J.b * Hs + y1) * Ws;
+  const float top = L.ul0 * MD2_LD(r0 + L.ux0) + L.ul1 * MD2_LD(r0 + L.ux1);
+  const float bot = L.ul0 * MD2_LD(r1 + L.ux0) + L.ul1 * MD2_LD(r1 + L.ux1);
+  return l0 * top + l1 * bot;
+}
+
+// ------------------------------------------------------------------ stage A
+// Row t: depth, projection into every source, border-clamped bilinear gather.
+// Exports pr/tg for the neighbour exchange and stashes what the adjoint of row t
+// will need two steps later.
+template <class C>
+MD2_HD void stage_a(Lane<C>& L, const Params& P, const WarpJob& J, int t, const Stash& st) {
+  const bool act = L.colok && (t >= 0) && (t < P.H);
+  const int slot = ring_slot(t);
+  float z = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) L.tg[c] = 0.f;
+  if (act) {
+    const size_t plane = (size_t)P.H * P.W;
+    const float* tp = P.tgt + (size_t)J.b * 3 * plane + (size_t)t * P.W + L.xi;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) L.tg[c] = MD2_LD(tp + c * plane);
+    const float D = sample_disp(L, P, J, t);
+    const float sd = MD2_FADD(P.a_disp, MD2_FMUL(P.c_disp, D));
+    z = MD2_RCP(sd);
+    if (P.depth[J.s] && t >= J.y0 && t < J.y1 && L.x >= J.x0 && L.x < J.x0 + kOwnCols)
+      P.depth[J.s][((size_t)J.b * P.H + t) * P.W + L.xi] = z;
+  }
+  if (C::GRAD) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) st.at(slot, c, C::STASH) = L.tg[c];
+    st.at(slot, 3, C::STASH) = z;
+  }
+  const float yf = (float)t;
+#pragma unroll
+  for (int f = 0; f < C::NSRC; ++f) {
+    float pr[3] = {0.f, 0.f, 0.f}, dxp[3] = {0.f, 0.f, 0.f}, dyp[3] = {0.f, 0.f, 0.f};
+    float u = 0.f, v = 0.f;
+    if (act) {
+      const float q0 = fmaf(L.qb[f][0], yf, L.qa[f][0]);
+      const float q1 = fmaf(L.qb[f][1], yf, L.qa[f][1]);
+      const float q2 = fmaf(L.qb[f][2], yf, L.qa[f][2]);
+      const float c0 = fmaf(z, q0, L.p4[f][0]);
+      const float c1 = fmaf(z, q1, L.p4[f][1]);
+      const float c2 = fmaf(z, q2, L.p4[f][2]);
+      const float inv = MD2_RCP(c2 + P.eps);
+      u = c0 * inv;
+      v = c1 * inv;
+      const float ix = fmaf(u, P.sx, P.ox);
+      const float iy = fmaf(v, P.sy, P.oy);
+      const bool mx = (ix > 0.0f) && (ix < P.wmax);
+      const bool my = (iy > 0.0f) && (iy < P.hmax);
+      const float ixc = fminf(fmaxf(ix, 0.0f), P.wmax);
+      const float iyc = fminf(fmaxf(iy, 0.0f), P.hmax);
+      const float fx0 = MD2_FLOORF(ixc), fy0 = MD2_FLOORF(iyc);
+      const float wx = ixc - fx0, wy = iyc - fy0;
+      const int x0 = (int)fx0, y0 = (int)fy0;
+      const int x1 = (x0 + 1 < P.W) ? x0 + 1 : P.W - 1;
+      const int y1 = (y0 + 1 < P.H) ? y0 + 1 : P.H - 1;
+      const size_t plane = (size_t)P.H * P.W;
+      const float* sp = P.src[f] + (size_t)J.b * 3 * plane;
+      const float* r0 = sp + (size_t)y0 * P.W;
+      const float* r1 = sp + (size_t)y1 * P.W;
+      const float gxs = mx ? P.sx * inv : 0.0f;
+      const float gys = my ? P.sy * inv : 0.0f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float nw = MD2_LD(r0 + c * plane + x0), ne = MD2_LD(r0 + c * plane + x1);
+        const float sw = MD2_LD(r1 + c * plane + x0), se = MD2_LD(r1 + c * plane + x1);
+        const float dn = ne - nw, ds = se - sw;
+        const float top = fmaf(wx, dn, nw), bot = fmaf(wx, ds, sw);
+        const float dv = bot - top;
+        pr[c] = fmaf(wy, dv, top);
+        dxp[c] = fmaf(wy, ds - dn, dn) * gxs;
+        dyp[c] = dv * gys;
+      }
+      float* wout = P.warped[f][J.s];
+      if (wout && t >= J.y0 && t < J.y1 && L.x >= J.x0 && L.x < J.x0 + kOwnCols) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) wout[((size_t)J.b * 3 + c) * plane + (size_t)t * P.W + L.xi] = pr[c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) L.pr[f][c] = pr[c];
+    if (C::GRAD) {
+      const int o = 4 + 11 * f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        st.at(slot, o + c, C::STASH) = pr[c];
+        st.at(slot, o + 3 + c, C::STASH) = dxp[c];
+        st.at(slot, o + 6 + c, C::STASH) = dyp[c];
+      }
+      st.at(slot, o + 9, C::STASH) = u;
+      st.at(slot, o + 10, C::STASH) = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ stage B
+// Horizontal sums of row t, SSIM + L1 of window row t-1, per-pixel minimum and the
+// SSIM-adjoint coefficients of the winning source.  `own_win` = this lane owns the
+// window (adds it to the loss).
+template <class C>
+MD2_HD void stage_b(Lane<C>& L, const Params& P, const WarpJob& J, int t, int lane,
+                    const Xchg1<C>& lf, const Xchg1<C>& rt) {
+  const int yw = t - 1;
+  const bool left_edge = (L.x == 0), right_edge = (L.x == P.W - 1);
+  // horizontal 3-sums of row t with the reflection of ReflectionPad2d(1) (layers.py:235-236)
+  float H0[C::NSRC][3][3], HY0[3][2];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float yl = left_edge ? rt.tg[c] : lf.tg[c];
+    const float yr = right_edge ? lf.tg[c] : rt.tg[c];
+    const float yc = L.tg[c];
+    HY0[c][0] = yl + yc + yr;
+    HY0[c][1] = fmaf(yr, yr, fmaf(yc, yc, yl * yl));
+#pragma unroll
+    for (int f = 0; f < C::NSRC; ++f) {
+      const float xl = left_edge ? rt.pr[f][c] : lf.pr[f][c];
+      const float xr = right_edge ? lf.pr[f][c] : rt.pr[f][c];
+      const float xc = L.pr[f][c];
+      H0[f][c][0] = xl + xc + xr;
+      H0[f][c][1] = fmaf(xr, xr, fmaf(xc, xc, xl * xl));
+      H0[f][c][2] = fmaf(xr, yr, fmaf(xc, yc, xl * yl));
+    }
+  }
+  // windows this job needs: its own rows plus one halo row each side (for the adjoint)
+  const bool win_ok = L.colok && (yw >= 0) && (yw < P.H) && (lane >= 1) && (lane <= kLanes - 2) &&
+                      (yw >= J.y0 - (C::GRAD ? 1 : 0)) && (yw < J.y1 + (C::GRAD ? 1 : 0));
+  const bool own_win = win_ok && (lane >= 2) && (lane < 2 + kOwnCols) && (yw >= J.y0) && (yw < J.y1);
+  int tag = -1;
+#pragma unroll
+  for (int n = 0; n < C::NCS; ++n)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) L.coef[n][k] = 0.f;
+  if (win_ok) {
+    const bool top_edge = (yw == 0), bot_edge = (yw == P.H - 1);
+    float V[C::NSRC][3][3], VY[3][2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float up = top_edge ? HY0[c][k] : L.HY2[c][k];
+        const float dn = bot_edge ? L.HY2[c][k] : HY0[c][k];
+        VY[c][k] = up + L.HY1[c][k] + dn;
+      }
+#pragma unroll
+      for (int f = 0; f < C::NSRC; ++f)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float up = top_edge ? H0[f][c][k] : L.H2[f][c][k];
+          const float dn = bot_edge ? L.H2[f][c][k] : H0[f][c][k];
+          V[f][c][k] = up + L.H1[f][c][k] + dn;
+        }
+    }
+    float rl[C::NSRC];
+#pragma unroll
+    for (int f = 0; f < C::NSRC; ++f) {
+      float ss = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        ss += ssim_window(V[f][c][0], V[f][c][1], V[f][c][2], VY[c][0], VY[c][1], nullptr);
+        l1 += fabsf(L.tg1[c] - L.pr1[f][c]);
+      }
+      // trainer.py:403: 0.85 * ssim.mean(1) + 0.15 * l1.mean(1)
+      rl[f] = MD2_FADD(MD2_FMUL(0.85f, ss / 3.0f), MD2_FMUL(0.15f, l1 / 3.0f));
+    }
+    // candidates in the order of trainer.py:471: identity first, then reprojection
+    float best = INFINITY;
+    const size_t plane = (size_t)P.H * P.W;
+    const size_t pix = (size_t)yw * P.W + L.xi;
+    if (C::AUTOMASK) {
+      if (C::AVG) {
+        float acc = 0.f;
+#pragma unroll
+        for (int f = 0; f < C::NSRC; ++f) acc += MD2_LD(P.idloss + ((size_t)J.b * C::NSRC + f) * plane + pix);
+        const float nz = MD2_LD(P.noise[J.s] + (size_t)J.b * plane + pix);
+        best = MD2_FADD(acc / (float)C::NSRC, MD2_FMUL(nz, 0.00001f));
+      } else {
+#pragma unroll
+        for (int f = 0; f < C::NSRC; ++f) {
+          const float idv = MD2_LD(P.idloss + ((size_t)J.b * C::NSRC + f) * plane + pix);
+          const float nz = MD2_LD(P.noise[J.s] + ((size_t)J.b * C::NSRC + f) * plane + pix);
+          const float cand = MD2_FADD(idv, MD2_FMUL(nz, 0.00001f));
+          if (cand < best) best = cand;
+        }
+      }
+    }
+    if (C::AVG) {
+      float acc = 0.f;
+#pragma unroll
+      for (int f = 0; f < C::NSRC; ++f) acc += rl[f];
+      const float cand = acc / (float)C::NSRC;
+      if (cand < best) { best = cand; tag = 0; }
+    } else {
+#pragma unroll
+      for (int f = 0; f < C::NSRC; ++f)
+        if (rl[f] < best) { best = rl[f]; tag = f; }
+    }
+    if (own_win) {
+      L.loss += best;
+      if (C::AUTOMASK && P.idsel[J.s]) P.idsel[J.s][(size_t)J.b * plane + pix] = (tag >= 0) ? 1.0f : 0.0f;
+    }
+    if (C::GRAD && tag >= 0) {
+      if (C::AVG) {
+#pragma unroll
+        for (int f = 0; f < C::NSRC; ++f)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            ssim_window(V[f][c][0], V[f][c][1], V[f][c][2], VY[c][0], VY[c][1], &L.coef[f][c * 3]);
+      } else {
+        // select the winner's window sums without dynamic register indexing
+        float W3[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            float v = V[0][c][k];
+#pragma unroll
+            for (int f = 1; f < C::NSRC; ++f) v = (tag == f) ? V[f][c][k] : v;
+            W3[c][k] = v;
+          }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          ssim_window(W3[c][0], W3[c][1], W3[c][2], VY[c][0], VY[c][1], &L.coef[0][c * 3]);
+      }
+    }
+  }
+  L.tag = tag;
+  // roll the forward state
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { L.HY2[c][k] = L.HY1[c][k]; L.HY1[c][k] = HY0[c][k]; }
+    L.tg1[c] = L.tg[c];
+#pragma unroll
+    for (int f = 0; f < C::NSRC; ++f) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { L.H2[f][c][k] = L.H1[f][c][k]; L.H1[f][c][k] = H0[f][c][k]; }
+      L.pr1[f][c] = L.pr[f][c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ stage C
+// Adjoint for pixel row t-2: 3x3 box adjoint of the coefficient maps (with the fold
+// of the reflection ring), d loss/d pred, grid-sample and projection
+// adjoints (A.3).  Writes d loss / d D for owned pixels and accumulates the pose sums.
+template <class C>
+MD2_HD void stage_c(Lane<C>& L, const Params& P, const WarpJob& J, int t, int lane,
+                    const Xchg2<C>& lf, const Xchg2<C>& rt, const Stash& st) {
+  const int yp = t - 2;
+  const float wl = (L.x == 1) ? 2.0f : 1.0f;
+  const float wr = (L.x == P.W - 2) ? 2.0f : 1.0f;
+  float B0[C::NSRC][9];
+#pragma unroll
+  for (int f = 0; f < C::NSRC; ++f) {
+    const int n = C::AVG ? f : 0;
+    const float ml = (C::AVG || lf.tag == f) ? wl : 0.0f;
+    const float mc = (C::AVG || L.tag == f) ? 1.0f : 0.0f;
+    const float mr = (C::AVG || rt.tag == f) ? wr : 0.0f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+      B0[f][k] = fmaf(ml, lf.coef[n][k], fmaf(mr, rt.coef[n][k], mc * L.coef[n][k]));
+  }
+  const bool own = L.colok && (lane >= 2) && (lane < 2 + kOwnCols) && (yp >= J.y0) && (yp < J.y1);
+  if (own) {
+    const float wu = (yp == 1) ? 2.0f : 1.0f;
+    const float wd = (yp == P.H - 2) ? 2.0f : 1.0f;
+    const int slot = ring_slot(yp);
+    float tg[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) tg[c] = st.at(slot, c, C::STASH);
+    const float z = st.at(slot, 3, C::STASH);
+    const float yf = (float)yp;
+    float dzsum = 0.f;
+#pragma unroll
+    for (int f = 0; f < C::NSRC; ++f) {
+      const int o = 4 + 11 * f;
+      const bool won = C::AVG ? (L.tag1 >= 0) : (L.tag1 == f);
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float xj = st.at(slot, o + c, C::STASH);
+        const float A = fmaf(wu, L.B2[f][c * 3 + 0], fmaf(wd, B0[f][c * 3 + 0], L.B1[f][c * 3 + 0]));
+        const float Bq = fmaf(wu, L.B2[f][c * 3 + 1], fmaf(wd, B0[f][c * 3 + 1], L.B1[f][c * 3 + 1]));
+        const float G = fmaf(wu, L.B2[f][c * 3 + 2], fmaf(wd, B0[f][c * 3 + 2], L.B1[f][c * 3 + 2]));
+        // d loss / d pred_c = 0.85/3 * SSIM part + 0.15/3 * sign(x - y) [if this source won here]
+        float g = (0.85f / 3.0f) * fmaf(xj, Bq, fmaf(tg[c], G, A));
+        if (won) {
+          const float df = xj - tg[c];
+          g += (df > 0.f) ? (0.15f / 3.0f) : ((df < 0.f) ? -(0.15f / 3.0f) : 0.0f);
+        }
+        d0 = fmaf(g, st.at(slot, o + 3 + c, C::STASH), d0);
+        d1 = fmaf(g, st.at(slot, o + 6 + c, C::STASH), d1);
+      }
+      const float u = st.at(slot, o + 9, C::STASH), v = st.at(slot, o + 10, C::STASH);
+      const float d2 = -fmaf(u, d0, v * d1);
+      const float q0 = fmaf(L.qb[f][0], yf, L.qa[f][0]);
+      const float q1 = fmaf(L.qb[f][1], yf, L.qa[f][1]);
+      const float q2 = fmaf(L.qb[f][2], yf, L.qa[f][2]);
+      dzsum += fmaf(d0, q0, fmaf(d1, q1, d2 * q2));
+      const float zy = z * yf;
+      L.S1[f][0] = fmaf(d0, z, L.S1[f][0]); L.S1[f][1] = fmaf(d1, z, L.S1[f][1]); L.S1[f][2] = fmaf(d2, z, L.S1[f][2]);
+      L.S2[f][0] = fmaf(d0, zy, L.S2[f][0]); L.S2[f][1] = fmaf(d1, zy, L.S2[f][1]); L.S2[f][2] = fmaf(d2, zy, L.S2[f][2]);
+      L.S3[f][0] += d0; L.S3[f][1] += d1; L.S3[f][2] += d2;
+    }
+    // d depth / d D = -c * z^2  (layers.py:23-24)
+    const float dD = -P.c_disp * z * z * dzsum * P.gscale;
+    P.dD[J.s][((size_t)J.b * P.H + yp) * P.W + L.xi] = dD;
+  }
+#pragma unroll
+  for (int f = 0; f < C::NSRC; ++f)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { L.B2[f][k] = L.B1[f][k]; L.B1[f][k] = B0[f][k]; }
+  L.tag1 = L.tag;
+}
+
+// Turns the lane's pose sums into its share of dP (3x4, row-major) for source f:
+// dP[i][k<3] = a_k S1_i + b_k S2_i with inv_K3 (x,y,1)_k = a_k + b_k y ; dP[i][3] = S3_i.
+template <class C>
+MD2_HD void lane_dP(const Lane<C>& L, const Params& P, const WarpJob& J, int f, float* dP) {
+  const float* ik = P.invK + (size_t)J.b * 16;
+  const float xf = (float)L.xi;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float ak = fmaf(MD2_LD(ik + k * 4 + 0), xf, MD2_LD(ik + k * 4 + 2));
+    const float bk = MD2_LD(ik + k * 4 + 1);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) dP[i * 4 + k] = fmaf(ak, L.S1[f][i], bk * L.S2[f][i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) dP[i * 4 + 3] = L.S3[f][i];
+}
+
+// ------------------------------------------------------------------ identity pass
+// Scale-independent identity reprojection losses (trainer.py:432-439): SSIM+L1 between
+// the unwarped source f and the target.  One lane per column, halo 1.
+template <int NSRC>
+struct IdLane {
+  int x, xi;
+  bool colok;
+  float H1[NSRC][3][3], H2[NSRC][3][3];
+  float HY1[3][2], HY2[3][2];
+  float pr1[NSRC][3], tg1[3];
+  float pr[NSRC][3], tg[3];
+};
+template <int NSRC>
+struct IdXchg {
+  float pr[NSRC][3];
+  float tg[3];
+};
+
+template <int NSRC>
+MD2_HD void id_init(IdLane<NSRC>& L, const Params& P, int x0, int lane) {
+  L.x = x0 - 1 + lane;
+  L.colok = (L.x >= 0) && (L.x < P.W);
+  L.xi = L.x < 0 ? 0 : (L.x >= P.W ? P.W - 1 : L.x);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    L.HY1[c][0] = L.HY1[c][1] = L.HY2[c][0] = L.HY2[c][1] = 0.f;
+    L.tg1[c] = L.tg[c] = 0.f;
+#pragma unroll
+    for (int f = 0; f < NSRC; ++f) {
+      L.pr1[f][c] = L.pr[f][c] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) L.H1[f][c][k] = L.H2[f][c][k] = 0.f;
+    }
+  }
+}
+
+template <int NSRC>
+MD2_HD void id_stage_a(IdLane<NSRC>& L, const Params& P, int b, int t) {
+  const bool act = L.colok && t >= 0 && t < P.H;
+  const size_t plane = (size_t)P.H * P.W;
+  const size_t off = (size_t)b * 3 * plane + (size_t)(act ? t : 0) * P.W + L.xi;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    L.tg[c] = act ? MD2_LD(P.tgt + off + c * plane) : 0.f;
+#pragma unroll
+    for (int f = 0; f < NSRC; ++f) L.pr[f][c] = act ? MD2_LD(P.src[f] + off + c * plane) : 0.f;
+  }
+}
+
+template <int NSRC>
+MD2_HD void id_stage_b(IdLane<NSRC>& L, const Params& P, int b, int t, int lane, int y0, int y1,
+                       const IdXchg<NSRC>& lf, const IdXchg<NSRC>& rt) {
+  const int yw = t - 1;
+  const bool left_edge = (L.x == 0), right_edge = (L.x == P.W - 1);
+  float H0[NSRC][3][3], HY0[3][2];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float yl = left_edge ? rt.tg[c] : lf.tg[c];
+    const float yr = right_edge ? lf.tg[c] : rt.tg[c];
+    const float yc = L.tg[c];
+    HY0[c][0] = yl + yc + yr;
+    HY0[c][1] = fmaf(yr, yr, fmaf(yc, yc, yl * yl));
+#pragma unroll
+    for (int f = 0; f < NSRC; ++f) {
+      const float xl = left_edge ? rt.pr[f][c] : lf.pr[f][c];
+      const float xr = right_edge ? lf.pr[f][c] : rt.pr[f][c];
+      const float xc = L.pr[f][c];
+      H0[f][c][0] = xl + xc + xr;
+      H0[f][c][1] = fmaf(xr, xr, fmaf(xc, xc, xl * xl));
+      H0[f][c][2] = fmaf(xr, yr, fmaf(xc, yc, xl * yl));
+    }
+  }
+  const bool own = L.colok && yw >= y0 && yw < y1 && lane >= 1 && lane <= kIdCols;
+  if (own) {
+    const bool top_edge = (yw == 0), bot_edge = (yw == P.H - 1);
+    const size_t plane = (size_t)P.H * P.W;
+#pragma unroll
+    for (int f = 0; f < NSRC; ++f) {
+      float ss = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float vy[2], vx[3];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const float up = top_edge ? HY0[c][k] : L.HY2[c][k];
+          const float dn = bot_edge ? L.HY2[c][k] : HY0[c][k];
+          vy[k] = up + L.HY1[c][k] + dn;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float up = top_edge ? H0[f][c][k] : L.H2[f][c][k];
+          const float dn = bot_edge ? L.H2[f][c][k] : H0[f][c][k];
+          vx[k] = up + L.H1[f][c][k] + dn;
+        }
+        ss += ssim_window(vx[0], vx[1], vx[2], vy[0], vy[1], nullptr);
+        l1 += fabsf(L.tg1[c] - L.pr1[f][c]);
+      }
+      P.idloss[((size_t)b * NSRC + f) * plane + (size_t)yw * P.W + L.xi] =
+          MD2_FADD(MD2_FMUL(0.85f, ss / 3.0f), MD2_FMUL(0.15f, l1 / 3.0f));
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { L.HY2[c][k] = L.HY1[c][k]; L.HY1[c][k] = HY0[c][k]; }
+    L.tg1[c] = L.tg[c];
+#pragma unroll
+    for (int f = 0; f < NSRC; ++f) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { L.H2[f][c][k] = L.H1[f][c][k]; L.H1[f][c][k] = H0[f][c][k]; }
+      L.pr1[f][c] = L.pr[f][c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ small per-element pieces
+// proj table: M = (K T)[:3,:3] * invK[:3,:3], p4 = (K T)[:3,3], in double then rounded once.
+MD2_HD void setup_projection(const Params& P, int b, int f) {
+  const float* K = P.K + (size_t)b * 16;
+  const float* T = P.Tm[f] + (size_t)b * 16;
+  const float* iK = P.invK + (size_t)b * 16;
+  double Pm[3][4];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 4; ++j) {
+      double a = 0.0;
+      for (int k = 0; k < 4; ++k) a += (double)MD2_LD(K + i * 4 + k) * (double)MD2_LD(T + k * 4 + j);
+      Pm[i][j] = a;
+    }
+  float* o = P.proj + (size_t)(b * P.nsrc + f) * 12;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) {
+      double a = 0.0;
+      for (int k = 0; k < 3; ++k) a += Pm[i][k] * (double)MD2_LD(iK + k * 4 + j);
+      o[i * 3 + j] = (float)a;
+    }
+    o[9 + i] = (float)Pm[i][3];
+  }
+}
+
+// Edge-aware smoothness at pixel (x,y) of scale s (layers.py:202-215 on the
+// mean-normalised disparity of trainer.py:486-487).  Returns the pixel's two forward
+// edge terms and gn = d(sum_x/Nx + sum_y/Ny) / d norm_disp(x,y).
+MD2_HD void smooth_pixel(const Params& P, int s, int b, int y, int x, float m,
+                         float& ex_out, float& ey_out, float& gn_out) {
+  const int Hs = P.H >> s, Ws = P.W >> s;
+  const size_t plane = (size_t)Hs * Ws;
+  const float* d = P.disp[s] + (size_t)b * plane;
+  const float* im = P.color[s] + (size_t)b * 3 * plane;
+  const size_t p = (size_t)y * Ws + x;
+  const float inx = 1.0f / ((float)P.B * (float)Hs * (float)(Ws - 1));
+  const float iny = 1.0f / ((float)P.B * (float)(Hs - 1) * (float)Ws);
+  const float n0 = MD2_DIV(MD2_LD(d + p), m);
+  float gn = 0.f, ex = 0.f, ey = 0.f;
+  auto edge = [&](size_t pa, size_t pb, float na, float nb, float& e) -> float {
+    // returns sign(na - nb) * exp(-mean_c |I(pa) - I(pb)|)
+    float g = 0.f;
+    for (int c = 0; c < 3; ++c) g += fabsf(MD2_LD(im + c * plane + pa) - MD2_LD(im + c * plane + pb));
+    const float w = expf(-(g / 3.0f));
+    const float df = na - nb;
+    e = fabsf(df) * w;
+    return (df > 0.f) ? w : ((df < 0.f) ? -w : 0.f);
+  };
+  float e;
+  if (x + 1 < Ws) { gn += inx * edge(p, p + 1, n0, MD2_DIV(MD2_LD(d + p + 1), m), e); ex = e; }
+  if (x > 0)      { gn -= inx * edge(p - 1, p, MD2_DIV(MD2_LD(d + p - 1), m), n0, e); }
+  if (y + 1 < Hs) { gn += iny * edge(p, p + Ws, n0, MD2_DIV(MD2_LD(d + p + Ws), m), e); ey = e; }
+  if (y > 0)      { gn -= iny * edge(p - Ws, p, MD2_DIV(MD2_LD(d + p - Ws), m), n0, e); }
+  ex_out = ex; ey_out = ey; gn_out = gn;
+}
+
+// Final gradient of disp_s at coarse pixel (X,Y): adjoint of the bilinear up-sampling
+// (gather over the fine pixels whose taps hit (X,Y)) plus the smoothness term (A.4).
+MD2_HD float final_grad_disp(const Params& P, int s, int b, int Y, int X) {
+  const int Hs = P.H >> s, Ws = P.W >> s;
+  const size_t p = ((size_t)b * Hs + Y) * Ws + X;
+  const double sum = P.acc[acc_dispsum(P, s, b)];
+  const float m = (float)(sum / ((double)Hs * Ws)) + 1e-7f;
+  const float dot = (float)P.acc[acc_dot(P, s, b)];
+  const float wsm = P.smooth_w[s] / (float)P.S;
+  float g = wsm * (MD2_LD(P.gn[s] + p) / m - dot / (m * m * (float)Hs * (float)Ws));
+  const float* dD = P.dD[s] + (size_t)b * P.H * P.W;
+  if (s == 0) return g + MD2_LD(dD + (size_t)Y * P.W + X);
+  const int k = 1 << s;
+  const float r = 1.0f / (float)k;
+  const int ylo = (Y - 1) * k - 1 < 0 ? 0 : (Y - 1) * k - 1;
+  const int yhi = (Y + 2) * k + 1 > P.H ? P.H : (Y + 2) * k + 1;
+  const int xlo = (X - 1) * k - 1 < 0 ? 0 : (X - 1) * k - 1;
+  const int xhi = (X + 2) * k + 1 > P.W ? P.W : (X + 2) * k + 1;
+  float acc = 0.f;
+  for (int y = ylo; y < yhi; ++y) {
+    float syr = fmaf(r, (float)y + 0.5f, -0.5f);
+    syr = syr < 0.f ? 0.f : syr;
+    const int y0 = (int)syr;
+    const int y1 = y0 + ((y0 < Hs - 1) ? 1 : 0);
+    const float l1 = syr - (float)y0, l0 = 1.0f - l1;
+    const float wy = (y0 == Y ? l0 : 0.f) + (y1 == Y ? l1 : 0.f);
+    if (wy == 0.f) continue;
+    float row = 0.f;
+    for (int x = xlo; x < xhi; ++x) {
+      float sxr = fmaf(r, (float)x + 0.5f, -0.5f);
+      sxr = sxr < 0.f ? 0.f : sxr;
+      const int x0 = (int)sxr;
+      const int x1 = x0 + ((x0 < Ws - 1) ? 1 : 0);
+      const float m1 = sxr - (float)x0, m0 = 1.0f - m1;
+      const float wx = (x0 == X ? m0 : 0.f) + (x1 == X ? m1 : 0.f);
+      if (wx != 0.f) row = fmaf(wx, MD2_LD(dD + (size_t)y * P.W + x), row);
+    }
+    acc = fmaf(wy, row, acc);
+  }
+  return g + acc;
+}
+
+// Scalar epilogue: losses and d loss / d cam_T_cam = K[:3,:]^T dP  (A.3).
+MD2_HD void final_scalars(const Params& P) {
+  double total = 0.0;
+  for (int s = 0; s < P.S; ++s) {
+    const int Hs = P.H >> s, Ws = P.W >> s;
+    const double photo = P.acc[acc_photo(s)] / ((double)P.B * P.H * P.W);
+    const double sm = P.acc[acc_smx(s)] / ((double)P.B * Hs * (Ws - 1)) +
+                      P.acc[acc_smy(s)] / ((double)P.B * (Hs - 1) * Ws);
+    const double ls = photo + (double)P.smooth_w[s] * sm;
+    P.losses[1 + s] = (float)ls;
+    total += ls;
+  }
+  P.losses[0] = (float)(total / P.S);
+}
+MD2_HD void final_grad_T(const Params& P, int b, int f) {
+  float* g = P.grad_T[f];
+  if (!g) return;
+  const float* K = P.K + (size_t)b * 16;
+  for (int k = 0; k < 4; ++k)
+    for (int j = 0; j < 4; ++j) {
+      double a = 0.0;
+      if (P.pose_grad[f])
+        for (int i = 0; i < 3; ++i) a += (double)MD2_LD(K + i * 4 + k) * P.acc[acc_dP(P, b, f, i * 4 + j)];
+      g[(size_t)b * 16 + k * 4 + j] = (float)(a * (double)P.gscale);
+    }
+}
+
+}  // namespace md2

@@ -1,0 +1,280 @@
+// md2_kernels.cu - sm_100a kernels of the fused view-synthesis loss and their launcher.
+//
+// Launch sequence of one md2_view_synthesis_loss() call (one stream, no host sync):
+//   1. md2_prologue        zero the accumulators, build the per-(sample,source) projection
+//   2. md2_disp_mean       per-sample mean of disp_s            (trainer.py:486)
+//   3. md2_identity        scale-independent identity losses    (trainer.py:432-439)
+//   4. md2_smooth          edge-aware smoothness, fwd + numerator gradient (layers.py:202-215)
+//   5. md2_march           fused warp + photometric loss + min/automask + adjoint, all scales
+//   6. md2_final           up-sampling adjoint + smoothness adjoint -> grad_disp_s, losses, grad_T
+//
+// md2_march is the hot kernel.  One warp owns a band of 28 columns and marches down a
+// segment of rows; lane l holds column x0-2+l.  Horizontal neighbours are exchanged with
+// warp shuffles, vertical neighbours live in registers (rolling 3-row sums), the values the
+// adjoint needs two rows later sit in a thread-private shared-memory ring.  No block-level
+// synchronisation, no tensor cores (the path is gather/stream work, BASELINE.json).
+#include <cuda_runtime.h>
+
+#include "md2_core.cuh"
+#include "md2_plan.h"
+
+namespace md2 {
+
+constexpr int kWarpsPerCta = 4;
+constexpr int kThreads = kWarpsPerCta * 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kSmoothPerThread = 4;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------ 1. prologue
+__global__ void md2_prologue(Params P) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nacc = acc_count(P);
+  for (int i = tid; i < nacc; i += gridDim.x * blockDim.x) P.acc[i] = 0.0;
+  if (tid < P.B * P.nsrc) setup_projection(P, tid / P.nsrc, tid % P.nsrc);
+}
+
+// ------------------------------------------------------------------ 2. disparity means
+__global__ void md2_disp_mean(Params P) {
+  const int s = blockIdx.z, b = blockIdx.y;
+  if (s >= P.S) return;
+  const int n = (P.H >> s) * (P.W >> s);
+  if (blockIdx.x * blockDim.x >= n) return;                      // uniform per block
+  const float* d = P.disp[s] + (size_t)b * n;
+  float a = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a += __ldg(d + i);
+  a = warp_sum(a);
+  __shared__ float part[32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) part[w] = a;
+  __syncthreads();
+  if (w == 0) {
+    a = (l < (blockDim.x >> 5)) ? part[l] : 0.f;
+    a = warp_sum(a);
+    if (l == 0) atomicAdd(&P.acc[acc_dispsum(P, s, b)], (double)a);
+  }
+}
+
+// ------------------------------------------------------------------ 3. identity losses
+template <int NSRC>
+__global__ void __launch_bounds__(kThreads) md2_identity(Params P) {
+  const int lane = threadIdx.x & 31;
+  const int job = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const int njobs = P.B * P.nseg * P.nband_id;
+  if (job >= njobs) return;
+  const int band = job % P.nband_id;
+  const int seg = (job / P.nband_id) % P.nseg;
+  const int b = job / (P.nband_id * P.nseg);
+  const int y0 = seg * P.seg_rows;
+  const int y1 = min(y0 + P.seg_rows, P.H);
+  IdLane<NSRC> L;
+  id_init(L, P, band * kIdCols, lane);
+  for (int t = y0 - 1; t <= y1; ++t) {
+    id_stage_a(L, P, b, t);
+    IdXchg<NSRC> lf, rt;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      lf.tg[c] = __shfl_up_sync(kFull, L.tg[c], 1);
+      rt.tg[c] = __shfl_down_sync(kFull, L.tg[c], 1);
+#pragma unroll
+      for (int f = 0; f < NSRC; ++f) {
+        lf.pr[f][c] = __shfl_up_sync(kFull, L.pr[f][c], 1);
+        rt.pr[f][c] = __shfl_down_sync(kFull, L.pr[f][c], 1);
+      }
+    }
+    id_stage_b(L, P, b, t, lane, y0, y1, lf, rt);
+  }
+}
+
+// ------------------------------------------------------------------ 4. smoothness
+__global__ void md2_smooth(Params P) {
+  const int s = blockIdx.z, b = blockIdx.y;
+  const int Hs = P.H >> s, Ws = P.W >> s;
+  const int n = Hs * Ws;
+  if (blockIdx.x * blockDim.x >= n) return;                      // uniform per block
+  const float m = (float)(P.acc[acc_dispsum(P, s, b)] / (double)n) + 1e-7f;
+  float ex = 0.f, ey = 0.f, dot = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float e0, e1, g;
+    smooth_pixel(P, s, b, i / Ws, i % Ws, m, e0, e1, g);
+    P.gn[s][(size_t)b * n + i] = g;
+    ex += e0; ey += e1;
+    dot = fmaf(g, __ldg(P.disp[s] + (size_t)b * n + i), dot);
+  }
+  ex = warp_sum(ex); ey = warp_sum(ey); dot = warp_sum(dot);
+  __shared__ float part[3][32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { part[0][w] = ex; part[1][w] = ey; part[2][w] = dot; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    ex = warp_sum(l < nw ? part[0][l] : 0.f);
+    ey = warp_sum(l < nw ? part[1][l] : 0.f);
+    dot = warp_sum(l < nw ? part[2][l] : 0.f);
+    if (l == 0) {
+      atomicAdd(&P.acc[acc_smx(s)], (double)ex);
+      atomicAdd(&P.acc[acc_smy(s)], (double)ey);
+      atomicAdd(&P.acc[acc_dot(P, s, b)], (double)dot);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ 5. the marching kernel
+template <class C>
+__global__ void __launch_bounds__(kThreads) md2_march(Params P) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31;
+  const int job = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const int per_scale = P.B * P.nseg * P.nband;
+  if (job >= per_scale * P.S) return;
+  WarpJob J;
+  J.s = job / per_scale;
+  const int r = job - J.s * per_scale;
+  J.b = r / (P.nseg * P.nband);
+  const int r2 = r - J.b * (P.nseg * P.nband);
+  const int seg = r2 / P.nband;
+  J.x0 = (r2 - seg * P.nband) * kOwnCols;
+  J.y0 = seg * P.seg_rows;
+  J.y1 = min(J.y0 + P.seg_rows, P.H);
+
+  Stash st;
+  st.base = smem + threadIdx.x;
+  st.stride = kThreads;
+
+  Lane<C> L;
+  lane_init(L, P, J, lane);
+  for (int t = J.y0 - 2; t <= J.y1 + 1; ++t) {
+    stage_a(L, P, J, t, st);
+    Xchg1<C> l1, r1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      l1.tg[c] = __shfl_up_sync(kFull, L.tg[c], 1);
+      r1.tg[c] = __shfl_down_sync(kFull, L.tg[c], 1);
+#pragma unroll
+      for (int f = 0; f < C::NSRC; ++f) {
+        l1.pr[f][c] = __shfl_up_sync(kFull, L.pr[f][c], 1);
+        r1.pr[f][c] = __shfl_down_sync(kFull, L.pr[f][c], 1);
+      }
+    }
+    stage_b(L, P, J, t, lane, l1, r1);
+    if (C::GRAD) {
+      Xchg2<C> l2, r2x;
+      l2.tag = __shfl_up_sync(kFull, L.tag, 1);
+      r2x.tag = __shfl_down_sync(kFull, L.tag, 1);
+#pragma unroll
+      for (int n = 0; n < C::NCS; ++n)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          l2.coef[n][k] = __shfl_up_sync(kFull, L.coef[n][k], 1);
+          r2x.coef[n][k] = __shfl_down_sync(kFull, L.coef[n][k], 1);
+        }
+      stage_c(L, P, J, t, lane, l2, r2x, st);
+    }
+  }
+  const float ls = warp_sum(L.loss);
+  if (lane == 0) atomicAdd(&P.acc[acc_photo(J.s)], (double)ls);
+  if (C::GRAD) {
+#pragma unroll
+    for (int f = 0; f < C::NSRC; ++f) {
+      if (!P.pose_grad[f]) continue;
+      float dP[12];
+      lane_dP(L, P, J, f, dP);
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const float v = warp_sum(dP[k]);
+        if (lane == 0) atomicAdd(&P.acc[acc_dP(P, J.b, f, k)], (double)v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ 6. final
+__global__ void md2_final(Params P) {
+  const int s = blockIdx.z, b = blockIdx.y;
+  if (blockIdx.x == 0 && b == 0 && s == 0) {
+    if (threadIdx.x == 0) final_scalars(P);
+    if (P.want_grad && threadIdx.x < P.B * P.nsrc) final_grad_T(P, threadIdx.x / P.nsrc, threadIdx.x % P.nsrc);
+  }
+  if (!P.want_grad || s >= P.S) return;
+  const int Hs = P.H >> s, Ws = P.W >> s;
+  const int n = Hs * Ws;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    P.grad_disp[s][(size_t)b * n + i] = final_grad_disp(P, s, b, i / Ws, i % Ws);
+}
+
+// ------------------------------------------------------------------ launcher
+template <class C>
+static cudaError_t launch_march(const Params& P, cudaStream_t stream) {
+  const int jobs = P.S * P.B * P.nseg * P.nband;
+  const int grid = (jobs + kWarpsPerCta - 1) / kWarpsPerCta;
+  const size_t smem = C::GRAD ? (size_t)kThreads * kRing * C::STASH * sizeof(float) : 0;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(md2_march<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  md2_march<C><<<grid, kThreads, smem, stream>>>(P);
+  return cudaGetLastError();
+}
+
+template <int NSRC>
+static cudaError_t launch_march_n(const Params& P, cudaStream_t stream) {
+  const int key = (P.avg ? 4 : 0) | (P.automask ? 2 : 0) | (P.want_grad ? 1 : 0);
+  switch (key) {
+    case 0: return launch_march<Cfg<NSRC, false, false, false>>(P, stream);
+    case 1: return launch_march<Cfg<NSRC, false, false, true>>(P, stream);
+    case 2: return launch_march<Cfg<NSRC, false, true, false>>(P, stream);
+    case 3: return launch_march<Cfg<NSRC, false, true, true>>(P, stream);
+    case 4: return launch_march<Cfg<NSRC, true, false, false>>(P, stream);
+    case 5: return launch_march<Cfg<NSRC, true, false, true>>(P, stream);
+    case 6: return launch_march<Cfg<NSRC, true, true, false>>(P, stream);
+    default: return launch_march<Cfg<NSRC, true, true, true>>(P, stream);
+  }
+}
+
+cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
+  cudaError_t e;
+  md2_prologue<<<4, 256, 0, stream>>>(P);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  {
+    const int n0 = P.H * P.W;
+    dim3 grid((n0 + 256 * 8 - 1) / (256 * 8), P.B, P.S);
+    md2_disp_mean<<<grid, 256, 0, stream>>>(P);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  if (P.automask) {
+    const int jobs = P.B * P.nseg * P.nband_id;
+    const int grid = (jobs + kWarpsPerCta - 1) / kWarpsPerCta;
+    switch (P.nsrc) {
+      case 1: md2_identity<1><<<grid, kThreads, 0, stream>>>(P); break;
+      case 2: md2_identity<2><<<grid, kThreads, 0, stream>>>(P); break;
+      default: md2_identity<3><<<grid, kThreads, 0, stream>>>(P); break;
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  {
+    const int n0 = P.H * P.W;
+    dim3 grid((n0 + 256 * kSmoothPerThread - 1) / (256 * kSmoothPerThread), P.B, P.S);
+    md2_smooth<<<grid, 256, 0, stream>>>(P);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  switch (P.nsrc) {
+    case 1: e = launch_march_n<1>(P, stream); break;
+    case 2: e = launch_march_n<2>(P, stream); break;
+    default: e = launch_march_n<3>(P, stream); break;
+  }
+  if (e != cudaSuccess) return e;
+  {
+    const int n0 = P.H * P.W;
+    dim3 grid((n0 + 255) / 256, P.B, P.S);
+    md2_final<<<grid, 256, 0, stream>>>(P);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace md2

@@ -1,0 +1,121 @@
+// md2_plan.h - host-side planner: validates an md2_problem, lays out the workspace
+// and fills the device-side Params block.  Shared by the CUDA C-ABI (md2_capi.cu) and
+// by the host emulator used in tests (tests/emu/md2_emu.cpp).
+#pragma once
+
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/md2_loss.h"
+#include "md2_core.cuh"
+
+namespace md2 {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Layout {
+  size_t acc_off, acc_bytes;
+  size_t proj_off, idloss_off;
+  size_t dD_off[kMaxScales], gn_off[kMaxScales];
+  size_t total;
+};
+
+inline int validate(const md2_problem* p) {
+  if (!p) return MD2_ERR_INVALID_ARGUMENT;
+  if (p->batch < 1 || p->height < 4 || p->width < 4) return MD2_ERR_INVALID_ARGUMENT;
+  if (p->num_scales < 1 || p->num_scales > MD2_MAX_SCALES) return MD2_ERR_INVALID_ARGUMENT;
+  if (p->num_src < 1 || p->num_src > MD2_MAX_SRC) return MD2_ERR_INVALID_ARGUMENT;
+  const int div = 1 << (p->num_scales - 1);
+  if (p->height % div || p->width % div) return MD2_ERR_INVALID_ARGUMENT;
+  if ((p->height >> (p->num_scales - 1)) < 2 || (p->width >> (p->num_scales - 1)) < 2)
+    return MD2_ERR_INVALID_ARGUMENT;
+  if (!(p->min_depth > 0.f) || !(p->max_depth > p->min_depth)) return MD2_ERR_INVALID_ARGUMENT;
+  if ((long long)p->batch * 3 * p->height * p->width * MD2_MAX_SRC >= (1LL << 31)) return MD2_ERR_UNSUPPORTED;
+  return MD2_OK;
+}
+
+inline Layout make_layout(const md2_problem* p) {
+  Layout L;
+  memset(&L, 0, sizeof(L));
+  const size_t B = p->batch, H = p->height, W = p->width;
+  size_t off = 0;
+  const size_t nacc = 3 * kMaxScales + 2 * kMaxScales * B + B * p->num_src * 12;
+  L.acc_off = off; L.acc_bytes = nacc * sizeof(double);
+  off = align_up(off + L.acc_bytes, 256);
+  L.proj_off = off; off = align_up(off + B * p->num_src * 12 * sizeof(float), 256);
+  L.idloss_off = off; off = align_up(off + B * p->num_src * H * W * sizeof(float), 256);
+  for (int s = 0; s < p->num_scales; ++s) {
+    L.dD_off[s] = off; off = align_up(off + B * H * W * sizeof(float), 256);
+    L.gn_off[s] = off; off = align_up(off + B * (H >> s) * (W >> s) * sizeof(float), 256);
+  }
+  L.total = off;
+  return L;
+}
+
+inline int default_seg_rows(const md2_problem* p) {
+  int r = p->rows_per_segment > 0 ? p->rows_per_segment : 32;
+  if (r > p->height) r = p->height;
+  return r;
+}
+
+// Fills `P`.  Returns MD2_OK or an error when required tensors are missing.
+inline int fill_params(const md2_problem* p, const md2_tensors* t, void* workspace, Params* P) {
+  if (!t || !workspace) return MD2_ERR_INVALID_ARGUMENT;
+  memset(P, 0, sizeof(*P));
+  const Layout L = make_layout(p);
+  char* ws = (char*)workspace;
+  P->B = p->batch; P->H = p->height; P->W = p->width; P->S = p->num_scales; P->nsrc = p->num_src;
+  P->automask = p->automask ? 1 : 0;
+  P->avg = p->avg_reprojection ? 1 : 0;
+  P->nid = P->automask ? (P->avg ? 1 : P->nsrc) : 0;
+  P->align_corners = p->align_corners ? 1 : 0;
+  P->want_grad = p->want_grad ? 1 : 0;
+  // layers.py:21-23: min_disp = 1/max_depth, max_disp = 1/min_depth (python doubles -> fp32 scalars)
+  const double lo = 1.0 / (double)p->max_depth, hi = 1.0 / (double)p->min_depth;
+  P->a_disp = (float)lo;
+  P->c_disp = (float)(hi - lo);
+  const double W = p->width, H = p->height;
+  if (P->align_corners) { P->sx = 1.f; P->ox = 0.f; P->sy = 1.f; P->oy = 0.f; }
+  else {
+    // layers.py:190-192 then grid_sample un-normalisation with align_corners=False:
+    // ix = ((u/(W-1) - 0.5)*2 + 1) * W/2 - 0.5 = u*W/(W-1) - 0.5
+    P->sx = (float)(W / (W - 1.0)); P->ox = -0.5f;
+    P->sy = (float)(H / (H - 1.0)); P->oy = -0.5f;
+  }
+  P->wmax = (float)(p->width - 1); P->hmax = (float)(p->height - 1);
+  P->eps = 1e-7f;
+  P->gscale = (float)(1.0 / ((double)p->num_scales * p->batch * H * W) / (P->avg ? (double)p->num_src : 1.0));
+  for (int s = 0; s < p->num_scales; ++s) P->smooth_w[s] = (float)((double)p->disparity_smoothness / (double)(1 << s));
+  P->seg_rows = default_seg_rows(p);
+  P->nseg = (p->height + P->seg_rows - 1) / P->seg_rows;
+  P->nband = (p->width + kOwnCols - 1) / kOwnCols;
+  P->nband_id = (p->width + kIdCols - 1) / kIdCols;
+  if (!t->target || !t->K || !t->inv_K || !t->losses) return MD2_ERR_INVALID_ARGUMENT;
+  P->tgt = t->target; P->K = t->K; P->invK = t->inv_K;
+  for (int f = 0; f < p->num_src; ++f) {
+    if (!t->source[f] || !t->T[f]) return MD2_ERR_INVALID_ARGUMENT;
+    P->src[f] = t->source[f]; P->Tm[f] = t->T[f];
+    P->pose_grad[f] = (t->pose_requires_grad[f] && p->want_grad) ? 1 : 0;
+    P->grad_T[f] = p->want_grad ? t->grad_T[f] : nullptr;
+  }
+  for (int s = 0; s < p->num_scales; ++s) {
+    if (!t->disp[s] || !t->color[s]) return MD2_ERR_INVALID_ARGUMENT;
+    if (P->automask && !t->noise[s]) return MD2_ERR_INVALID_ARGUMENT;
+    if (p->want_grad && !t->grad_disp[s]) return MD2_ERR_INVALID_ARGUMENT;
+    P->disp[s] = t->disp[s]; P->color[s] = t->color[s]; P->noise[s] = t->noise[s];
+    P->grad_disp[s] = t->grad_disp[s];
+    P->depth[s] = t->depth[s];
+    P->idsel[s] = t->identity_selection[s];
+    for (int f = 0; f < p->num_src; ++f) P->warped[f][s] = t->warped[f][s];
+    P->dD[s] = t->grad_depth_dbg[s] ? t->grad_depth_dbg[s] : (float*)(ws + L.dD_off[s]);
+    P->gn[s] = (float*)(ws + L.gn_off[s]);
+  }
+  P->losses = t->losses;
+  P->acc = (double*)(ws + L.acc_off);
+  P->proj = (float*)(ws + L.proj_off);
+  P->idloss = (float*)(ws + L.idloss_off);
+  return MD2_OK;
+}
+
+}  // namespace md2

@@ -1,0 +1,244 @@
+"""Host side of the fused view-synthesis loss: a ``torch.autograd.Function`` over the
+C ABI (include/md2_loss.h) and drop-in replacements for the two Trainer methods.
+
+Replaces, in one call into libmd2loss.so,
+``Trainer.generate_images_pred`` (/root/reference/trainer.py:341-391) and
+``Trainer.compute_losses`` (/root/reference/trainer.py:407-496); gradients flow to
+``outputs[("disp", s)]`` and ``outputs[("cam_T_cam", 0, f)]`` exactly where
+``losses["loss"].backward()`` (trainer.py:208) would send them.  PyTorch is used for
+device memory, streams and autograd plumbing only; there is no PyTorch or CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _capi
+from ._capi import MAX_SCALES, Md2Problem, Md2Tensors
+
+
+def _check_f32_cuda(t: torch.Tensor, name: str, shape=None) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (the fused loss has no CPU path)" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be float32, got %s" % (name, t.dtype))
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise RuntimeError("%s has shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
+    return t.contiguous()
+
+
+class LossPlan:
+    """Static description of one loss configuration (mirrors the ``opt`` flags the path reads)."""
+
+    def __init__(self, batch_size: int, height: int, width: int, frame_ids: Sequence,
+                 scales: Sequence[int] = (0, 1, 2, 3), min_depth: float = 0.1, max_depth: float = 100.0,
+                 disparity_smoothness: float = 1e-3, avg_reprojection: bool = False,
+                 disable_automasking: bool = False, align_corners: bool = False,
+                 rows_per_segment: int = 0):
+        if list(scales) != list(range(len(scales))):
+            raise RuntimeError("scales must be 0..n-1, got %s" % (list(scales),))
+        self.batch_size, self.height, self.width = int(batch_size), int(height), int(width)
+        self.frame_ids = list(frame_ids)
+        self.src_ids = self.frame_ids[1:]
+        self.scales = list(scales)
+        self.min_depth, self.max_depth = float(min_depth), float(max_depth)
+        self.disparity_smoothness = float(disparity_smoothness)
+        self.avg_reprojection = bool(avg_reprojection)
+        self.automask = not bool(disable_automasking)
+        self.align_corners = bool(align_corners)
+        self.rows_per_segment = int(rows_per_segment)
+        self.n_src = len(self.src_ids)
+        self.n_id = 0 if not self.automask else (1 if self.avg_reprojection else self.n_src)
+        self.lib = _capi.load_library()
+        self._workspace: Dict = {}
+
+    @classmethod
+    def from_opt(cls, opt, **kw) -> "LossPlan":
+        """Build from a reference ``options.py`` namespace (after trainer.py:51-52 appended "s")."""
+        for flag in ("v1_multiscale", "predictive_mask", "no_ssim"):
+            if getattr(opt, flag, False):
+                raise RuntimeError("--%s is not supported by the fused loss yet" % flag)
+        if getattr(opt, "pose_model_type", "separate_resnet") == "posecnn":
+            raise RuntimeError("--pose_model_type posecnn is not supported by the fused loss yet")
+        return cls(opt.batch_size, opt.height, opt.width, opt.frame_ids, opt.scales, opt.min_depth,
+                   opt.max_depth, opt.disparity_smoothness, opt.avg_reprojection,
+                   opt.disable_automasking, **kw)
+
+    def problem(self, want_grad: bool) -> Md2Problem:
+        return Md2Problem(batch=self.batch_size, height=self.height, width=self.width,
+                          num_scales=len(self.scales), num_src=self.n_src, automask=int(self.automask),
+                          avg_reprojection=int(self.avg_reprojection), align_corners=int(self.align_corners),
+                          min_depth=self.min_depth, max_depth=self.max_depth,
+                          disparity_smoothness=self.disparity_smoothness, want_grad=int(want_grad),
+                          rows_per_segment=self.rows_per_segment)
+
+    def workspace(self, device: torch.device) -> torch.Tensor:
+        key = (device.type, device.index)
+        ws = self._workspace.get(key)
+        if ws is None:
+            n = C.c_size_t(0)
+            p = self.problem(True)
+            _capi.check(self.lib, self.lib.md2_loss_workspace_bytes(C.byref(p), C.byref(n)), "md2_loss_workspace_bytes")
+            ws = torch.empty(n.value, dtype=torch.uint8, device=device)
+            self._workspace[key] = ws
+        return ws
+
+
+class _ViewSynthesisLossFn(torch.autograd.Function):
+    """forward(plan, side, target, sources, K, inv_K, colors, noise, n_disp, *disps_and_Ts)"""
+
+    @staticmethod
+    def forward(ctx, plan: LossPlan, side: Optional[dict], target, sources, K, inv_K, colors, noise, pose_grad,
+                *leaves):
+        S, F = len(plan.scales), plan.n_src
+        disps, Ts = leaves[:S], leaves[S:]
+        B, H, W = plan.batch_size, plan.height, plan.width
+        dev = target.device
+        want_grad = any(ctx.needs_input_grad[9:])
+        t = Md2Tensors()
+        keep = []
+
+        def ptr(x):
+            keep.append(x)
+            return x.data_ptr()
+
+        t.target = ptr(_check_f32_cuda(target, "target", (B, 3, H, W)))
+        for i in range(F):
+            t.source[i] = ptr(_check_f32_cuda(sources[i], "source[%d]" % i, (B, 3, H, W)))
+            t.T[i] = ptr(_check_f32_cuda(Ts[i], "T[%d]" % i, (B, 4, 4)))
+            t.pose_requires_grad[i] = int(bool(pose_grad[i]))
+        t.K = ptr(_check_f32_cuda(K, "K", (B, 4, 4)))
+        t.inv_K = ptr(_check_f32_cuda(inv_K, "inv_K", (B, 4, 4)))
+        grad_disp, grad_T = [], []
+        for s in range(S):
+            hs, ws = H >> s, W >> s
+            t.disp[s] = ptr(_check_f32_cuda(disps[s], "disp[%d]" % s, (B, 1, hs, ws)))
+            t.color[s] = ptr(_check_f32_cuda(colors[s], "color[%d]" % s, (B, 3, hs, ws)))
+            if plan.n_id > 0:
+                t.noise[s] = ptr(_check_f32_cuda(noise[s], "noise[%d]" % s, (B, plan.n_id, H, W)))
+            if want_grad:
+                g = torch.empty((B, 1, hs, ws), dtype=torch.float32, device=dev)
+                grad_disp.append(g)
+                t.grad_disp[s] = ptr(g)
+        if want_grad:
+            for i in range(F):
+                g = torch.empty((B, 4, 4), dtype=torch.float32, device=dev)
+                grad_T.append(g)
+                t.grad_T[i] = ptr(g)
+        if side is not None:
+            for s in side.get("depth_scales", []):
+                d = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+                side[("depth", 0, s)] = d
+                t.depth[s] = ptr(d)
+            for s in side.get("color_scales", []):
+                for i, f in enumerate(plan.src_ids):
+                    c = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+                    side[("color", f, s)] = c
+                    t.warped[i][s] = ptr(c)
+            if plan.automask:
+                for s in side.get("mask_scales", []):
+                    m = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+                    side["identity_selection/{}".format(s)] = m
+                    t.identity_selection[s] = ptr(m)
+            if want_grad:
+                for s in side.get("grad_updisp_scales", []):
+                    gd = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+                    side[("grad_updisp", s)] = gd
+                    t.grad_depth_dbg[s] = ptr(gd)
+        losses = torch.empty(MAX_SCALES + 1, dtype=torch.float32, device=dev)
+        t.losses = ptr(losses)
+        ws_buf = plan.workspace(dev)
+        p = plan.problem(want_grad)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            st = plan.lib.md2_view_synthesis_loss(C.byref(p), C.byref(t), ws_buf.data_ptr(), ws_buf.numel(),
+                                                  C.c_void_p(stream))
+        _capi.check(plan.lib, st, "md2_view_synthesis_loss")
+        ctx.S, ctx.F = S, F
+        ctx.pose_grad = list(pose_grad)
+        if want_grad:
+            ctx.save_for_backward(*grad_disp, *grad_T)
+        total = losses[0]
+        per_scale = losses[1:1 + S]
+        ctx.mark_non_differentiable(per_scale)
+        return total, per_scale
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_total, _g_scales):
+        saved = ctx.saved_tensors
+        S, F = ctx.S, ctx.F
+        out = [None] * 9
+        for s in range(S):
+            out.append(saved[s] * g_total if ctx.needs_input_grad[9 + s] else None)
+        for i in range(F):
+            need = ctx.needs_input_grad[9 + S + i] and ctx.pose_grad[i]
+            out.append(saved[S + i] * g_total if need else None)
+        return tuple(out)
+
+
+def view_synthesis_loss(plan: LossPlan, inputs: Dict, outputs: Dict,
+                        noise: Optional[List[torch.Tensor]] = None,
+                        side: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+    """Fused generate_images_pred + compute_losses on the reference's ``inputs``/``outputs`` dicts.
+
+    ``noise`` (one (B,n_id,H,W) tensor per scale) replaces the ``torch.randn`` draws of
+    trainer.py:468-469; when omitted they are drawn here, one call per scale in scale order, so the
+    CUDA generator stream advances exactly as in the reference.
+    ``side`` selects optional outputs: {"depth_scales": [...], "color_scales": [...], "mask_scales": [...]};
+    the produced tensors are stored both in ``side`` and in ``outputs`` under the reference's keys.
+    """
+    S = len(plan.scales)
+    target = inputs[("color", 0, 0)]
+    dev = target.device
+    sources = [inputs[("color", f, 0)] for f in plan.src_ids]
+    colors = [inputs[("color", 0, s)] for s in plan.scales]
+    disps = [outputs[("disp", s)] for s in plan.scales]
+    Ts, pose_grad = [], []
+    for f in plan.src_ids:
+        if f == "s":
+            Ts.append(inputs["stereo_T"])
+            pose_grad.append(False)
+        else:
+            T = outputs[("cam_T_cam", 0, f)]
+            Ts.append(T)
+            pose_grad.append(bool(T.requires_grad) and torch.is_grad_enabled())
+    if plan.n_id > 0 and noise is None:
+        shape = (plan.batch_size, plan.n_id, plan.height, plan.width)
+        noise = [torch.randn(shape, device=dev) for _ in plan.scales]
+    total, per_scale = _ViewSynthesisLossFn.apply(plan, side, target, sources, inputs[("K", 0)],
+                                                  inputs[("inv_K", 0)], colors, noise, pose_grad,
+                                                  *disps, *Ts)
+    losses = {"loss": total}
+    for i, s in enumerate(plan.scales):
+        losses["loss/{}".format(s)] = per_scale[i]
+    if side is not None:
+        for k, v in side.items():
+            if isinstance(k, tuple) and k[0] in ("depth", "color") or (isinstance(k, str) and k.startswith("identity_selection/")):
+                outputs[k] = v
+    return losses
+
+
+class FusedLossMixin:
+    """Mix into (or bind onto) the reference ``Trainer``: overrides only the two hot-path methods.
+
+        class FusedTrainer(FusedLossMixin, Trainer): pass
+
+    ``self.opt`` must be the reference options namespace.  Set ``self.md2_side`` to e.g.
+    ``{"depth_scales": [0], "color_scales": [0], "mask_scales": [0, 1, 2, 3]}`` on logging steps to
+    materialise what ``Trainer.log`` / ``compute_depth_losses`` read.
+    """
+
+    md2_side: Optional[dict] = None
+    _md2_plan: Optional[LossPlan] = None
+
+    def generate_images_pred(self, inputs, outputs):
+        if self._md2_plan is None:
+            self._md2_plan = LossPlan.from_opt(self.opt)
+        side = dict(self.md2_side) if self.md2_side else None
+        outputs["_md2_losses"] = view_synthesis_loss(self._md2_plan, inputs, outputs, side=side)
+
+    def compute_losses(self, inputs, outputs):
+        return outputs.pop("_md2_losses")

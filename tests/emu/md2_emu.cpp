@@ -1,0 +1,171 @@
+// md2_emu.cpp - lock-step HOST emulator of the marching kernels.  TEST INFRASTRUCTURE ONLY.
+//
+// Compiles monodepth2_b200/csrc/md2_core.cuh (the per-lane arithmetic the CUDA kernels
+// run) with g++ and drives it the way md2_kernels.cu does: 32 lanes per warp job in an
+// array, neighbour exchange by array index instead of warp shuffle.  It lets the
+// tile/halo/reflection/adjoint logic be compared with the oracle in a container that has
+// no GPU.  Nothing under monodepth2_b200/ links or loads this file; it is never a
+// fallback for the CUDA library.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../monodepth2_b200/csrc/md2_core.cuh"
+#include "../../monodepth2_b200/csrc/md2_plan.h"
+
+using namespace md2;
+
+template <int NSRC>
+static void emu_identity(const Params& P) {
+  for (int b = 0; b < P.B; ++b)
+    for (int seg = 0; seg < P.nseg; ++seg)
+      for (int band = 0; band < P.nband_id; ++band) {
+        const int y0 = seg * P.seg_rows, y1 = std::min(y0 + P.seg_rows, P.H);
+        IdLane<NSRC> L[32];
+        for (int l = 0; l < 32; ++l) id_init(L[l], P, band * kIdCols, l);
+        for (int t = y0 - 1; t <= y1; ++t) {
+          for (int l = 0; l < 32; ++l) id_stage_a(L[l], P, b, t);
+          IdXchg<NSRC> X[34];
+          memset(X, 0, sizeof(X));
+          for (int l = 0; l < 32; ++l) {
+            memcpy(X[l + 1].pr, L[l].pr, sizeof(L[l].pr));
+            memcpy(X[l + 1].tg, L[l].tg, sizeof(L[l].tg));
+          }
+          for (int l = 0; l < 32; ++l) id_stage_b(L[l], P, b, t, l, y0, y1, X[l], X[l + 2]);
+        }
+      }
+}
+
+template <class C>
+static void emu_march(const Params& P) {
+  std::vector<float> ring((size_t)32 * kRing * C::STASH);
+  for (int s = 0; s < P.S; ++s)
+    for (int b = 0; b < P.B; ++b)
+      for (int seg = 0; seg < P.nseg; ++seg)
+        for (int band = 0; band < P.nband; ++band) {
+          WarpJob J;
+          J.s = s; J.b = b; J.x0 = band * kOwnCols;
+          J.y0 = seg * P.seg_rows; J.y1 = std::min(J.y0 + P.seg_rows, P.H);
+          std::fill(ring.begin(), ring.end(), 0.f);
+          Lane<C> L[32];
+          Stash st[32];
+          for (int l = 0; l < 32; ++l) {
+            lane_init(L[l], P, J, l);
+            st[l].base = ring.data() + l;
+            st[l].stride = 32;
+          }
+          for (int t = J.y0 - 2; t <= J.y1 + 1; ++t) {
+            for (int l = 0; l < 32; ++l) stage_a(L[l], P, J, t, st[l]);
+            Xchg1<C> X1[34];
+            memset(X1, 0, sizeof(X1));
+            for (int l = 0; l < 32; ++l) {
+              memcpy(X1[l + 1].pr, L[l].pr, sizeof(L[l].pr));
+              memcpy(X1[l + 1].tg, L[l].tg, sizeof(L[l].tg));
+            }
+            for (int l = 0; l < 32; ++l) stage_b(L[l], P, J, t, l, X1[l], X1[l + 2]);
+            if (C::GRAD) {
+              Xchg2<C> X2[34];
+              memset(X2, 0, sizeof(X2));
+              X2[0].tag = X2[33].tag = -1;
+              for (int l = 0; l < 32; ++l) {
+                memcpy(X2[l + 1].coef, L[l].coef, sizeof(L[l].coef));
+                X2[l + 1].tag = L[l].tag;
+              }
+              for (int l = 0; l < 32; ++l) stage_c(L[l], P, J, t, l, X2[l], X2[l + 2], st[l]);
+            }
+          }
+          float ls = 0.f;
+          for (int l = 0; l < 32; ++l) ls += L[l].loss;
+          P.acc[acc_photo(s)] += (double)ls;
+          if (C::GRAD)
+            for (int f = 0; f < C::NSRC; ++f) {
+              if (!P.pose_grad[f]) continue;
+              float sum[12] = {0};
+              for (int l = 0; l < 32; ++l) {
+                float dP[12];
+                lane_dP(L[l], P, J, f, dP);
+                for (int k = 0; k < 12; ++k) sum[k] += dP[k];
+              }
+              for (int k = 0; k < 12; ++k) P.acc[acc_dP(P, b, f, k)] += (double)sum[k];
+            }
+        }
+}
+
+template <int NSRC>
+static void emu_march_n(const Params& P) {
+  const int key = (P.avg ? 4 : 0) | (P.automask ? 2 : 0) | (P.want_grad ? 1 : 0);
+  switch (key) {
+    case 0: emu_march<Cfg<NSRC, false, false, false>>(P); break;
+    case 1: emu_march<Cfg<NSRC, false, false, true>>(P); break;
+    case 2: emu_march<Cfg<NSRC, false, true, false>>(P); break;
+    case 3: emu_march<Cfg<NSRC, false, true, true>>(P); break;
+    case 4: emu_march<Cfg<NSRC, true, false, false>>(P); break;
+    case 5: emu_march<Cfg<NSRC, true, false, true>>(P); break;
+    case 6: emu_march<Cfg<NSRC, true, true, false>>(P); break;
+    default: emu_march<Cfg<NSRC, true, true, true>>(P); break;
+  }
+}
+
+extern "C" int md2_emu_workspace_bytes(const md2_problem* p, size_t* bytes) {
+  const int st = validate(p);
+  if (st != MD2_OK) return st;
+  *bytes = make_layout(p).total;
+  return MD2_OK;
+}
+
+// Same contract as md2_view_synthesis_loss, but every pointer is HOST memory.
+extern "C" int md2_emu_view_synthesis_loss(const md2_problem* p, const md2_tensors* t, void* workspace,
+                                           size_t workspace_bytes) {
+  int st = validate(p);
+  if (st != MD2_OK) return st;
+  if (p->num_src > 3) return MD2_ERR_UNSUPPORTED;
+  if (workspace_bytes < make_layout(p).total) return MD2_ERR_WORKSPACE_TOO_SMALL;
+  Params P;
+  st = fill_params(p, t, workspace, &P);
+  if (st != MD2_OK) return st;
+  // 1. prologue
+  for (int i = 0; i < acc_count(P); ++i) P.acc[i] = 0.0;
+  for (int b = 0; b < P.B; ++b)
+    for (int f = 0; f < P.nsrc; ++f) setup_projection(P, b, f);
+  // 2. disparity means
+  for (int s = 0; s < P.S; ++s)
+    for (int b = 0; b < P.B; ++b) {
+      const int n = (P.H >> s) * (P.W >> s);
+      double a = 0.0;
+      for (int i = 0; i < n; ++i) a += P.disp[s][(size_t)b * n + i];
+      P.acc[acc_dispsum(P, s, b)] = a;
+    }
+  // 3. identity
+  if (P.automask) {
+    if (P.nsrc == 1) emu_identity<1>(P); else if (P.nsrc == 2) emu_identity<2>(P); else emu_identity<3>(P);
+  }
+  // 4. smoothness
+  for (int s = 0; s < P.S; ++s)
+    for (int b = 0; b < P.B; ++b) {
+      const int Hs = P.H >> s, Ws = P.W >> s, n = Hs * Ws;
+      const float m = (float)(P.acc[acc_dispsum(P, s, b)] / (double)n) + 1e-7f;
+      for (int i = 0; i < n; ++i) {
+        float e0, e1, g;
+        smooth_pixel(P, s, b, i / Ws, i % Ws, m, e0, e1, g);
+        P.gn[s][(size_t)b * n + i] = g;
+        P.acc[acc_smx(s)] += e0;
+        P.acc[acc_smy(s)] += e1;
+        P.acc[acc_dot(P, s, b)] += (double)g * P.disp[s][(size_t)b * n + i];
+      }
+    }
+  // 5. march
+  if (P.nsrc == 1) emu_march_n<1>(P); else if (P.nsrc == 2) emu_march_n<2>(P); else emu_march_n<3>(P);
+  // 6. final
+  final_scalars(P);
+  if (P.want_grad) {
+    for (int b = 0; b < P.B; ++b)
+      for (int f = 0; f < P.nsrc; ++f) final_grad_T(P, b, f);
+    for (int s = 0; s < P.S; ++s)
+      for (int b = 0; b < P.B; ++b) {
+        const int Hs = P.H >> s, Ws = P.W >> s, n = Hs * Ws;
+        for (int i = 0; i < n; ++i) P.grad_disp[s][(size_t)b * n + i] = final_grad_disp(P, s, b, i / Ws, i % Ws);
+      }
+  }
+  return MD2_OK;
+}

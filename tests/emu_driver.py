@@ -1,0 +1,102 @@
+"""Builds and drives the host emulator of the marching kernels (tests/emu/md2_emu.cpp).
+
+Test infrastructure only: it checks the kernel arithmetic and tiling on a box with no
+GPU.  The product path (monodepth2_b200) never imports this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from monodepth2_b200._capi import MAX_SCALES, Md2Problem, Md2Tensors
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "emu", "md2_emu.cpp")
+OUT = os.path.join(HERE, "emu", "_build", "libmd2emu.so")
+CORE = [os.path.join(HERE, "..", "monodepth2_b200", "csrc", f) for f in ("md2_core.cuh", "md2_plan.h")] + \
+       [os.path.join(HERE, "..", "include", "md2_loss.h")]
+
+
+def build_emu():
+    deps = [SRC] + CORE
+    if os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
+        return OUT
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off",
+                           "-o", OUT, SRC])
+    return OUT
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def run_emu(g, want_grad=True, rows_per_segment=0, align_corners=False, side_outputs=True):
+    """Run the emulator on a Golden fixture; returns dict of numpy outputs."""
+    lib = C.CDLL(build_emu())
+    lib.md2_emu_workspace_bytes.argtypes = [C.POINTER(Md2Problem), C.POINTER(C.c_size_t)]
+    lib.md2_emu_view_synthesis_loss.argtypes = [C.POINTER(Md2Problem), C.POINTER(Md2Tensors), C.c_void_p, C.c_size_t]
+    z = g.z
+    B, H, W = g.B, g.H, g.W
+    srcs = g.frame_ids[1:]
+    p = Md2Problem(batch=B, height=H, width=W, num_scales=4, num_src=len(srcs),
+                   automask=int(not g.disable_automasking), avg_reprojection=int(g.avg_reprojection),
+                   align_corners=int(align_corners), min_depth=0.1, max_depth=100.0,
+                   disparity_smoothness=1e-3, want_grad=int(want_grad), rows_per_segment=rows_per_segment)
+    keep = []
+
+    def arr(a):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        keep.append(a)
+        return a
+
+    t = Md2Tensors()
+    t.target = _ptr(arr(z["in__color__0__0"]))
+    out = {"grad_T": {}, "warped": {}}
+    for i, f in enumerate(srcs):
+        t.source[i] = _ptr(arr(z["in__color__%s__0" % f]))
+        if f == "s":
+            t.T[i] = _ptr(arr(z["in__stereo_T"]))
+            t.pose_requires_grad[i] = 0
+        else:
+            t.T[i] = _ptr(arr(z["cam_T_cam__%s" % f]))
+            t.pose_requires_grad[i] = 1
+        gT = np.zeros((B, 4, 4), np.float32)
+        out["grad_T"][f] = gT
+        t.grad_T[i] = _ptr(gT)
+    t.K = _ptr(arr(z["in__K__0"]))
+    t.inv_K = _ptr(arr(z["in__inv_K__0"]))
+    out["grad_disp"], out["grad_updisp"], out["idsel"], out["depth"] = [], [], [], []
+    for s in range(4):
+        t.disp[s] = _ptr(arr(z["disp__%d" % s]))
+        t.color[s] = _ptr(arr(z["in__color__0__%d" % s]))
+        if g.n_id > 0:
+            t.noise[s] = _ptr(arr(z["noise__%d" % s][:, :g.n_id]))
+        gd = np.zeros((B, 1, H >> s, W >> s), np.float32)
+        out["grad_disp"].append(gd)
+        t.grad_disp[s] = _ptr(gd)
+        if side_outputs:
+            gu = np.zeros((B, 1, H, W), np.float32)
+            out["grad_updisp"].append(gu)
+            t.grad_depth_dbg[s] = _ptr(gu)
+            m = np.zeros((B, H, W), np.float32)
+            out["idsel"].append(m)
+            t.identity_selection[s] = _ptr(m)
+            d = np.zeros((B, 1, H, W), np.float32)
+            out["depth"].append(d)
+            t.depth[s] = _ptr(d)
+            for i, f in enumerate(srcs):
+                w = np.zeros((B, 3, H, W), np.float32)
+                out["warped"][(f, s)] = w
+                t.warped[i][s] = _ptr(w)
+    losses = np.zeros(5, np.float32)
+    t.losses = _ptr(losses)
+    nbytes = C.c_size_t(0)
+    st = lib.md2_emu_workspace_bytes(C.byref(p), C.byref(nbytes))
+    assert st == 0, st
+    ws = np.zeros(nbytes.value + 64, np.uint8)
+    st = lib.md2_emu_view_synthesis_loss(C.byref(p), C.byref(t), _ptr(ws), nbytes.value)
+    assert st == 0, st
+    out["losses"] = losses
+    return out

@@ -1,0 +1,35 @@
+"""Drives the CUDA library (through monodepth2_b200.fused_loss, i.e. the C ABI) on a Golden fixture."""
+import torch
+
+from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
+
+
+def run_cuda(g, rows_per_segment=0, align_corners=False, want_grad=True, side_all=True, dev="cuda:0"):
+    plan = LossPlan(g.B, g.H, g.W, g.frame_ids, avg_reprojection=g.avg_reprojection,
+                    disable_automasking=g.disable_automasking, align_corners=align_corners,
+                    rows_per_segment=rows_per_segment)
+    inputs = {k: v.to(dev) for k, v in g.inputs().items()}
+    outs, leaves = {}, {}
+    for s in range(4):
+        d = g.t("disp__%d" % s).to(dev).requires_grad_(want_grad)
+        outs[("disp", s)] = d
+        leaves[("disp", s)] = d
+    for f in g.frame_ids[1:]:
+        if f == "s":
+            continue
+        T = g.t("cam_T_cam__%s" % f).to(dev).requires_grad_(want_grad)
+        outs[("cam_T_cam", 0, f)] = T
+        leaves[("T", f)] = T
+    noise = [n.to(dev) for n in g.noise()] if g.n_id > 0 else None
+    side = None
+    if side_all:
+        side = {"depth_scales": [0, 1, 2, 3], "color_scales": [0, 1, 2, 3], "mask_scales": [0, 1, 2, 3],
+                "grad_updisp_scales": [0, 1, 2, 3]}
+    if want_grad:
+        losses = view_synthesis_loss(plan, inputs, outs, noise, side)
+        losses["loss"].backward()
+    else:
+        with torch.no_grad():
+            losses = view_synthesis_loss(plan, inputs, outs, noise, side)
+    torch.cuda.synchronize()
+    return dict(losses=losses, outs=outs, leaves=leaves, side=side)
