@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""Benchmark of the fused view-synthesis loss (BASELINE.json metric: reproj-loss fwd+bwd frames/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+Own arm: a "step" is one md2_view_synthesis_loss call (generate_images_pred + compute_losses +
+the adjoint to the 4 disparities and the poses) over one synthetic batch of 12 frames per GPU,
+inputs resident in HBM; N GPUs = N independent shards of the batch dimension (no data-path
+collective), time = max over ranks of the CUDA-event duration of K steps.
+Reference arm (--impl reference): the CPU restatement of the reference's own PyTorch path
+(oracle/view_synthesis.py = the reference's --no_cuda path) on the box's host cores.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (H, W, frame_ids, avg_reprojection, disable_automasking)
+    "mono_640x192_b12": (192, 640, [0, -1, 1], False, False),
+    "mono+stereo_640x192_b12": (192, 640, [0, -1, 1, "s"], False, False),
+    "mono_1024x320_b12": (320, 1024, [0, -1, 1], False, False),
+    "mono_640x192_b12_avg_reprojection": (192, 640, [0, -1, 1], True, False),
+    "mono_640x192_b12_disable_automasking": (192, 640, [0, -1, 1], False, True),
+}
+BATCH = 12
+METRIC = "reproj-loss fwd+bwd frames/s"
+UNIT = "frames/s"
+
+
+def algorithmic_bytes(B, H, W, n_src, n_id, S=4):
+    """A_alg of SURVEY.md 8(d): compulsory reads/writes of one batch, loss fwd+bwd."""
+    tot = 0
+    for s in range(S):
+        hw, hsws = H * W, (H >> s) * (W >> s)
+        fwd = 3 * hw + 3 * n_src * hw + hsws + (3 * hsws if s > 0 else 0) + n_id * hw
+        bwd = 3 * hw + 3 * n_src * hw + hsws + (3 * hsws if s > 0 else 0) + hsws
+        tot += fwd + bwd
+    return 4 * B * tot
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------- reference arm
+def oracle_step(B, H, W, frame_ids, avg, noauto, batch, threads):
+    from oracle import view_synthesis as O
+    inputs, outputs, pose, noise = batch
+    cfg = O.OracleConfig(height=H, width=W, frame_ids=tuple(frame_ids), avg_reprojection=avg,
+                         disable_automasking=noauto)
+    outs = {}
+    leaves = []
+    for s in range(4):
+        d = outputs[("disp", s)][:B].clone().requires_grad_(True)
+        outs[("disp", s)] = d
+        leaves.append(d)
+    for f, (aa, tr) in pose.items():
+        a = aa[:B].reshape(B, 1, 3).clone().requires_grad_(True)
+        t = tr[:B].reshape(B, 1, 3).clone().requires_grad_(True)
+        leaves += [a, t]
+        outs[("cam_T_cam", 0, f)] = O.transformation_from_parameters(a, t, invert=(f < 0))
+    ins = {k: v[:B] for k, v in inputs.items()}
+    nz = [n[:B] for n in noise] if noise is not None else None
+    t0 = time.perf_counter()
+    losses = O.view_synthesis_loss(ins, outs, cfg, nz)
+    losses["loss"].backward()
+    return time.perf_counter() - t0, float(losses["loss"])
+
+
+def run_reference(args, wl):
+    """The reference's CPU implementation of the path (oracle port), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from monodepth2_b200.synthetic import make_batch
+    H, W, frame_ids, avg, noauto = WORKLOADS[wl]
+    n_src = len(frame_ids) - 1
+    n_id = 0 if noauto else (1 if avg else n_src)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    batch = make_batch(BATCH, H, W, frame_ids, 4, 0, "iid", n_id=max(n_id, 1))
+    if n_id == 0:
+        batch = (batch[0], batch[1], batch[2], None)
+    # size the per-step sample so that (K+W) steps finish in a few minutes
+    t_probe, _ = oracle_step(1, H, W, frame_ids, avg, noauto, batch, threads)
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    Bs = int(max(1, min(BATCH, budget / max(t_probe, 1e-3))))
+    for _ in range(args.warmup):
+        oracle_step(Bs, H, W, frame_ids, avg, noauto, batch, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_step(Bs, H, W, frame_ids, avg, noauto, batch, threads)
+    dt = time.perf_counter() - t0
+    fps = Bs * args.steps / dt
+    sample = "%d of %d frames of the batch per step, %d steps" % (Bs, BATCH, args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": wl, "batch_per_gpu": BATCH, "frame_ids": [str(f) for f in frame_ids],
+                   "scales": 4, "device": "cpu (reference --no_cuda path, oracle port)"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- own arm
+class DeviceBatch:
+    """One synthetic batch resident in HBM plus the prebuilt C-ABI argument block."""
+
+    def __init__(self, plan, batch, dev):
+        from monodepth2_b200._capi import Md2Tensors, MAX_SCALES
+        inputs, outputs, pose, noise = batch
+        self.keep = []
+        t = Md2Tensors()
+
+        def put(x):
+            x = x.to(dev).contiguous()
+            self.keep.append(x)
+            return x.data_ptr()
+
+        B, H, W = plan.batch_size, plan.height, plan.width
+        t.target = put(inputs[("color", 0, 0)])
+        for i, f in enumerate(plan.src_ids):
+            t.source[i] = put(inputs[("color", f, 0)])
+            if f == "s":
+                t.T[i] = put(inputs["stereo_T"])
+                t.pose_requires_grad[i] = 0
+            else:
+                t.T[i] = put(outputs[("cam_T_cam", 0, f)])
+                t.pose_requires_grad[i] = 1
+            g = torch.empty((B, 4, 4), device=dev)
+            self.keep.append(g)
+            t.grad_T[i] = g.data_ptr()
+        t.K = put(inputs[("K", 0)])
+        t.inv_K = put(inputs[("inv_K", 0)])
+        self.grad_disp = []
+        for s in range(4):
+            t.disp[s] = put(outputs[("disp", s)])
+            t.color[s] = put(inputs[("color", 0, s)])
+            if plan.n_id > 0:
+                t.noise[s] = put(noise[s])
+            g = torch.empty((B, 1, H >> s, W >> s), device=dev)
+            self.grad_disp.append(g)
+            t.grad_disp[s] = g.data_ptr()
+        self.losses = torch.zeros(MAX_SCALES + 1, device=dev)
+        t.losses = self.losses.data_ptr()
+        self.t = t
+
+
+def run_own(args, wl):
+    from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
+    from monodepth2_b200.synthetic import make_batch
+    from monodepth2_b200 import _capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the fused loss has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    H, W, frame_ids, avg, noauto = WORKLOADS[wl]
+    plan = LossPlan(BATCH, H, W, frame_ids, avg_reprojection=avg, disable_automasking=noauto,
+                    rows_per_segment=args.rows)
+    lib = plan.lib
+    n_src, n_id = plan.n_src, plan.n_id
+    nrot = 4        # rotating batches: ~110 MB each, together larger than the 126 MB L2
+    host = [make_batch(BATCH, H, W, frame_ids, 4, seed=1000 * rank + i, kind="iid", n_id=max(n_id, 1))
+            for i in range(nrot)]
+    devb = [DeviceBatch(plan, b, dev) for b in host]
+    ws = plan.workspace(dev)
+    prob = plan.problem(True)
+    stream = torch.cuda.current_stream()
+    sptr = C.c_void_p(stream.cuda_stream)
+
+    def step(i):
+        st = lib.md2_view_synthesis_loss(C.byref(prob), C.byref(devb[i % nrot].t), ws.data_ptr(), ws.numel(), sptr)
+        if st != 0:
+            _capi.check(lib, st, "md2_view_synthesis_loss")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: K steps, inputs resident in HBM, CUDA events, max over ranks
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    tt = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total = float(tt.item())
+    value = world * BATCH * args.steps / (ms_total * 1e-3)
+    loss_val = float(devb[(args.steps - 1) % nrot].losses[0].item())
+
+    # ---- roofline of the dominant kernel (md2_march): per-launch CUDA events, live
+    lib.md2_profile_enable(1)
+    march = []
+    for i in range(min(args.steps, 20)):
+        step(i)
+        ms = C.c_float(0)
+        lib.md2_profile_march_ms(C.byref(ms))
+        march.append(ms.value)
+    lib.md2_profile_enable(0)
+    march_ms = sum(march) / len(march)
+    a_alg = algorithmic_bytes(BATCH, H, W, n_src, n_id)
+    peak, peak_src = measured_peak_gbs()
+    achieved = a_alg / (march_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "march_traffic.json"))).get(wl)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "md2_march", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": a_alg, "kernel_ms": march_ms,
+                "frac_of_8TBs_nominal": achieved / 8000.0,
+                "whole_step_achieved": a_alg / (ms_total / args.steps * 1e-3) / 1e9}
+
+    # ---- e2e: public API, pinned host inputs copied every step, loss read back every step
+    pinned = []
+    for b in host[:2]:
+        inputs, outputs, pose, noise = b
+        pin_in = {k: v.pin_memory() for k, v in inputs.items()}
+        pin_out = {k: v.pin_memory() for k, v in outputs.items()}
+        pinned.append((pin_in, pin_out))
+    h2d = sum(v.numel() * 4 for v in pinned[0][0].values()) + sum(v.numel() * 4 for v in pinned[0][1].values())
+
+    def e2e_step(i):
+        pin_in, pin_out = pinned[i % 2]
+        ins = {k: v.to(dev, non_blocking=True) for k, v in pin_in.items()}
+        outs = {}
+        for k, v in pin_out.items():
+            outs[k] = v.to(dev, non_blocking=True).requires_grad_(True)
+        losses = view_synthesis_loss(plan, ins, outs)       # tie-break noise drawn on device, as the reference
+        losses["loss"].backward()
+        return float(losses["loss"].item())                 # D2H read of the step's result
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    n_e2e = max(5, min(args.steps, 30))
+    t0 = time.perf_counter()
+    for i in range(n_e2e):
+        e2e_step(i)
+    barrier()
+    dt = time.perf_counter() - t0
+    te = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * BATCH * n_e2e / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": 4, "steps": n_e2e}
+
+    # ---- CPU baseline (oracle port) on rank 0 at N=1, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        cb = host[0] if n_id > 0 else (host[0][0], host[0][1], host[0][2], None)
+        oracle_step(2, H, W, frame_ids, avg, noauto, cb, threads)          # warm-up
+        t_used, n_fr, reps = 0.0, 0, 0
+        while t_used < 10.0 and reps < 5:
+            dt1, _ = oracle_step(BATCH, H, W, frame_ids, avg, noauto, cb, threads)
+            t_used += dt1
+            n_fr += BATCH
+            reps += 1
+        cpu = {"value": n_fr / t_used, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d full batches of %d frames (oracle/view_synthesis.py, fwd+bwd)" % (reps, BATCH)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl, "batch_per_gpu": BATCH, "frame_ids": [str(f) for f in frame_ids],
+                       "scales": 4, "l2": "inputs larger than L2: %d rotating batches of ~%d MB each" %
+                       (nrot, int((h2d + n_id * BATCH * H * W * 4 * 4) / 1e6)),
+                       "rows_per_segment": plan.problem(True).rows_per_segment or 32, "loss": loss_val},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": 6 * args.steps if plan.automask else 5 * args.steps,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--workload", default="mono_640x192_b12", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0, help="rows per marching segment (0 = library default)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args, args.workload)
+    else:
+        run_own(args, args.workload)
+
+
+if __name__ == "__main__":
+    main()

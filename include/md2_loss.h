@@ -86,6 +86,12 @@ int md2_loss_workspace_bytes(const md2_problem *p, size_t *bytes);
 int md2_view_synthesis_loss(const md2_problem *p, const md2_tensors *t,
                             void *workspace, size_t workspace_bytes, void *stream);
 
+/* Measurement hook (bench.py roofline leg): when enabled, every md2_view_synthesis_loss call
+ * records CUDA events on its stream around the dominant kernel (md2_march);
+ * md2_profile_march_ms waits for the last call's pair and returns its duration. */
+int md2_profile_enable(int on);
+int md2_profile_march_ms(float *ms);
+
 /* ---- per-layer entry points: one per layers.py symbol on the path ---- */
 
 /* layers.py:16-25 disp_to_depth -> scaled_disp, depth (either output may be NULL). n elements. */

@@ -51,6 +51,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libmd2loss.so")
 # every symbol include/md2_loss.h declares (tests/test_capi_symbols.py checks the header against this)
 SYMBOLS = [
     "md2_version", "md2_status_string", "md2_loss_workspace_bytes", "md2_view_synthesis_loss",
+    "md2_profile_enable", "md2_profile_march_ms",
     "md2_disp_to_depth", "md2_disp_to_depth_backward",
     "md2_backproject_depth", "md2_backproject_depth_backward",
     "md2_project3d", "md2_project3d_backward",

@@ -7,6 +7,8 @@
 
 namespace md2 {
 cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream);
+cudaError_t profile_enable(bool on);
+cudaError_t profile_march_ms(float* ms);
 }
 
 extern "C" {
@@ -44,6 +46,15 @@ int md2_view_synthesis_loss(const md2_problem* p, const md2_tensors* t, void* wo
   if (st != MD2_OK) return st;
   const cudaError_t e = md2::launch_view_synthesis_loss(P, (cudaStream_t)stream);
   return e == cudaSuccess ? MD2_OK : MD2_ERR_CUDA;
+}
+
+int md2_profile_enable(int on) {
+  return md2::profile_enable(on != 0) == cudaSuccess ? MD2_OK : MD2_ERR_CUDA;
+}
+
+int md2_profile_march_ms(float* ms) {
+  if (!ms) return MD2_ERR_INVALID_ARGUMENT;
+  return md2::profile_march_ms(ms) == cudaSuccess ? MD2_OK : MD2_ERR_CUDA;
 }
 
 }  // extern "C"

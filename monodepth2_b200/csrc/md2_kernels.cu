@@ -236,6 +236,27 @@ static cudaError_t launch_march_n(const Params& P, cudaStream_t stream) {
   }
 }
 
+// optional CUDA events recorded around the marching kernel (bench.py roofline leg)
+static cudaEvent_t g_prof_ev[2] = {nullptr, nullptr};
+static bool g_prof_on = false;
+
+cudaError_t profile_enable(bool on) {
+  if (on && !g_prof_ev[0]) {
+    cudaError_t e = cudaEventCreate(&g_prof_ev[0]);
+    if (e != cudaSuccess) return e;
+    e = cudaEventCreate(&g_prof_ev[1]);
+    if (e != cudaSuccess) return e;
+  }
+  g_prof_on = on;
+  return cudaSuccess;
+}
+cudaError_t profile_march_ms(float* ms) {
+  if (!g_prof_ev[0]) return cudaErrorNotReady;
+  cudaError_t e = cudaEventSynchronize(g_prof_ev[1]);
+  if (e != cudaSuccess) return e;
+  return cudaEventElapsedTime(ms, g_prof_ev[0], g_prof_ev[1]);
+}
+
 cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
   cudaError_t e;
   md2_prologue<<<4, 256, 0, stream>>>(P);
@@ -262,12 +283,14 @@ cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
     md2_smooth<<<grid, 256, 0, stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
+  if (g_prof_on) cudaEventRecord(g_prof_ev[0], stream);
   switch (P.nsrc) {
     case 1: e = launch_march_n<1>(P, stream); break;
     case 2: e = launch_march_n<2>(P, stream); break;
     default: e = launch_march_n<3>(P, stream); break;
   }
   if (e != cudaSuccess) return e;
+  if (g_prof_on) cudaEventRecord(g_prof_ev[1], stream);
   {
     const int n0 = P.H * P.W;
     dim3 grid((n0 + 255) / 256, P.B, P.S);

@@ -1,0 +1,60 @@
+"""CPU-side checks of the C-ABI boundary: the library builds, loads and exports every symbol
+include/md2_loss.h declares; argument validation works without touching a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from monodepth2_b200 import build, _capi
+    build.build()
+    return _capi.load_library()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "md2_loss.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(md2_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported(lib):
+    from monodepth2_b200 import _capi
+    syms = header_symbols()
+    assert len(syms) >= 18
+    assert sorted(_capi.SYMBOLS) == syms
+    for s in syms:
+        assert hasattr(lib, s), "libmd2loss.so does not export %s" % s
+
+
+def test_struct_layout_matches_header():
+    from monodepth2_b200._capi import Md2Problem, Md2Tensors
+    assert C.sizeof(Md2Problem) == 14 * 4
+    # 1 + 4 + 4 pointers, 4 ints, 2 + 3*4 + 1 + 4 + 4 + 4 + 16 + 4 + 4 pointers
+    nptr = 1 + 4 + 4 + 2 + 12 + 1 + 4 + 4 + 4 + 16 + 4 + 4
+    assert C.sizeof(Md2Tensors) == nptr * 8 + 4 * 4
+
+
+def test_validation_without_gpu(lib):
+    from monodepth2_b200._capi import Md2Problem
+    n = C.c_size_t(0)
+    good = Md2Problem(batch=12, height=192, width=640, num_scales=4, num_src=2, automask=1,
+                      min_depth=0.1, max_depth=100.0, disparity_smoothness=1e-3, want_grad=1)
+    assert lib.md2_loss_workspace_bytes(C.byref(good), C.byref(n)) == 0
+    assert 30e6 < n.value < 80e6
+    bad = Md2Problem(batch=12, height=190, width=640, num_scales=4, num_src=2, min_depth=0.1, max_depth=100.0)
+    assert lib.md2_loss_workspace_bytes(C.byref(bad), C.byref(n)) == -1
+    bad2 = Md2Problem(batch=12, height=192, width=640, num_scales=4, num_src=4, min_depth=0.1, max_depth=100.0)
+    assert lib.md2_loss_workspace_bytes(C.byref(bad2), C.byref(n)) == -2
+    assert lib.md2_status_string(-3) == b"workspace too small"
+    assert lib.md2_version() >= 100
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    from monodepth2_b200 import _capi
+    with pytest.raises(_capi.Md2Error):
+        _capi.load_library(str(tmp_path / "nope.so"))
