@@ -29,13 +29,15 @@
 
 #if defined(__CUDA_ARCH__)
 #define MD2_LD(p) __ldg(p)
+#define MD2_LD4(p) __ldg(reinterpret_cast<const float4*>(p))
 #define MD2_FMUL(a, b) __fmul_rn(a, b)
 #define MD2_FADD(a, b) __fadd_rn(a, b)
-#define MD2_RCP(a) __frcp_rn(a)
+#define MD2_RCP(a) md2::rcp_nr(a)
 #define MD2_DIV(a, b) __fdiv_rn(a, b)
 #define MD2_FLOORF(a) floorf(a)
 #else
 #define MD2_LD(p) (*(p))
+#define MD2_LD4(p) (*reinterpret_cast<const md2::F4*>(p))
 #define MD2_FMUL(a, b) md2::host_fmul(a, b)
 #define MD2_FADD(a, b) md2::host_fadd(a, b)
 #define MD2_RCP(a) (1.0f / (a))
@@ -44,6 +46,22 @@
 #endif
 
 namespace md2 {
+
+#if defined(__CUDACC__)
+typedef float4 F4;
+#else
+struct alignas(16) F4 { float x, y, z, w; };
+#endif
+MD2_HD F4 make_f4(float a, float b, float c, float d) { F4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
+
+#if defined(__CUDA_ARCH__)
+// MUFU.RCP + one Newton step: <= 1 ulp, 3 instructions instead of the IEEE sequence
+__device__ __forceinline__ float rcp_nr(float a) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return fmaf(r, fmaf(-a, r, 1.0f), r);
+}
+#endif
 
 #if !defined(__CUDA_ARCH__)
 // keep the host compiler from contracting these into an fma
@@ -82,6 +100,8 @@ struct Params {
   const float* color[kMaxScales];
   const float* noise[kMaxScales];
   // workspace
+  float* tgt4;             // (B,H,W,4) target re-laid out as RGBx texels
+  float* src4[kMaxSrc];    // (B,H,W,4) sources as RGBx texels: one 16-byte load per bilinear tap
   float* proj;     // (B,nsrc,12): M=P3*invK3 (row-major 3x3) then p4
   float* idloss;   // (B,nsrc,H,W)
   float* dD[kMaxScales];   // (B,H,W)   d loss / d upsampled disp_s
@@ -121,7 +141,7 @@ struct Cfg {
   static constexpr bool GRAD = GRAD_;
   static constexpr int NCS = AVG_ ? NSRC_ : 1;                   // coefficient sets shipped per window
   static constexpr int NID = AUTOMASK_ ? (AVG_ ? 1 : NSRC_) : 0; // identity candidates
-  static constexpr int STASH = 4 + 11 * NSRC_;                   // floats per ring row
+  static constexpr int STASH4 = 1 + 3 * NSRC_;                   // 16-byte fields per ring row
 };
 
 // ------------------------------------------------------------------ SSIM pieces
@@ -160,18 +180,30 @@ MD2_HD float ssim_window(float sx, float sxx, float sxy, float sy, float syy, fl
   return S;
 }
 
+// index reflection of ReflectionPad2d(1) (layers.py:235-236), then clamped so that lanes /
+// rows beyond the pad ring still address valid memory (their values are never used)
+MD2_HD int reflect_clamp(int i, int n) {
+  i = i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i);
+  return i < 0 ? 0 : (i >= n ? n - 1 : i);
+}
+
 // ------------------------------------------------------------------ lane state
 template <class C>
 struct Lane {
   // constants of the job
   int x;            // column of this lane (may be outside the image)
-  int xi;           // x clamped into the image (safe for addressing)
+  int xi;           // reflected/clamped column: where this lane actually reads
   bool colok;
-  float qa[C::NSRC][3];   // M[i][0]*x + M[i][2]
+  float qa[C::NSRC][3];   // M[i][0]*xi + M[i][2]
   float qb[C::NSRC][3];   // M[i][1]
   float p4[C::NSRC][3];   // (K T)[i][3]
   int ux0, ux1;           // bilinear up-sampling taps of disp_s in x
   float ul0, ul1;
+  // software prefetch: inputs of the NEXT row, in flight during the current step
+  F4 ntg;                 // target texel of row t+1
+  float nd[4];            // disparity taps of row t+1 (d00,d01,d10,d11; scale 0: d00 only)
+  // identity loss + noise of the current window row (loaded at the top of the step)
+  float idv[C::NSRC], nzv[C::NSRC];
   // forward rolling state (horizontal 3-sums of the two previous rows)
   float H1[C::NSRC][3][3], H2[C::NSRC][3][3];   // [f][c][x,xx,xy]
   float HY1[3][2], HY2[3][2];                   // [c][y,yy]
@@ -201,20 +233,41 @@ struct Xchg2 {   // what stage C needs from a horizontal neighbour
 
 MD2_HD int ring_slot(int t) { return ((t % kRing) + kRing) % kRing; }
 
-// thread-private stash: element (slot, field) of lane `lane_off` with lane stride `stride`
+// thread-private stash of 16-byte fields: element (slot, field) of this lane; consecutive
+// lanes are 16 bytes apart, so 128-bit shared accesses are conflict-free
 struct Stash {
-  float* base;
-  int stride;     // distance between consecutive fields of one lane (threads per CTA / lanes)
-  MD2_HD float& at(int slot, int field, int nfields) const {
-    return base[(slot * nfields + field) * stride];
-  }
+  F4* base;
+  int stride;     // threads sharing the ring (lane stride of one field)
+  MD2_HD F4& at(int slot, int field, int nfields) const { return base[(slot * nfields + field) * stride]; }
 };
+
+// issue the loads of row `t`'s target texel and disparity taps (consumed one step later)
+template <class C>
+MD2_HD void prefetch_row(Lane<C>& L, const Params& P, const WarpJob& J, int t) {
+  const int tr = reflect_clamp(t, P.H);
+  L.ntg = MD2_LD4(P.tgt4 + (((size_t)J.b * P.H + tr) * P.W + L.xi) * 4);
+  const float* d = P.disp[J.s];
+  if (J.s == 0) {
+    L.nd[0] = MD2_LD(d + ((size_t)J.b * P.H + tr) * P.W + L.xi);
+  } else {
+    const int Hs = P.H >> J.s, Ws = P.W >> J.s;
+    const float r = 1.0f / (float)(1 << J.s);
+    float syr = fmaf(r, (float)tr + 0.5f, -0.5f);
+    syr = syr < 0.0f ? 0.0f : syr;
+    const int y0 = (int)syr;
+    const int y1 = y0 + ((y0 < Hs - 1) ? 1 : 0);
+    const float* r0 = d + ((size_t)J.b * Hs + y0) * Ws;
+    const float* r1 = d + ((size_t)J.b * Hs + y1) * Ws;
+    L.nd[0] = MD2_LD(r0 + L.ux0); L.nd[1] = MD2_LD(r0 + L.ux1);
+    L.nd[2] = MD2_LD(r1 + L.ux0); L.nd[3] = MD2_LD(r1 + L.ux1);
+  }
+}
 
 template <class C>
 MD2_HD void lane_init(Lane<C>& L, const Params& P, const WarpJob& J, int lane) {
   L.x = J.x0 - 2 + lane;
   L.colok = (L.x >= 0) && (L.x < P.W);
-  L.xi = L.x < 0 ? 0 : (L.x >= P.W ? P.W - 1 : L.x);
+  L.xi = reflect_clamp(L.x, P.W);
   const float xf = (float)L.xi;
 #pragma unroll
   for (int f = 0; f < C::NSRC; ++f) {
@@ -225,6 +278,7 @@ MD2_HD void lane_init(Lane<C>& L, const Params& P, const WarpJob& J, int lane) {
       L.qb[f][i] = MD2_LD(m + i * 3 + 1);
       L.p4[f][i] = MD2_LD(m + 9 + i);
     }
+    L.idv[f] = 0.f; L.nzv[f] = 0.f;
   }
   if (J.s > 0) {
     const int Ws = P.W >> J.s;
@@ -239,6 +293,7 @@ MD2_HD void lane_init(Lane<C>& L, const Params& P, const WarpJob& J, int lane) {
     L.ux0 = L.ux1 = L.xi;
     L.ul0 = 1.0f; L.ul1 = 0.0f;
   }
+  L.nd[0] = L.nd[1] = L.nd[2] = L.nd[3] = 0.f;
 #pragma unroll
   for (int f = 0; f < C::NSRC; ++f) {
 #pragma unroll
@@ -262,143 +317,126 @@ MD2_HD void lane_init(Lane<C>& L, const Params& P, const WarpJob& J, int lane) {
     for (int k = 0; k < 9; ++k) L.coef[n][k] = 0.f;
   L.tag = -1; L.tag1 = -1;
   L.loss = 0.f;
-}
-
-// Up-sampled disparity D at (x, y) of the full-resolution grid (trainer.py:350-351,
-// torch upsample_bilinear2d, align_corners=False); scale 0 is the identity.
-template <class C>
-MD2_HD float sample_disp(const Lane<C>& L, const Params& P, const WarpJob& J, int y) {
-  const float* d = P.disp[J.s];
-  if (J.s == 0) return MD2_LD(d + ((size_t)J.b * P.H + y) * P.W + L.xi);
-  const int Hs = P.H >> J.s, Ws = P.W >> J.s;
-  const float r = 1.0f / (float)(1 << J.s);
-  float syr = fmaf(r, (float)y + 0.5f, -0.5f);
-  syr = syr < 0.0f ? 0.0f : syr;
-  const int y0 = (int)syr;
-  const int y1 = y0 + ((y0 < Hs - 1) ? 1 : 0);
-  const float l1 = syr - (float)y0, l0 = 1.0f - l1;
-  const float* r0 = d + ((size_t)J.b * Hs + y0) * Ws;
-  const float* r1 = d + ((size_t)J.b * Hs + y1) * Ws;
-  const float top = L.ul0 * MD2_LD(r0 + L.ux0) + L.ul1 * MD2_LD(r0 + L.ux1);
-  const float bot = L.ul0 * MD2_LD(r1 + L.ux0) + L.ul1 * MD2_LD(r1 + L.ux1);
-  return l0 * top + l1 * bot;
+  prefetch_row(L, P, J, J.y0 - 2);
 }
 
 // ------------------------------------------------------------------ stage A
-// Row t: depth, projection into every source, border-clamped bilinear gather.
-// Exports pr/tg for the neighbour exchange and stashes what the adjoint of row t
-// will need two steps later.
+// Row t (read at its reflected position, so pad-ring rows/lanes carry the reflected values
+// and no edge case is needed downstream): up-sampled disparity (trainer.py:350-351, torch
+// upsample_bilinear2d, align_corners=False) -> depth, projection into every source,
+// border-clamped bilinear gather.  Exports pr/tg for the neighbour exchange and stashes what
+// the adjoint of row t needs two steps later.  Also issues the loads of row t+1 and of the
+// identity loss / noise of window row t-1.
 template <class C>
 MD2_HD void stage_a(Lane<C>& L, const Params& P, const WarpJob& J, int t, const Stash& st) {
-  const bool act = L.colok && (t >= 0) && (t < P.H);
   const int slot = ring_slot(t);
-  float z = 0.f;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) L.tg[c] = 0.f;
-  if (act) {
+  const int tr = reflect_clamp(t, P.H);
+  // consume the prefetched row, then put the next one in flight
+  const F4 tg4 = L.ntg;
+  float D;
+  if (J.s == 0) {
+    D = L.nd[0];
+  } else {
+    const float r = 1.0f / (float)(1 << J.s);
+    float syr = fmaf(r, (float)tr + 0.5f, -0.5f);
+    syr = syr < 0.0f ? 0.0f : syr;
+    const float l1 = syr - (float)(int)syr, l0 = 1.0f - l1;
+    const float top = L.ul0 * L.nd[0] + L.ul1 * L.nd[1];
+    const float bot = L.ul0 * L.nd[2] + L.ul1 * L.nd[3];
+    D = l0 * top + l1 * bot;
+  }
+  prefetch_row(L, P, J, t + 1);
+  {
     const size_t plane = (size_t)P.H * P.W;
-    const float* tp = P.tgt + (size_t)J.b * 3 * plane + (size_t)t * P.W + L.xi;
+    const int yw = t - 1;
+    const size_t pix = (size_t)(yw < 0 ? 0 : (yw >= P.H ? P.H - 1 : yw)) * P.W + L.xi;
+    if (C::AUTOMASK) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) L.tg[c] = MD2_LD(tp + c * plane);
-    const float D = sample_disp(L, P, J, t);
-    const float sd = MD2_FADD(P.a_disp, MD2_FMUL(P.c_disp, D));
-    z = MD2_RCP(sd);
-    if (P.depth[J.s] && t >= J.y0 && t < J.y1 && L.x >= J.x0 && L.x < J.x0 + kOwnCols)
-      P.depth[J.s][((size_t)J.b * P.H + t) * P.W + L.xi] = z;
-  }
-  if (C::GRAD) {
+      for (int f = 0; f < C::NSRC; ++f) L.idv[f] = MD2_LD(P.idloss + ((size_t)J.b * C::NSRC + f) * plane + pix);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) st.at(slot, c, C::STASH) = L.tg[c];
-    st.at(slot, 3, C::STASH) = z;
+      for (int f = 0; f < C::NID; ++f) L.nzv[f] = MD2_LD(P.noise[J.s] + ((size_t)J.b * C::NID + f) * plane + pix);
+    }
   }
-  const float yf = (float)t;
+  L.tg[0] = tg4.x; L.tg[1] = tg4.y; L.tg[2] = tg4.z;
+  const float sd = MD2_FADD(P.a_disp, MD2_FMUL(P.c_disp, D));
+  const float z = MD2_RCP(sd);
+  const bool own = (t >= J.y0) && (t < J.y1) && (L.x >= J.x0) && (L.x < J.x0 + kOwnCols) && L.colok;
+  if (P.depth[J.s] && own) P.depth[J.s][((size_t)J.b * P.H + t) * P.W + L.xi] = z;
+  if (C::GRAD) st.at(slot, 0, C::STASH4) = make_f4(tg4.x, tg4.y, tg4.z, z);
+  const float yf = (float)tr;
 #pragma unroll
   for (int f = 0; f < C::NSRC; ++f) {
-    float pr[3] = {0.f, 0.f, 0.f}, dxp[3] = {0.f, 0.f, 0.f}, dyp[3] = {0.f, 0.f, 0.f};
-    float u = 0.f, v = 0.f;
-    if (act) {
-      const float q0 = fmaf(L.qb[f][0], yf, L.qa[f][0]);
-      const float q1 = fmaf(L.qb[f][1], yf, L.qa[f][1]);
-      const float q2 = fmaf(L.qb[f][2], yf, L.qa[f][2]);
-      const float c0 = fmaf(z, q0, L.p4[f][0]);
-      const float c1 = fmaf(z, q1, L.p4[f][1]);
-      const float c2 = fmaf(z, q2, L.p4[f][2]);
-      const float inv = MD2_RCP(c2 + P.eps);
-      u = c0 * inv;
-      v = c1 * inv;
-      const float ix = fmaf(u, P.sx, P.ox);
-      const float iy = fmaf(v, P.sy, P.oy);
-      const bool mx = (ix > 0.0f) && (ix < P.wmax);
-      const bool my = (iy > 0.0f) && (iy < P.hmax);
-      const float ixc = fminf(fmaxf(ix, 0.0f), P.wmax);
-      const float iyc = fminf(fmaxf(iy, 0.0f), P.hmax);
-      const float fx0 = MD2_FLOORF(ixc), fy0 = MD2_FLOORF(iyc);
-      const float wx = ixc - fx0, wy = iyc - fy0;
-      const int x0 = (int)fx0, y0 = (int)fy0;
-      const int x1 = (x0 + 1 < P.W) ? x0 + 1 : P.W - 1;
-      const int y1 = (y0 + 1 < P.H) ? y0 + 1 : P.H - 1;
-      const size_t plane = (size_t)P.H * P.W;
-      const float* sp = P.src[f] + (size_t)J.b * 3 * plane;
-      const float* r0 = sp + (size_t)y0 * P.W;
-      const float* r1 = sp + (size_t)y1 * P.W;
-      const float gxs = mx ? P.sx * inv : 0.0f;
-      const float gys = my ? P.sy * inv : 0.0f;
+    const float q0 = fmaf(L.qb[f][0], yf, L.qa[f][0]);
+    const float q1 = fmaf(L.qb[f][1], yf, L.qa[f][1]);
+    const float q2 = fmaf(L.qb[f][2], yf, L.qa[f][2]);
+    const float c0 = fmaf(z, q0, L.p4[f][0]);
+    const float c1 = fmaf(z, q1, L.p4[f][1]);
+    const float c2 = fmaf(z, q2, L.p4[f][2]);
+    const float inv = MD2_RCP(c2 + P.eps);
+    const float u = c0 * inv;
+    const float v = c1 * inv;
+    const float ix = fmaf(u, P.sx, P.ox);
+    const float iy = fmaf(v, P.sy, P.oy);
+    const bool mx = (ix > 0.0f) && (ix < P.wmax);
+    const bool my = (iy > 0.0f) && (iy < P.hmax);
+    const float ixc = fminf(fmaxf(ix, 0.0f), P.wmax);
+    const float iyc = fminf(fmaxf(iy, 0.0f), P.hmax);
+    const float fx0 = MD2_FLOORF(ixc), fy0 = MD2_FLOORF(iyc);
+    const float wx = ixc - fx0, wy = iyc - fy0;
+    const int x0 = (int)fx0, y0 = (int)fy0;
+    const int dx1 = (x0 + 1 < P.W) ? 4 : 0;                 // texel step to the east tap
+    const int dy1 = (y0 + 1 < P.H) ? P.W * 4 : 0;           // texel step to the south tap
+    const float* t00 = P.src4[f] + (((size_t)J.b * P.H + y0) * P.W + x0) * 4;
+    const F4 nw = MD2_LD4(t00), ne = MD2_LD4(t00 + dx1);
+    const F4 sw = MD2_LD4(t00 + dy1), se = MD2_LD4(t00 + dy1 + dx1);
+    const float gxs = mx ? P.sx * inv : 0.0f;
+    const float gys = my ? P.sy * inv : 0.0f;
+    float pr[3], dxp[3], dyp[3];
+    {
+      const float nwc[3] = {nw.x, nw.y, nw.z}, nec[3] = {ne.x, ne.y, ne.z};
+      const float swc[3] = {sw.x, sw.y, sw.z}, sec[3] = {se.x, se.y, se.z};
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float nw = MD2_LD(r0 + c * plane + x0), ne = MD2_LD(r0 + c * plane + x1);
-        const float sw = MD2_LD(r1 + c * plane + x0), se = MD2_LD(r1 + c * plane + x1);
-        const float dn = ne - nw, ds = se - sw;
-        const float top = fmaf(wx, dn, nw), bot = fmaf(wx, ds, sw);
+        const float dn = nec[c] - nwc[c], ds = sec[c] - swc[c];
+        const float top = fmaf(wx, dn, nwc[c]), bot = fmaf(wx, ds, swc[c]);
         const float dv = bot - top;
         pr[c] = fmaf(wy, dv, top);
         dxp[c] = fmaf(wy, ds - dn, dn) * gxs;
         dyp[c] = dv * gys;
       }
-      float* wout = P.warped[f][J.s];
-      if (wout && t >= J.y0 && t < J.y1 && L.x >= J.x0 && L.x < J.x0 + kOwnCols) {
+    }
+    float* wout = P.warped[f][J.s];
+    if (wout && own) {
+      const size_t plane = (size_t)P.H * P.W;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) wout[((size_t)J.b * 3 + c) * plane + (size_t)t * P.W + L.xi] = pr[c];
-      }
+      for (int c = 0; c < 3; ++c) wout[((size_t)J.b * 3 + c) * plane + (size_t)t * P.W + L.xi] = pr[c];
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) L.pr[f][c] = pr[c];
     if (C::GRAD) {
-      const int o = 4 + 11 * f;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        st.at(slot, o + c, C::STASH) = pr[c];
-        st.at(slot, o + 3 + c, C::STASH) = dxp[c];
-        st.at(slot, o + 6 + c, C::STASH) = dyp[c];
-      }
-      st.at(slot, o + 9, C::STASH) = u;
-      st.at(slot, o + 10, C::STASH) = v;
+      st.at(slot, 1 + 3 * f, C::STASH4) = make_f4(pr[0], pr[1], pr[2], u);
+      st.at(slot, 2 + 3 * f, C::STASH4) = make_f4(dxp[0], dxp[1], dxp[2], v);
+      st.at(slot, 3 + 3 * f, C::STASH4) = make_f4(dyp[0], dyp[1], dyp[2], 0.f);
     }
   }
 }
 
 // ------------------------------------------------------------------ stage B
 // Horizontal sums of row t, SSIM + L1 of window row t-1, per-pixel minimum and the
-// SSIM-adjoint coefficients of the winning source.  `own_win` = this lane owns the
-// window (adds it to the loss).
+// SSIM-adjoint coefficients of the winning source.
 template <class C>
 MD2_HD void stage_b(Lane<C>& L, const Params& P, const WarpJob& J, int t, int lane,
                     const Xchg1<C>& lf, const Xchg1<C>& rt) {
   const int yw = t - 1;
-  const bool left_edge = (L.x == 0), right_edge = (L.x == P.W - 1);
-  // horizontal 3-sums of row t with the reflection of ReflectionPad2d(1) (layers.py:235-236)
   float H0[C::NSRC][3][3], HY0[3][2];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float yl = left_edge ? rt.tg[c] : lf.tg[c];
-    const float yr = right_edge ? lf.tg[c] : rt.tg[c];
-    const float yc = L.tg[c];
+    const float yl = lf.tg[c], yr = rt.tg[c], yc = L.tg[c];
     HY0[c][0] = yl + yc + yr;
     HY0[c][1] = fmaf(yr, yr, fmaf(yc, yc, yl * yl));
 #pragma unroll
     for (int f = 0; f < C::NSRC; ++f) {
-      const float xl = left_edge ? rt.pr[f][c] : lf.pr[f][c];
-      const float xr = right_edge ? lf.pr[f][c] : rt.pr[f][c];
-      const float xc = L.pr[f][c];
+      const float xl = lf.pr[f][c], xr = rt.pr[f][c], xc = L.pr[f][c];
       H0[f][c][0] = xl + xc + xr;
       H0[f][c][1] = fmaf(xr, xr, fmaf(xc, xc, xl * xl));
       H0[f][c][2] = fmaf(xr, yr, fmaf(xc, yc, xl * yl));
@@ -414,24 +452,15 @@ MD2_HD void stage_b(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
 #pragma unroll
     for (int k = 0; k < 9; ++k) L.coef[n][k] = 0.f;
   if (win_ok) {
-    const bool top_edge = (yw == 0), bot_edge = (yw == P.H - 1);
     float V[C::NSRC][3][3], VY[3][2];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const float up = top_edge ? HY0[c][k] : L.HY2[c][k];
-        const float dn = bot_edge ? L.HY2[c][k] : HY0[c][k];
-        VY[c][k] = up + L.HY1[c][k] + dn;
-      }
+      for (int k = 0; k < 2; ++k) VY[c][k] = L.HY2[c][k] + L.HY1[c][k] + HY0[c][k];
 #pragma unroll
       for (int f = 0; f < C::NSRC; ++f)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const float up = top_edge ? H0[f][c][k] : L.H2[f][c][k];
-          const float dn = bot_edge ? L.H2[f][c][k] : H0[f][c][k];
-          V[f][c][k] = up + L.H1[f][c][k] + dn;
-        }
+        for (int k = 0; k < 3; ++k) V[f][c][k] = L.H2[f][c][k] + L.H1[f][c][k] + H0[f][c][k];
     }
     float rl[C::NSRC];
 #pragma unroll
@@ -443,25 +472,20 @@ MD2_HD void stage_b(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
         l1 += fabsf(L.tg1[c] - L.pr1[f][c]);
       }
       // trainer.py:403: 0.85 * ssim.mean(1) + 0.15 * l1.mean(1)
-      rl[f] = MD2_FADD(MD2_FMUL(0.85f, ss / 3.0f), MD2_FMUL(0.15f, l1 / 3.0f));
+      rl[f] = fmaf(0.85f / 3.0f, ss, (0.15f / 3.0f) * l1);
     }
     // candidates in the order of trainer.py:471: identity first, then reprojection
     float best = INFINITY;
-    const size_t plane = (size_t)P.H * P.W;
-    const size_t pix = (size_t)yw * P.W + L.xi;
     if (C::AUTOMASK) {
       if (C::AVG) {
         float acc = 0.f;
 #pragma unroll
-        for (int f = 0; f < C::NSRC; ++f) acc += MD2_LD(P.idloss + ((size_t)J.b * C::NSRC + f) * plane + pix);
-        const float nz = MD2_LD(P.noise[J.s] + (size_t)J.b * plane + pix);
-        best = MD2_FADD(acc / (float)C::NSRC, MD2_FMUL(nz, 0.00001f));
+        for (int f = 0; f < C::NSRC; ++f) acc += L.idv[f];
+        best = MD2_FADD(acc * (1.0f / (float)C::NSRC), MD2_FMUL(L.nzv[0], 0.00001f));
       } else {
 #pragma unroll
         for (int f = 0; f < C::NSRC; ++f) {
-          const float idv = MD2_LD(P.idloss + ((size_t)J.b * C::NSRC + f) * plane + pix);
-          const float nz = MD2_LD(P.noise[J.s] + ((size_t)J.b * C::NSRC + f) * plane + pix);
-          const float cand = MD2_FADD(idv, MD2_FMUL(nz, 0.00001f));
+          const float cand = MD2_FADD(L.idv[f], MD2_FMUL(L.nzv[f], 0.00001f));
           if (cand < best) best = cand;
         }
       }
@@ -470,7 +494,7 @@ MD2_HD void stage_b(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
       float acc = 0.f;
 #pragma unroll
       for (int f = 0; f < C::NSRC; ++f) acc += rl[f];
-      const float cand = acc / (float)C::NSRC;
+      const float cand = acc * (1.0f / (float)C::NSRC);
       if (cand < best) { best = cand; tag = 0; }
     } else {
 #pragma unroll
@@ -479,7 +503,8 @@ MD2_HD void stage_b(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
     }
     if (own_win) {
       L.loss += best;
-      if (C::AUTOMASK && P.idsel[J.s]) P.idsel[J.s][(size_t)J.b * plane + pix] = (tag >= 0) ? 1.0f : 0.0f;
+      if (C::AUTOMASK && P.idsel[J.s])
+        P.idsel[J.s][((size_t)J.b * P.H + yw) * P.W + L.xi] = (tag >= 0) ? 1.0f : 0.0f;
     }
     if (C::GRAD && tag >= 0) {
       if (C::AVG) {
@@ -548,20 +573,23 @@ MD2_HD void stage_c(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
     const float wu = (yp == 1) ? 2.0f : 1.0f;
     const float wd = (yp == P.H - 2) ? 2.0f : 1.0f;
     const int slot = ring_slot(yp);
-    float tg[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) tg[c] = st.at(slot, c, C::STASH);
-    const float z = st.at(slot, 3, C::STASH);
+    const F4 s0 = st.at(slot, 0, C::STASH4);
+    const float tg[3] = {s0.x, s0.y, s0.z};
+    const float z = s0.w;
     const float yf = (float)yp;
     float dzsum = 0.f;
 #pragma unroll
     for (int f = 0; f < C::NSRC; ++f) {
-      const int o = 4 + 11 * f;
+      const F4 sp = st.at(slot, 1 + 3 * f, C::STASH4);
+      const F4 sdx = st.at(slot, 2 + 3 * f, C::STASH4);
+      const F4 sdy = st.at(slot, 3 + 3 * f, C::STASH4);
+      const float xs[3] = {sp.x, sp.y, sp.z};
+      const float dxs[3] = {sdx.x, sdx.y, sdx.z}, dys[3] = {sdy.x, sdy.y, sdy.z};
       const bool won = C::AVG ? (L.tag1 >= 0) : (L.tag1 == f);
       float d0 = 0.f, d1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float xj = st.at(slot, o + c, C::STASH);
+        const float xj = xs[c];
         const float A = fmaf(wu, L.B2[f][c * 3 + 0], fmaf(wd, B0[f][c * 3 + 0], L.B1[f][c * 3 + 0]));
         const float Bq = fmaf(wu, L.B2[f][c * 3 + 1], fmaf(wd, B0[f][c * 3 + 1], L.B1[f][c * 3 + 1]));
         const float G = fmaf(wu, L.B2[f][c * 3 + 2], fmaf(wd, B0[f][c * 3 + 2], L.B1[f][c * 3 + 2]));
@@ -571,10 +599,10 @@ MD2_HD void stage_c(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
           const float df = xj - tg[c];
           g += (df > 0.f) ? (0.15f / 3.0f) : ((df < 0.f) ? -(0.15f / 3.0f) : 0.0f);
         }
-        d0 = fmaf(g, st.at(slot, o + 3 + c, C::STASH), d0);
-        d1 = fmaf(g, st.at(slot, o + 6 + c, C::STASH), d1);
+        d0 = fmaf(g, dxs[c], d0);
+        d1 = fmaf(g, dys[c], d1);
       }
-      const float u = st.at(slot, o + 9, C::STASH), v = st.at(slot, o + 10, C::STASH);
+      const float u = sp.w, v = sdx.w;
       const float d2 = -fmaf(u, d0, v * d1);
       const float q0 = fmaf(L.qb[f][0], yf, L.qa[f][0]);
       const float q1 = fmaf(L.qb[f][1], yf, L.qa[f][1]);
@@ -615,7 +643,8 @@ MD2_HD void lane_dP(const Lane<C>& L, const Params& P, const WarpJob& J, int f, 
 
 // ------------------------------------------------------------------ identity pass
 // Scale-independent identity reprojection losses (trainer.py:432-439): SSIM+L1 between
-// the unwarped source f and the target.  One lane per column, halo 1.
+// the unwarped source f and the target.  One lane per column, halo 1; rows and columns are
+// read at their reflected positions.
 template <int NSRC>
 struct IdLane {
   int x, xi;
@@ -635,7 +664,7 @@ template <int NSRC>
 MD2_HD void id_init(IdLane<NSRC>& L, const Params& P, int x0, int lane) {
   L.x = x0 - 1 + lane;
   L.colok = (L.x >= 0) && (L.x < P.W);
-  L.xi = L.x < 0 ? 0 : (L.x >= P.W ? P.W - 1 : L.x);
+  L.xi = reflect_clamp(L.x, P.W);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     L.HY1[c][0] = L.HY1[c][1] = L.HY2[c][0] = L.HY2[c][1] = 0.f;
@@ -651,14 +680,14 @@ MD2_HD void id_init(IdLane<NSRC>& L, const Params& P, int x0, int lane) {
 
 template <int NSRC>
 MD2_HD void id_stage_a(IdLane<NSRC>& L, const Params& P, int b, int t) {
-  const bool act = L.colok && t >= 0 && t < P.H;
-  const size_t plane = (size_t)P.H * P.W;
-  const size_t off = (size_t)b * 3 * plane + (size_t)(act ? t : 0) * P.W + L.xi;
+  const int tr = reflect_clamp(t, P.H);
+  const size_t off = (((size_t)b * P.H + tr) * P.W + L.xi) * 4;
+  const F4 tg = MD2_LD4(P.tgt4 + off);
+  L.tg[0] = tg.x; L.tg[1] = tg.y; L.tg[2] = tg.z;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    L.tg[c] = act ? MD2_LD(P.tgt + off + c * plane) : 0.f;
-#pragma unroll
-    for (int f = 0; f < NSRC; ++f) L.pr[f][c] = act ? MD2_LD(P.src[f] + off + c * plane) : 0.f;
+  for (int f = 0; f < NSRC; ++f) {
+    const F4 s = MD2_LD4(P.src4[f] + off);
+    L.pr[f][0] = s.x; L.pr[f][1] = s.y; L.pr[f][2] = s.z;
   }
 }
 
@@ -666,20 +695,15 @@ template <int NSRC>
 MD2_HD void id_stage_b(IdLane<NSRC>& L, const Params& P, int b, int t, int lane, int y0, int y1,
                        const IdXchg<NSRC>& lf, const IdXchg<NSRC>& rt) {
   const int yw = t - 1;
-  const bool left_edge = (L.x == 0), right_edge = (L.x == P.W - 1);
   float H0[NSRC][3][3], HY0[3][2];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float yl = left_edge ? rt.tg[c] : lf.tg[c];
-    const float yr = right_edge ? lf.tg[c] : rt.tg[c];
-    const float yc = L.tg[c];
+    const float yl = lf.tg[c], yr = rt.tg[c], yc = L.tg[c];
     HY0[c][0] = yl + yc + yr;
     HY0[c][1] = fmaf(yr, yr, fmaf(yc, yc, yl * yl));
 #pragma unroll
     for (int f = 0; f < NSRC; ++f) {
-      const float xl = left_edge ? rt.pr[f][c] : lf.pr[f][c];
-      const float xr = right_edge ? lf.pr[f][c] : rt.pr[f][c];
-      const float xc = L.pr[f][c];
+      const float xl = lf.pr[f][c], xr = rt.pr[f][c], xc = L.pr[f][c];
       H0[f][c][0] = xl + xc + xr;
       H0[f][c][1] = fmaf(xr, xr, fmaf(xc, xc, xl * xl));
       H0[f][c][2] = fmaf(xr, yr, fmaf(xc, yc, xl * yl));
@@ -687,31 +711,22 @@ MD2_HD void id_stage_b(IdLane<NSRC>& L, const Params& P, int b, int t, int lane,
   }
   const bool own = L.colok && yw >= y0 && yw < y1 && lane >= 1 && lane <= kIdCols;
   if (own) {
-    const bool top_edge = (yw == 0), bot_edge = (yw == P.H - 1);
     const size_t plane = (size_t)P.H * P.W;
 #pragma unroll
     for (int f = 0; f < NSRC; ++f) {
       float ss = 0.f, l1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        float vy[2], vx[3];
+        const float vy0 = L.HY2[c][0] + L.HY1[c][0] + HY0[c][0];
+        const float vy1 = L.HY2[c][1] + L.HY1[c][1] + HY0[c][1];
+        float vx[3];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const float up = top_edge ? HY0[c][k] : L.HY2[c][k];
-          const float dn = bot_edge ? L.HY2[c][k] : HY0[c][k];
-          vy[k] = up + L.HY1[c][k] + dn;
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const float up = top_edge ? H0[f][c][k] : L.H2[f][c][k];
-          const float dn = bot_edge ? L.H2[f][c][k] : H0[f][c][k];
-          vx[k] = up + L.H1[f][c][k] + dn;
-        }
-        ss += ssim_window(vx[0], vx[1], vx[2], vy[0], vy[1], nullptr);
+        for (int k = 0; k < 3; ++k) vx[k] = L.H2[f][c][k] + L.H1[f][c][k] + H0[f][c][k];
+        ss += ssim_window(vx[0], vx[1], vx[2], vy0, vy1, nullptr);
         l1 += fabsf(L.tg1[c] - L.pr1[f][c]);
       }
       P.idloss[((size_t)b * NSRC + f) * plane + (size_t)yw * P.W + L.xi] =
-          MD2_FADD(MD2_FMUL(0.85f, ss / 3.0f), MD2_FMUL(0.15f, l1 / 3.0f));
+          fmaf(0.85f / 3.0f, ss, (0.15f / 3.0f) * l1);
     }
   }
 #pragma unroll
@@ -726,6 +741,14 @@ MD2_HD void id_stage_b(IdLane<NSRC>& L, const Params& P, int b, int t, int lane,
       L.pr1[f][c] = L.pr[f][c];
     }
   }
+}
+
+// Re-layout of one pixel of image `img` (0 = target, 1+f = source f) from planar NCHW to RGBx.
+MD2_HD void pack_pixel(const Params& P, int img, int b, int p) {
+  const size_t plane = (size_t)P.H * P.W;
+  const float* in = (img == 0 ? P.tgt : P.src[img - 1]) + (size_t)b * 3 * plane + p;
+  float* out = (img == 0 ? P.tgt4 : P.src4[img - 1]) + ((size_t)b * plane + p) * 4;
+  *reinterpret_cast<F4*>(out) = make_f4(MD2_LD(in), MD2_LD(in + plane), MD2_LD(in + 2 * plane), 0.f);
 }
 
 // ------------------------------------------------------------------ small per-element pieces

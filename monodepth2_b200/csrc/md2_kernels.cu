@@ -2,6 +2,7 @@
 //
 // Launch sequence of one md2_view_synthesis_loss() call (one stream, no host sync):
 //   1. md2_prologue        zero the accumulators, build the per-(sample,source) projection
+//  1b. md2_pack            target / sources NCHW -> RGBx texels (B,H,W,4)
 //   2. md2_disp_mean       per-sample mean of disp_s            (trainer.py:486)
 //   3. md2_identity        scale-independent identity losses    (trainer.py:432-439)
 //   4. md2_smooth          edge-aware smoothness, fwd + numerator gradient (layers.py:202-215)
@@ -37,6 +38,13 @@ __global__ void md2_prologue(Params P) {
   const int nacc = acc_count(P);
   for (int i = tid; i < nacc; i += gridDim.x * blockDim.x) P.acc[i] = 0.0;
   if (tid < P.B * P.nsrc) setup_projection(P, tid / P.nsrc, tid % P.nsrc);
+}
+
+// re-layout of target and sources to RGBx texels (one 16-byte load per bilinear tap later on)
+__global__ void md2_pack(Params P) {
+  const int img = blockIdx.z, b = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P.H * P.W) pack_pixel(P, img, b, p);
 }
 
 // ------------------------------------------------------------------ 2. disparity means
@@ -127,7 +135,7 @@ __global__ void md2_smooth(Params P) {
 // ------------------------------------------------------------------ 5. the marching kernel
 template <class C>
 __global__ void __launch_bounds__(kThreads) md2_march(Params P) {
-  extern __shared__ float smem[];
+  extern __shared__ float4 smem[];
   const int lane = threadIdx.x & 31;
   const int job = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   const int per_scale = P.B * P.nseg * P.nband;
@@ -212,7 +220,7 @@ template <class C>
 static cudaError_t launch_march(const Params& P, cudaStream_t stream) {
   const int jobs = P.S * P.B * P.nseg * P.nband;
   const int grid = (jobs + kWarpsPerCta - 1) / kWarpsPerCta;
-  const size_t smem = C::GRAD ? (size_t)kThreads * kRing * C::STASH * sizeof(float) : 0;
+  const size_t smem = C::GRAD ? (size_t)kThreads * kRing * C::STASH4 * sizeof(float4) : 0;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(md2_march<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -261,6 +269,11 @@ cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
   cudaError_t e;
   md2_prologue<<<4, 256, 0, stream>>>(P);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  {
+    dim3 grid((P.H * P.W + 255) / 256, P.B, 1 + P.nsrc);
+    md2_pack<<<grid, 256, 0, stream>>>(P);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
   {
     const int n0 = P.H * P.W;
     dim3 grid((n0 + 256 * 8 - 1) / (256 * 8), P.B, P.S);

@@ -39,7 +39,7 @@ static void emu_identity(const Params& P) {
 
 template <class C>
 static void emu_march(const Params& P) {
-  std::vector<float> ring((size_t)32 * kRing * C::STASH);
+  std::vector<F4> ring((size_t)32 * kRing * C::STASH4);
   for (int s = 0; s < P.S; ++s)
     for (int b = 0; b < P.B; ++b)
       for (int seg = 0; seg < P.nseg; ++seg)
@@ -47,7 +47,7 @@ static void emu_march(const Params& P) {
           WarpJob J;
           J.s = s; J.b = b; J.x0 = band * kOwnCols;
           J.y0 = seg * P.seg_rows; J.y1 = std::min(J.y0 + P.seg_rows, P.H);
-          std::fill(ring.begin(), ring.end(), 0.f);
+          std::fill(ring.begin(), ring.end(), make_f4(0.f, 0.f, 0.f, 0.f));
           Lane<C> L[32];
           Stash st[32];
           for (int l = 0; l < 32; ++l) {
@@ -128,6 +128,9 @@ extern "C" int md2_emu_view_synthesis_loss(const md2_problem* p, const md2_tenso
   for (int i = 0; i < acc_count(P); ++i) P.acc[i] = 0.0;
   for (int b = 0; b < P.B; ++b)
     for (int f = 0; f < P.nsrc; ++f) setup_projection(P, b, f);
+  for (int img = 0; img <= P.nsrc; ++img)
+    for (int b = 0; b < P.B; ++b)
+      for (int p2 = 0; p2 < P.H * P.W; ++p2) pack_pixel(P, img, b, p2);
   // 2. disparity means
   for (int s = 0; s < P.S; ++s)
     for (int b = 0; b < P.B; ++b) {
