@@ -73,7 +73,7 @@ def load_library(path: str = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("MD2_LIB_PATH") or LIB_PATH
     if not os.path.exists(p):
         raise Md2Error(
             "libmd2loss.so not found at %s - run `python -m monodepth2_b200.build` "

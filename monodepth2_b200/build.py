@@ -11,7 +11,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIB_DIR, "libmd2loss.so")
+# development knobs: MD2_LIB_NAME / MD2_NVCC_DEFS build an experimental variant next to the product library
+LIB = os.path.join(LIB_DIR, os.environ.get("MD2_LIB_NAME", "libmd2loss.so"))
+EXTRA_DEFS = os.environ.get("MD2_NVCC_DEFS", "").split()
 SOURCES = ["md2_kernels.cu", "md2_ops.cu", "md2_capi.cu"]
 HEADERS = ["md2_core.cuh", "md2_plan.h", os.path.join("..", "..", "include", "md2_loss.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -43,9 +45,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         src = os.path.join(CSRC, s)
         if not os.path.exists(src):
             continue
-        obj = os.path.join(LIB_DIR, s.replace(".cu", ".o"))
-        cmd = [nvcc()] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + ["-c", src, "-o", obj]
-        log = open(os.path.join(LIB_DIR, s + ".ptxas.log"), "w")
+        tag = os.path.basename(LIB).replace(".so", "")
+        obj = os.path.join(LIB_DIR, tag + "." + s.replace(".cu", ".o"))
+        cmd = [nvcc()] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + EXTRA_DEFS + ["-c", src, "-o", obj]
+        log = open(os.path.join(LIB_DIR, tag + "." + s + ".ptxas.log"), "w")
         procs.append((subprocess.Popen(cmd, stdout=log, stderr=subprocess.STDOUT), cmd, log))
         objs.append(obj)
     for p, cmd, log in procs:

@@ -35,7 +35,9 @@
 #define MD2_RCP(a) md2::rcp_nr(a)
 #define MD2_DIV(a, b) __fdiv_rn(a, b)
 #define MD2_FLOORF(a) floorf(a)
+#define MD2_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
 #else
+#define MD2_PREFETCH_L1(p) ((void)(p))
 #define MD2_LD(p) (*(p))
 #define MD2_LD4(p) (*reinterpret_cast<const md2::F4*>(p))
 #define MD2_FMUL(a, b) md2::host_fmul(a, b)
@@ -260,6 +262,41 @@ MD2_HD void prefetch_row(Lane<C>& L, const Params& P, const WarpJob& J, int t) {
     const float* r1 = d + ((size_t)J.b * Hs + y1) * Ws;
     L.nd[0] = MD2_LD(r0 + L.ux0); L.nd[1] = MD2_LD(r0 + L.ux1);
     L.nd[2] = MD2_LD(r1 + L.ux0); L.nd[3] = MD2_LD(r1 + L.ux1);
+  }
+}
+
+// Warm L1 with the bilinear taps row `t` will gather: recomputes the projection of row t from
+// the already prefetched disparity taps and issues prefetch.global.L1 for the tap texels, so
+// that the data-dependent loads of the next step hit L1 instead of exposing L2 latency.
+template <class C>
+MD2_HD void prefetch_gather(const Lane<C>& L, const Params& P, const WarpJob& J, int t) {
+  const int tr = reflect_clamp(t, P.H);
+  float D;
+  if (J.s == 0) {
+    D = L.nd[0];
+  } else {
+    const float r = 1.0f / (float)(1 << J.s);
+    float syr = fmaf(r, (float)tr + 0.5f, -0.5f);
+    syr = syr < 0.0f ? 0.0f : syr;
+    const float l1 = syr - (float)(int)syr, l0 = 1.0f - l1;
+    D = l0 * (L.ul0 * L.nd[0] + L.ul1 * L.nd[1]) + l1 * (L.ul0 * L.nd[2] + L.ul1 * L.nd[3]);
+  }
+  const float z = MD2_RCP(fmaf(P.c_disp, D, P.a_disp));
+  const float yf = (float)tr;
+#pragma unroll
+  for (int f = 0; f < C::NSRC; ++f) {
+    const float c0 = fmaf(z, fmaf(L.qb[f][0], yf, L.qa[f][0]), L.p4[f][0]);
+    const float c1 = fmaf(z, fmaf(L.qb[f][1], yf, L.qa[f][1]), L.p4[f][1]);
+    const float c2 = fmaf(z, fmaf(L.qb[f][2], yf, L.qa[f][2]), L.p4[f][2]);
+    const float inv = MD2_RCP(c2 + P.eps);
+    const float ixc = fminf(fmaxf(fmaf(c0 * inv, P.sx, P.ox), 0.0f), P.wmax);
+    const float iyc = fminf(fmaxf(fmaf(c1 * inv, P.sy, P.oy), 0.0f), P.hmax);
+    const int x0 = (int)ixc, y0 = (int)iyc;
+    const int dy1 = (y0 + 1 < P.H) ? P.W * 4 : 0;
+    const float* t00 = P.src4[f] + (((size_t)J.b * P.H + y0) * P.W + x0) * 4;
+    MD2_PREFETCH_L1(t00);
+    MD2_PREFETCH_L1(t00 + dy1);
+    (void)t00; (void)dy1;
   }
 }
 
@@ -778,7 +815,14 @@ MD2_HD void setup_projection(const Params& P, int b, int f) {
 // Edge-aware smoothness at pixel (x,y) of scale s (layers.py:202-215 on the
 // mean-normalised disparity of trainer.py:486-487).  Returns the pixel's two forward
 // edge terms and gn = d(sum_x/Nx + sum_y/Ny) / d norm_disp(x,y).
-MD2_HD void smooth_pixel(const Params& P, int s, int b, int y, int x, float m,
+MD2_HD float md2_exp_neg(float g) {
+#if defined(__CUDA_ARCH__)
+  return __expf(-g);
+#else
+  return expf(-g);
+#endif
+}
+MD2_HD void smooth_pixel(const Params& P, int s, int b, int y, int x, float inv_m,
                          float& ex_out, float& ey_out, float& gn_out) {
   const int Hs = P.H >> s, Ws = P.W >> s;
   const size_t plane = (size_t)Hs * Ws;
@@ -787,65 +831,78 @@ MD2_HD void smooth_pixel(const Params& P, int s, int b, int y, int x, float m,
   const size_t p = (size_t)y * Ws + x;
   const float inx = 1.0f / ((float)P.B * (float)Hs * (float)(Ws - 1));
   const float iny = 1.0f / ((float)P.B * (float)(Hs - 1) * (float)Ws);
-  const float n0 = MD2_DIV(MD2_LD(d + p), m);
+  const float n0 = MD2_LD(d + p) * inv_m;
+  const float i0 = MD2_LD(im + p), i1 = MD2_LD(im + plane + p), i2 = MD2_LD(im + 2 * plane + p);
   float gn = 0.f, ex = 0.f, ey = 0.f;
-  auto edge = [&](size_t pa, size_t pb, float na, float nb, float& e) -> float {
-    // returns sign(na - nb) * exp(-mean_c |I(pa) - I(pb)|)
-    float g = 0.f;
-    for (int c = 0; c < 3; ++c) g += fabsf(MD2_LD(im + c * plane + pa) - MD2_LD(im + c * plane + pb));
-    const float w = expf(-(g / 3.0f));
-    const float df = na - nb;
-    e = fabsf(df) * w;
-    return (df > 0.f) ? w : ((df < 0.f) ? -w : 0.f);
+  // one edge between this pixel and the neighbour at offset `o`; `fwd` = this pixel is the first end
+  auto edge = [&](size_t q, bool fwd, float scale, float& e_out) {
+    const float g = fabsf(i0 - MD2_LD(im + q)) + fabsf(i1 - MD2_LD(im + plane + q)) + fabsf(i2 - MD2_LD(im + 2 * plane + q));
+    const float w = md2_exp_neg(g * (1.0f / 3.0f));
+    const float df = n0 - MD2_LD(d + q) * inv_m;          // n(this) - n(neighbour)
+    if (fwd) e_out = fabsf(df) * w;
+    // d|n_a - n_b| / d n(this) = sign(n(this) - n(neighbour)) for either end of the edge
+    gn += scale * ((df > 0.f) ? w : ((df < 0.f) ? -w : 0.f));
   };
-  float e;
-  if (x + 1 < Ws) { gn += inx * edge(p, p + 1, n0, MD2_DIV(MD2_LD(d + p + 1), m), e); ex = e; }
-  if (x > 0)      { gn -= inx * edge(p - 1, p, MD2_DIV(MD2_LD(d + p - 1), m), n0, e); }
-  if (y + 1 < Hs) { gn += iny * edge(p, p + Ws, n0, MD2_DIV(MD2_LD(d + p + Ws), m), e); ey = e; }
-  if (y > 0)      { gn -= iny * edge(p - Ws, p, MD2_DIV(MD2_LD(d + p - Ws), m), n0, e); }
+  float dummy;
+  if (x + 1 < Ws) edge(p + 1, true, inx, ex);
+  if (x > 0) edge(p - 1, false, inx, dummy);
+  if (y + 1 < Hs) edge(p + Ws, true, iny, ey);
+  if (y > 0) edge(p - Ws, false, iny, dummy);
   ex_out = ex; ey_out = ey; gn_out = gn;
 }
 
-// Final gradient of disp_s at coarse pixel (X,Y): adjoint of the bilinear up-sampling
-// (gather over the fine pixels whose taps hit (X,Y)) plus the smoothness term (A.4).
-MD2_HD float final_grad_disp(const Params& P, int s, int b, int Y, int X) {
+// Smoothness part of d loss / d disp_s at pixel p (A.4).
+MD2_HD float final_smooth_grad(const Params& P, int s, int b, int p) {
   const int Hs = P.H >> s, Ws = P.W >> s;
-  const size_t p = ((size_t)b * Hs + Y) * Ws + X;
   const double sum = P.acc[acc_dispsum(P, s, b)];
   const float m = (float)(sum / ((double)Hs * Ws)) + 1e-7f;
   const float dot = (float)P.acc[acc_dot(P, s, b)];
   const float wsm = P.smooth_w[s] / (float)P.S;
-  float g = wsm * (MD2_LD(P.gn[s] + p) / m - dot / (m * m * (float)Hs * (float)Ws));
+  return wsm * (MD2_LD(P.gn[s] + (size_t)b * Hs * Ws + p) / m - dot / (m * m * (float)Hs * (float)Ws));
+}
+
+// Adjoint of the bilinear up-sampling (trainer.py:350-351) in gather form: the share of coarse
+// pixel (X,Y) of scale s contributed by the fine rows ylo+j, ylo+j+K, ... (j in [0,K), K = 2^s).
+// The 2K x 2K fine pixels whose taps can hit (X,Y) are visited with the forward weights.
+template <int K>
+MD2_HD float upsample_adjoint_part(const Params& P, int s, int b, int Y, int X, int j) {
+  const int Hs = P.H >> s, Ws = P.W >> s;
+  const float r = 1.0f / (float)K;
   const float* dD = P.dD[s] + (size_t)b * P.H * P.W;
-  if (s == 0) return g + MD2_LD(dD + (size_t)Y * P.W + X);
-  const int k = 1 << s;
-  const float r = 1.0f / (float)k;
-  const int ylo = (Y - 1) * k - 1 < 0 ? 0 : (Y - 1) * k - 1;
-  const int yhi = (Y + 2) * k + 1 > P.H ? P.H : (Y + 2) * k + 1;
-  const int xlo = (X - 1) * k - 1 < 0 ? 0 : (X - 1) * k - 1;
-  const int xhi = (X + 2) * k + 1 > P.W ? P.W : (X + 2) * k + 1;
+  const int xlo = K * X - K / 2, ylo = K * Y - K / 2;
+  float wx[2 * K];
+#pragma unroll
+  for (int i = 0; i < 2 * K; ++i) {
+    const int x = xlo + i;
+    float sxr = fmaf(r, (float)x + 0.5f, -0.5f);
+    sxr = sxr < 0.f ? 0.f : sxr;
+    const int x0 = (int)sxr;
+    const int x1 = x0 + ((x0 < Ws - 1) ? 1 : 0);
+    const float m1 = sxr - (float)x0, m0 = 1.0f - m1;
+    const float w = (x0 == X ? m0 : 0.f) + (x1 == X ? m1 : 0.f);
+    wx[i] = (x >= 0 && x < P.W) ? w : 0.f;
+  }
   float acc = 0.f;
-  for (int y = ylo; y < yhi; ++y) {
+#pragma unroll
+  for (int ry = 0; ry < 2; ++ry) {
+    const int y = ylo + j + ry * K;
+    if (y < 0 || y >= P.H) continue;
     float syr = fmaf(r, (float)y + 0.5f, -0.5f);
     syr = syr < 0.f ? 0.f : syr;
     const int y0 = (int)syr;
     const int y1 = y0 + ((y0 < Hs - 1) ? 1 : 0);
     const float l1 = syr - (float)y0, l0 = 1.0f - l1;
     const float wy = (y0 == Y ? l0 : 0.f) + (y1 == Y ? l1 : 0.f);
-    if (wy == 0.f) continue;
     float row = 0.f;
-    for (int x = xlo; x < xhi; ++x) {
-      float sxr = fmaf(r, (float)x + 0.5f, -0.5f);
-      sxr = sxr < 0.f ? 0.f : sxr;
-      const int x0 = (int)sxr;
-      const int x1 = x0 + ((x0 < Ws - 1) ? 1 : 0);
-      const float m1 = sxr - (float)x0, m0 = 1.0f - m1;
-      const float wx = (x0 == X ? m0 : 0.f) + (x1 == X ? m1 : 0.f);
-      if (wx != 0.f) row = fmaf(wx, MD2_LD(dD + (size_t)y * P.W + x), row);
+#pragma unroll
+    for (int i = 0; i < 2 * K; ++i) {
+      const int x = xlo + i;
+      const int xc = x < 0 ? 0 : (x >= P.W ? P.W - 1 : x);
+      row = fmaf(wx[i], MD2_LD(dD + (size_t)y * P.W + xc), row);
     }
     acc = fmaf(wy, row, acc);
   }
-  return g + acc;
+  return acc;
 }
 
 // Scalar epilogue: losses and d loss / d cam_T_cam = K[:3,:]^T dP  (A.3).

@@ -106,10 +106,11 @@ __global__ void md2_smooth(Params P) {
   const int n = Hs * Ws;
   if (blockIdx.x * blockDim.x >= n) return;                      // uniform per block
   const float m = (float)(P.acc[acc_dispsum(P, s, b)] / (double)n) + 1e-7f;
+  const float inv_m = 1.0f / m;
   float ex = 0.f, ey = 0.f, dot = 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float e0, e1, g;
-    smooth_pixel(P, s, b, i / Ws, i % Ws, m, e0, e1, g);
+    smooth_pixel(P, s, b, i / Ws, i % Ws, inv_m, e0, e1, g);
     P.gn[s][(size_t)b * n + i] = g;
     ex += e0; ey += e1;
     dot = fmaf(g, __ldg(P.disp[s] + (size_t)b * n + i), dot);
@@ -133,8 +134,13 @@ __global__ void md2_smooth(Params P) {
 }
 
 // ------------------------------------------------------------------ 5. the marching kernel
+#if defined(MD2_MIN_CTAS)
+#define MD2_MARCH_BOUNDS __launch_bounds__(kThreads, MD2_MIN_CTAS)
+#else
+#define MD2_MARCH_BOUNDS __launch_bounds__(kThreads)
+#endif
 template <class C>
-__global__ void __launch_bounds__(kThreads) md2_march(Params P) {
+__global__ void MD2_MARCH_BOUNDS md2_march(Params P) {
   extern __shared__ float4 smem[];
   const int lane = threadIdx.x & 31;
   const int job = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
@@ -183,6 +189,9 @@ __global__ void __launch_bounds__(kThreads) md2_march(Params P) {
         }
       stage_c(L, P, J, t, lane, l2, r2x, st);
     }
+#ifdef MD2_GATHER_PREFETCH
+    if (t <= J.y1) prefetch_gather(L, P, J, t + 1);
+#endif
   }
   const float ls = warp_sum(L.loss);
   if (lane == 0) atomicAdd(&P.acc[acc_photo(J.s)], (double)ls);
@@ -202,6 +211,23 @@ __global__ void __launch_bounds__(kThreads) md2_march(Params P) {
 }
 
 // ------------------------------------------------------------------ 6. final
+// grad_disp_s = up-sampling adjoint of dD_s (K = 2^s threads per coarse pixel, each visiting
+// 2 fine rows x 2K fine columns, combined with shuffles) + smoothness adjoint; block (0,0,0)
+// also writes the losses and grad_T.
+template <int K>
+__device__ __forceinline__ void final_scale(const Params& P, int s, int b) {
+  const int Hs = P.H >> s, Ws = P.W >> s;
+  const int n = Hs * Ws;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cp = gid / K, j = gid % K;
+  const bool ok = cp < n;
+  float part = 0.f;
+  if (ok) part = (K == 1) ? __ldg(P.dD[s] + (size_t)b * n + cp) : upsample_adjoint_part<K>(P, s, b, cp / Ws, cp % Ws, j);
+#pragma unroll
+  for (int o = K / 2; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
+  if (ok && j == 0) P.grad_disp[s][(size_t)b * n + cp] = part + final_smooth_grad(P, s, b, cp);
+}
+
 __global__ void md2_final(Params P) {
   const int s = blockIdx.z, b = blockIdx.y;
   if (blockIdx.x == 0 && b == 0 && s == 0) {
@@ -209,10 +235,14 @@ __global__ void md2_final(Params P) {
     if (P.want_grad && threadIdx.x < P.B * P.nsrc) final_grad_T(P, threadIdx.x / P.nsrc, threadIdx.x % P.nsrc);
   }
   if (!P.want_grad || s >= P.S) return;
-  const int Hs = P.H >> s, Ws = P.W >> s;
-  const int n = Hs * Ws;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    P.grad_disp[s][(size_t)b * n + i] = final_grad_disp(P, s, b, i / Ws, i % Ws);
+  // every scale needs (H>>s)*(W>>s)*2^s = H*W / 2^s threads
+  if (blockIdx.x * blockDim.x >= (P.H * P.W) >> s) return;
+  switch (s) {
+    case 0: final_scale<1>(P, 0, b); break;
+    case 1: final_scale<2>(P, 1, b); break;
+    case 2: final_scale<4>(P, 2, b); break;
+    default: final_scale<8>(P, 3, b); break;
+  }
 }
 
 // ------------------------------------------------------------------ launcher

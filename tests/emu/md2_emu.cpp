@@ -148,9 +148,10 @@ extern "C" int md2_emu_view_synthesis_loss(const md2_problem* p, const md2_tenso
     for (int b = 0; b < P.B; ++b) {
       const int Hs = P.H >> s, Ws = P.W >> s, n = Hs * Ws;
       const float m = (float)(P.acc[acc_dispsum(P, s, b)] / (double)n) + 1e-7f;
+      const float inv_m = 1.0f / m;
       for (int i = 0; i < n; ++i) {
         float e0, e1, g;
-        smooth_pixel(P, s, b, i / Ws, i % Ws, m, e0, e1, g);
+        smooth_pixel(P, s, b, i / Ws, i % Ws, inv_m, e0, e1, g);
         P.gn[s][(size_t)b * n + i] = g;
         P.acc[acc_smx(s)] += e0;
         P.acc[acc_smy(s)] += e1;
@@ -167,7 +168,15 @@ extern "C" int md2_emu_view_synthesis_loss(const md2_problem* p, const md2_tenso
     for (int s = 0; s < P.S; ++s)
       for (int b = 0; b < P.B; ++b) {
         const int Hs = P.H >> s, Ws = P.W >> s, n = Hs * Ws;
-        for (int i = 0; i < n; ++i) P.grad_disp[s][(size_t)b * n + i] = final_grad_disp(P, s, b, i / Ws, i % Ws);
+        for (int i = 0; i < n; ++i) {
+          float up = 0.f;
+          const int Y = i / Ws, X = i % Ws;
+          if (s == 0) up = P.dD[0][(size_t)b * n + i];
+          else if (s == 1) { for (int j = 0; j < 2; ++j) up += upsample_adjoint_part<2>(P, s, b, Y, X, j); }
+          else if (s == 2) { for (int j = 0; j < 4; ++j) up += upsample_adjoint_part<4>(P, s, b, Y, X, j); }
+          else { for (int j = 0; j < 8; ++j) up += upsample_adjoint_part<8>(P, s, b, Y, X, j); }
+          P.grad_disp[s][(size_t)b * n + i] = up + final_smooth_grad(P, s, b, i);
+        }
       }
   }
   return MD2_OK;
