@@ -129,11 +129,45 @@ MD2_HD int acc_dP(const Params& P, int b, int f, int k) {
 }
 MD2_HD int acc_count(const Params& P) { return 3 * kMaxScales + 2 * kMaxScales * P.B + P.B * P.nsrc * 12; }
 
+// One marching job (warp-uniform): a band of kOwnCols columns x rows [y0,y1) of sample b at
+// scale s, with every base pointer already offset to the sample so that per-pixel addressing
+// is 32-bit index arithmetic (validate() bounds the tensors below 2^31 elements).
 struct WarpJob {
   int s, b;
   int x0;        // first owned column
   int y0, y1;    // owned rows [y0, y1)
+  int H, W, Hs, Ws, plane;
+  float rs;      // 1 / 2^s
+  const float* tgt4;
+  const float* src4[kMaxSrc];
+  const float* disp;
+  const float* idl;
+  const float* noise;
+  float* dD;
+  float* idsel;
+  float* depth;
+  float* warped[kMaxSrc];
 };
+
+MD2_HD WarpJob make_job(const Params& P, int s, int b, int x0, int y0, int y1) {
+  WarpJob J;
+  J.s = s; J.b = b; J.x0 = x0; J.y0 = y0; J.y1 = y1;
+  J.H = P.H; J.W = P.W; J.Hs = P.H >> s; J.Ws = P.W >> s; J.plane = P.H * P.W;
+  J.rs = 1.0f / (float)(1 << s);
+  const int boff = b * J.plane;
+  J.tgt4 = P.tgt4 + 4 * boff;
+  for (int f = 0; f < kMaxSrc; ++f) {
+    J.src4[f] = f < P.nsrc ? P.src4[f] + 4 * boff : nullptr;
+    J.warped[f] = (f < P.nsrc && P.warped[f][s]) ? P.warped[f][s] + 3 * boff : nullptr;
+  }
+  J.disp = P.disp[s] + b * J.Hs * J.Ws;
+  J.idl = P.idloss + P.nsrc * boff;
+  J.noise = P.noise[s] ? P.noise[s] + P.nid * boff : nullptr;
+  J.dD = P.dD[s] + boff;
+  J.idsel = P.idsel[s] ? P.idsel[s] + boff : nullptr;
+  J.depth = P.depth[s] ? P.depth[s] + boff : nullptr;
+  return J;
+}
 
 template <int NSRC_, bool AVG_, bool AUTOMASK_, bool GRAD_>
 struct Cfg {
@@ -245,58 +279,20 @@ struct Stash {
 
 // issue the loads of row `t`'s target texel and disparity taps (consumed one step later)
 template <class C>
-MD2_HD void prefetch_row(Lane<C>& L, const Params& P, const WarpJob& J, int t) {
-  const int tr = reflect_clamp(t, P.H);
-  L.ntg = MD2_LD4(P.tgt4 + (((size_t)J.b * P.H + tr) * P.W + L.xi) * 4);
-  const float* d = P.disp[J.s];
+MD2_HD void prefetch_row(Lane<C>& L, const WarpJob& J, int t) {
+  const int tr = reflect_clamp(t, J.H);
+  L.ntg = MD2_LD4(J.tgt4 + 4 * (tr * J.W + L.xi));
   if (J.s == 0) {
-    L.nd[0] = MD2_LD(d + ((size_t)J.b * P.H + tr) * P.W + L.xi);
+    L.nd[0] = MD2_LD(J.disp + tr * J.W + L.xi);
   } else {
-    const int Hs = P.H >> J.s, Ws = P.W >> J.s;
-    const float r = 1.0f / (float)(1 << J.s);
-    float syr = fmaf(r, (float)tr + 0.5f, -0.5f);
+    float syr = fmaf(J.rs, (float)tr + 0.5f, -0.5f);
     syr = syr < 0.0f ? 0.0f : syr;
     const int y0 = (int)syr;
-    const int y1 = y0 + ((y0 < Hs - 1) ? 1 : 0);
-    const float* r0 = d + ((size_t)J.b * Hs + y0) * Ws;
-    const float* r1 = d + ((size_t)J.b * Hs + y1) * Ws;
+    const int y1 = y0 + ((y0 < J.Hs - 1) ? 1 : 0);
+    const float* r0 = J.disp + y0 * J.Ws;
+    const float* r1 = J.disp + y1 * J.Ws;
     L.nd[0] = MD2_LD(r0 + L.ux0); L.nd[1] = MD2_LD(r0 + L.ux1);
     L.nd[2] = MD2_LD(r1 + L.ux0); L.nd[3] = MD2_LD(r1 + L.ux1);
-  }
-}
-
-// Warm L1 with the bilinear taps row `t` will gather: recomputes the projection of row t from
-// the already prefetched disparity taps and issues prefetch.global.L1 for the tap texels, so
-// that the data-dependent loads of the next step hit L1 instead of exposing L2 latency.
-template <class C>
-MD2_HD void prefetch_gather(const Lane<C>& L, const Params& P, const WarpJob& J, int t) {
-  const int tr = reflect_clamp(t, P.H);
-  float D;
-  if (J.s == 0) {
-    D = L.nd[0];
-  } else {
-    const float r = 1.0f / (float)(1 << J.s);
-    float syr = fmaf(r, (float)tr + 0.5f, -0.5f);
-    syr = syr < 0.0f ? 0.0f : syr;
-    const float l1 = syr - (float)(int)syr, l0 = 1.0f - l1;
-    D = l0 * (L.ul0 * L.nd[0] + L.ul1 * L.nd[1]) + l1 * (L.ul0 * L.nd[2] + L.ul1 * L.nd[3]);
-  }
-  const float z = MD2_RCP(fmaf(P.c_disp, D, P.a_disp));
-  const float yf = (float)tr;
-#pragma unroll
-  for (int f = 0; f < C::NSRC; ++f) {
-    const float c0 = fmaf(z, fmaf(L.qb[f][0], yf, L.qa[f][0]), L.p4[f][0]);
-    const float c1 = fmaf(z, fmaf(L.qb[f][1], yf, L.qa[f][1]), L.p4[f][1]);
-    const float c2 = fmaf(z, fmaf(L.qb[f][2], yf, L.qa[f][2]), L.p4[f][2]);
-    const float inv = MD2_RCP(c2 + P.eps);
-    const float ixc = fminf(fmaxf(fmaf(c0 * inv, P.sx, P.ox), 0.0f), P.wmax);
-    const float iyc = fminf(fmaxf(fmaf(c1 * inv, P.sy, P.oy), 0.0f), P.hmax);
-    const int x0 = (int)ixc, y0 = (int)iyc;
-    const int dy1 = (y0 + 1 < P.H) ? P.W * 4 : 0;
-    const float* t00 = P.src4[f] + (((size_t)J.b * P.H + y0) * P.W + x0) * 4;
-    MD2_PREFETCH_L1(t00);
-    MD2_PREFETCH_L1(t00 + dy1);
-    (void)t00; (void)dy1;
   }
 }
 
@@ -318,12 +314,10 @@ MD2_HD void lane_init(Lane<C>& L, const Params& P, const WarpJob& J, int lane) {
     L.idv[f] = 0.f; L.nzv[f] = 0.f;
   }
   if (J.s > 0) {
-    const int Ws = P.W >> J.s;
-    const float r = 1.0f / (float)(1 << J.s);
-    float sxr = fmaf(r, (float)L.xi + 0.5f, -0.5f);
+    float sxr = fmaf(J.rs, (float)L.xi + 0.5f, -0.5f);
     sxr = sxr < 0.0f ? 0.0f : sxr;
     L.ux0 = (int)sxr;
-    L.ux1 = L.ux0 + ((L.ux0 < Ws - 1) ? 1 : 0);
+    L.ux1 = L.ux0 + ((L.ux0 < J.Ws - 1) ? 1 : 0);
     L.ul1 = sxr - (float)L.ux0;
     L.ul0 = 1.0f - L.ul1;
   } else {
@@ -354,7 +348,7 @@ MD2_HD void lane_init(Lane<C>& L, const Params& P, const WarpJob& J, int lane) {
     for (int k = 0; k < 9; ++k) L.coef[n][k] = 0.f;
   L.tag = -1; L.tag1 = -1;
   L.loss = 0.f;
-  prefetch_row(L, P, J, J.y0 - 2);
+  prefetch_row(L, J, J.y0 - 2);
 }
 
 // ------------------------------------------------------------------ stage A
@@ -367,38 +361,34 @@ MD2_HD void lane_init(Lane<C>& L, const Params& P, const WarpJob& J, int lane) {
 template <class C>
 MD2_HD void stage_a(Lane<C>& L, const Params& P, const WarpJob& J, int t, const Stash& st) {
   const int slot = ring_slot(t);
-  const int tr = reflect_clamp(t, P.H);
+  const int tr = reflect_clamp(t, J.H);
   // consume the prefetched row, then put the next one in flight
   const F4 tg4 = L.ntg;
   float D;
   if (J.s == 0) {
     D = L.nd[0];
   } else {
-    const float r = 1.0f / (float)(1 << J.s);
-    float syr = fmaf(r, (float)tr + 0.5f, -0.5f);
+    float syr = fmaf(J.rs, (float)tr + 0.5f, -0.5f);
     syr = syr < 0.0f ? 0.0f : syr;
     const float l1 = syr - (float)(int)syr, l0 = 1.0f - l1;
     const float top = L.ul0 * L.nd[0] + L.ul1 * L.nd[1];
     const float bot = L.ul0 * L.nd[2] + L.ul1 * L.nd[3];
     D = l0 * top + l1 * bot;
   }
-  prefetch_row(L, P, J, t + 1);
-  {
-    const size_t plane = (size_t)P.H * P.W;
+  prefetch_row(L, J, t + 1);
+  if (C::AUTOMASK) {
     const int yw = t - 1;
-    const size_t pix = (size_t)(yw < 0 ? 0 : (yw >= P.H ? P.H - 1 : yw)) * P.W + L.xi;
-    if (C::AUTOMASK) {
+    const int pix = (yw < 0 ? 0 : (yw >= J.H ? J.H - 1 : yw)) * J.W + L.xi;
 #pragma unroll
-      for (int f = 0; f < C::NSRC; ++f) L.idv[f] = MD2_LD(P.idloss + ((size_t)J.b * C::NSRC + f) * plane + pix);
+    for (int f = 0; f < C::NSRC; ++f) L.idv[f] = MD2_LD(J.idl + f * J.plane + pix);
 #pragma unroll
-      for (int f = 0; f < C::NID; ++f) L.nzv[f] = MD2_LD(P.noise[J.s] + ((size_t)J.b * C::NID + f) * plane + pix);
-    }
+    for (int f = 0; f < C::NID; ++f) L.nzv[f] = MD2_LD(J.noise + f * J.plane + pix);
   }
   L.tg[0] = tg4.x; L.tg[1] = tg4.y; L.tg[2] = tg4.z;
   const float sd = MD2_FADD(P.a_disp, MD2_FMUL(P.c_disp, D));
   const float z = MD2_RCP(sd);
   const bool own = (t >= J.y0) && (t < J.y1) && (L.x >= J.x0) && (L.x < J.x0 + kOwnCols) && L.colok;
-  if (P.depth[J.s] && own) P.depth[J.s][((size_t)J.b * P.H + t) * P.W + L.xi] = z;
+  if (J.depth && own) J.depth[t * J.W + L.xi] = z;
   if (C::GRAD) st.at(slot, 0, C::STASH4) = make_f4(tg4.x, tg4.y, tg4.z, z);
   const float yf = (float)tr;
 #pragma unroll
@@ -421,9 +411,9 @@ MD2_HD void stage_a(Lane<C>& L, const Params& P, const WarpJob& J, int t, const 
     const float fx0 = MD2_FLOORF(ixc), fy0 = MD2_FLOORF(iyc);
     const float wx = ixc - fx0, wy = iyc - fy0;
     const int x0 = (int)fx0, y0 = (int)fy0;
-    const int dx1 = (x0 + 1 < P.W) ? 4 : 0;                 // texel step to the east tap
-    const int dy1 = (y0 + 1 < P.H) ? P.W * 4 : 0;           // texel step to the south tap
-    const float* t00 = P.src4[f] + (((size_t)J.b * P.H + y0) * P.W + x0) * 4;
+    const int dx1 = (x0 + 1 < J.W) ? 4 : 0;                 // texel step to the east tap
+    const int dy1 = (y0 + 1 < J.H) ? J.W * 4 : 0;           // texel step to the south tap
+    const float* t00 = J.src4[f] + 4 * (y0 * J.W + x0);
     const F4 nw = MD2_LD4(t00), ne = MD2_LD4(t00 + dx1);
     const F4 sw = MD2_LD4(t00 + dy1), se = MD2_LD4(t00 + dy1 + dx1);
     const float gxs = mx ? P.sx * inv : 0.0f;
@@ -442,11 +432,9 @@ MD2_HD void stage_a(Lane<C>& L, const Params& P, const WarpJob& J, int t, const 
         dyp[c] = dv * gys;
       }
     }
-    float* wout = P.warped[f][J.s];
-    if (wout && own) {
-      const size_t plane = (size_t)P.H * P.W;
+    if (J.warped[f] && own) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) wout[((size_t)J.b * 3 + c) * plane + (size_t)t * P.W + L.xi] = pr[c];
+      for (int c = 0; c < 3; ++c) J.warped[f][c * J.plane + t * J.W + L.xi] = pr[c];
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) L.pr[f][c] = pr[c];
@@ -540,8 +528,7 @@ MD2_HD void stage_b(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
     }
     if (own_win) {
       L.loss += best;
-      if (C::AUTOMASK && P.idsel[J.s])
-        P.idsel[J.s][((size_t)J.b * P.H + yw) * P.W + L.xi] = (tag >= 0) ? 1.0f : 0.0f;
+      if (C::AUTOMASK && J.idsel) J.idsel[yw * J.W + L.xi] = (tag >= 0) ? 1.0f : 0.0f;
     }
     if (C::GRAD && tag >= 0) {
       if (C::AVG) {
@@ -652,7 +639,7 @@ MD2_HD void stage_c(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
     }
     // d depth / d D = -c * z^2  (layers.py:23-24)
     const float dD = -P.c_disp * z * z * dzsum * P.gscale;
-    P.dD[J.s][((size_t)J.b * P.H + yp) * P.W + L.xi] = dD;
+    J.dD[yp * J.W + L.xi] = dD;
   }
 #pragma unroll
   for (int f = 0; f < C::NSRC; ++f)

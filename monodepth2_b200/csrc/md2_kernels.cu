@@ -134,6 +134,13 @@ __global__ void md2_smooth(Params P) {
 }
 
 // ------------------------------------------------------------------ 5. the marching kernel
+#define MD2_PRAGMA_(x) _Pragma(#x)
+#define MD2_PRAGMA(x) MD2_PRAGMA_(x)
+#ifdef MD2_UNROLL
+#define MD2_LOOP_UNROLL MD2_PRAGMA(unroll MD2_UNROLL)
+#else
+#define MD2_LOOP_UNROLL MD2_PRAGMA(unroll 1)
+#endif
 #if defined(MD2_MIN_CTAS)
 #define MD2_MARCH_BOUNDS __launch_bounds__(kThreads, MD2_MIN_CTAS)
 #else
@@ -143,18 +150,19 @@ template <class C>
 __global__ void MD2_MARCH_BOUNDS md2_march(Params P) {
   extern __shared__ float4 smem[];
   const int lane = threadIdx.x & 31;
-  const int job = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  // warp index through a shuffle: lets the compiler treat everything derived from the job as
+  // warp-uniform (uniform registers / uniform datapath for the address arithmetic)
+  const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
+  const int job = blockIdx.x * kWarpsPerCta + warp;
   const int per_scale = P.B * P.nseg * P.nband;
   if (job >= per_scale * P.S) return;
-  WarpJob J;
-  J.s = job / per_scale;
-  const int r = job - J.s * per_scale;
-  J.b = r / (P.nseg * P.nband);
-  const int r2 = r - J.b * (P.nseg * P.nband);
+  const int js = job / per_scale;
+  const int r = job - js * per_scale;
+  const int jb = r / (P.nseg * P.nband);
+  const int r2 = r - jb * (P.nseg * P.nband);
   const int seg = r2 / P.nband;
-  J.x0 = (r2 - seg * P.nband) * kOwnCols;
-  J.y0 = seg * P.seg_rows;
-  J.y1 = min(J.y0 + P.seg_rows, P.H);
+  const int jy0 = seg * P.seg_rows;
+  const WarpJob J = make_job(P, js, jb, (r2 - seg * P.nband) * kOwnCols, jy0, min(jy0 + P.seg_rows, P.H));
 
   Stash st;
   st.base = smem + threadIdx.x;
@@ -162,6 +170,7 @@ __global__ void MD2_MARCH_BOUNDS md2_march(Params P) {
 
   Lane<C> L;
   lane_init(L, P, J, lane);
+  MD2_LOOP_UNROLL
   for (int t = J.y0 - 2; t <= J.y1 + 1; ++t) {
     stage_a(L, P, J, t, st);
     Xchg1<C> l1, r1;
@@ -189,9 +198,6 @@ __global__ void MD2_MARCH_BOUNDS md2_march(Params P) {
         }
       stage_c(L, P, J, t, lane, l2, r2x, st);
     }
-#ifdef MD2_GATHER_PREFETCH
-    if (t <= J.y1) prefetch_gather(L, P, J, t + 1);
-#endif
   }
   const float ls = warp_sum(L.loss);
   if (lane == 0) atomicAdd(&P.acc[acc_photo(J.s)], (double)ls);

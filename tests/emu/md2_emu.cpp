@@ -44,9 +44,8 @@ static void emu_march(const Params& P) {
     for (int b = 0; b < P.B; ++b)
       for (int seg = 0; seg < P.nseg; ++seg)
         for (int band = 0; band < P.nband; ++band) {
-          WarpJob J;
-          J.s = s; J.b = b; J.x0 = band * kOwnCols;
-          J.y0 = seg * P.seg_rows; J.y1 = std::min(J.y0 + P.seg_rows, P.H);
+          const int jy0 = seg * P.seg_rows;
+          const WarpJob J = make_job(P, s, b, band * kOwnCols, jy0, std::min(jy0 + P.seg_rows, P.H));
           std::fill(ring.begin(), ring.end(), make_f4(0.f, 0.f, 0.f, 0.f));
           Lane<C> L[32];
           Stash st[32];
