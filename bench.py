@@ -362,7 +362,7 @@ def run_own(args, wl):
                        (nrot, int((h2d + n_id * BATCH * H * W * 4 * 4) / 1e6)),
                        "rows_per_segment": plan.problem(True).rows_per_segment or 32, "loss": loss_val},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": (7 if plan.automask else 6) * args.steps,
+            "gpu_launches": 6 * args.steps,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

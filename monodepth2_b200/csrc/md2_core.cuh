@@ -144,10 +144,16 @@ struct WarpJob {
   const float* idl;
   const float* noise;
   float* dD;
+  // scale 0 only: the smoothness adjoint is added in place and grad_disp_0 written directly
+  float* gd0;
+  const float* gn0;
+  float sm_inv_m, sm_dterm, sm_w;
   float* idsel;
   float* depth;
   float* warped[kMaxSrc];
 };
+
+MD2_HD void smooth_scalars(const Params& P, int s, int b, float& inv_m, float& dterm);
 
 MD2_HD WarpJob make_job(const Params& P, int s, int b, int x0, int y0, int y1) {
   WarpJob J;
@@ -164,6 +170,13 @@ MD2_HD WarpJob make_job(const Params& P, int s, int b, int x0, int y0, int y1) {
   J.idl = P.idloss + P.nsrc * boff;
   J.noise = P.noise[s] ? P.noise[s] + P.nid * boff : nullptr;
   J.dD = P.dD[s] + boff;
+  J.gd0 = nullptr; J.gn0 = nullptr; J.sm_inv_m = 0.f; J.sm_dterm = 0.f; J.sm_w = 0.f;
+  if (s == 0 && P.want_grad) {
+    J.gd0 = P.grad_disp[0] + boff;
+    J.gn0 = P.gn[0] + boff;
+    smooth_scalars(P, 0, b, J.sm_inv_m, J.sm_dterm);
+    J.sm_w = P.smooth_w[0] / (float)P.S;
+  }
   J.idsel = P.idsel[s] ? P.idsel[s] + boff : nullptr;
   J.depth = P.depth[s] ? P.depth[s] + boff : nullptr;
   return J;
@@ -640,6 +653,8 @@ MD2_HD void stage_c(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
     // d depth / d D = -c * z^2  (layers.py:23-24)
     const float dD = -P.c_disp * z * z * dzsum * P.gscale;
     J.dD[yp * J.W + L.xi] = dD;
+    if (J.s == 0)   // up-sampling is the identity at scale 0: finish grad_disp_0 here (A.4 + A.3)
+      J.gd0[yp * J.W + L.xi] = dD + J.sm_w * (MD2_LD(J.gn0 + yp * J.W + L.xi) * J.sm_inv_m - J.sm_dterm);
   }
 #pragma unroll
   for (int f = 0; f < C::NSRC; ++f)
@@ -702,16 +717,24 @@ MD2_HD void id_init(IdLane<NSRC>& L, const Params& P, int x0, int lane) {
   }
 }
 
+// Reads row t of the planar NCHW target / sources (at the reflected position) and, for the
+// pixels this lane owns, writes the RGBx texels the marching kernel gathers from: the
+// re-layout costs no extra pass over the images.
 template <int NSRC>
-MD2_HD void id_stage_a(IdLane<NSRC>& L, const Params& P, int b, int t) {
+MD2_HD void id_stage_a(IdLane<NSRC>& L, const Params& P, int b, int t, int lane, int y0, int y1) {
   const int tr = reflect_clamp(t, P.H);
-  const size_t off = (((size_t)b * P.H + tr) * P.W + L.xi) * 4;
-  const F4 tg = MD2_LD4(P.tgt4 + off);
-  L.tg[0] = tg.x; L.tg[1] = tg.y; L.tg[2] = tg.z;
+  const int plane = P.H * P.W;
+  const int off = b * 3 * plane + tr * P.W + L.xi;
+  const bool own = L.colok && t >= y0 && t < y1 && lane >= 1 && lane <= kIdCols;
+  const int o4 = 4 * (b * plane + tr * P.W + L.xi);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) L.tg[c] = MD2_LD(P.tgt + off + c * plane);
+  if (own) *reinterpret_cast<F4*>(P.tgt4 + o4) = make_f4(L.tg[0], L.tg[1], L.tg[2], 0.f);
 #pragma unroll
   for (int f = 0; f < NSRC; ++f) {
-    const F4 s = MD2_LD4(P.src4[f] + off);
-    L.pr[f][0] = s.x; L.pr[f][1] = s.y; L.pr[f][2] = s.z;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) L.pr[f][c] = MD2_LD(P.src[f] + off + c * plane);
+    if (own) *reinterpret_cast<F4*>(P.src4[f] + o4) = make_f4(L.pr[f][0], L.pr[f][1], L.pr[f][2], 0.f);
   }
 }
 
@@ -838,54 +861,53 @@ MD2_HD void smooth_pixel(const Params& P, int s, int b, int y, int x, float inv_
   ex_out = ex; ey_out = ey; gn_out = gn;
 }
 
+// Per-(scale, sample) scalars of the smoothness adjoint (A.4): 1/m and (sum gn*disp)/(m^2 N).
+MD2_HD void smooth_scalars(const Params& P, int s, int b, float& inv_m, float& dterm) {
+  const int n = (P.H >> s) * (P.W >> s);
+  const float m = (float)(P.acc[acc_dispsum(P, s, b)] / (double)n) + 1e-7f;
+  inv_m = 1.0f / m;
+  dterm = (float)P.acc[acc_dot(P, s, b)] / (m * m * (float)n);
+}
 // Smoothness part of d loss / d disp_s at pixel p (A.4).
-MD2_HD float final_smooth_grad(const Params& P, int s, int b, int p) {
-  const int Hs = P.H >> s, Ws = P.W >> s;
-  const double sum = P.acc[acc_dispsum(P, s, b)];
-  const float m = (float)(sum / ((double)Hs * Ws)) + 1e-7f;
-  const float dot = (float)P.acc[acc_dot(P, s, b)];
+MD2_HD float final_smooth_grad(const Params& P, int s, int b, int p, float inv_m, float dterm) {
+  const int n = (P.H >> s) * (P.W >> s);
   const float wsm = P.smooth_w[s] / (float)P.S;
-  return wsm * (MD2_LD(P.gn[s] + (size_t)b * Hs * Ws + p) / m - dot / (m * m * (float)Hs * (float)Ws));
+  return wsm * (MD2_LD(P.gn[s] + (size_t)b * n + p) * inv_m - dterm);
 }
 
 // Adjoint of the bilinear up-sampling (trainer.py:350-351) in gather form: the share of coarse
 // pixel (X,Y) of scale s contributed by the fine rows ylo+j, ylo+j+K, ... (j in [0,K), K = 2^s).
 // The 2K x 2K fine pixels whose taps can hit (X,Y) are visited with the forward weights.
+// Weight with which fine index K*X - K/2 + i (i in [0,2K)) feeds coarse index X under torch's
+// bilinear up-sampling with align_corners=False (src = (x+0.5)/K - 0.5 clamped at 0, second tap
+// clamped at n-1).  Interior: the triangle (i+0.5)/K | (2K-i-0.5)/K (all dyadic, exact in fp32);
+// first / last coarse index: the clamped taps add up to 1, fine indices outside the image get 0.
+template <int K>
+MD2_HD float up_weight(int i, int X, int n) {
+  const float tri = (i < K) ? ((float)i + 0.5f) * (1.0f / (float)K) : ((float)(2 * K - i) - 0.5f) * (1.0f / (float)K);
+  if (X == 0 && i < K) return (i < K / 2) ? 0.0f : 1.0f;
+  if (X == n - 1 && i >= K) return (i < K + K / 2) ? 1.0f : 0.0f;
+  return tri;
+}
 template <int K>
 MD2_HD float upsample_adjoint_part(const Params& P, int s, int b, int Y, int X, int j) {
   const int Hs = P.H >> s, Ws = P.W >> s;
-  const float r = 1.0f / (float)K;
   const float* dD = P.dD[s] + (size_t)b * P.H * P.W;
   const int xlo = K * X - K / 2, ylo = K * Y - K / 2;
-  float wx[2 * K];
-#pragma unroll
-  for (int i = 0; i < 2 * K; ++i) {
-    const int x = xlo + i;
-    float sxr = fmaf(r, (float)x + 0.5f, -0.5f);
-    sxr = sxr < 0.f ? 0.f : sxr;
-    const int x0 = (int)sxr;
-    const int x1 = x0 + ((x0 < Ws - 1) ? 1 : 0);
-    const float m1 = sxr - (float)x0, m0 = 1.0f - m1;
-    const float w = (x0 == X ? m0 : 0.f) + (x1 == X ? m1 : 0.f);
-    wx[i] = (x >= 0 && x < P.W) ? w : 0.f;
-  }
   float acc = 0.f;
 #pragma unroll
   for (int ry = 0; ry < 2; ++ry) {
-    const int y = ylo + j + ry * K;
-    if (y < 0 || y >= P.H) continue;
-    float syr = fmaf(r, (float)y + 0.5f, -0.5f);
-    syr = syr < 0.f ? 0.f : syr;
-    const int y0 = (int)syr;
-    const int y1 = y0 + ((y0 < Hs - 1) ? 1 : 0);
-    const float l1 = syr - (float)y0, l0 = 1.0f - l1;
-    const float wy = (y0 == Y ? l0 : 0.f) + (y1 == Y ? l1 : 0.f);
+    const int iy = j + ry * K;
+    const int y = ylo + iy;
+    const float wy = up_weight<K>(iy, Y, Hs);
+    const int yc = y < 0 ? 0 : (y >= P.H ? P.H - 1 : y);
+    const float* rowp = dD + yc * P.W;
     float row = 0.f;
 #pragma unroll
     for (int i = 0; i < 2 * K; ++i) {
       const int x = xlo + i;
       const int xc = x < 0 ? 0 : (x >= P.W ? P.W - 1 : x);
-      row = fmaf(wx[i], MD2_LD(dD + (size_t)y * P.W + xc), row);
+      row = fmaf(up_weight<K>(i, X, Ws), MD2_LD(rowp + xc), row);
     }
     acc = fmaf(wy, row, acc);
   }

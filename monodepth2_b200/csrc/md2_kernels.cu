@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kThreads) md2_identity(Params P) {
   IdLane<NSRC> L;
   id_init(L, P, band * kIdCols, lane);
   for (int t = y0 - 1; t <= y1; ++t) {
-    id_stage_a(L, P, b, t);
+    id_stage_a(L, P, b, t, lane, y0, y1);
     IdXchg<NSRC> lf, rt;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -105,8 +105,10 @@ __global__ void md2_smooth(Params P) {
   const int Hs = P.H >> s, Ws = P.W >> s;
   const int n = Hs * Ws;
   if (blockIdx.x * blockDim.x >= n) return;                      // uniform per block
-  const float m = (float)(P.acc[acc_dispsum(P, s, b)] / (double)n) + 1e-7f;
-  const float inv_m = 1.0f / m;
+  __shared__ float sh_inv_m;
+  if (threadIdx.x == 0) sh_inv_m = 1.0f / ((float)(P.acc[acc_dispsum(P, s, b)] / (double)n) + 1e-7f);
+  __syncthreads();
+  const float inv_m = sh_inv_m;
   float ex = 0.f, ey = 0.f, dot = 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float e0, e1, g;
@@ -222,6 +224,9 @@ __global__ void MD2_MARCH_BOUNDS md2_march(Params P) {
 // also writes the losses and grad_T.
 template <int K>
 __device__ __forceinline__ void final_scale(const Params& P, int s, int b) {
+  __shared__ float sh[2];
+  if (threadIdx.x == 0) smooth_scalars(P, s, b, sh[0], sh[1]);
+  __syncthreads();
   const int Hs = P.H >> s, Ws = P.W >> s;
   const int n = Hs * Ws;
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -231,20 +236,19 @@ __device__ __forceinline__ void final_scale(const Params& P, int s, int b) {
   if (ok) part = (K == 1) ? __ldg(P.dD[s] + (size_t)b * n + cp) : upsample_adjoint_part<K>(P, s, b, cp / Ws, cp % Ws, j);
 #pragma unroll
   for (int o = K / 2; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
-  if (ok && j == 0) P.grad_disp[s][(size_t)b * n + cp] = part + final_smooth_grad(P, s, b, cp);
+  if (ok && j == 0) P.grad_disp[s][(size_t)b * n + cp] = part + final_smooth_grad(P, s, b, cp, sh[0], sh[1]);
 }
 
 __global__ void md2_final(Params P) {
-  const int s = blockIdx.z, b = blockIdx.y;
-  if (blockIdx.x == 0 && b == 0 && s == 0) {
+  const int s = blockIdx.z + 1, b = blockIdx.y;      // scale 0 is finished by md2_march itself
+  if (blockIdx.x == 0 && b == 0 && blockIdx.z == 0) {
     if (threadIdx.x == 0) final_scalars(P);
     if (P.want_grad && threadIdx.x < P.B * P.nsrc) final_grad_T(P, threadIdx.x / P.nsrc, threadIdx.x % P.nsrc);
   }
   if (!P.want_grad || s >= P.S) return;
-  // every scale needs (H>>s)*(W>>s)*2^s = H*W / 2^s threads
+  // scale s needs (H>>s)*(W>>s)*2^s = H*W / 2^s threads
   if (blockIdx.x * blockDim.x >= (P.H * P.W) >> s) return;
   switch (s) {
-    case 0: final_scale<1>(P, 0, b); break;
     case 1: final_scale<2>(P, 1, b); break;
     case 2: final_scale<4>(P, 2, b); break;
     default: final_scale<8>(P, 3, b); break;
@@ -301,21 +305,50 @@ cudaError_t profile_march_ms(float* ms) {
   return cudaEventElapsedTime(ms, g_prof_ev[0], g_prof_ev[1]);
 }
 
+// side stream + events (per device) used to overlap the small smoothness kernels with the
+// identity / marching kernels; fork/join with events so that the caller's stream semantics
+// (and CUDA-graph capture of the caller's stream) are preserved
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream g_side[64];
+
+static cudaError_t get_side(SideStream** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  SideStream& s = g_side[dev];
+  if (!s.stream) {
+    if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming)) != cudaSuccess) return e;
+  }
+  *out = &s;
+  return cudaSuccess;
+}
+
 cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
   cudaError_t e;
+  SideStream* side = nullptr;
+  if ((e = get_side(&side)) != cudaSuccess) return e;
   md2_prologue<<<4, 256, 0, stream>>>(P);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  {
-    dim3 grid((P.H * P.W + 255) / 256, P.B, 1 + P.nsrc);
-    md2_pack<<<grid, 256, 0, stream>>>(P);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  }
+  // ---- fork: disparity means + smoothness on the side stream
+  if ((e = cudaEventRecord(side->fork, stream)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return e;
   {
     const int n0 = P.H * P.W;
     dim3 grid((n0 + 256 * 8 - 1) / (256 * 8), P.B, P.S);
-    md2_disp_mean<<<grid, 256, 0, stream>>>(P);
+    md2_disp_mean<<<grid, 256, 0, side->stream>>>(P);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    dim3 grid2((n0 + 256 * kSmoothPerThread - 1) / (256 * kSmoothPerThread), P.B, P.S);
+    md2_smooth<<<grid2, 256, 0, side->stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
+  if ((e = cudaEventRecord(side->join, side->stream)) != cudaSuccess) return e;
+  // ---- main stream: (identity + re-layout) or re-layout alone, then the marching kernel
   if (P.automask) {
     const int jobs = P.B * P.nseg * P.nband_id;
     const int grid = (jobs + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -325,13 +358,13 @@ cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
       default: md2_identity<3><<<grid, kThreads, 0, stream>>>(P); break;
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  }
-  {
-    const int n0 = P.H * P.W;
-    dim3 grid((n0 + 256 * kSmoothPerThread - 1) / (256 * kSmoothPerThread), P.B, P.S);
-    md2_smooth<<<grid, 256, 0, stream>>>(P);
+  } else {
+    dim3 grid((P.H * P.W + 255) / 256, P.B, 1 + P.nsrc);
+    md2_pack<<<grid, 256, 0, stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
+  // ---- join: the marching kernel finishes grad_disp_0 and needs the smoothness sums
+  if ((e = cudaStreamWaitEvent(stream, side->join, 0)) != cudaSuccess) return e;
   if (g_prof_on) cudaEventRecord(g_prof_ev[0], stream);
   switch (P.nsrc) {
     case 1: e = launch_march_n<1>(P, stream); break;
@@ -340,9 +373,10 @@ cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
   }
   if (e != cudaSuccess) return e;
   if (g_prof_on) cudaEventRecord(g_prof_ev[1], stream);
+  // ---- scales >= 1: up-sampling adjoint + smoothness adjoint; losses; grad_T
   {
-    const int n0 = P.H * P.W;
-    dim3 grid((n0 + 255) / 256, P.B, P.S);
+    const int n1 = (P.H * P.W) >> 1;
+    dim3 grid((n1 + 255) / 256, P.B, P.S > 1 ? P.S - 1 : 1);
     md2_final<<<grid, 256, 0, stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }

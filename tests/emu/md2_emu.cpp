@@ -25,7 +25,7 @@ static void emu_identity(const Params& P) {
         IdLane<NSRC> L[32];
         for (int l = 0; l < 32; ++l) id_init(L[l], P, band * kIdCols, l);
         for (int t = y0 - 1; t <= y1; ++t) {
-          for (int l = 0; l < 32; ++l) id_stage_a(L[l], P, b, t);
+          for (int l = 0; l < 32; ++l) id_stage_a(L[l], P, b, t, l, y0, y1);
           IdXchg<NSRC> X[34];
           memset(X, 0, sizeof(X));
           for (int l = 0; l < 32; ++l) {
@@ -127,9 +127,10 @@ extern "C" int md2_emu_view_synthesis_loss(const md2_problem* p, const md2_tenso
   for (int i = 0; i < acc_count(P); ++i) P.acc[i] = 0.0;
   for (int b = 0; b < P.B; ++b)
     for (int f = 0; f < P.nsrc; ++f) setup_projection(P, b, f);
-  for (int img = 0; img <= P.nsrc; ++img)
-    for (int b = 0; b < P.B; ++b)
-      for (int p2 = 0; p2 < P.H * P.W; ++p2) pack_pixel(P, img, b, p2);
+  if (!P.automask)   // with automasking the identity pass writes the RGBx texels itself
+    for (int img = 0; img <= P.nsrc; ++img)
+      for (int b = 0; b < P.B; ++b)
+        for (int p2 = 0; p2 < P.H * P.W; ++p2) pack_pixel(P, img, b, p2);
   // 2. disparity means
   for (int s = 0; s < P.S; ++s)
     for (int b = 0; b < P.B; ++b) {
@@ -167,14 +168,16 @@ extern "C" int md2_emu_view_synthesis_loss(const md2_problem* p, const md2_tenso
     for (int s = 0; s < P.S; ++s)
       for (int b = 0; b < P.B; ++b) {
         const int Hs = P.H >> s, Ws = P.W >> s, n = Hs * Ws;
+        float inv_m2, dterm;
+        smooth_scalars(P, s, b, inv_m2, dterm);
         for (int i = 0; i < n; ++i) {
           float up = 0.f;
           const int Y = i / Ws, X = i % Ws;
-          if (s == 0) up = P.dD[0][(size_t)b * n + i];
+          if (s == 0) continue;   // finished by the marching pass
           else if (s == 1) { for (int j = 0; j < 2; ++j) up += upsample_adjoint_part<2>(P, s, b, Y, X, j); }
           else if (s == 2) { for (int j = 0; j < 4; ++j) up += upsample_adjoint_part<4>(P, s, b, Y, X, j); }
           else { for (int j = 0; j < 8; ++j) up += upsample_adjoint_part<8>(P, s, b, Y, X, j); }
-          P.grad_disp[s][(size_t)b * n + i] = up + final_smooth_grad(P, s, b, i);
+          P.grad_disp[s][(size_t)b * n + i] = up + final_smooth_grad(P, s, b, i, inv_m2, dterm);
         }
       }
   }
