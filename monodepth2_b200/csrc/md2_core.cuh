@@ -251,6 +251,13 @@ struct Lane {
   // software prefetch: inputs of the NEXT row, in flight during the current step
   F4 ntg;                 // target texel of row t+1
   float nd[4];            // disparity taps of row t+1 (d00,d01,d10,d11; scale 0: d00 only)
+  // gather of the current row, in flight between stage_a_issue and stage_a_finish
+  F4 tap[C::NSRC][4];                           // nw, ne, sw, se texels
+  float cz;                                     // depth
+  float cu[C::NSRC], cv[C::NSRC];               // projected pixel coordinates
+  float cwx[C::NSRC], cwy[C::NSRC];             // bilinear weights
+  float cgx[C::NSRC], cgy[C::NSRC];             // clip mask * d(ix,iy)/d(u,v) / den
+  F4 ctg;                                       // target texel of the current row
   // identity loss + noise of the current window row (loaded at the top of the step)
   float idv[C::NSRC], nzv[C::NSRC];
   // forward rolling state (horizontal 3-sums of the two previous rows)
@@ -365,18 +372,18 @@ MD2_HD void lane_init(Lane<C>& L, const Params& P, const WarpJob& J, int lane) {
 }
 
 // ------------------------------------------------------------------ stage A
-// Row t (read at its reflected position, so pad-ring rows/lanes carry the reflected values
-// and no edge case is needed downstream): up-sampled disparity (trainer.py:350-351, torch
-// upsample_bilinear2d, align_corners=False) -> depth, projection into every source,
-// border-clamped bilinear gather.  Exports pr/tg for the neighbour exchange and stashes what
-// the adjoint of row t needs two steps later.  Also issues the loads of row t+1 and of the
-// identity loss / noise of window row t-1.
+// Row t is read at its reflected position, so pad-ring rows/lanes carry the reflected values
+// and no edge case is needed downstream.
+// stage_a_issue: up-sampled disparity (trainer.py:350-351, torch upsample_bilinear2d,
+// align_corners=False) -> depth (layers.py:16-25) -> projection into every source
+// (layers.py:139-193) -> border-clamped bilinear cell (trainer.py:384-387); issues the 4 tap
+// loads per source and the loads of the following row (target, disparity) and of the identity
+// loss / noise of window row t-1.  Nothing here waits for memory: the caller runs the adjoint of
+// an earlier row (stage_c) while the gather is in flight.
 template <class C>
-MD2_HD void stage_a(Lane<C>& L, const Params& P, const WarpJob& J, int t, const Stash& st) {
-  const int slot = ring_slot(t);
+MD2_HD void stage_a_issue(Lane<C>& L, const Params& P, const WarpJob& J, int t) {
   const int tr = reflect_clamp(t, J.H);
-  // consume the prefetched row, then put the next one in flight
-  const F4 tg4 = L.ntg;
+  L.ctg = L.ntg;
   float D;
   if (J.s == 0) {
     D = L.nd[0];
@@ -397,12 +404,9 @@ MD2_HD void stage_a(Lane<C>& L, const Params& P, const WarpJob& J, int t, const 
 #pragma unroll
     for (int f = 0; f < C::NID; ++f) L.nzv[f] = MD2_LD(J.noise + f * J.plane + pix);
   }
-  L.tg[0] = tg4.x; L.tg[1] = tg4.y; L.tg[2] = tg4.z;
   const float sd = MD2_FADD(P.a_disp, MD2_FMUL(P.c_disp, D));
   const float z = MD2_RCP(sd);
-  const bool own = (t >= J.y0) && (t < J.y1) && (L.x >= J.x0) && (L.x < J.x0 + kOwnCols) && L.colok;
-  if (J.depth && own) J.depth[t * J.W + L.xi] = z;
-  if (C::GRAD) st.at(slot, 0, C::STASH4) = make_f4(tg4.x, tg4.y, tg4.z, z);
+  L.cz = z;
   const float yf = (float)tr;
 #pragma unroll
   for (int f = 0; f < C::NSRC; ++f) {
@@ -422,15 +426,36 @@ MD2_HD void stage_a(Lane<C>& L, const Params& P, const WarpJob& J, int t, const 
     const float ixc = fminf(fmaxf(ix, 0.0f), P.wmax);
     const float iyc = fminf(fmaxf(iy, 0.0f), P.hmax);
     const float fx0 = MD2_FLOORF(ixc), fy0 = MD2_FLOORF(iyc);
-    const float wx = ixc - fx0, wy = iyc - fy0;
     const int x0 = (int)fx0, y0 = (int)fy0;
     const int dx1 = (x0 + 1 < J.W) ? 4 : 0;                 // texel step to the east tap
     const int dy1 = (y0 + 1 < J.H) ? J.W * 4 : 0;           // texel step to the south tap
     const float* t00 = J.src4[f] + 4 * (y0 * J.W + x0);
-    const F4 nw = MD2_LD4(t00), ne = MD2_LD4(t00 + dx1);
-    const F4 sw = MD2_LD4(t00 + dy1), se = MD2_LD4(t00 + dy1 + dx1);
-    const float gxs = mx ? P.sx * inv : 0.0f;
-    const float gys = my ? P.sy * inv : 0.0f;
+    L.tap[f][0] = MD2_LD4(t00);
+    L.tap[f][1] = MD2_LD4(t00 + dx1);
+    L.tap[f][2] = MD2_LD4(t00 + dy1);
+    L.tap[f][3] = MD2_LD4(t00 + dy1 + dx1);
+    L.cu[f] = u; L.cv[f] = v;
+    L.cwx[f] = ixc - fx0; L.cwy[f] = iyc - fy0;
+    L.cgx[f] = mx ? P.sx * inv : 0.0f;
+    L.cgy[f] = my ? P.sy * inv : 0.0f;
+  }
+}
+
+// stage_a_finish: the taps have arrived; interpolate pred and its derivatives, export pr/tg for
+// the neighbour exchange and stash what the adjoint of row t needs later.
+template <class C>
+MD2_HD void stage_a_finish(Lane<C>& L, const Params& P, const WarpJob& J, int t, const Stash& st) {
+  const int slot = ring_slot(t);
+  const F4 tg4 = L.ctg;
+  const float z = L.cz;
+  const bool own = (t >= J.y0) && (t < J.y1) && (L.x >= J.x0) && (L.x < J.x0 + kOwnCols) && L.colok;
+  L.tg[0] = tg4.x; L.tg[1] = tg4.y; L.tg[2] = tg4.z;
+  if (J.depth && own) J.depth[t * J.W + L.xi] = z;
+  if (C::GRAD) st.at(slot, 0, C::STASH4) = make_f4(tg4.x, tg4.y, tg4.z, z);
+#pragma unroll
+  for (int f = 0; f < C::NSRC; ++f) {
+    const F4 nw = L.tap[f][0], ne = L.tap[f][1], sw = L.tap[f][2], se = L.tap[f][3];
+    const float wx = L.cwx[f], wy = L.cwy[f], gxs = L.cgx[f], gys = L.cgy[f];
     float pr[3], dxp[3], dyp[3];
     {
       const float nwc[3] = {nw.x, nw.y, nw.z}, nec[3] = {ne.x, ne.y, ne.z};
@@ -452,8 +477,8 @@ MD2_HD void stage_a(Lane<C>& L, const Params& P, const WarpJob& J, int t, const 
 #pragma unroll
     for (int c = 0; c < 3; ++c) L.pr[f][c] = pr[c];
     if (C::GRAD) {
-      st.at(slot, 1 + 3 * f, C::STASH4) = make_f4(pr[0], pr[1], pr[2], u);
-      st.at(slot, 2 + 3 * f, C::STASH4) = make_f4(dxp[0], dxp[1], dxp[2], v);
+      st.at(slot, 1 + 3 * f, C::STASH4) = make_f4(pr[0], pr[1], pr[2], L.cu[f]);
+      st.at(slot, 2 + 3 * f, C::STASH4) = make_f4(dxp[0], dxp[1], dxp[2], L.cv[f]);
       st.at(slot, 3 + 3 * f, C::STASH4) = make_f4(dyp[0], dyp[1], dyp[2], 0.f);
     }
   }

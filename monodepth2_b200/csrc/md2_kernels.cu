@@ -136,6 +136,22 @@ __global__ void md2_smooth(Params P) {
 }
 
 // ------------------------------------------------------------------ 5. the marching kernel
+template <class C>
+__device__ __forceinline__ void exchange_and_stage_c(Lane<C>& L, const Params& P, const WarpJob& J, int t, int lane,
+                                                     const Stash& st) {
+  Xchg2<C> l2, r2;
+  l2.tag = __shfl_up_sync(kFull, L.tag, 1);
+  r2.tag = __shfl_down_sync(kFull, L.tag, 1);
+#pragma unroll
+  for (int n = 0; n < C::NCS; ++n)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      l2.coef[n][k] = __shfl_up_sync(kFull, L.coef[n][k], 1);
+      r2.coef[n][k] = __shfl_down_sync(kFull, L.coef[n][k], 1);
+    }
+  stage_c(L, P, J, t, lane, l2, r2, st);
+}
+
 #define MD2_PRAGMA_(x) _Pragma(#x)
 #define MD2_PRAGMA(x) MD2_PRAGMA_(x)
 #ifdef MD2_UNROLL
@@ -173,8 +189,13 @@ __global__ void MD2_MARCH_BOUNDS md2_march(Params P) {
   Lane<C> L;
   lane_init(L, P, J, lane);
   MD2_LOOP_UNROLL
+  // Software-pipelined row loop: the gather of row t is issued first, the adjoint of the
+  // previous step (stage C, independent of row t) runs while it is in flight, then row t is
+  // interpolated and its window row evaluated (stage B).
   for (int t = J.y0 - 2; t <= J.y1 + 1; ++t) {
-    stage_a(L, P, J, t, st);
+    stage_a_issue(L, P, J, t);
+    if (C::GRAD && t > J.y0 - 2) exchange_and_stage_c(L, P, J, t - 1, lane, st);
+    stage_a_finish(L, P, J, t, st);
     Xchg1<C> l1, r1;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -187,20 +208,8 @@ __global__ void MD2_MARCH_BOUNDS md2_march(Params P) {
       }
     }
     stage_b(L, P, J, t, lane, l1, r1);
-    if (C::GRAD) {
-      Xchg2<C> l2, r2x;
-      l2.tag = __shfl_up_sync(kFull, L.tag, 1);
-      r2x.tag = __shfl_down_sync(kFull, L.tag, 1);
-#pragma unroll
-      for (int n = 0; n < C::NCS; ++n)
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          l2.coef[n][k] = __shfl_up_sync(kFull, L.coef[n][k], 1);
-          r2x.coef[n][k] = __shfl_down_sync(kFull, L.coef[n][k], 1);
-        }
-      stage_c(L, P, J, t, lane, l2, r2x, st);
-    }
   }
+  if (C::GRAD) exchange_and_stage_c(L, P, J, J.y1 + 1, lane, st);
   const float ls = warp_sum(L.loss);
   if (lane == 0) atomicAdd(&P.acc[acc_photo(J.s)], (double)ls);
   if (C::GRAD) {

@@ -54,8 +54,21 @@ static void emu_march(const Params& P) {
             st[l].base = ring.data() + l;
             st[l].stride = 32;
           }
+          auto run_c = [&](int t) {
+            Xchg2<C> X2[34];
+            memset(X2, 0, sizeof(X2));
+            X2[0].tag = X2[33].tag = -1;
+            for (int l = 0; l < 32; ++l) {
+              memcpy(X2[l + 1].coef, L[l].coef, sizeof(L[l].coef));
+              X2[l + 1].tag = L[l].tag;
+            }
+            for (int l = 0; l < 32; ++l) stage_c(L[l], P, J, t, l, X2[l], X2[l + 2], st[l]);
+          };
+          // same software-pipelined order as md2_march
           for (int t = J.y0 - 2; t <= J.y1 + 1; ++t) {
-            for (int l = 0; l < 32; ++l) stage_a(L[l], P, J, t, st[l]);
+            for (int l = 0; l < 32; ++l) stage_a_issue(L[l], P, J, t);
+            if (C::GRAD && t > J.y0 - 2) run_c(t - 1);
+            for (int l = 0; l < 32; ++l) stage_a_finish(L[l], P, J, t, st[l]);
             Xchg1<C> X1[34];
             memset(X1, 0, sizeof(X1));
             for (int l = 0; l < 32; ++l) {
@@ -63,17 +76,8 @@ static void emu_march(const Params& P) {
               memcpy(X1[l + 1].tg, L[l].tg, sizeof(L[l].tg));
             }
             for (int l = 0; l < 32; ++l) stage_b(L[l], P, J, t, l, X1[l], X1[l + 2]);
-            if (C::GRAD) {
-              Xchg2<C> X2[34];
-              memset(X2, 0, sizeof(X2));
-              X2[0].tag = X2[33].tag = -1;
-              for (int l = 0; l < 32; ++l) {
-                memcpy(X2[l + 1].coef, L[l].coef, sizeof(L[l].coef));
-                X2[l + 1].tag = L[l].tag;
-              }
-              for (int l = 0; l < 32; ++l) stage_c(L[l], P, J, t, l, X2[l], X2[l + 2], st[l]);
-            }
           }
+          if (C::GRAD) run_c(J.y1 + 1);
           float ls = 0.f;
           for (int l = 0; l < 32; ++l) ls += L[l].loss;
           P.acc[acc_photo(s)] += (double)ls;
