@@ -59,7 +59,7 @@ inline Layout make_layout(const md2_problem* p) {
 }
 
 inline int default_seg_rows(const md2_problem* p) {
-  int r = p->rows_per_segment > 0 ? p->rows_per_segment : 32;
+  int r = p->rows_per_segment > 0 ? p->rows_per_segment : 48;
   if (r > p->height) r = p->height;
   return r;
 }
