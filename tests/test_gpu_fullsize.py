@@ -1,0 +1,160 @@
+"""Full-size (BASELINE.json configs 1-2: B=12, 640x192, frames [0,-1,1], 4 scales) parity of the CUDA path
+against the oracle run live on the host, with the flip-robust protocol of SURVEY.md 8(c):
+
+  P1  loss, loss/s        |d|/|ref| <= 1e-5 against the fp32 oracle
+  P2  per-pixel gradient  d loss / d (up-sampled disp_s): >= 99.9 % of elements within 1e-4*max|g_ref|
+  P3  aggregated grads    relL2(kernel, ref64) <= 1.5 * relL2(ref32, ref64) (+1e-4), per tensor
+  P5  identity_selection  <= 1e-4 of pixels differ
+plus size-independent properties (batch-permutation equivariance, linearity in the upstream gradient,
+forward-only == forward of the grad mode, run-to-run reproducibility of the per-pixel gradient).
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_l2
+from oracle import view_synthesis as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+A_DISP, C_DISP = 0.01, 9.99
+
+
+def _oracle(batch, fids, dtype, **cfgkw):
+    inputs, outputs, pose, noise = batch
+    H, W = inputs[("color", 0, 0)].shape[-2:]
+    cfg = O.OracleConfig(height=H, width=W, frame_ids=tuple(fids), **cfgkw)
+    ins = {k: v.to(dtype) for k, v in inputs.items()}
+    outs, leaves = {}, {}
+    for s in range(4):
+        leaves[("disp", s)] = outputs[("disp", s)].to(dtype).clone().requires_grad_(True)
+        outs[("disp", s)] = leaves[("disp", s)]
+    for f in fids[1:]:
+        if f == "s":
+            continue
+        leaves[("T", f)] = outputs[("cam_T_cam", 0, f)].to(dtype).clone().requires_grad_(True)
+        outs[("cam_T_cam", 0, f)] = leaves[("T", f)]
+    O.generate_images_pred(ins, outs, cfg)
+    for s in range(4):
+        outs[("depth", 0, s)].retain_grad()
+    nz = [n.to(dtype) for n in noise] if not cfgkw.get("disable_automasking") else None
+    losses = O.compute_losses(ins, outs, cfg, nz)
+    losses["loss"].backward()
+    return losses, outs, leaves
+
+
+def _cuda(batch, fids, side=True, grad=True, **plankw):
+    from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
+    inputs, outputs, pose, noise = batch
+    B, _, H, W = inputs[("color", 0, 0)].shape
+    plan = LossPlan(B, H, W, fids, **plankw)
+    ins = {k: v.to(DEV) for k, v in inputs.items()}
+    outs = {k: v.to(DEV).requires_grad_(grad) for k, v in outputs.items()}
+    nz = [n.to(DEV)[:, :max(plan.n_id, 1)] for n in noise] if plan.n_id else None
+    sd = {"mask_scales": [0, 1, 2, 3], "grad_updisp_scales": [0, 1, 2, 3]} if side else None
+    if grad:
+        losses = view_synthesis_loss(plan, ins, outs, nz, sd)
+        losses["loss"].backward()
+    else:
+        with torch.no_grad():
+            losses = view_synthesis_loss(plan, ins, outs, nz, sd)
+    torch.cuda.synchronize()
+    return losses, outs, sd
+
+
+@pytest.mark.parametrize("kind,seed,B", [("iid", 0, 12), ("structured", 5, 6)])
+def test_full_size_protocol(kind, seed, B):
+    from monodepth2_b200.synthetic import make_batch
+    fids = [0, -1, 1]
+    batch = make_batch(B, 192, 640, fids, 4, seed, kind)
+    l32, o32, g32 = _oracle(batch, fids, torch.float32)
+    l64, o64, g64 = _oracle(batch, fids, torch.float64)
+    lk, ok, side = _cuda(batch, fids)
+    # P1
+    for key in ["loss"] + ["loss/%d" % s for s in range(4)]:
+        ref = float(l32[key].detach())
+        assert abs(float(lk[key].detach()) - ref) <= 1e-5 * abs(ref), key
+    # P2: pre-aggregation per-pixel gradient
+    for s in range(4):
+        depth = o32[("depth", 0, s)].detach()
+        ref = (o32[("depth", 0, s)].grad * (-C_DISP * depth * depth)).numpy()
+        got = side[("grad_updisp", s)].cpu().numpy()
+        frac = float((np.abs(got - ref) <= 1e-4 * np.abs(ref).max()).mean())
+        assert frac >= 0.999, (s, frac)
+    # P3: aggregated gradients no worse than the reference's own fp32 noise
+    for s in range(4):
+        ref_noise = rel_l2(g32[("disp", s)].grad, g64[("disp", s)].grad)
+        mine = rel_l2(ok[("disp", s)].grad.cpu(), g64[("disp", s)].grad)
+        assert mine <= 1.5 * ref_noise + 1e-4, (s, mine, ref_noise)
+    for f in fids[1:]:
+        ref_noise = rel_l2(g32[("T", f)].grad, g64[("T", f)].grad)
+        mine = rel_l2(ok[("cam_T_cam", 0, f)].grad.cpu(), g64[("T", f)].grad)
+        assert mine <= 1.5 * ref_noise + 1e-4, (f, mine, ref_noise)
+    # P5
+    for s in range(4):
+        m = side["identity_selection/%d" % s].cpu()
+        assert float((m != o32["identity_selection/%d" % s]).float().mean()) <= 1e-4
+
+
+def test_batch_permutation_linearity_forward_only_reproducibility():
+    from monodepth2_b200.synthetic import make_batch
+    fids = [0, -1, 1]
+    B = 12
+    batch = make_batch(B, 192, 640, fids, 4, 7, "structured")
+    l0, o0, s0 = _cuda(batch, fids)
+    # reproducibility: the per-pixel gradient has no atomics on its path
+    l1, o1, s1 = _cuda(batch, fids)
+    for s in range(4):
+        assert torch.equal(s0[("grad_updisp", s)], s1[("grad_updisp", s)])
+        assert torch.equal(o0[("disp", s)].grad, o1[("disp", s)].grad)
+    assert abs(float(l0["loss"]) - float(l1["loss"])) <= 1e-7 * abs(float(l0["loss"]))
+    # permuting the samples permutes the per-sample gradients exactly and keeps the loss
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1))
+    inputs, outputs, pose, noise = batch
+    pb = ({k: v[perm] for k, v in inputs.items()}, {k: v[perm] for k, v in outputs.items()}, pose,
+          [n[perm] for n in noise])
+    lp, op, sp = _cuda(pb, fids)
+    assert abs(float(lp["loss"]) - float(l0["loss"])) <= 1e-6 * abs(float(l0["loss"]))
+    for s in range(4):
+        assert torch.equal(op[("disp", s)].grad.cpu(), o0[("disp", s)].grad.cpu()[perm])
+    # forward-only (Trainer.val under no_grad) gives the same losses
+    lf, _, _ = _cuda(batch, fids, side=False, grad=False)
+    assert float(lf["loss"]) == float(l0["loss"])
+    # linearity in the upstream gradient
+    from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
+    plan = LossPlan(B, 192, 640, fids)
+    ins = {k: v.to(DEV) for k, v in inputs.items()}
+    outs = {k: v.to(DEV).requires_grad_(True) for k, v in outputs.items()}
+    (3.0 * view_synthesis_loss(plan, ins, outs, [n.to(DEV) for n in noise])["loss"]).backward()
+    for s in range(4):
+        torch.testing.assert_close(outs[("disp", s)].grad, 3.0 * o0[("disp", s)].grad, rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("wl", ["stereo", "avg", "noauto", "hires"])
+def test_other_baseline_configs_loss_parity(wl):
+    """BASELINE.json configs 3-5 at full resolution: loss parity (P1) + finite gradients."""
+    from monodepth2_b200.synthetic import make_batch
+    H, W, B = (320, 1024, 4) if wl == "hires" else (192, 640, 6)
+    fids = [0, -1, 1, "s"] if wl == "stereo" else [0, -1, 1]
+    kw = {"avg_reprojection": wl == "avg", "disable_automasking": wl == "noauto"}
+    n_id = 0 if wl == "noauto" else (1 if wl == "avg" else len(fids) - 1)
+    batch = make_batch(B, H, W, fids, 4, 21, "structured", n_id=max(n_id, 1))
+    l32, o32, g32 = _oracle(batch, fids, torch.float32, **kw)
+    from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
+    inputs, outputs, pose, noise = batch
+    plan = LossPlan(B, H, W, fids, **kw)
+    ins = {k: v.to(DEV) for k, v in inputs.items()}
+    outs = {k: v.to(DEV).requires_grad_(True) for k, v in outputs.items()}
+    nz = [n.to(DEV) for n in noise] if plan.n_id else None
+    lk = view_synthesis_loss(plan, ins, outs, nz)
+    lk["loss"].backward()
+    for key in ["loss"] + ["loss/%d" % s for s in range(4)]:
+        ref = float(l32[key].detach())
+        assert abs(float(lk[key].detach()) - ref) <= 1e-5 * abs(ref), key
+    for s in range(4):
+        g = outs[("disp", s)].grad
+        assert torch.isfinite(g).all()
+        assert rel_l2(g.cpu(), g32[("disp", s)].grad) < 5e-2
+    for f in fids[1:]:
+        if f != "s":
+            assert rel_l2(outs[("cam_T_cam", 0, f)].grad.cpu(), g32[("T", f)].grad) < 5e-2
