@@ -191,6 +191,15 @@ struct Cfg {
   static constexpr int NCS = AVG_ ? NSRC_ : 1;                   // coefficient sets shipped per window
   static constexpr int NID = AUTOMASK_ ? (AVG_ ? 1 : NSRC_) : 0; // identity candidates
   static constexpr int STASH4 = 1 + 3 * NSRC_;                   // 16-byte fields per ring row
+  // Backward rolling state (two rows of 9*NSRC box sums): registers for up to two sources, a
+  // thread-private shared-memory ring beyond that (3 sources would spill ~0.5 KB per thread).
+#ifdef MD2_BSMEM_ALL
+  static constexpr bool BSMEM = GRAD_;
+#else
+  static constexpr bool BSMEM = GRAD_ && (NSRC_ >= 3);
+#endif
+  static constexpr int NB4 = (9 * NSRC_ + 3) / 4;                // 16-byte fields per B row
+  static constexpr int SMEM4 = (GRAD_ ? kRing * STASH4 : 0) + (BSMEM ? 2 * NB4 : 0);  // per thread
 };
 
 // ------------------------------------------------------------------ SSIM pieces
@@ -293,8 +302,10 @@ MD2_HD int ring_slot(int t) { return ((t % kRing) + kRing) % kRing; }
 // lanes are 16 bytes apart, so 128-bit shared accesses are conflict-free
 struct Stash {
   F4* base;
+  F4* bring;      // ring of 2 rows x NB4 fields (backward box sums), only when Cfg::BSMEM
   int stride;     // threads sharing the ring (lane stride of one field)
   MD2_HD F4& at(int slot, int field, int nfields) const { return base[(slot * nfields + field) * stride]; }
+  MD2_HD F4& b(int slot, int field, int nfields) const { return bring[(slot * nfields + field) * stride]; }
 };
 
 // issue the loads of row `t`'s target texel and disparity taps (consumed one step later)
@@ -369,6 +380,15 @@ MD2_HD void lane_init(Lane<C>& L, const Params& P, const WarpJob& J, int lane) {
   L.tag = -1; L.tag1 = -1;
   L.loss = 0.f;
   prefetch_row(L, J, J.y0 - 2);
+}
+
+// zero the shared-memory ring of backward box sums at the start of a job
+template <class C>
+MD2_HD void bring_reset(const Stash& st) {
+  if (C::BSMEM) {
+#pragma unroll
+    for (int i = 0; i < 2 * C::NB4; ++i) st.bring[i * st.stride] = make_f4(0.f, 0.f, 0.f, 0.f);
+  }
 }
 
 // ------------------------------------------------------------------ stage A
@@ -631,7 +651,27 @@ MD2_HD void stage_c(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
       B0[f][k] = fmaf(ml, lf.coef[n][k], fmaf(mr, rt.coef[n][k], mc * L.coef[n][k]));
   }
   const bool own = L.colok && (lane >= 2) && (lane < 2 + kOwnCols) && (yp >= J.y0) && (yp < J.y1);
+  const int bslot = t & 1;          // ring slot of row t (holds row t-2 until overwritten below)
   if (own) {
+    float B1v[C::NSRC][9], B2v[C::NSRC][9];
+    if (C::BSMEM) {
+      float f1[4 * C::NB4], f2[4 * C::NB4];
+#pragma unroll
+      for (int i = 0; i < C::NB4; ++i) {
+        const F4 a = st.b(bslot ^ 1, i, C::NB4), c2 = st.b(bslot, i, C::NB4);
+        f1[4 * i] = a.x; f1[4 * i + 1] = a.y; f1[4 * i + 2] = a.z; f1[4 * i + 3] = a.w;
+        f2[4 * i] = c2.x; f2[4 * i + 1] = c2.y; f2[4 * i + 2] = c2.z; f2[4 * i + 3] = c2.w;
+      }
+#pragma unroll
+      for (int f = 0; f < C::NSRC; ++f)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { B1v[f][k] = f1[f * 9 + k]; B2v[f][k] = f2[f * 9 + k]; }
+    } else {
+#pragma unroll
+      for (int f = 0; f < C::NSRC; ++f)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { B1v[f][k] = L.B1[f][k]; B2v[f][k] = L.B2[f][k]; }
+    }
     const float wu = (yp == 1) ? 2.0f : 1.0f;
     const float wd = (yp == P.H - 2) ? 2.0f : 1.0f;
     const int slot = ring_slot(yp);
@@ -652,9 +692,9 @@ MD2_HD void stage_c(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float xj = xs[c];
-        const float A = fmaf(wu, L.B2[f][c * 3 + 0], fmaf(wd, B0[f][c * 3 + 0], L.B1[f][c * 3 + 0]));
-        const float Bq = fmaf(wu, L.B2[f][c * 3 + 1], fmaf(wd, B0[f][c * 3 + 1], L.B1[f][c * 3 + 1]));
-        const float G = fmaf(wu, L.B2[f][c * 3 + 2], fmaf(wd, B0[f][c * 3 + 2], L.B1[f][c * 3 + 2]));
+        const float A = fmaf(wu, B2v[f][c * 3 + 0], fmaf(wd, B0[f][c * 3 + 0], B1v[f][c * 3 + 0]));
+        const float Bq = fmaf(wu, B2v[f][c * 3 + 1], fmaf(wd, B0[f][c * 3 + 1], B1v[f][c * 3 + 1]));
+        const float G = fmaf(wu, B2v[f][c * 3 + 2], fmaf(wd, B0[f][c * 3 + 2], B1v[f][c * 3 + 2]));
         // d loss / d pred_c = 0.85/3 * SSIM part + 0.15/3 * sign(x - y) [if this source won here]
         float g = (0.85f / 3.0f) * fmaf(xj, Bq, fmaf(tg[c], G, A));
         if (won) {
@@ -681,10 +721,23 @@ MD2_HD void stage_c(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
     if (J.s == 0)   // up-sampling is the identity at scale 0: finish grad_disp_0 here (A.4 + A.3)
       J.gd0[yp * J.W + L.xi] = dD + J.sm_w * (MD2_LD(J.gn0 + yp * J.W + L.xi) * J.sm_inv_m - J.sm_dterm);
   }
+  if (C::BSMEM) {
+    float fl[4 * C::NB4];
 #pragma unroll
-  for (int f = 0; f < C::NSRC; ++f)
+    for (int i = 0; i < 4 * C::NB4; ++i) fl[i] = 0.f;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) { L.B2[f][k] = L.B1[f][k]; L.B1[f][k] = B0[f][k]; }
+    for (int f = 0; f < C::NSRC; ++f)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) fl[f * 9 + k] = B0[f][k];
+#pragma unroll
+    for (int i = 0; i < C::NB4; ++i)
+      st.b(bslot, i, C::NB4) = make_f4(fl[4 * i], fl[4 * i + 1], fl[4 * i + 2], fl[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int f = 0; f < C::NSRC; ++f)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { L.B2[f][k] = L.B1[f][k]; L.B1[f][k] = B0[f][k]; }
+  }
   L.tag1 = L.tag;
 }
 

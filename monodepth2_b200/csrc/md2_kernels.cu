@@ -184,7 +184,9 @@ __global__ void MD2_MARCH_BOUNDS md2_march(Params P) {
 
   Stash st;
   st.base = smem + threadIdx.x;
+  st.bring = smem + kRing * C::STASH4 * kThreads + threadIdx.x;
   st.stride = kThreads;
+  bring_reset<C>(st);
 
   Lane<C> L;
   lane_init(L, P, J, lane);
@@ -269,7 +271,7 @@ template <class C>
 static cudaError_t launch_march(const Params& P, cudaStream_t stream) {
   const int jobs = P.S * P.B * P.nseg * P.nband;
   const int grid = (jobs + kWarpsPerCta - 1) / kWarpsPerCta;
-  const size_t smem = C::GRAD ? (size_t)kThreads * kRing * C::STASH4 * sizeof(float4) : 0;
+  const size_t smem = (size_t)kThreads * C::SMEM4 * sizeof(float4);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(md2_march<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

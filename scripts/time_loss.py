@@ -1,18 +1,21 @@
-"""Quick device timing of the fused loss at full size (development aid)."""
+"""Quick device timing of the fused loss at full size (development aid).
+usage: time_loss.py [rows] [steps] [workload: mono|stereo|hires]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from monodepth2_b200.synthetic import make_batch
 from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
-rows = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+rows = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-B, H, W = 12, 192, 640
-inputs, outputs, pose, noise = make_batch(B, H, W)
+wl = sys.argv[3] if len(sys.argv) > 3 else "mono"
+B, H, W = (12, 320, 1024) if wl == "hires" else (12, 192, 640)
+fids = [0, -1, 1, "s"] if wl == "stereo" else [0, -1, 1]
+inputs, outputs, pose, noise = make_batch(B, H, W, fids)
 dev = 'cuda:0'
 inputs = {k: v.to(dev) for k, v in inputs.items()}
 outs = {k: v.to(dev).requires_grad_(True) for k, v in outputs.items()}
 noise = [x.to(dev) for x in noise]
-plan = LossPlan(B, H, W, [0, -1, 1], rows_per_segment=rows)
+plan = LossPlan(B, H, W, fids, rows_per_segment=rows)
 for i in range(3):
     l = view_synthesis_loss(plan, inputs, outs, noise)
 torch.cuda.synchronize()
@@ -22,4 +25,4 @@ for i in range(n):
     l = view_synthesis_loss(plan, inputs, outs, noise)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
-print("rows", rows, "ms/step", ms, "frames/s", B / ms * 1e3, "loss", float(l["loss"]))
+print(wl, "rows", rows, "ms/step %.4f" % ms, "frames/s %.0f" % (B / ms * 1e3), "loss", float(l["loss"].detach()))

@@ -39,7 +39,7 @@ static void emu_identity(const Params& P) {
 
 template <class C>
 static void emu_march(const Params& P) {
-  std::vector<F4> ring((size_t)32 * kRing * C::STASH4);
+  std::vector<F4> ring((size_t)32 * (kRing * C::STASH4 + 2 * C::NB4));
   for (int s = 0; s < P.S; ++s)
     for (int b = 0; b < P.B; ++b)
       for (int seg = 0; seg < P.nseg; ++seg)
@@ -52,7 +52,9 @@ static void emu_march(const Params& P) {
           for (int l = 0; l < 32; ++l) {
             lane_init(L[l], P, J, l);
             st[l].base = ring.data() + l;
+            st[l].bring = ring.data() + 32 * kRing * C::STASH4 + l;
             st[l].stride = 32;
+            bring_reset<C>(st[l]);
           }
           auto run_c = [&](int t) {
             Xchg2<C> X2[34];
