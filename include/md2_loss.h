@@ -47,7 +47,7 @@ typedef struct md2_problem {
   float disparity_smoothness; /* opt.disparity_smoothness              options.py:60  */
   int want_grad;              /* 0: forward only (Trainer.val under no_grad, trainer.py:330) */
   int rows_per_segment;       /* tuning: rows marched per warp job (0 = default) */
-  int reserved;
+  int no_ssim;                /* opt.no_ssim: L1 only                  options.py:117 */
 } md2_problem;
 
 /* Tensors of one evaluation.  Names follow the reference's dict keys. */

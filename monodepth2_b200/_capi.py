@@ -20,7 +20,7 @@ class Md2Problem(C.Structure):
         ("num_scales", C.c_int), ("num_src", C.c_int),
         ("automask", C.c_int), ("avg_reprojection", C.c_int), ("align_corners", C.c_int),
         ("min_depth", C.c_float), ("max_depth", C.c_float), ("disparity_smoothness", C.c_float),
-        ("want_grad", C.c_int), ("rows_per_segment", C.c_int), ("reserved", C.c_int),
+        ("want_grad", C.c_int), ("rows_per_segment", C.c_int), ("no_ssim", C.c_int),
     ]
 
 

@@ -84,7 +84,7 @@ constexpr float kSsimC2 = 0.0009f;
 // Device-side view of one evaluation (filled by the host planner in md2_plan.h).
 struct Params {
   int B, H, W, S, nsrc, nid;
-  int automask, avg, align_corners, want_grad;
+  int automask, avg, align_corners, want_grad, no_ssim;
   float a_disp, c_disp;      // scaled_disp = a + c*disp            layers.py:21-23
   float sx, ox, sy, oy;      // ix = u*sx + ox ; iy = v*sy + oy     (grid normalise o unnormalise)
   float wmax, hmax;          // W-1, H-1
@@ -182,9 +182,10 @@ MD2_HD WarpJob make_job(const Params& P, int s, int b, int x0, int y0, int y1) {
   return J;
 }
 
-template <int NSRC_, bool AVG_, bool AUTOMASK_, bool GRAD_>
+template <int NSRC_, bool AVG_, bool AUTOMASK_, bool GRAD_, bool NOSSIM_ = false>
 struct Cfg {
   static constexpr int NSRC = NSRC_;
+  static constexpr bool NOSSIM = NOSSIM_;                        // --no_ssim: L1 only (trainer.py:399-400)
   static constexpr bool AVG = AVG_;
   static constexpr bool AUTOMASK = AUTOMASK_;
   static constexpr bool GRAD = GRAD_;
@@ -551,11 +552,11 @@ MD2_HD void stage_b(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
       float ss = 0.f, l1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        ss += ssim_window(V[f][c][0], V[f][c][1], V[f][c][2], VY[c][0], VY[c][1], nullptr);
+        if (!C::NOSSIM) ss += ssim_window(V[f][c][0], V[f][c][1], V[f][c][2], VY[c][0], VY[c][1], nullptr);
         l1 += fabsf(L.tg1[c] - L.pr1[f][c]);
       }
-      // trainer.py:403: 0.85 * ssim.mean(1) + 0.15 * l1.mean(1)
-      rl[f] = fmaf(0.85f / 3.0f, ss, (0.15f / 3.0f) * l1);
+      // trainer.py:403: 0.85 * ssim.mean(1) + 0.15 * l1.mean(1)   (--no_ssim: l1.mean(1), :399-400)
+      rl[f] = C::NOSSIM ? l1 * (1.0f / 3.0f) : fmaf(0.85f / 3.0f, ss, (0.15f / 3.0f) * l1);
     }
     // candidates in the order of trainer.py:471: identity first, then reprojection
     float best = INFINITY;
@@ -588,7 +589,7 @@ MD2_HD void stage_b(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
       L.loss += best;
       if (C::AUTOMASK && J.idsel) J.idsel[yw * J.W + L.xi] = (tag >= 0) ? 1.0f : 0.0f;
     }
-    if (C::GRAD && tag >= 0) {
+    if (C::GRAD && !C::NOSSIM && tag >= 0) {
       if (C::AVG) {
 #pragma unroll
         for (int f = 0; f < C::NSRC; ++f)
@@ -696,10 +697,11 @@ MD2_HD void stage_c(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
         const float Bq = fmaf(wu, B2v[f][c * 3 + 1], fmaf(wd, B0[f][c * 3 + 1], B1v[f][c * 3 + 1]));
         const float G = fmaf(wu, B2v[f][c * 3 + 2], fmaf(wd, B0[f][c * 3 + 2], B1v[f][c * 3 + 2]));
         // d loss / d pred_c = 0.85/3 * SSIM part + 0.15/3 * sign(x - y) [if this source won here]
-        float g = (0.85f / 3.0f) * fmaf(xj, Bq, fmaf(tg[c], G, A));
+        float g = C::NOSSIM ? 0.0f : (0.85f / 3.0f) * fmaf(xj, Bq, fmaf(tg[c], G, A));
         if (won) {
+          const float kl1 = C::NOSSIM ? (1.0f / 3.0f) : (0.15f / 3.0f);
           const float df = xj - tg[c];
-          g += (df > 0.f) ? (0.15f / 3.0f) : ((df < 0.f) ? -(0.15f / 3.0f) : 0.0f);
+          g += (df > 0.f) ? kl1 : ((df < 0.f) ? -kl1 : 0.0f);
         }
         d0 = fmaf(g, dxs[c], d0);
         d1 = fmaf(g, dys[c], d1);
@@ -816,7 +818,7 @@ MD2_HD void id_stage_a(IdLane<NSRC>& L, const Params& P, int b, int t, int lane,
   }
 }
 
-template <int NSRC>
+template <int NSRC, bool NOSSIM = false>
 MD2_HD void id_stage_b(IdLane<NSRC>& L, const Params& P, int b, int t, int lane, int y0, int y1,
                        const IdXchg<NSRC>& lf, const IdXchg<NSRC>& rt) {
   const int yw = t - 1;
@@ -847,11 +849,11 @@ MD2_HD void id_stage_b(IdLane<NSRC>& L, const Params& P, int b, int t, int lane,
         float vx[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) vx[k] = L.H2[f][c][k] + L.H1[f][c][k] + H0[f][c][k];
-        ss += ssim_window(vx[0], vx[1], vx[2], vy0, vy1, nullptr);
+        if (!NOSSIM) ss += ssim_window(vx[0], vx[1], vx[2], vy0, vy1, nullptr);
         l1 += fabsf(L.tg1[c] - L.pr1[f][c]);
       }
       P.idloss[((size_t)b * NSRC + f) * plane + (size_t)yw * P.W + L.xi] =
-          fmaf(0.85f / 3.0f, ss, (0.15f / 3.0f) * l1);
+          NOSSIM ? l1 * (1.0f / 3.0f) : fmaf(0.85f / 3.0f, ss, (0.15f / 3.0f) * l1);
     }
   }
 #pragma unroll

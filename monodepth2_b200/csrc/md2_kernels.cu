@@ -69,7 +69,7 @@ __global__ void md2_disp_mean(Params P) {
 }
 
 // ------------------------------------------------------------------ 3. identity losses
-template <int NSRC>
+template <int NSRC, bool NOSSIM>
 __global__ void __launch_bounds__(kThreads) md2_identity(Params P) {
   const int lane = threadIdx.x & 31;
   const int job = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(kThreads) md2_identity(Params P) {
         rt.pr[f][c] = __shfl_down_sync(kFull, L.pr[f][c], 1);
       }
     }
-    id_stage_b(L, P, b, t, lane, y0, y1, lf, rt);
+    id_stage_b<NSRC, NOSSIM>(L, P, b, t, lane, y0, y1, lf, rt);
   }
 }
 
@@ -146,8 +146,8 @@ __device__ __forceinline__ void exchange_and_stage_c(Lane<C>& L, const Params& P
   for (int n = 0; n < C::NCS; ++n)
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      l2.coef[n][k] = __shfl_up_sync(kFull, L.coef[n][k], 1);
-      r2.coef[n][k] = __shfl_down_sync(kFull, L.coef[n][k], 1);
+      l2.coef[n][k] = C::NOSSIM ? 0.f : __shfl_up_sync(kFull, L.coef[n][k], 1);
+      r2.coef[n][k] = C::NOSSIM ? 0.f : __shfl_down_sync(kFull, L.coef[n][k], 1);
     }
   stage_c(L, P, J, t, lane, l2, r2, st);
 }
@@ -280,19 +280,28 @@ static cudaError_t launch_march(const Params& P, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-template <int NSRC>
+template <int NSRC, bool NOSSIM>
 static cudaError_t launch_march_n(const Params& P, cudaStream_t stream) {
   const int key = (P.avg ? 4 : 0) | (P.automask ? 2 : 0) | (P.want_grad ? 1 : 0);
   switch (key) {
-    case 0: return launch_march<Cfg<NSRC, false, false, false>>(P, stream);
-    case 1: return launch_march<Cfg<NSRC, false, false, true>>(P, stream);
-    case 2: return launch_march<Cfg<NSRC, false, true, false>>(P, stream);
-    case 3: return launch_march<Cfg<NSRC, false, true, true>>(P, stream);
-    case 4: return launch_march<Cfg<NSRC, true, false, false>>(P, stream);
-    case 5: return launch_march<Cfg<NSRC, true, false, true>>(P, stream);
-    case 6: return launch_march<Cfg<NSRC, true, true, false>>(P, stream);
-    default: return launch_march<Cfg<NSRC, true, true, true>>(P, stream);
+    case 0: return launch_march<Cfg<NSRC, false, false, false, NOSSIM>>(P, stream);
+    case 1: return launch_march<Cfg<NSRC, false, false, true, NOSSIM>>(P, stream);
+    case 2: return launch_march<Cfg<NSRC, false, true, false, NOSSIM>>(P, stream);
+    case 3: return launch_march<Cfg<NSRC, false, true, true, NOSSIM>>(P, stream);
+    case 4: return launch_march<Cfg<NSRC, true, false, false, NOSSIM>>(P, stream);
+    case 5: return launch_march<Cfg<NSRC, true, false, true, NOSSIM>>(P, stream);
+    case 6: return launch_march<Cfg<NSRC, true, true, false, NOSSIM>>(P, stream);
+    default: return launch_march<Cfg<NSRC, true, true, true, NOSSIM>>(P, stream);
   }
+}
+template <int NSRC>
+static cudaError_t launch_march_ns(const Params& P, cudaStream_t stream) {
+  return P.no_ssim ? launch_march_n<NSRC, true>(P, stream) : launch_march_n<NSRC, false>(P, stream);
+}
+template <int NSRC>
+static void launch_identity_ns(const Params& P, int grid, cudaStream_t stream) {
+  if (P.no_ssim) md2_identity<NSRC, true><<<grid, kThreads, 0, stream>>>(P);
+  else md2_identity<NSRC, false><<<grid, kThreads, 0, stream>>>(P);
 }
 
 // optional CUDA events recorded around the marching kernel (bench.py roofline leg)
@@ -364,9 +373,9 @@ cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
     const int jobs = P.B * P.nseg * P.nband_id;
     const int grid = (jobs + kWarpsPerCta - 1) / kWarpsPerCta;
     switch (P.nsrc) {
-      case 1: md2_identity<1><<<grid, kThreads, 0, stream>>>(P); break;
-      case 2: md2_identity<2><<<grid, kThreads, 0, stream>>>(P); break;
-      default: md2_identity<3><<<grid, kThreads, 0, stream>>>(P); break;
+      case 1: launch_identity_ns<1>(P, grid, stream); break;
+      case 2: launch_identity_ns<2>(P, grid, stream); break;
+      default: launch_identity_ns<3>(P, grid, stream); break;
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   } else {
@@ -378,9 +387,9 @@ cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
   if ((e = cudaStreamWaitEvent(stream, side->join, 0)) != cudaSuccess) return e;
   if (g_prof_on) cudaEventRecord(g_prof_ev[0], stream);
   switch (P.nsrc) {
-    case 1: e = launch_march_n<1>(P, stream); break;
-    case 2: e = launch_march_n<2>(P, stream); break;
-    default: e = launch_march_n<3>(P, stream); break;
+    case 1: e = launch_march_ns<1>(P, stream); break;
+    case 2: e = launch_march_ns<2>(P, stream); break;
+    default: e = launch_march_ns<3>(P, stream); break;
   }
   if (e != cudaSuccess) return e;
   if (g_prof_on) cudaEventRecord(g_prof_ev[1], stream);

@@ -76,6 +76,7 @@ inline int fill_params(const md2_problem* p, const md2_tensors* t, void* workspa
   P->nid = P->automask ? (P->avg ? 1 : P->nsrc) : 0;
   P->align_corners = p->align_corners ? 1 : 0;
   P->want_grad = p->want_grad ? 1 : 0;
+  P->no_ssim = p->no_ssim ? 1 : 0;
   // layers.py:21-23: min_disp = 1/max_depth, max_disp = 1/min_depth (python doubles -> fp32 scalars)
   const double lo = 1.0 / (double)p->max_depth, hi = 1.0 / (double)p->min_depth;
   P->a_disp = (float)lo;

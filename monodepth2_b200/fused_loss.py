@@ -36,7 +36,7 @@ class LossPlan:
                  scales: Sequence[int] = (0, 1, 2, 3), min_depth: float = 0.1, max_depth: float = 100.0,
                  disparity_smoothness: float = 1e-3, avg_reprojection: bool = False,
                  disable_automasking: bool = False, align_corners: bool = False,
-                 rows_per_segment: int = 0):
+                 rows_per_segment: int = 0, no_ssim: bool = False, v1_multiscale: bool = False):
         if list(scales) != list(range(len(scales))):
             raise RuntimeError("scales must be 0..n-1, got %s" % (list(scales),))
         self.batch_size, self.height, self.width = int(batch_size), int(height), int(width)
@@ -49,22 +49,33 @@ class LossPlan:
         self.automask = not bool(disable_automasking)
         self.align_corners = bool(align_corners)
         self.rows_per_segment = int(rows_per_segment)
+        self.no_ssim = bool(no_ssim)
+        self.v1_multiscale = bool(v1_multiscale)
         self.n_src = len(self.src_ids)
         self.n_id = 0 if not self.automask else (1 if self.avg_reprojection else self.n_src)
         self.lib = _capi.load_library()
         self._workspace: Dict = {}
+        # --v1_multiscale (trainer.py:347-352,417-420): every scale is an independent single-scale
+        # problem at its own resolution, with its own K / inv_K / colour pyramid level
+        self._scale_plans = None
+        if self.v1_multiscale:
+            self._scale_plans = [
+                LossPlan(self.batch_size, self.height >> s, self.width >> s, self.frame_ids, [0], self.min_depth,
+                         self.max_depth, self.disparity_smoothness / (2 ** s), self.avg_reprojection,
+                         not self.automask, self.align_corners, self.rows_per_segment, self.no_ssim, False)
+                for s in self.scales]
 
     @classmethod
     def from_opt(cls, opt, **kw) -> "LossPlan":
         """Build from a reference ``options.py`` namespace (after trainer.py:51-52 appended "s")."""
-        for flag in ("v1_multiscale", "predictive_mask", "no_ssim"):
-            if getattr(opt, flag, False):
-                raise RuntimeError("--%s is not supported by the fused loss yet" % flag)
+        if getattr(opt, "predictive_mask", False):
+            raise RuntimeError("--predictive_mask is not supported by the fused loss yet")
         if getattr(opt, "pose_model_type", "separate_resnet") == "posecnn":
             raise RuntimeError("--pose_model_type posecnn is not supported by the fused loss yet")
         return cls(opt.batch_size, opt.height, opt.width, opt.frame_ids, opt.scales, opt.min_depth,
                    opt.max_depth, opt.disparity_smoothness, opt.avg_reprojection,
-                   opt.disable_automasking, **kw)
+                   opt.disable_automasking, no_ssim=getattr(opt, "no_ssim", False),
+                   v1_multiscale=getattr(opt, "v1_multiscale", False), **kw)
 
     def problem(self, want_grad: bool) -> Md2Problem:
         return Md2Problem(batch=self.batch_size, height=self.height, width=self.width,
@@ -72,7 +83,7 @@ class LossPlan:
                           avg_reprojection=int(self.avg_reprojection), align_corners=int(self.align_corners),
                           min_depth=self.min_depth, max_depth=self.max_depth,
                           disparity_smoothness=self.disparity_smoothness, want_grad=int(want_grad),
-                          rows_per_segment=self.rows_per_segment)
+                          rows_per_segment=self.rows_per_segment, no_ssim=int(self.no_ssim))
 
     def workspace(self, device: torch.device) -> torch.Tensor:
         key = (device.type, device.index)
@@ -190,6 +201,8 @@ def view_synthesis_loss(plan: LossPlan, inputs: Dict, outputs: Dict,
     ``side`` selects optional outputs: {"depth_scales": [...], "color_scales": [...], "mask_scales": [...]};
     the produced tensors are stored both in ``side`` and in ``outputs`` under the reference's keys.
     """
+    if plan.v1_multiscale:
+        return _view_synthesis_loss_v1_multiscale(plan, inputs, outputs, noise, side)
     S = len(plan.scales)
     target = inputs[("color", 0, 0)]
     dev = target.device
@@ -218,6 +231,44 @@ def view_synthesis_loss(plan: LossPlan, inputs: Dict, outputs: Dict,
         for k, v in side.items():
             if isinstance(k, tuple) and k[0] in ("depth", "color") or (isinstance(k, str) and k.startswith("identity_selection/")):
                 outputs[k] = v
+    return losses
+
+
+def _view_synthesis_loss_v1_multiscale(plan: LossPlan, inputs: Dict, outputs: Dict, noise, side):
+    """--v1_multiscale: one single-scale fused call per pyramid level (source_scale = scale)."""
+    losses: Dict[str, torch.Tensor] = {}
+    total = 0
+    for i, s in enumerate(plan.scales):
+        sp = plan._scale_plans[i]
+        ins = {("K", 0): inputs[("K", s)], ("inv_K", 0): inputs[("inv_K", s)]}
+        if "stereo_T" in inputs:
+            ins["stereo_T"] = inputs["stereo_T"]
+        for f in plan.frame_ids:
+            ins[("color", f, 0)] = inputs[("color", f, s)]
+        outs = {("disp", 0): outputs[("disp", s)]}
+        for f in plan.src_ids:
+            if f != "s":
+                outs[("cam_T_cam", 0, f)] = outputs[("cam_T_cam", 0, f)]
+        sub_side = None
+        if side is not None:
+            sub_side = {k: ([0] if s in side.get(k, []) else []) for k in
+                        ("depth_scales", "color_scales", "mask_scales", "grad_updisp_scales")}
+        ls = view_synthesis_loss(sp, ins, outs, [noise[i]] if noise is not None else None, sub_side)
+        losses["loss/{}".format(s)] = ls["loss"]
+        total = total + ls["loss"]
+        if sub_side is not None:
+            for k, v in sub_side.items():
+                if isinstance(k, tuple):
+                    key = (k[0], k[1], s) if len(k) == 3 else (k[0], s)
+                    if k[0] == "grad_updisp":          # test hook: gradient of the averaged total loss
+                        v = v / len(plan.scales)
+                    side[key] = v
+                    if k[0] in ("depth", "color"):
+                        outputs[key] = v
+                elif isinstance(k, str) and k.startswith("identity_selection/"):
+                    side["identity_selection/{}".format(s)] = v
+                    outputs["identity_selection/{}".format(s)] = v
+    losses["loss"] = total / len(plan.scales)
     return losses
 
 

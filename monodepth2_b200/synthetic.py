@@ -78,7 +78,7 @@ def _box_blur(x: torch.Tensor, k: int) -> torch.Tensor:
 def make_batch(batch: int = 12, height: int = 192, width: int = 640,
                frame_ids: Sequence = (0, -1, 1), num_scales: int = 4, seed: int = 0,
                kind: str = "iid", jitter_K: bool = False,
-               noise_seed: int = 99, n_id: int = None):
+               noise_seed: int = 99, n_id: int = None, all_scale_K: bool = False, multiscale_noise: bool = False):
     """Returns ``(inputs, outputs, pose, noise)`` on the CPU in fp32.
 
     inputs : {("color", f, s)}, ("K", 0), ("inv_K", 0), "stereo_T"
@@ -118,6 +118,14 @@ def make_batch(batch: int = 12, height: int = 192, width: int = 640,
     K, inv_K = intrinsics(B, H, W, g, jitter_K)
     inputs[("K", 0)] = K
     inputs[("inv_K", 0)] = inv_K
+    if all_scale_K:      # mono_dataset.py:164-173: one K / inv_K per pyramid level (for --v1_multiscale)
+        for s in range(1, num_scales):
+            Ks = K.clone()
+            Ks[:, 0, :] /= 2 ** s
+            Ks[:, 1, :] /= 2 ** s
+            inputs[("K", s)] = Ks
+            inputs[("inv_K", s)] = torch.from_numpy(
+                np.stack([np.linalg.pinv(k.numpy()).astype(np.float32) for k in Ks]))
     stereo_T = torch.eye(4).repeat(B, 1, 1)
     stereo_T[:, 0, 3] = 0.1
     inputs["stereo_T"] = stereo_T
@@ -135,5 +143,7 @@ def make_batch(batch: int = 12, height: int = 192, width: int = 640,
     if n_id is None:
         n_id = n_src
     gn = torch.Generator().manual_seed(noise_seed)
-    noise: List[torch.Tensor] = [torch.randn(B, n_id, H, W, generator=gn) for _ in range(num_scales)]
+    noise: List[torch.Tensor] = [torch.randn(B, n_id, H >> (s if multiscale_noise else 0),
+                                             W >> (s if multiscale_noise else 0), generator=gn)
+                                 for s in range(num_scales)]
     return inputs, outputs, pose, noise

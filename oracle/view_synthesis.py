@@ -51,6 +51,7 @@ class OracleConfig:
     avg_reprojection: bool = False
     disable_automasking: bool = False
     no_ssim: bool = False
+    v1_multiscale: bool = False               # trainer.py:347-352,417-420: source_scale = scale
     # trainer.py:384-387 leaves align_corners unspecified -> False on torch >= 1.3.
     align_corners: bool = False
     ssim_c1: float = 0.01 ** 2
@@ -161,20 +162,25 @@ def smooth_loss(disp, img):
 
 
 def generate_images_pred(inputs: Dict, outputs: Dict, cfg: OracleConfig) -> None:
-    """trainer.py:341-391 (source_scale = 0 branch; --v1_multiscale / posecnn not covered)."""
+    """trainer.py:341-391 (both source_scale branches; the posecnn translation rescale is not covered)."""
     H, W = cfg.height, cfg.width
     for s in cfg.scales:
         disp = outputs[("disp", s)]
-        disp = F.interpolate(disp, [H, W], mode="bilinear", align_corners=False)
+        if cfg.v1_multiscale:
+            src_scale = s
+        else:
+            disp = F.interpolate(disp, [H, W], mode="bilinear", align_corners=False)
+            src_scale = 0
+        hs, ws = H >> src_scale, W >> src_scale
         _, depth = disp_to_depth(disp, cfg.min_depth, cfg.max_depth)
         outputs[("depth", 0, s)] = depth
         for f in cfg.frame_ids[1:]:
             T = inputs["stereo_T"] if f == "s" else outputs[("cam_T_cam", 0, f)]
-            pts = backproject(depth, inputs[("inv_K", 0)])
-            grid = project(pts, inputs[("K", 0)], T, H, W, cfg.eps)
+            pts = backproject(depth, inputs[("inv_K", src_scale)])
+            grid = project(pts, inputs[("K", src_scale)], T, hs, ws, cfg.eps)
             outputs[("sample", f, s)] = grid
             outputs[("color", f, s)] = F.grid_sample(
-                inputs[("color", f, 0)], grid, mode="bilinear", padding_mode="border",
+                inputs[("color", f, src_scale)], grid, mode="bilinear", padding_mode="border",
                 align_corners=cfg.align_corners)
 
 
@@ -185,15 +191,16 @@ def compute_losses(inputs: Dict, outputs: Dict, cfg: OracleConfig,
     losses: Dict[str, torch.Tensor] = {}
     total = 0
     srcs = list(cfg.frame_ids[1:])
-    target = inputs[("color", 0, 0)]
     for i, s in enumerate(cfg.scales):
+        src_scale = s if cfg.v1_multiscale else 0
+        target = inputs[("color", 0, src_scale)]
         disp = outputs[("disp", s)]
         color = inputs[("color", 0, s)]
         reproj = torch.cat([reprojection_loss(outputs[("color", f, s)], target, cfg) for f in srcs], 1)
         if cfg.avg_reprojection:
             reproj = reproj.mean(1, keepdim=True)
         if not cfg.disable_automasking:
-            ident = torch.cat([reprojection_loss(inputs[("color", f, 0)], target, cfg) for f in srcs], 1)
+            ident = torch.cat([reprojection_loss(inputs[("color", f, src_scale)], target, cfg) for f in srcs], 1)
             if cfg.avg_reprojection:
                 ident = ident.mean(1, keepdim=True)
             z = noise[i] if noise is not None else torch.randn(ident.shape, dtype=ident.dtype,

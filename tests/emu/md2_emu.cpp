@@ -16,8 +16,8 @@
 
 using namespace md2;
 
-template <int NSRC>
-static void emu_identity(const Params& P) {
+template <int NSRC, bool NOSSIM>
+static void emu_identity_t(const Params& P) {
   for (int b = 0; b < P.B; ++b)
     for (int seg = 0; seg < P.nseg; ++seg)
       for (int band = 0; band < P.nband_id; ++band) {
@@ -32,9 +32,14 @@ static void emu_identity(const Params& P) {
             memcpy(X[l + 1].pr, L[l].pr, sizeof(L[l].pr));
             memcpy(X[l + 1].tg, L[l].tg, sizeof(L[l].tg));
           }
-          for (int l = 0; l < 32; ++l) id_stage_b(L[l], P, b, t, l, y0, y1, X[l], X[l + 2]);
+          for (int l = 0; l < 32; ++l) id_stage_b<NSRC, NOSSIM>(L[l], P, b, t, l, y0, y1, X[l], X[l + 2]);
         }
       }
+}
+
+template <int NSRC>
+static void emu_identity(const Params& P) {
+  if (P.no_ssim) emu_identity_t<NSRC, true>(P); else emu_identity_t<NSRC, false>(P);
 }
 
 template <class C>
@@ -97,19 +102,23 @@ static void emu_march(const Params& P) {
         }
 }
 
-template <int NSRC>
-static void emu_march_n(const Params& P) {
+template <int NSRC, bool NOSSIM>
+static void emu_march_k(const Params& P) {
   const int key = (P.avg ? 4 : 0) | (P.automask ? 2 : 0) | (P.want_grad ? 1 : 0);
   switch (key) {
-    case 0: emu_march<Cfg<NSRC, false, false, false>>(P); break;
-    case 1: emu_march<Cfg<NSRC, false, false, true>>(P); break;
-    case 2: emu_march<Cfg<NSRC, false, true, false>>(P); break;
-    case 3: emu_march<Cfg<NSRC, false, true, true>>(P); break;
-    case 4: emu_march<Cfg<NSRC, true, false, false>>(P); break;
-    case 5: emu_march<Cfg<NSRC, true, false, true>>(P); break;
-    case 6: emu_march<Cfg<NSRC, true, true, false>>(P); break;
-    default: emu_march<Cfg<NSRC, true, true, true>>(P); break;
+    case 0: emu_march<Cfg<NSRC, false, false, false, NOSSIM>>(P); break;
+    case 1: emu_march<Cfg<NSRC, false, false, true, NOSSIM>>(P); break;
+    case 2: emu_march<Cfg<NSRC, false, true, false, NOSSIM>>(P); break;
+    case 3: emu_march<Cfg<NSRC, false, true, true, NOSSIM>>(P); break;
+    case 4: emu_march<Cfg<NSRC, true, false, false, NOSSIM>>(P); break;
+    case 5: emu_march<Cfg<NSRC, true, false, true, NOSSIM>>(P); break;
+    case 6: emu_march<Cfg<NSRC, true, true, false, NOSSIM>>(P); break;
+    default: emu_march<Cfg<NSRC, true, true, true, NOSSIM>>(P); break;
   }
+}
+template <int NSRC>
+static void emu_march_n(const Params& P) {
+  if (P.no_ssim) emu_march_k<NSRC, true>(P); else emu_march_k<NSRC, false>(P);
 }
 
 extern "C" int md2_emu_workspace_bytes(const md2_problem* p, size_t* bytes) {

@@ -43,7 +43,8 @@ def run_emu(g, want_grad=True, rows_per_segment=0, align_corners=False, side_out
     p = Md2Problem(batch=B, height=H, width=W, num_scales=4, num_src=len(srcs),
                    automask=int(not g.disable_automasking), avg_reprojection=int(g.avg_reprojection),
                    align_corners=int(align_corners), min_depth=0.1, max_depth=100.0,
-                   disparity_smoothness=1e-3, want_grad=int(want_grad), rows_per_segment=rows_per_segment)
+                   disparity_smoothness=1e-3, want_grad=int(want_grad), rows_per_segment=rows_per_segment,
+                   no_ssim=int(g.no_ssim))
     keep = []
 
     def arr(a):

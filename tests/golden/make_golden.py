@@ -41,6 +41,9 @@ CASES = {
                              flags=["--avg_reprojection"]),
     "disable_automasking": dict(B=2, H=48, W=80, frame_ids=[0, -1, 1], kind="structured", seed=4,
                                 flags=["--disable_automasking"]),
+    "no_ssim": dict(B=2, H=48, W=80, frame_ids=[0, -1, 1], kind="structured", seed=8, flags=["--no_ssim"]),
+    "v1_multiscale": dict(B=2, H=64, W=96, frame_ids=[0, -1, 1], kind="structured", seed=9,
+                          flags=["--v1_multiscale"]),
     "stereo_only": dict(B=2, H=32, W=64, frame_ids=[0], kind="structured", seed=7,
                         flags=["--use_stereo", "--frame_ids", "0"]),
 }
@@ -99,8 +102,10 @@ def run_reference(T, MonodepthOptions, case, dtype=torch.float32, batch=None):
     n_src = len(frame_ids) - 1
     n_id = 0 if opt.disable_automasking else (1 if opt.avg_reprojection else n_src)
     if batch is None:
+        ms = bool(opt.v1_multiscale)
         batch = make_batch(case["B"], case["H"], case["W"], frame_ids, 4, case["seed"], case["kind"],
-                           jitter_K=case.get("jitter", False), n_id=max(n_id, 1))
+                           jitter_K=case.get("jitter", False), n_id=max(n_id, 1), all_scale_K=ms,
+                           multiscale_noise=ms)
     inputs, outputs, pose, noise = batch
     inputs = {k: v.to(dtype) for k, v in inputs.items()}
     leaves = {}
@@ -144,7 +149,8 @@ def pack(res):
     fids = res["frame_ids"]
     d["frame_ids"] = np.array([str(f) for f in fids])
     opt = res["opt"]
-    d["flags"] = np.array([int(opt.avg_reprojection), int(opt.disable_automasking), int(opt.no_ssim)])
+    d["flags"] = np.array([int(opt.avg_reprojection), int(opt.disable_automasking), int(opt.no_ssim),
+                           int(opt.v1_multiscale)])
     for k, v in res["inputs"].items():
         name = "in__" + "__".join(str(x) for x in (k if isinstance(k, tuple) else (k,)))
         d[name] = v.detach().numpy()

@@ -7,7 +7,7 @@ from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
 def run_cuda(g, rows_per_segment=0, align_corners=False, want_grad=True, side_all=True, dev="cuda:0"):
     plan = LossPlan(g.B, g.H, g.W, g.frame_ids, avg_reprojection=g.avg_reprojection,
                     disable_automasking=g.disable_automasking, align_corners=align_corners,
-                    rows_per_segment=rows_per_segment)
+                    rows_per_segment=rows_per_segment, no_ssim=g.no_ssim, v1_multiscale=g.v1_multiscale)
     inputs = {k: v.to(dev) for k, v in g.inputs().items()}
     outs, leaves = {}, {}
     for s in range(4):

@@ -27,8 +27,8 @@ class Golden:
         z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
         self.z = z
         self.frame_ids = [_fid(str(s)) for s in z["frame_ids"]]
-        fl = z["flags"]
-        self.avg_reprojection, self.disable_automasking, self.no_ssim = (bool(int(x)) for x in fl)
+        fl = [bool(int(x)) for x in z["flags"]] + [False]
+        self.avg_reprojection, self.disable_automasking, self.no_ssim, self.v1_multiscale = fl[:4]
         self.B, _, self.H, self.W = z["in__color__0__0"].shape
         self.n_src = len(self.frame_ids) - 1
         self.n_id = 0 if self.disable_automasking else (1 if self.avg_reprojection else self.n_src)
@@ -36,7 +36,8 @@ class Golden:
     def cfg(self, **kw):
         return O.OracleConfig(height=self.H, width=self.W, frame_ids=tuple(self.frame_ids),
                               avg_reprojection=self.avg_reprojection,
-                              disable_automasking=self.disable_automasking, no_ssim=self.no_ssim, **kw)
+                              disable_automasking=self.disable_automasking, no_ssim=self.no_ssim,
+                              v1_multiscale=self.v1_multiscale, **kw)
 
     def t(self, key, dtype=torch.float32):
         return torch.from_numpy(np.asarray(self.z[key])).to(dtype)

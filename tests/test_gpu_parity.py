@@ -39,8 +39,10 @@ def test_cuda_matches_reference_golden(name, rows):
     a, c = 0.01, 9.99
     for s in range(4):
         gd = r["side"][("grad_updisp", s)].cpu().numpy()
-        depth = 1.0 / (a + c * torch.nn.functional.interpolate(
-            g.t("disp__%d" % s), [g.H, g.W], mode="bilinear", align_corners=False).numpy())
+        d_s = g.t("disp__%d" % s)
+        if not g.v1_multiscale:
+            d_s = torch.nn.functional.interpolate(d_s, [g.H, g.W], mode="bilinear", align_corners=False)
+        depth = 1.0 / (a + c * d_s.numpy())
         ref = z["grad_depth__%d" % s] * (-c * depth * depth)       # d loss / d upsampled disp
         assert frac_within(gd, ref, P2_TOL) >= 0.995, (name, s)    # small fixture: a few flips weigh more
     # aggregated gradients: relL2 bounded (flips allowed, see test_full_size for the P3 protocol)
