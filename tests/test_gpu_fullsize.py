@@ -158,3 +158,46 @@ def test_other_baseline_configs_loss_parity(wl):
     for f in fids[1:]:
         if f != "s":
             assert rel_l2(outs[("cam_T_cam", 0, f)].grad.cpu(), g32[("T", f)].grad) < 5e-2
+
+
+@pytest.mark.parametrize("shape", [(1, 40, 72), (3, 64, 200), (2, 32, 32)])
+def test_odd_shapes_and_align_corners_true(shape):
+    """Protocol P6 (align_corners=True, the torch-0.4.1 behaviour the reference was written for) and
+    widths that are not multiples of the 28-column band / 48-row segment, against the live oracle."""
+    from monodepth2_b200.synthetic import make_batch
+    from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
+    B, H, W = shape
+    fids = [0, -1, 1]
+    batch = make_batch(B, H, W, fids, 4, 31, "structured")
+    inputs, outputs, pose, noise = batch
+    for ac in (False, True):
+        l32, o32, g32 = _oracle(batch, fids, torch.float32, align_corners=ac)
+        plan = LossPlan(B, H, W, fids, align_corners=ac)
+        ins = {k: v.to(DEV) for k, v in inputs.items()}
+        outs = {k: v.to(DEV).requires_grad_(True) for k, v in outputs.items()}
+        lk = view_synthesis_loss(plan, ins, outs, [n.to(DEV) for n in noise])
+        lk["loss"].backward()
+        for key in ["loss"] + ["loss/%d" % s for s in range(4)]:
+            ref = float(l32[key].detach())
+            assert abs(float(lk[key].detach()) - ref) <= 1e-5 * abs(ref), (key, ac)
+        for s in range(4):
+            assert rel_l2(outs[("disp", s)].grad.cpu(), g32[("disp", s)].grad) < 0.25, (s, ac)   # tiny images: one flip weighs a lot
+
+
+def test_bad_arguments_raise():
+    from monodepth2_b200.synthetic import make_batch
+    from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
+    fids = [0, -1, 1]
+    inputs, outputs, pose, noise = make_batch(2, 32, 64, fids, 4, 1, "iid")
+    plan = LossPlan(2, 32, 64, fids)
+    ins = {k: v.to(DEV) for k, v in inputs.items()}
+    outs = {k: v.to(DEV) for k, v in outputs.items()}
+    bad = dict(outs)
+    bad[("disp", 1)] = outs[("disp", 1)][:, :, :-1]                       # wrong shape
+    with pytest.raises(RuntimeError):
+        view_synthesis_loss(plan, ins, bad, [n.to(DEV) for n in noise])
+    with pytest.raises(RuntimeError):                                     # CPU tensor: no fallback
+        view_synthesis_loss(plan, dict(inputs), dict(outputs), noise)
+    with pytest.raises(RuntimeError):                                     # height not divisible by 8
+        p2 = LossPlan(2, 36, 64, fids)
+        p2.workspace(torch.device(DEV))
