@@ -306,7 +306,11 @@ def run_own(args, wl):
     pinned = []
     for b in host[:2]:
         inputs, outputs, pose, noise = b
-        pin_in = {k: v.pin_memory() for k, v in inputs.items()}
+        # exactly the tensors the path reads: source and target frames at scale 0,
+        # the target pyramid for the smoothness term, K / inv_K / stereo_T; disparities and poses
+        need = [("color", f, 0) for f in frame_ids] + [("color", 0, s) for s in range(1, 4)] + \
+               [("K", 0), ("inv_K", 0)] + (["stereo_T"] if "s" in frame_ids else [])
+        pin_in = {k: inputs[k].pin_memory() for k in need}
         pin_out = {k: v.pin_memory() for k, v in outputs.items()}
         pinned.append((pin_in, pin_out))
     h2d = sum(v.numel() * 4 for v in pinned[0][0].values()) + sum(v.numel() * 4 for v in pinned[0][1].values())
