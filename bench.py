@@ -382,7 +382,7 @@ def run_own(args, wl):
             "config": {"workload": wl, "batch_per_gpu": BATCH, "frame_ids": [str(f) for f in frame_ids],
                        "scales": 4, "l2": "inputs larger than L2: %d rotating batches of ~%d MB each" %
                        (nrot, int((h2d + n_id * BATCH * H * W * 4 * 4) / 1e6)),
-                       "rows_per_segment": plan.problem(True).rows_per_segment or 48, "loss": loss_val},
+                       "rows_per_segment": plan.problem(True).rows_per_segment or max(32, (H + 3) // 4), "loss": loss_val},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": 6 * args.steps,
             "clocks": clocks,

@@ -172,15 +172,19 @@ __global__ void MD2_MARCH_BOUNDS md2_march(Params P) {
   // warp-uniform (uniform registers / uniform datapath for the address arithmetic)
   const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
   const int job = blockIdx.x * kWarpsPerCta + warp;
-  const int per_scale = P.B * P.nseg * P.nband;
-  if (job >= per_scale * P.S) return;
-  const int js = job / per_scale;
-  const int r = job - js * per_scale;
-  const int jb = r / (P.nseg * P.nband);
-  const int r2 = r - jb * (P.nseg * P.nband);
-  const int seg = r2 / P.nband;
+  // Job order: sample-major, then row segment, then scale, then band.  The four scales of one
+  // image region read the same target / source rows, so running them close together in time keeps
+  // those rows in L1/L2 (scale-major order streamed every image four times).
+  const int per_seg = P.S * P.nband;
+  const int per_b = P.nseg * per_seg;
+  if (job >= per_b * P.B) return;
+  const int jb = job / per_b;
+  const int r = job - jb * per_b;
+  const int seg = r / per_seg;
+  const int r2 = r - seg * per_seg;
+  const int js = r2 / P.nband;
   const int jy0 = seg * P.seg_rows;
-  const WarpJob J = make_job(P, js, jb, (r2 - seg * P.nband) * kOwnCols, jy0, min(jy0 + P.seg_rows, P.H));
+  const WarpJob J = make_job(P, js, jb, (r2 - js * P.nband) * kOwnCols, jy0, min(jy0 + P.seg_rows, P.H));
 
   Stash st;
   st.base = smem + threadIdx.x;

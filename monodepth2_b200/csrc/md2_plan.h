@@ -59,7 +59,10 @@ inline Layout make_layout(const md2_problem* p) {
 }
 
 inline int default_seg_rows(const md2_problem* p) {
-  int r = p->rows_per_segment > 0 ? p->rows_per_segment : 48;
+  // default: a quarter of the image height (48 rows at 192, 80 at 320), measured optimum of the
+  // wave-quantisation vs halo-row trade-off on B200 (profiles/r01_optimization_log.md)
+  int r = p->rows_per_segment > 0 ? p->rows_per_segment : (p->height + 3) / 4;
+  if (r < 32) r = 32;
   if (r > p->height) r = p->height;
   return r;
 }
