@@ -92,6 +92,7 @@ struct Params {
   float gscale;              // 1/(S*B*H*W) [* 1/nsrc under avg_reprojection]
   float smooth_w[kMaxScales];  // disparity_smoothness / 2^s
   int seg_rows, nseg, nband, nband_id;
+  int id_rows, nseg_id;      // row segments of the (much lighter) identity pass
   const float* tgt;
   const float* src[kMaxSrc];
   const float* Tm[kMaxSrc];
@@ -772,6 +773,7 @@ struct IdLane {
   float HY1[3][2], HY2[3][2];
   float pr1[NSRC][3], tg1[3];
   float pr[NSRC][3], tg[3];
+  float npr[NSRC][3], ntg[3];     // next row, in flight
 };
 template <int NSRC>
 struct IdXchg {
@@ -797,24 +799,41 @@ MD2_HD void id_init(IdLane<NSRC>& L, const Params& P, int x0, int lane) {
   }
 }
 
-// Reads row t of the planar NCHW target / sources (at the reflected position) and, for the
-// pixels this lane owns, writes the RGBx texels the marching kernel gathers from: the
-// re-layout costs no extra pass over the images.
+// issue the planar loads of row t (target + sources, at the reflected position)
+template <int NSRC>
+MD2_HD void id_prefetch(IdLane<NSRC>& L, const Params& P, int b, int t) {
+  const int tr = reflect_clamp(t, P.H);
+  const int plane = P.H * P.W;
+  const int off = b * 3 * plane + tr * P.W + L.xi;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) L.ntg[c] = MD2_LD(P.tgt + off + c * plane);
+#pragma unroll
+  for (int f = 0; f < NSRC; ++f)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) L.npr[f][c] = MD2_LD(P.src[f] + off + c * plane);
+}
+
+// Consumes row t of the planar NCHW target / sources (prefetched one step earlier), puts row t+1 in
+// flight and, for the pixels this lane owns, writes the RGBx texels the marching kernel gathers
+// from: the re-layout costs no extra pass over the images.
 template <int NSRC>
 MD2_HD void id_stage_a(IdLane<NSRC>& L, const Params& P, int b, int t, int lane, int y0, int y1) {
   const int tr = reflect_clamp(t, P.H);
   const int plane = P.H * P.W;
-  const int off = b * 3 * plane + tr * P.W + L.xi;
   const bool own = L.colok && t >= y0 && t < y1 && lane >= 1 && lane <= kIdCols;
   const int o4 = 4 * (b * plane + tr * P.W + L.xi);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) L.tg[c] = MD2_LD(P.tgt + off + c * plane);
-  if (own) *reinterpret_cast<F4*>(P.tgt4 + o4) = make_f4(L.tg[0], L.tg[1], L.tg[2], 0.f);
+  for (int c = 0; c < 3; ++c) L.tg[c] = L.ntg[c];
 #pragma unroll
-  for (int f = 0; f < NSRC; ++f) {
+  for (int f = 0; f < NSRC; ++f)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) L.pr[f][c] = MD2_LD(P.src[f] + off + c * plane);
-    if (own) *reinterpret_cast<F4*>(P.src4[f] + o4) = make_f4(L.pr[f][0], L.pr[f][1], L.pr[f][2], 0.f);
+    for (int c = 0; c < 3; ++c) L.pr[f][c] = L.npr[f][c];
+  id_prefetch(L, P, b, t + 1);
+  if (own) {
+    *reinterpret_cast<F4*>(P.tgt4 + o4) = make_f4(L.tg[0], L.tg[1], L.tg[2], 0.f);
+#pragma unroll
+    for (int f = 0; f < NSRC; ++f)
+      *reinterpret_cast<F4*>(P.src4[f] + o4) = make_f4(L.pr[f][0], L.pr[f][1], L.pr[f][2], 0.f);
   }
 }
 

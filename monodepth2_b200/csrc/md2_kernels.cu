@@ -73,15 +73,16 @@ template <int NSRC, bool NOSSIM>
 __global__ void __launch_bounds__(kThreads) md2_identity(Params P) {
   const int lane = threadIdx.x & 31;
   const int job = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-  const int njobs = P.B * P.nseg * P.nband_id;
+  const int njobs = P.B * P.nseg_id * P.nband_id;
   if (job >= njobs) return;
   const int band = job % P.nband_id;
-  const int seg = (job / P.nband_id) % P.nseg;
-  const int b = job / (P.nband_id * P.nseg);
-  const int y0 = seg * P.seg_rows;
-  const int y1 = min(y0 + P.seg_rows, P.H);
+  const int seg = (job / P.nband_id) % P.nseg_id;
+  const int b = job / (P.nband_id * P.nseg_id);
+  const int y0 = seg * P.id_rows;
+  const int y1 = min(y0 + P.id_rows, P.H);
   IdLane<NSRC> L;
   id_init(L, P, band * kIdCols, lane);
+  id_prefetch(L, P, b, y0 - 1);
   for (int t = y0 - 1; t <= y1; ++t) {
     id_stage_a(L, P, b, t, lane, y0, y1);
     IdXchg<NSRC> lf, rt;
@@ -374,7 +375,7 @@ cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
   if ((e = cudaEventRecord(side->join, side->stream)) != cudaSuccess) return e;
   // ---- main stream: (identity + re-layout) or re-layout alone, then the marching kernel
   if (P.automask) {
-    const int jobs = P.B * P.nseg * P.nband_id;
+    const int jobs = P.B * P.nseg_id * P.nband_id;
     const int grid = (jobs + kWarpsPerCta - 1) / kWarpsPerCta;
     switch (P.nsrc) {
       case 1: launch_identity_ns<1>(P, grid, stream); break;

@@ -100,6 +100,9 @@ inline int fill_params(const md2_problem* p, const md2_tensors* t, void* workspa
   P->nseg = (p->height + P->seg_rows - 1) / P->seg_rows;
   P->nband = (p->width + kOwnCols - 1) / kOwnCols;
   P->nband_id = (p->width + kIdCols - 1) / kIdCols;
+  // the identity pass keeps ~110 registers per thread: short segments fill the SMs (4 CTAs each)
+  P->id_rows = p->height < 16 ? p->height : 16;
+  P->nseg_id = (p->height + P->id_rows - 1) / P->id_rows;
   if (!t->target || !t->K || !t->inv_K || !t->losses) return MD2_ERR_INVALID_ARGUMENT;
   P->tgt = t->target; P->K = t->K; P->invK = t->inv_K;
   for (int f = 0; f < p->num_src; ++f) {

@@ -19,11 +19,11 @@ using namespace md2;
 template <int NSRC, bool NOSSIM>
 static void emu_identity_t(const Params& P) {
   for (int b = 0; b < P.B; ++b)
-    for (int seg = 0; seg < P.nseg; ++seg)
+    for (int seg = 0; seg < P.nseg_id; ++seg)
       for (int band = 0; band < P.nband_id; ++band) {
-        const int y0 = seg * P.seg_rows, y1 = std::min(y0 + P.seg_rows, P.H);
+        const int y0 = seg * P.id_rows, y1 = std::min(y0 + P.id_rows, P.H);
         IdLane<NSRC> L[32];
-        for (int l = 0; l < 32; ++l) id_init(L[l], P, band * kIdCols, l);
+        for (int l = 0; l < 32; ++l) { id_init(L[l], P, band * kIdCols, l); id_prefetch(L[l], P, b, y0 - 1); }
         for (int t = y0 - 1; t <= y1; ++t) {
           for (int l = 0; l < 32; ++l) id_stage_a(L[l], P, b, t, l, y0, y1);
           IdXchg<NSRC> X[34];
