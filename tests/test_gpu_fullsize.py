@@ -201,3 +201,27 @@ def test_bad_arguments_raise():
     with pytest.raises(RuntimeError):                                     # height not divisible by 8
         p2 = LossPlan(2, 36, 64, fids)
         p2.workspace(torch.device(DEV))
+
+
+def test_cuda_graph_capture_replays_identically():
+    """The fused call (6 launches + the library's internal side stream) can be captured in a CUDA
+    graph on the caller's stream and replayed with the same results."""
+    from monodepth2_b200.synthetic import make_batch
+    from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
+    fids = [0, -1, 1]
+    inputs, outputs, pose, noise = make_batch(2, 64, 96, fids, 4, 3, "structured")
+    plan = LossPlan(2, 64, 96, fids)
+    ins = {k: v.to(DEV) for k, v in inputs.items()}
+    outs = {k: v.to(DEV).requires_grad_(True) for k, v in outputs.items()}
+    nz = [n.to(DEV) for n in noise]
+    eager = view_synthesis_loss(plan, ins, outs, nz)          # also creates the side stream outside capture
+    eager_loss = float(eager["loss"].detach())
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        cap = view_synthesis_loss(plan, ins, outs, nz)
+        cap_loss = cap["loss"].detach().clone()
+    cap_loss.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert float(cap_loss) == eager_loss
