@@ -33,6 +33,13 @@
 #define MD2_FMUL(a, b) __fmul_rn(a, b)
 #define MD2_FADD(a, b) __fadd_rn(a, b)
 #define MD2_RCP(a) md2::rcp_nr(a)
+// the SSIM ratio n/d tolerates the 1-ulp MUFU.RCP result (loss parity budget 1e-5); the depth and
+// projection reciprocals keep the Newton step because they decide bilinear cells
+#ifdef MD2_SSIM_RCP_EXACT
+#define MD2_RCP_SSIM(a) md2::rcp_nr(a)
+#else
+#define MD2_RCP_SSIM(a) md2::rcp_approx(a)
+#endif
 #define MD2_DIV(a, b) __fdiv_rn(a, b)
 #define MD2_FLOORF(a) floorf(a)
 #define MD2_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
@@ -43,6 +50,7 @@
 #define MD2_FMUL(a, b) md2::host_fmul(a, b)
 #define MD2_FADD(a, b) md2::host_fadd(a, b)
 #define MD2_RCP(a) (1.0f / (a))
+#define MD2_RCP_SSIM(a) (1.0f / (a))
 #define MD2_DIV(a, b) ((a) / (b))
 #define MD2_FLOORF(a) floorf(a)
 #endif
@@ -58,6 +66,11 @@ MD2_HD F4 make_f4(float a, float b, float c, float d) { F4 r; r.x = a; r.y = b; 
 
 #if defined(__CUDA_ARCH__)
 // MUFU.RCP + one Newton step: <= 1 ulp, 3 instructions instead of the IEEE sequence
+__device__ __forceinline__ float rcp_approx(float a) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
 __device__ __forceinline__ float rcp_nr(float a) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
@@ -222,7 +235,7 @@ MD2_HD float ssim_window(float sx, float sxx, float sxy, float sy, float syy, fl
   const float d1 = pp + c1;
   const float d2 = fmaf(9.0f, sxx + syy, -pp) + c2;
   const float N = n1 * n2, D = d1 * d2;
-  const float invD = MD2_RCP(D);
+  const float invD = MD2_RCP_SSIM(D);
   const float Q = N * invD;
   const float raw = fmaf(-0.5f, Q, 0.5f);
   const float S = fminf(fmaxf(raw, 0.0f), 1.0f);
