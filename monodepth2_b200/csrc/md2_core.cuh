@@ -285,7 +285,7 @@ struct Lane {
   // identity loss + noise of the current window row (loaded at the top of the step)
   float idv[C::NSRC], nzv[C::NSRC];
   // forward rolling state (horizontal 3-sums of the two previous rows)
-  float H1[C::NSRC][3][3], H2[C::NSRC][3][3];   // [f][c][x,xx,xy]
+  float H1[C::NSRC][3][3], H2[C::NSRC][3][3];   // [f][c][x,xx,xy]: previous row | sum of the two previous rows
   float HY1[3][2], HY2[3][2];                   // [c][y,yy]
   float pr1[C::NSRC][3], tg1[3];                // own pred / target of the previous row
   // exports of the current step
@@ -553,12 +553,13 @@ MD2_HD void stage_b(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
     float V[C::NSRC][3][3], VY[3][2];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
+      // H2 / HY2 hold the SUM of the two previous rows (one add here, one add and one move below)
 #pragma unroll
-      for (int k = 0; k < 2; ++k) VY[c][k] = L.HY2[c][k] + L.HY1[c][k] + HY0[c][k];
+      for (int k = 0; k < 2; ++k) VY[c][k] = L.HY2[c][k] + HY0[c][k];
 #pragma unroll
       for (int f = 0; f < C::NSRC; ++f)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) V[f][c][k] = L.H2[f][c][k] + L.H1[f][c][k] + H0[f][c][k];
+        for (int k = 0; k < 3; ++k) V[f][c][k] = L.H2[f][c][k] + H0[f][c][k];
     }
     float rl[C::NSRC];
 #pragma unroll
@@ -633,12 +634,12 @@ MD2_HD void stage_b(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
 #pragma unroll
-    for (int k = 0; k < 2; ++k) { L.HY2[c][k] = L.HY1[c][k]; L.HY1[c][k] = HY0[c][k]; }
+    for (int k = 0; k < 2; ++k) { L.HY2[c][k] = L.HY1[c][k] + HY0[c][k]; L.HY1[c][k] = HY0[c][k]; }
     L.tg1[c] = L.tg[c];
 #pragma unroll
     for (int f = 0; f < C::NSRC; ++f) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) { L.H2[f][c][k] = L.H1[f][c][k]; L.H1[f][c][k] = H0[f][c][k]; }
+      for (int k = 0; k < 3; ++k) { L.H2[f][c][k] = L.H1[f][c][k] + H0[f][c][k]; L.H1[f][c][k] = H0[f][c][k]; }
       L.pr1[f][c] = L.pr[f][c];
     }
   }
@@ -715,7 +716,7 @@ MD2_HD void stage_c(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
         if (won) {
           const float kl1 = C::NOSSIM ? (1.0f / 3.0f) : (0.15f / 3.0f);
           const float df = xj - tg[c];
-          g += (df > 0.f) ? kl1 : ((df < 0.f) ? -kl1 : 0.0f);
+          g += (df != 0.f) ? copysignf(kl1, df) : 0.0f;
         }
         d0 = fmaf(g, dxs[c], d0);
         d1 = fmaf(g, dys[c], d1);
