@@ -877,11 +877,11 @@ MD2_HD void id_stage_b(IdLane<NSRC>& L, const Params& P, int b, int t, int lane,
       float ss = 0.f, l1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float vy0 = L.HY2[c][0] + L.HY1[c][0] + HY0[c][0];
-        const float vy1 = L.HY2[c][1] + L.HY1[c][1] + HY0[c][1];
+        const float vy0 = L.HY2[c][0] + HY0[c][0];      // H2 / HY2 = sum of the two previous rows
+        const float vy1 = L.HY2[c][1] + HY0[c][1];
         float vx[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) vx[k] = L.H2[f][c][k] + L.H1[f][c][k] + H0[f][c][k];
+        for (int k = 0; k < 3; ++k) vx[k] = L.H2[f][c][k] + H0[f][c][k];
         if (!NOSSIM) ss += ssim_window(vx[0], vx[1], vx[2], vy0, vy1, nullptr);
         l1 += fabsf(L.tg1[c] - L.pr1[f][c]);
       }
@@ -892,12 +892,12 @@ MD2_HD void id_stage_b(IdLane<NSRC>& L, const Params& P, int b, int t, int lane,
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
 #pragma unroll
-    for (int k = 0; k < 2; ++k) { L.HY2[c][k] = L.HY1[c][k]; L.HY1[c][k] = HY0[c][k]; }
+    for (int k = 0; k < 2; ++k) { L.HY2[c][k] = L.HY1[c][k] + HY0[c][k]; L.HY1[c][k] = HY0[c][k]; }
     L.tg1[c] = L.tg[c];
 #pragma unroll
     for (int f = 0; f < NSRC; ++f) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) { L.H2[f][c][k] = L.H1[f][c][k]; L.H1[f][c][k] = H0[f][c][k]; }
+      for (int k = 0; k < 3; ++k) { L.H2[f][c][k] = L.H1[f][c][k] + H0[f][c][k]; L.H1[f][c][k] = H0[f][c][k]; }
       L.pr1[f][c] = L.pr[f][c];
     }
   }
