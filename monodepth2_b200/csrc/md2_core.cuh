@@ -213,6 +213,9 @@ struct Cfg {
 #else
   static constexpr bool BSMEM = GRAD_ && (NSRC_ >= 3);
 #endif
+  // Control-flow shape of stages B/C: with 3 sources the branch-free form (every lane computes, results
+  // masked) is 7 % faster, with 1-2 sources the divergent form is 3 % faster (measured, r01 log).
+  static constexpr bool STRAIGHT = (NSRC_ >= 3);
   static constexpr int NB4 = (9 * NSRC_ + 3) / 4;                // 16-byte fields per B row
   static constexpr int SMEM4 = (GRAD_ ? kRing * STASH4 : 0) + (BSMEM ? 2 * NB4 : 0);  // per thread
 };
@@ -226,7 +229,7 @@ struct Cfg {
 //   81 d1 = sx^2 + sy^2 + 81 C1      81 d2 = 9 (sxx + syy) - sx^2 - sy^2 + 81 C2
 // When `coef` is non-null it receives -0.5*live*(alpha, beta, gamma) with
 // d(n/d)/dx_j = alpha + beta*x_j + gamma*y_j for every x_j of the window.
-MD2_HD float ssim_window(float sx, float sxx, float sxy, float sy, float syy, float* coef) {
+MD2_HD float ssim_window(float sx, float sxx, float sxy, float sy, float syy, float* coef, bool valid = true) {
   const float c1 = 81.0f * kSsimC1, c2 = 81.0f * kSsimC2;
   const float pxy = sx * sy;
   const float pp = fmaf(sx, sx, sy * sy);
@@ -241,7 +244,7 @@ MD2_HD float ssim_window(float sx, float sxx, float sxy, float sy, float syy, fl
   const float S = fminf(fmaxf(raw, 0.0f), 1.0f);
   if (coef) {
     const bool live = (raw >= 0.0f) && (raw <= 1.0f);
-    const float k = live ? -0.5f : 0.0f;
+    const float k = (live && valid) ? -0.5f : 0.0f;
     const float QD = Q * invD;                       // N / D^2
     const float alpha = 2.0f * (sy * (n2 - n1) * invD - sx * (d2 - d1) * QD);
     const float beta = -18.0f * d1 * QD;
@@ -523,7 +526,7 @@ MD2_HD void stage_a_finish(Lane<C>& L, const Params& P, const WarpJob& J, int t,
 // Horizontal sums of row t, SSIM + L1 of window row t-1, per-pixel minimum and the
 // SSIM-adjoint coefficients of the winning source.
 template <class C>
-MD2_HD void stage_b(Lane<C>& L, const Params& P, const WarpJob& J, int t, int lane,
+MD2_HD void stage_b_divergent(Lane<C>& L, const Params& P, const WarpJob& J, int t, int lane,
                     const Xchg1<C>& lf, const Xchg1<C>& rt) {
   const int yw = t - 1;
   float H0[C::NSRC][3][3], HY0[3][2];
@@ -645,12 +648,153 @@ MD2_HD void stage_b(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
   }
 }
 
+template <class C>
+MD2_HD void stage_b_straight(Lane<C>& L, const Params& P, const WarpJob& J, int t, int lane,
+                    const Xchg1<C>& lf, const Xchg1<C>& rt) {
+  const int yw = t - 1;
+  float H0[C::NSRC][3][3], HY0[3][2];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float yl = lf.tg[c], yr = rt.tg[c], yc = L.tg[c];
+    HY0[c][0] = yl + yc + yr;
+    HY0[c][1] = fmaf(yr, yr, fmaf(yc, yc, yl * yl));
+#pragma unroll
+    for (int f = 0; f < C::NSRC; ++f) {
+      const float xl = lf.pr[f][c], xr = rt.pr[f][c], xc = L.pr[f][c];
+      H0[f][c][0] = xl + xc + xr;
+      H0[f][c][1] = fmaf(xr, xr, fmaf(xc, xc, xl * xl));
+      H0[f][c][2] = fmaf(xr, yr, fmaf(xc, yc, xl * yl));
+    }
+  }
+  // windows this job needs: its own rows plus one halo row each side (for the adjoint)
+  const bool win_ok = L.colok && (yw >= 0) && (yw < P.H) && (lane >= 1) && (lane <= kLanes - 2) &&
+                      (yw >= J.y0 - (C::GRAD ? 1 : 0)) && (yw < J.y1 + (C::GRAD ? 1 : 0));
+  const bool own_win = win_ok && (lane >= 2) && (lane < 2 + kOwnCols) && (yw >= J.y0) && (yw < J.y1);
+  // Cfg::STRAIGHT: lanes / rows that do not need the window compute it anyway (the warp executes the
+  // code as long as one lane needs it) and are masked at the end, which avoids a divergent region and
+  // the register copies at its join; otherwise the block is skipped by the lanes that do not need it.
+  int tag = -1;
+  {
+    float V[C::NSRC][3][3], VY[3][2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      // H2 / HY2 hold the SUM of the two previous rows (one add here, one add and one move below)
+#pragma unroll
+      for (int k = 0; k < 2; ++k) VY[c][k] = L.HY2[c][k] + HY0[c][k];
+#pragma unroll
+      for (int f = 0; f < C::NSRC; ++f)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) V[f][c][k] = L.H2[f][c][k] + H0[f][c][k];
+    }
+    float rl[C::NSRC];
+#pragma unroll
+    for (int f = 0; f < C::NSRC; ++f) {
+      float ss = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (!C::NOSSIM) ss += ssim_window(V[f][c][0], V[f][c][1], V[f][c][2], VY[c][0], VY[c][1], nullptr);
+        l1 += fabsf(L.tg1[c] - L.pr1[f][c]);
+      }
+      // trainer.py:403: 0.85 * ssim.mean(1) + 0.15 * l1.mean(1)   (--no_ssim: l1.mean(1), :399-400)
+      rl[f] = C::NOSSIM ? l1 * (1.0f / 3.0f) : fmaf(0.85f / 3.0f, ss, (0.15f / 3.0f) * l1);
+    }
+    // candidates in the order of trainer.py:471: identity first, then reprojection
+    float best = INFINITY;
+    if (C::AUTOMASK) {
+      if (C::AVG) {
+        float acc = 0.f;
+#pragma unroll
+        for (int f = 0; f < C::NSRC; ++f) acc += L.idv[f];
+        best = MD2_FADD(acc * (1.0f / (float)C::NSRC), MD2_FMUL(L.nzv[0], 0.00001f));
+      } else {
+#pragma unroll
+        for (int f = 0; f < C::NSRC; ++f) {
+          const float cand = MD2_FADD(L.idv[f], MD2_FMUL(L.nzv[f], 0.00001f));
+          best = (cand < best) ? cand : best;
+        }
+      }
+    }
+    if (C::AVG) {
+      float acc = 0.f;
+#pragma unroll
+      for (int f = 0; f < C::NSRC; ++f) acc += rl[f];
+      const float cand = acc * (1.0f / (float)C::NSRC);
+      tag = (cand < best) ? 0 : tag;
+      best = (cand < best) ? cand : best;
+    } else {
+#pragma unroll
+      for (int f = 0; f < C::NSRC; ++f) {
+        tag = (rl[f] < best) ? f : tag;
+        best = (rl[f] < best) ? rl[f] : best;
+      }
+    }
+    tag = win_ok ? tag : -1;
+    L.loss += own_win ? best : 0.0f;
+    if (C::AUTOMASK && J.idsel && own_win) J.idsel[yw * J.W + L.xi] = (tag >= 0) ? 1.0f : 0.0f;
+    if (C::GRAD && !C::NOSSIM) {
+      const bool valid = tag >= 0;
+      if (C::AVG) {
+#pragma unroll
+        for (int f = 0; f < C::NSRC; ++f)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            ssim_window(V[f][c][0], V[f][c][1], V[f][c][2], VY[c][0], VY[c][1], &L.coef[f][c * 3], valid);
+      } else {
+        // select the winner's window sums without dynamic register indexing
+        float W3[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            float v = V[0][c][k];
+#pragma unroll
+            for (int f = 1; f < C::NSRC; ++f) v = (tag == f) ? V[f][c][k] : v;
+            W3[c][k] = v;
+          }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          ssim_window(W3[c][0], W3[c][1], W3[c][2], VY[c][0], VY[c][1], &L.coef[0][c * 3], valid);
+      }
+    } else {
+#pragma unroll
+      for (int n = 0; n < C::NCS; ++n)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) L.coef[n][k] = 0.f;
+    }
+  }
+  L.tag = tag;
+  // roll the forward state
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { L.HY2[c][k] = L.HY1[c][k] + HY0[c][k]; L.HY1[c][k] = HY0[c][k]; }
+    L.tg1[c] = L.tg[c];
+#pragma unroll
+    for (int f = 0; f < C::NSRC; ++f) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { L.H2[f][c][k] = L.H1[f][c][k] + H0[f][c][k]; L.H1[f][c][k] = H0[f][c][k]; }
+      L.pr1[f][c] = L.pr[f][c];
+    }
+  }
+}
+
+// Two control-flow shapes of the same arithmetic (Cfg::STRAIGHT): "divergent" skips the window /
+// pixel block for the lanes that do not need it, "straight" lets every lane compute and masks the
+// results (no divergent region, no register copies at its join).  Measured on B200 (r01 log): with 3
+// sources straight is 7 % faster, with 1-2 sources divergent is 3 % faster.
+template <class C>
+MD2_HD void stage_b(Lane<C>& L, const Params& P, const WarpJob& J, int t, int lane,
+                    const Xchg1<C>& lf, const Xchg1<C>& rt) {
+  if (C::STRAIGHT) stage_b_straight(L, P, J, t, lane, lf, rt);
+  else stage_b_divergent(L, P, J, t, lane, lf, rt);
+}
+
 // ------------------------------------------------------------------ stage C
 // Adjoint for pixel row t-2: 3x3 box adjoint of the coefficient maps (with the fold
 // of the reflection ring), d loss/d pred, grid-sample and projection
 // adjoints (A.3).  Writes d loss / d D for owned pixels and accumulates the pose sums.
 template <class C>
-MD2_HD void stage_c(Lane<C>& L, const Params& P, const WarpJob& J, int t, int lane,
+MD2_HD void stage_c_divergent(Lane<C>& L, const Params& P, const WarpJob& J, int t, int lane,
                     const Xchg2<C>& lf, const Xchg2<C>& rt, const Stash& st) {
   const int yp = t - 2;
   const float wl = (L.x == 1) ? 2.0f : 1.0f;
@@ -756,6 +900,127 @@ MD2_HD void stage_c(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
       for (int k = 0; k < 9; ++k) { L.B2[f][k] = L.B1[f][k]; L.B1[f][k] = B0[f][k]; }
   }
   L.tag1 = L.tag;
+}
+
+template <class C>
+MD2_HD void stage_c_straight(Lane<C>& L, const Params& P, const WarpJob& J, int t, int lane,
+                    const Xchg2<C>& lf, const Xchg2<C>& rt, const Stash& st) {
+  const int yp = t - 2;
+  const float wl = (L.x == 1) ? 2.0f : 1.0f;
+  const float wr = (L.x == P.W - 2) ? 2.0f : 1.0f;
+  float B0[C::NSRC][9];
+#pragma unroll
+  for (int f = 0; f < C::NSRC; ++f) {
+    const int n = C::AVG ? f : 0;
+    const float ml = (C::AVG || lf.tag == f) ? wl : 0.0f;
+    const float mc = (C::AVG || L.tag == f) ? 1.0f : 0.0f;
+    const float mr = (C::AVG || rt.tag == f) ? wr : 0.0f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+      B0[f][k] = fmaf(ml, lf.coef[n][k], fmaf(mr, rt.coef[n][k], mc * L.coef[n][k]));
+  }
+  const bool own = L.colok && (lane >= 2) && (lane < 2 + kOwnCols) && (yp >= J.y0) && (yp < J.y1);
+  const int bslot = t & 1;          // ring slot of row t (holds row t-2 until overwritten below)
+  // Cfg::STRAIGHT (see stage_b): every lane computes, only owners accumulate and store
+  {
+    float B1v[C::NSRC][9], B2v[C::NSRC][9];
+    if (C::BSMEM) {
+      float f1[4 * C::NB4], f2[4 * C::NB4];
+#pragma unroll
+      for (int i = 0; i < C::NB4; ++i) {
+        const F4 a = st.b(bslot ^ 1, i, C::NB4), c2 = st.b(bslot, i, C::NB4);
+        f1[4 * i] = a.x; f1[4 * i + 1] = a.y; f1[4 * i + 2] = a.z; f1[4 * i + 3] = a.w;
+        f2[4 * i] = c2.x; f2[4 * i + 1] = c2.y; f2[4 * i + 2] = c2.z; f2[4 * i + 3] = c2.w;
+      }
+#pragma unroll
+      for (int f = 0; f < C::NSRC; ++f)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { B1v[f][k] = f1[f * 9 + k]; B2v[f][k] = f2[f * 9 + k]; }
+    } else {
+#pragma unroll
+      for (int f = 0; f < C::NSRC; ++f)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { B1v[f][k] = L.B1[f][k]; B2v[f][k] = L.B2[f][k]; }
+    }
+    const float wu = (yp == 1) ? 2.0f : 1.0f;
+    const float wd = (yp == P.H - 2) ? 2.0f : 1.0f;
+    const int slot = ring_slot(yp);
+    const F4 s0 = st.at(slot, 0, C::STASH4);
+    const float tg[3] = {s0.x, s0.y, s0.z};
+    const float z = s0.w;
+    const float yf = (float)yp;
+    float dzsum = 0.f;
+#pragma unroll
+    for (int f = 0; f < C::NSRC; ++f) {
+      const F4 sp = st.at(slot, 1 + 3 * f, C::STASH4);
+      const F4 sdx = st.at(slot, 2 + 3 * f, C::STASH4);
+      const F4 sdy = st.at(slot, 3 + 3 * f, C::STASH4);
+      const float xs[3] = {sp.x, sp.y, sp.z};
+      const float dxs[3] = {sdx.x, sdx.y, sdx.z}, dys[3] = {sdy.x, sdy.y, sdy.z};
+      const bool won = C::AVG ? (L.tag1 >= 0) : (L.tag1 == f);
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float xj = xs[c];
+        const float A = fmaf(wu, B2v[f][c * 3 + 0], fmaf(wd, B0[f][c * 3 + 0], B1v[f][c * 3 + 0]));
+        const float Bq = fmaf(wu, B2v[f][c * 3 + 1], fmaf(wd, B0[f][c * 3 + 1], B1v[f][c * 3 + 1]));
+        const float G = fmaf(wu, B2v[f][c * 3 + 2], fmaf(wd, B0[f][c * 3 + 2], B1v[f][c * 3 + 2]));
+        // d loss / d pred_c = 0.85/3 * SSIM part + 0.15/3 * sign(x - y) [if this source won here]
+        float g = C::NOSSIM ? 0.0f : (0.85f / 3.0f) * fmaf(xj, Bq, fmaf(tg[c], G, A));
+        {
+          const float kl1 = C::NOSSIM ? (1.0f / 3.0f) : (0.15f / 3.0f);
+          const float df = xj - tg[c];
+          g += (won && df != 0.f) ? copysignf(kl1, df) : 0.0f;
+        }
+        d0 = fmaf(g, dxs[c], d0);
+        d1 = fmaf(g, dys[c], d1);
+      }
+      d0 = own ? d0 : 0.0f;      // selects, not products: non-owners may hold stale (non-finite) stash
+      d1 = own ? d1 : 0.0f;
+      const float u = sp.w, v = sdx.w;
+      const float d2 = own ? -fmaf(u, d0, v * d1) : 0.0f;
+      const float q0 = fmaf(L.qb[f][0], yf, L.qa[f][0]);
+      const float q1 = fmaf(L.qb[f][1], yf, L.qa[f][1]);
+      const float q2 = fmaf(L.qb[f][2], yf, L.qa[f][2]);
+      dzsum += fmaf(d0, q0, fmaf(d1, q1, d2 * q2));
+      const float zy = z * yf;
+      L.S1[f][0] = fmaf(d0, z, L.S1[f][0]); L.S1[f][1] = fmaf(d1, z, L.S1[f][1]); L.S1[f][2] = fmaf(d2, z, L.S1[f][2]);
+      L.S2[f][0] = fmaf(d0, zy, L.S2[f][0]); L.S2[f][1] = fmaf(d1, zy, L.S2[f][1]); L.S2[f][2] = fmaf(d2, zy, L.S2[f][2]);
+      L.S3[f][0] += d0; L.S3[f][1] += d1; L.S3[f][2] += d2;
+    }
+    // d depth / d D = -c * z^2  (layers.py:23-24)
+    const float dD = -P.c_disp * z * z * dzsum * P.gscale;
+    if (own) {
+      J.dD[yp * J.W + L.xi] = dD;
+      if (J.s == 0)   // up-sampling is the identity at scale 0: finish grad_disp_0 here (A.4 + A.3)
+        J.gd0[yp * J.W + L.xi] = dD + J.sm_w * (MD2_LD(J.gn0 + yp * J.W + L.xi) * J.sm_inv_m - J.sm_dterm);
+    }
+  }
+  if (C::BSMEM) {
+    float fl[4 * C::NB4];
+#pragma unroll
+    for (int i = 0; i < 4 * C::NB4; ++i) fl[i] = 0.f;
+#pragma unroll
+    for (int f = 0; f < C::NSRC; ++f)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) fl[f * 9 + k] = B0[f][k];
+#pragma unroll
+    for (int i = 0; i < C::NB4; ++i)
+      st.b(bslot, i, C::NB4) = make_f4(fl[4 * i], fl[4 * i + 1], fl[4 * i + 2], fl[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int f = 0; f < C::NSRC; ++f)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { L.B2[f][k] = L.B1[f][k]; L.B1[f][k] = B0[f][k]; }
+  }
+  L.tag1 = L.tag;
+}
+
+template <class C>
+MD2_HD void stage_c(Lane<C>& L, const Params& P, const WarpJob& J, int t, int lane,
+                    const Xchg2<C>& lf, const Xchg2<C>& rt, const Stash& st) {
+  if (C::STRAIGHT) stage_c_straight(L, P, J, t, lane, lf, rt, st);
+  else stage_c_divergent(L, P, J, t, lane, lf, rt, st);
 }
 
 // Turns the lane's pose sums into its share of dP (3x4, row-major) for source f:
