@@ -84,6 +84,29 @@ inline float host_fmul(float a, float b) { volatile float r = a * b; return r; }
 inline float host_fadd(float a, float b) { volatile float r = a + b; return r; }
 #endif
 
+#if !defined(__CUDACC__)
+// Host-emulator-only export of the discrete decisions the kernels take (bilinear cell + clip
+// masks, per-pixel winner, SSIM clamp-live bits, L1 / smoothness signs).  Used by the
+// decision-locked fp64 test (protocol P4); never compiled into the CUDA build.
+struct DebugSink {
+  int B, H, W, S, nsrc;
+  short* x0;            // [S][B][nsrc][H][W]
+  short* y0;
+  unsigned char* mxy;   // bit0 = mx, bit1 = my
+  signed char* tag;     // [S][B][H][W]   winner (-1: an identity candidate)
+  unsigned char* live;  // [S][B][nsrc][3][H][W]  clamp-live bit of the SSIM window of source f, channel c
+  signed char* l1sgn;   // [S][B][nsrc][3][H][W]  sign(pred - target)
+  signed char* smx;     // per scale [B][Hs][Ws]  sign(n(p) - n(p+1x))
+  signed char* smy;
+  long smoff[4];
+};
+inline DebugSink*& debug_sink() { static DebugSink* g = nullptr; return g; }
+inline unsigned char*& dbg_live_slot() { static unsigned char* p = nullptr; return p; }   // where ssim_window puts its live bit
+#define MD2_DBG(stmt) do { if (md2::debug_sink()) { md2::DebugSink& D = *md2::debug_sink(); stmt; } } while (0)
+#else
+#define MD2_DBG(stmt) do { } while (0)
+#endif
+
 constexpr int kMaxScales = 4;
 constexpr int kMaxSrc = 4;
 constexpr int kLanes = 32;
@@ -244,6 +267,7 @@ MD2_HD float ssim_window(float sx, float sxx, float sxy, float sy, float syy, fl
   const float S = fminf(fmaxf(raw, 0.0f), 1.0f);
   if (coef) {
     const bool live = (raw >= 0.0f) && (raw <= 1.0f);
+    MD2_DBG((void)D; if (dbg_live_slot()) *dbg_live_slot() = live ? 1 : 0;);
     const float k = (live && valid) ? -0.5f : 0.0f;
     const float QD = Q * invD;                       // N / D^2
     const float alpha = 2.0f * (sy * (n2 - n1) * invD - sx * (d2 - d1) * QD);
@@ -465,6 +489,10 @@ MD2_HD void stage_a_issue(Lane<C>& L, const Params& P, const WarpJob& J, int t) 
     const float iyc = fminf(fmaxf(iy, 0.0f), P.hmax);
     const float fx0 = MD2_FLOORF(ixc), fy0 = MD2_FLOORF(iyc);
     const int x0 = (int)fx0, y0 = (int)fy0;
+    MD2_DBG(if (L.colok && t >= 0 && t < J.H) {
+      const long o = ((((long)J.s * D.B + J.b) * D.nsrc + f) * D.H + t) * D.W + L.x;
+      D.x0[o] = (short)x0; D.y0[o] = (short)y0; D.mxy[o] = (unsigned char)((mx ? 1 : 0) | (my ? 2 : 0));
+    });
     const int dx1 = (x0 + 1 < J.W) ? 4 : 0;                 // texel step to the east tap
     const int dy1 = (y0 + 1 < J.H) ? J.W * 4 : 0;           // texel step to the south tap
     const float* t00 = J.src4[f] + 4 * (y0 * J.W + x0);
@@ -613,7 +641,12 @@ MD2_HD void stage_b_divergent(Lane<C>& L, const Params& P, const WarpJob& J, int
         for (int f = 0; f < C::NSRC; ++f)
 #pragma unroll
           for (int c = 0; c < 3; ++c)
+          {
+            MD2_DBG(dbg_live_slot() = (L.colok && yw >= 0 && yw < J.H)
+                        ? &D.live[(((((long)J.s * D.B + J.b) * D.nsrc + f) * 3 + c) * D.H + yw) * D.W + L.x] : nullptr;);
             ssim_window(V[f][c][0], V[f][c][1], V[f][c][2], VY[c][0], VY[c][1], &L.coef[f][c * 3]);
+            MD2_DBG(dbg_live_slot() = nullptr;);
+          }
       } else {
         // select the winner's window sums without dynamic register indexing
         float W3[3][3];
@@ -628,11 +661,17 @@ MD2_HD void stage_b_divergent(Lane<C>& L, const Params& P, const WarpJob& J, int
           }
 #pragma unroll
         for (int c = 0; c < 3; ++c)
+        {
+          MD2_DBG(dbg_live_slot() = (tag >= 0 && L.colok && yw >= 0 && yw < J.H)
+                      ? &D.live[(((((long)J.s * D.B + J.b) * D.nsrc + tag) * 3 + c) * D.H + yw) * D.W + L.x] : nullptr;);
           ssim_window(W3[c][0], W3[c][1], W3[c][2], VY[c][0], VY[c][1], &L.coef[0][c * 3]);
+          MD2_DBG(dbg_live_slot() = nullptr;);
+        }
       }
     }
   }
   L.tag = tag;
+  MD2_DBG(if (own_win) D.tag[(((long)J.s * D.B + J.b) * D.H + yw) * D.W + L.x] = (signed char)tag;);
   // roll the forward state
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -738,7 +777,12 @@ MD2_HD void stage_b_straight(Lane<C>& L, const Params& P, const WarpJob& J, int 
         for (int f = 0; f < C::NSRC; ++f)
 #pragma unroll
           for (int c = 0; c < 3; ++c)
+          {
+            MD2_DBG(dbg_live_slot() = (L.colok && yw >= 0 && yw < J.H)
+                        ? &D.live[(((((long)J.s * D.B + J.b) * D.nsrc + f) * 3 + c) * D.H + yw) * D.W + L.x] : nullptr;);
             ssim_window(V[f][c][0], V[f][c][1], V[f][c][2], VY[c][0], VY[c][1], &L.coef[f][c * 3], valid);
+            MD2_DBG(dbg_live_slot() = nullptr;);
+          }
       } else {
         // select the winner's window sums without dynamic register indexing
         float W3[3][3];
@@ -753,7 +797,12 @@ MD2_HD void stage_b_straight(Lane<C>& L, const Params& P, const WarpJob& J, int 
           }
 #pragma unroll
         for (int c = 0; c < 3; ++c)
+        {
+          MD2_DBG(dbg_live_slot() = (tag >= 0 && L.colok && yw >= 0 && yw < J.H)
+                      ? &D.live[(((((long)J.s * D.B + J.b) * D.nsrc + tag) * 3 + c) * D.H + yw) * D.W + L.x] : nullptr;);
           ssim_window(W3[c][0], W3[c][1], W3[c][2], VY[c][0], VY[c][1], &L.coef[0][c * 3], valid);
+          MD2_DBG(dbg_live_slot() = nullptr;);
+        }
       }
     } else {
 #pragma unroll
@@ -763,6 +812,7 @@ MD2_HD void stage_b_straight(Lane<C>& L, const Params& P, const WarpJob& J, int 
     }
   }
   L.tag = tag;
+  MD2_DBG(if (own_win) D.tag[(((long)J.s * D.B + J.b) * D.H + yw) * D.W + L.x] = (signed char)tag;);
   // roll the forward state
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -861,6 +911,8 @@ MD2_HD void stage_c_divergent(Lane<C>& L, const Params& P, const WarpJob& J, int
           const float kl1 = C::NOSSIM ? (1.0f / 3.0f) : (0.15f / 3.0f);
           const float df = xj - tg[c];
           g += (df != 0.f) ? copysignf(kl1, df) : 0.0f;
+          MD2_DBG(D.l1sgn[(((((long)J.s * D.B + J.b) * D.nsrc + f) * 3 + c) * D.H + yp) * D.W + L.x] =
+                      (signed char)(df > 0.f ? 1 : (df < 0.f ? -1 : 0)););
         }
         d0 = fmaf(g, dxs[c], d0);
         d1 = fmaf(g, dys[c], d1);
@@ -971,6 +1023,8 @@ MD2_HD void stage_c_straight(Lane<C>& L, const Params& P, const WarpJob& J, int 
           const float kl1 = C::NOSSIM ? (1.0f / 3.0f) : (0.15f / 3.0f);
           const float df = xj - tg[c];
           g += (won && df != 0.f) ? copysignf(kl1, df) : 0.0f;
+          MD2_DBG(if (own) D.l1sgn[(((((long)J.s * D.B + J.b) * D.nsrc + f) * 3 + c) * D.H + yp) * D.W + L.x] =
+                      (signed char)(df > 0.f ? 1 : (df < 0.f ? -1 : 0)););
         }
         d0 = fmaf(g, dxs[c], d0);
         d1 = fmaf(g, dys[c], d1);
@@ -1227,6 +1281,10 @@ MD2_HD void smooth_pixel(const Params& P, int s, int b, int y, int x, float inv_
     const float g = fabsf(i0 - MD2_LD(im + q)) + fabsf(i1 - MD2_LD(im + plane + q)) + fabsf(i2 - MD2_LD(im + 2 * plane + q));
     const float w = md2_exp_neg(g * (1.0f / 3.0f));
     const float df = n0 - MD2_LD(d + q) * inv_m;          // n(this) - n(neighbour)
+    MD2_DBG(if (fwd) {
+      signed char* arr = (q == p + 1) ? D.smx : D.smy;
+      arr[D.smoff[s] + (long)b * plane + (long)p] = (signed char)(df > 0.f ? 1 : (df < 0.f ? -1 : 0));
+    });
     if (fwd) e_out = fabsf(df) * w;
     // d|n_a - n_b| / d n(this) = sign(n(this) - n(neighbour)) for either end of the edge
     gn += scale * ((df > 0.f) ? w : ((df < 0.f) ? -w : 0.f));

@@ -121,6 +121,9 @@ static void emu_march_n(const Params& P) {
   if (P.no_ssim) emu_march_k<NSRC, true>(P); else emu_march_k<NSRC, false>(P);
 }
 
+// decision export for the decision-locked fp64 test (protocol P4): pass NULL to switch it off
+extern "C" void md2_emu_set_debug(md2::DebugSink* sink) { md2::debug_sink() = sink; }
+
 extern "C" int md2_emu_workspace_bytes(const md2_problem* p, size_t* bytes) {
   const int st = validate(p);
   if (st != MD2_OK) return st;

@@ -32,7 +32,15 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-def run_emu(g, want_grad=True, rows_per_segment=0, align_corners=False, side_outputs=True):
+class DebugSink(C.Structure):
+    """ctypes mirror of md2::DebugSink (monodepth2_b200/csrc/md2_core.cuh, host build only)."""
+    _fields_ = [("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("S", C.c_int), ("nsrc", C.c_int),
+                ("x0", C.c_void_p), ("y0", C.c_void_p), ("mxy", C.c_void_p), ("tag", C.c_void_p),
+                ("live", C.c_void_p), ("l1sgn", C.c_void_p), ("smx", C.c_void_p), ("smy", C.c_void_p),
+                ("smoff", C.c_long * 4)]
+
+
+def run_emu(g, want_grad=True, rows_per_segment=0, align_corners=False, side_outputs=True, decisions=False):
     """Run the emulator on a Golden fixture; returns dict of numpy outputs."""
     lib = C.CDLL(build_emu())
     lib.md2_emu_workspace_bytes.argtypes = [C.POINTER(Md2Problem), C.POINTER(C.c_size_t)]
@@ -97,7 +105,30 @@ def run_emu(g, want_grad=True, rows_per_segment=0, align_corners=False, side_out
     st = lib.md2_emu_workspace_bytes(C.byref(p), C.byref(nbytes))
     assert st == 0, st
     ws = np.zeros(nbytes.value + 64, np.uint8)
-    st = lib.md2_emu_view_synthesis_loss(C.byref(p), C.byref(t), _ptr(ws), nbytes.value)
+    dbg = None
+    if decisions:
+        n_src = len(srcs)
+        dbg = dict(x0=np.zeros((4, B, n_src, H, W), np.int16), y0=np.zeros((4, B, n_src, H, W), np.int16),
+                   mxy=np.zeros((4, B, n_src, H, W), np.uint8), tag=np.full((4, B, H, W), -1, np.int8),
+                   live=np.zeros((4, B, n_src, 3, H, W), np.uint8), l1sgn=np.zeros((4, B, n_src, 3, H, W), np.int8))
+        sizes = [B * (H >> s) * (W >> s) for s in range(4)]
+        offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+        dbg["smx"] = np.zeros(int(sum(sizes)), np.int8)
+        dbg["smy"] = np.zeros(int(sum(sizes)), np.int8)
+        sink = DebugSink(B=B, H=H, W=W, S=4, nsrc=n_src, x0=_ptr(dbg["x0"]), y0=_ptr(dbg["y0"]), mxy=_ptr(dbg["mxy"]),
+                         tag=_ptr(dbg["tag"]), live=_ptr(dbg["live"]), l1sgn=_ptr(dbg["l1sgn"]),
+                         smx=_ptr(dbg["smx"]), smy=_ptr(dbg["smy"]))
+        for s in range(4):
+            sink.smoff[s] = int(offs[s])
+        dbg["smoff"], dbg["smsizes"] = offs, sizes
+        lib.md2_emu_set_debug.argtypes = [C.POINTER(DebugSink)]
+        lib.md2_emu_set_debug(C.byref(sink))
+    try:
+        st = lib.md2_emu_view_synthesis_loss(C.byref(p), C.byref(t), _ptr(ws), nbytes.value)
+    finally:
+        if decisions:
+            lib.md2_emu_set_debug(None)
     assert st == 0, st
+    out["decisions"] = dbg
     out["losses"] = losses
     return out

@@ -59,3 +59,22 @@ def test_forward_only_matches_and_makes_no_grads():
     r = run_cuda(g, want_grad=False)
     assert abs(float(r["losses"]["loss"]) - float(g.z["loss"])) <= LOSS_RTOL * abs(float(g.z["loss"]))
     assert not r["losses"]["loss"].requires_grad
+
+
+@pytest.mark.parametrize("name", ["mono_structured", "stereo_iid", "avg_reprojection"])
+def test_cuda_matches_host_emulator_of_the_same_source(name):
+    """The CUDA build and the g++ build (tests/emu) of md2_core.cuh take the same decisions except where
+    fma contraction differs, so the decision-locked exactness shown for the emulator (test_decision_locked.py,
+    protocol P4) carries over to the kernels: per-pixel gradients agree to 1e-5*max on >= 99.9 % of pixels."""
+    from emu_driver import run_emu
+    from gpu_driver import run_cuda
+    g = Golden(name)
+    e = run_emu(g, rows_per_segment=16)
+    r = run_cuda(g, rows_per_segment=16)
+    assert abs(float(r["losses"]["loss"]) - float(e["losses"][0])) <= 2e-6 * abs(float(e["losses"][0]))
+    for s in range(4):
+        got = r["side"][("grad_updisp", s)].cpu().numpy()
+        assert frac_within(got, e["grad_updisp"][s], 1e-5) >= 0.999, (name, s)
+        if g.n_id > 0:
+            m = r["side"]["identity_selection/%d" % s].cpu().numpy()
+            assert (m != e["idsel"][s]).mean() <= 5e-4
