@@ -404,7 +404,7 @@ def run_own(args, wl):
                        "rows_per_segment": plan.problem(True).rows_per_segment or max(32, (H + 3) // 4), "loss": loss_val,
                        "launch": "plain C-ABI calls" if graphs is None else "CUDA-graph replay of the C-ABI call"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": 6 * args.steps,
+            "gpu_launches": 7 * args.steps,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -145,6 +145,7 @@ struct Params {
   float* idloss;   // (B,nsrc,H,W)
   float* dD[kMaxScales];   // (B,H,W)   d loss / d upsampled disp_s
   float* gn[kMaxScales];   // (B,Hs,Ws) smoothness numerator gradient
+  float* smsc;             // (S,B,2): 1/m and (sum gn*disp)/(m^2 N) of the smoothness adjoint, as floats
   double* acc;     // accumulators, layout below
   // outputs
   float* losses;
@@ -211,7 +212,8 @@ MD2_HD WarpJob make_job(const Params& P, int s, int b, int x0, int y0, int y1) {
   if (s == 0 && P.want_grad) {
     J.gd0 = P.grad_disp[0] + boff;
     J.gn0 = P.gn[0] + boff;
-    smooth_scalars(P, 0, b, J.sm_inv_m, J.sm_dterm);
+    J.sm_inv_m = MD2_LD(P.smsc + 2 * b);            // scale 0, sample b
+    J.sm_dterm = MD2_LD(P.smsc + 2 * b + 1);
     J.sm_w = P.smooth_w[0] / (float)P.S;
   }
   J.idsel = P.idsel[s] ? P.idsel[s] + boff : nullptr;
@@ -1330,6 +1332,7 @@ MD2_HD float upsample_adjoint_part(const Params& P, int s, int b, int Y, int X, 
   const int Hs = P.H >> s, Ws = P.W >> s;
   const float* dD = P.dD[s] + (size_t)b * P.H * P.W;
   const int xlo = K * X - K / 2, ylo = K * Y - K / 2;
+  const bool interior_x = (X > 0) && (X < Ws - 1);
   float acc = 0.f;
 #pragma unroll
   for (int ry = 0; ry < 2; ++ry) {
@@ -1339,11 +1342,20 @@ MD2_HD float upsample_adjoint_part(const Params& P, int s, int b, int Y, int X, 
     const int yc = y < 0 ? 0 : (y >= P.H ? P.H - 1 : y);
     const float* rowp = dD + yc * P.W;
     float row = 0.f;
+    if (interior_x) {
+      // fast path: all 2K fine columns are inside the image, compile-time triangle weights
 #pragma unroll
-    for (int i = 0; i < 2 * K; ++i) {
-      const int x = xlo + i;
-      const int xc = x < 0 ? 0 : (x >= P.W ? P.W - 1 : x);
-      row = fmaf(up_weight<K>(i, X, Ws), MD2_LD(rowp + xc), row);
+      for (int i = 0; i < 2 * K; ++i) {
+        const float w = (i < K) ? ((float)i + 0.5f) * (1.0f / (float)K) : ((float)(2 * K - i) - 0.5f) * (1.0f / (float)K);
+        row = fmaf(w, MD2_LD(rowp + xlo + i), row);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 2 * K; ++i) {
+        const int x = xlo + i;
+        const int xc = x < 0 ? 0 : (x >= P.W ? P.W - 1 : x);
+        row = fmaf(up_weight<K>(i, X, Ws), MD2_LD(rowp + xc), row);
+      }
     }
     acc = fmaf(wy, row, acc);
   }

@@ -136,6 +136,17 @@ __global__ void md2_smooth(Params P) {
   }
 }
 
+// per-(scale, sample) scalars of the smoothness adjoint, once, in fp64 (the fp64 pipe is slow on B200:
+// doing this at the top of every block of md2_final cost ~20 us)
+__global__ void md2_smooth_scalars(Params P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.S * P.B) return;
+  float inv_m, dterm;
+  smooth_scalars(P, i / P.B, i % P.B, inv_m, dterm);
+  P.smsc[2 * i] = inv_m;
+  P.smsc[2 * i + 1] = dterm;
+}
+
 // ------------------------------------------------------------------ 5. the marching kernel
 template <class C>
 __device__ __forceinline__ void exchange_and_stage_c(Lane<C>& L, const Params& P, const WarpJob& J, int t, int lane,
@@ -240,9 +251,7 @@ __global__ void MD2_MARCH_BOUNDS md2_march(Params P) {
 // also writes the losses and grad_T.
 template <int K>
 __device__ __forceinline__ void final_scale(const Params& P, int s, int b) {
-  __shared__ float sh[2];
-  if (threadIdx.x == 0) smooth_scalars(P, s, b, sh[0], sh[1]);
-  __syncthreads();
+  const float inv_m = __ldg(P.smsc + 2 * (s * P.B + b)), dterm = __ldg(P.smsc + 2 * (s * P.B + b) + 1);
   const int Hs = P.H >> s, Ws = P.W >> s;
   const int n = Hs * Ws;
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -252,7 +261,7 @@ __device__ __forceinline__ void final_scale(const Params& P, int s, int b) {
   if (ok) part = (K == 1) ? __ldg(P.dD[s] + (size_t)b * n + cp) : upsample_adjoint_part<K>(P, s, b, cp / Ws, cp % Ws, j);
 #pragma unroll
   for (int o = K / 2; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
-  if (ok && j == 0) P.grad_disp[s][(size_t)b * n + cp] = part + final_smooth_grad(P, s, b, cp, sh[0], sh[1]);
+  if (ok && j == 0) P.grad_disp[s][(size_t)b * n + cp] = part + final_smooth_grad(P, s, b, cp, inv_m, dterm);
 }
 
 __global__ void md2_final(Params P) {
@@ -370,6 +379,8 @@ cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     dim3 grid2((n0 + 256 * kSmoothPerThread - 1) / (256 * kSmoothPerThread), P.B, P.S);
     md2_smooth<<<grid2, 256, 0, side->stream>>>(P);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    md2_smooth_scalars<<<1, 64, 0, side->stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   if ((e = cudaEventRecord(side->join, side->stream)) != cudaSuccess) return e;

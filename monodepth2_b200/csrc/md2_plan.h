@@ -16,7 +16,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
   size_t acc_off, acc_bytes;
-  size_t proj_off, idloss_off;
+  size_t proj_off, idloss_off, smsc_off;
   size_t tgt4_off, src4_off[kMaxSrc];
   size_t dD_off[kMaxScales], gn_off[kMaxScales];
   size_t total;
@@ -45,6 +45,7 @@ inline Layout make_layout(const md2_problem* p) {
   L.acc_off = off; L.acc_bytes = nacc * sizeof(double);
   off = align_up(off + L.acc_bytes, 256);
   L.proj_off = off; off = align_up(off + B * p->num_src * 12 * sizeof(float), 256);
+  L.smsc_off = off; off = align_up(off + kMaxScales * B * 2 * sizeof(float), 256);
   L.idloss_off = off; off = align_up(off + B * p->num_src * H * W * sizeof(float), 256);
   L.tgt4_off = off; off = align_up(off + B * H * W * 4 * sizeof(float), 256);
   for (int f = 0; f < p->num_src; ++f) {
@@ -127,6 +128,7 @@ inline int fill_params(const md2_problem* p, const md2_tensors* t, void* workspa
   P->acc = (double*)(ws + L.acc_off);
   P->proj = (float*)(ws + L.proj_off);
   P->idloss = (float*)(ws + L.idloss_off);
+  P->smsc = (float*)(ws + L.smsc_off);
   P->tgt4 = (float*)(ws + L.tgt4_off);
   for (int f = 0; f < p->num_src; ++f) P->src4[f] = (float*)(ws + L.src4_off[f]);
   return MD2_OK;

@@ -176,6 +176,8 @@ extern "C" int md2_emu_view_synthesis_loss(const md2_problem* p, const md2_tenso
         P.acc[acc_dot(P, s, b)] += (double)g * P.disp[s][(size_t)b * n + i];
       }
     }
+  for (int s = 0; s < P.S; ++s)
+    for (int b = 0; b < P.B; ++b) smooth_scalars(P, s, b, P.smsc[2 * (s * P.B + b)], P.smsc[2 * (s * P.B + b) + 1]);
   // 5. march
   if (P.nsrc == 1) emu_march_n<1>(P); else if (P.nsrc == 2) emu_march_n<2>(P); else emu_march_n<3>(P);
   // 6. final
@@ -186,8 +188,7 @@ extern "C" int md2_emu_view_synthesis_loss(const md2_problem* p, const md2_tenso
     for (int s = 0; s < P.S; ++s)
       for (int b = 0; b < P.B; ++b) {
         const int Hs = P.H >> s, Ws = P.W >> s, n = Hs * Ws;
-        float inv_m2, dterm;
-        smooth_scalars(P, s, b, inv_m2, dterm);
+        const float inv_m2 = P.smsc[2 * (s * P.B + b)], dterm = P.smsc[2 * (s * P.B + b) + 1];
         for (int i = 0; i < n; ++i) {
           float up = 0.f;
           const int Y = i / Ws, X = i % Ws;
