@@ -190,8 +190,8 @@ __global__ void MD2_MARCH_BOUNDS md2_march(Params P) {
   const int per_seg = P.S * P.nband;
   const int per_b = P.nseg * per_seg;
   if (job >= per_b * P.B) return;
-  const int jb = job / per_b;
-  const int r = job - jb * per_b;
+  const int jb = P.B - 1 - job / per_b;     // last sample first: the identity pass wrote it most recently (L2)
+  const int r = job - (job / per_b) * per_b;
   const int seg = r / per_seg;
   const int r2 = r - seg * per_seg;
   const int js = r2 / P.nband;
