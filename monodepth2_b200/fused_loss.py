@@ -36,7 +36,8 @@ class LossPlan:
                  scales: Sequence[int] = (0, 1, 2, 3), min_depth: float = 0.1, max_depth: float = 100.0,
                  disparity_smoothness: float = 1e-3, avg_reprojection: bool = False,
                  disable_automasking: bool = False, align_corners: bool = False,
-                 rows_per_segment: int = 0, no_ssim: bool = False, v1_multiscale: bool = False):
+                 rows_per_segment: int = 0, no_ssim: bool = False, v1_multiscale: bool = False,
+                 posecnn: bool = False):
         if list(scales) != list(range(len(scales))):
             raise RuntimeError("scales must be 0..n-1, got %s" % (list(scales),))
         self.batch_size, self.height, self.width = int(batch_size), int(height), int(width)
@@ -51,6 +52,9 @@ class LossPlan:
         self.rows_per_segment = int(rows_per_segment)
         self.no_ssim = bool(no_ssim)
         self.v1_multiscale = bool(v1_multiscale)
+        self.posecnn = bool(posecnn)
+        if self.posecnn and self.v1_multiscale:
+            raise RuntimeError("posecnn together with --v1_multiscale is not supported by the fused loss")
         self.n_src = len(self.src_ids)
         self.n_id = 0 if not self.automask else (1 if self.avg_reprojection else self.n_src)
         self.lib = _capi.load_library()
@@ -64,18 +68,26 @@ class LossPlan:
                          self.max_depth, self.disparity_smoothness / (2 ** s), self.avg_reprojection,
                          not self.automask, self.align_corners, self.rows_per_segment, self.no_ssim, False)
                 for s in self.scales]
+        # --pose_model_type posecnn (trainer.py:366-375): T depends on the mean inverse depth of each
+        # scale, so every scale is a single-scale photometric call at full resolution on the up-sampled
+        # disparity with its own T; the smoothness term is evaluated by the per-layer op
+        self._photo_plan = None
+        if self.posecnn:
+            self._photo_plan = LossPlan(self.batch_size, self.height, self.width, self.frame_ids, [0],
+                                        self.min_depth, self.max_depth, 0.0, self.avg_reprojection,
+                                        not self.automask, self.align_corners, self.rows_per_segment,
+                                        self.no_ssim, False)
 
     @classmethod
     def from_opt(cls, opt, **kw) -> "LossPlan":
         """Build from a reference ``options.py`` namespace (after trainer.py:51-52 appended "s")."""
         if getattr(opt, "predictive_mask", False):
             raise RuntimeError("--predictive_mask is not supported by the fused loss yet")
-        if getattr(opt, "pose_model_type", "separate_resnet") == "posecnn":
-            raise RuntimeError("--pose_model_type posecnn is not supported by the fused loss yet")
         return cls(opt.batch_size, opt.height, opt.width, opt.frame_ids, opt.scales, opt.min_depth,
                    opt.max_depth, opt.disparity_smoothness, opt.avg_reprojection,
                    opt.disable_automasking, no_ssim=getattr(opt, "no_ssim", False),
-                   v1_multiscale=getattr(opt, "v1_multiscale", False), **kw)
+                   v1_multiscale=getattr(opt, "v1_multiscale", False),
+                   posecnn=(getattr(opt, "pose_model_type", "separate_resnet") == "posecnn"), **kw)
 
     def problem(self, want_grad: bool) -> Md2Problem:
         return Md2Problem(batch=self.batch_size, height=self.height, width=self.width,
@@ -203,6 +215,8 @@ def view_synthesis_loss(plan: LossPlan, inputs: Dict, outputs: Dict,
     """
     if plan.v1_multiscale:
         return _view_synthesis_loss_v1_multiscale(plan, inputs, outputs, noise, side)
+    if plan.posecnn:
+        return _view_synthesis_loss_posecnn(plan, inputs, outputs, noise, side)
     S = len(plan.scales)
     target = inputs[("color", 0, 0)]
     dev = target.device
@@ -261,6 +275,54 @@ def _view_synthesis_loss_v1_multiscale(plan: LossPlan, inputs: Dict, outputs: Di
                 if isinstance(k, tuple):
                     key = (k[0], k[1], s) if len(k) == 3 else (k[0], s)
                     if k[0] == "grad_updisp":          # test hook: gradient of the averaged total loss
+                        v = v / len(plan.scales)
+                    side[key] = v
+                    if k[0] in ("depth", "color"):
+                        outputs[key] = v
+                elif isinstance(k, str) and k.startswith("identity_selection/"):
+                    side["identity_selection/{}".format(s)] = v
+                    outputs["identity_selection/{}".format(s)] = v
+    losses["loss"] = total / len(plan.scales)
+    return losses
+
+
+def _view_synthesis_loss_posecnn(plan: LossPlan, inputs: Dict, outputs: Dict, noise, side):
+    """--pose_model_type posecnn (trainer.py:366-375): the translation is rescaled by the mean inverse
+    depth of the scale before T is built, so T differs per scale and depends on the disparity."""
+    import torch.nn.functional as F
+    from . import layers as L
+    losses: Dict[str, torch.Tensor] = {}
+    total = 0
+    H, W = plan.height, plan.width
+    lo, hi = 1.0 / plan.max_depth, 1.0 / plan.min_depth
+    for i, s in enumerate(plan.scales):
+        disp = outputs[("disp", s)]
+        up = F.interpolate(disp, [H, W], mode="bilinear", align_corners=False) if s > 0 else disp
+        # inv_depth = 1/depth = scaled disparity (layers.py:21-24); mean over H then W (trainer.py:371-372)
+        mean_inv_depth = (lo + (hi - lo) * up).mean(3, True).mean(2, True)
+        outs = {("disp", 0): up}
+        for f in plan.src_ids:
+            if f == "s":
+                continue
+            aa = outputs[("axisangle", 0, f)][:, 0]
+            tr = outputs[("translation", 0, f)][:, 0] * mean_inv_depth[:, 0]
+            outs[("cam_T_cam", 0, f)] = L.transformation_from_parameters(aa, tr, f < 0)
+        ins = {k: v for k, v in inputs.items() if not (isinstance(k, tuple) and k[0] == "color" and k[2] != 0)}
+        sub_side = None
+        if side is not None:
+            sub_side = {k: ([0] if s in side.get(k, []) else []) for k in
+                        ("depth_scales", "color_scales", "mask_scales", "grad_updisp_scales")}
+        ls = view_synthesis_loss(plan._photo_plan, ins, outs, [noise[i]] if noise is not None else None, sub_side)
+        mean_disp = disp.mean(2, True).mean(3, True)
+        smooth = L.get_smooth_loss(disp / (mean_disp + 1e-7), inputs[("color", 0, s)])
+        loss = ls["loss"] + plan.disparity_smoothness * smooth / (2 ** s)
+        losses["loss/{}".format(s)] = loss
+        total = total + loss
+        if sub_side is not None:
+            for k, v in sub_side.items():
+                if isinstance(k, tuple):
+                    key = (k[0], k[1], s) if len(k) == 3 else (k[0], s)
+                    if k[0] == "grad_updisp":
                         v = v / len(plan.scales)
                     side[key] = v
                     if k[0] in ("depth", "color"):

@@ -52,6 +52,7 @@ class OracleConfig:
     disable_automasking: bool = False
     no_ssim: bool = False
     v1_multiscale: bool = False               # trainer.py:347-352,417-420: source_scale = scale
+    posecnn: bool = False                     # trainer.py:366-375: translation scaled by the mean inverse depth
     # trainer.py:384-387 leaves align_corners unspecified -> False on torch >= 1.3.
     align_corners: bool = False
     ssim_c1: float = 0.01 ** 2
@@ -162,7 +163,7 @@ def smooth_loss(disp, img):
 
 
 def generate_images_pred(inputs: Dict, outputs: Dict, cfg: OracleConfig) -> None:
-    """trainer.py:341-391 (both source_scale branches; the posecnn translation rescale is not covered)."""
+    """trainer.py:341-391 (both source_scale branches and the posecnn translation rescale)."""
     H, W = cfg.height, cfg.width
     for s in cfg.scales:
         disp = outputs[("disp", s)]
@@ -176,6 +177,10 @@ def generate_images_pred(inputs: Dict, outputs: Dict, cfg: OracleConfig) -> None
         outputs[("depth", 0, s)] = depth
         for f in cfg.frame_ids[1:]:
             T = inputs["stereo_T"] if f == "s" else outputs[("cam_T_cam", 0, f)]
+            if cfg.posecnn and f != "s":
+                mean_inv_depth = (1 / depth).mean(3, True).mean(2, True)
+                T = transformation_from_parameters(outputs[("axisangle", 0, f)][:, 0],
+                                                   outputs[("translation", 0, f)][:, 0] * mean_inv_depth[:, 0], f < 0)
             pts = backproject(depth, inputs[("inv_K", src_scale)])
             grid = project(pts, inputs[("K", src_scale)], T, hs, ws, cfg.eps)
             outputs[("sample", f, s)] = grid

@@ -44,6 +44,8 @@ CASES = {
     "no_ssim": dict(B=2, H=48, W=80, frame_ids=[0, -1, 1], kind="structured", seed=8, flags=["--no_ssim"]),
     "v1_multiscale": dict(B=2, H=64, W=96, frame_ids=[0, -1, 1], kind="structured", seed=9,
                           flags=["--v1_multiscale"]),
+    "posecnn": dict(B=2, H=48, W=80, frame_ids=[0, -1, 1], kind="structured", seed=10,
+                    flags=["--pose_model_type", "posecnn"]),
     "stereo_only": dict(B=2, H=32, W=64, frame_ids=[0], kind="structured", seed=7,
                         flags=["--use_stereo", "--frame_ids", "0"]),
 }
@@ -122,6 +124,10 @@ def run_reference(T, MonodepthOptions, case, dtype=torch.float32, batch=None):
         Tm = T.transformation_from_parameters(a, t, invert=(f < 0))
         Tm.retain_grad()
         outs[("cam_T_cam", 0, f)] = Tm
+        # what PoseDecoder / PoseCNN emit (pose_decoder.py:49-54): (B, n, 1, 3); the posecnn branch of
+        # generate_images_pred (trainer.py:366-375) rebuilds T from these
+        outs[("axisangle", 0, f)] = a.reshape(-1, 1, 1, 3)
+        outs[("translation", 0, f)] = t.reshape(-1, 1, 1, 3)
     me = build_self(T, opt, dtype)
     me.generate_images_pred(inputs, outs)
     for s in range(4):
@@ -150,7 +156,7 @@ def pack(res):
     d["frame_ids"] = np.array([str(f) for f in fids])
     opt = res["opt"]
     d["flags"] = np.array([int(opt.avg_reprojection), int(opt.disable_automasking), int(opt.no_ssim),
-                           int(opt.v1_multiscale)])
+                           int(opt.v1_multiscale), int(opt.pose_model_type == "posecnn")])
     for k, v in res["inputs"].items():
         name = "in__" + "__".join(str(x) for x in (k if isinstance(k, tuple) else (k,)))
         d[name] = v.detach().numpy()
@@ -173,7 +179,8 @@ def pack(res):
             d["grad_axisangle__%s" % f] = res["leaves"][("axisangle", f)].grad.numpy()
             d["grad_translation__%s" % f] = res["leaves"][("translation", f)].grad.numpy()
             d["cam_T_cam__%s" % f] = res["outs"][("cam_T_cam", 0, f)].detach().numpy()
-            d["grad_cam_T_cam__%s" % f] = res["outs"][("cam_T_cam", 0, f)].grad.numpy()
+            gT = res["outs"][("cam_T_cam", 0, f)].grad          # None under posecnn (T is rebuilt per scale)
+            d["grad_cam_T_cam__%s" % f] = gT.numpy() if gT is not None else np.zeros((1,), np.float32)
     return d
 
 

@@ -7,7 +7,8 @@ from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
 def run_cuda(g, rows_per_segment=0, align_corners=False, want_grad=True, side_all=True, dev="cuda:0"):
     plan = LossPlan(g.B, g.H, g.W, g.frame_ids, avg_reprojection=g.avg_reprojection,
                     disable_automasking=g.disable_automasking, align_corners=align_corners,
-                    rows_per_segment=rows_per_segment, no_ssim=g.no_ssim, v1_multiscale=g.v1_multiscale)
+                    rows_per_segment=rows_per_segment, no_ssim=g.no_ssim, v1_multiscale=g.v1_multiscale,
+                    posecnn=g.posecnn)
     inputs = {k: v.to(dev) for k, v in g.inputs().items()}
     outs, leaves = {}, {}
     for s in range(4):
@@ -20,6 +21,11 @@ def run_cuda(g, rows_per_segment=0, align_corners=False, want_grad=True, side_al
         T = g.t("cam_T_cam__%s" % f).to(dev).requires_grad_(want_grad)
         outs[("cam_T_cam", 0, f)] = T
         leaves[("T", f)] = T
+        if g.posecnn:          # the leaves are the pose-net outputs (B,n,1,3), trainer.py:366-375
+            aa = g.t("axisangle__%s" % f).to(dev).reshape(-1, 1, 1, 3).requires_grad_(want_grad)
+            tr = g.t("translation__%s" % f).to(dev).reshape(-1, 1, 1, 3).requires_grad_(want_grad)
+            outs[("axisangle", 0, f)], outs[("translation", 0, f)] = aa, tr
+            leaves[("axisangle", f)], leaves[("translation", f)] = aa, tr
     noise = [n.to(dev) for n in g.noise()] if g.n_id > 0 else None
     side = None
     if side_all:

@@ -27,8 +27,8 @@ class Golden:
         z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
         self.z = z
         self.frame_ids = [_fid(str(s)) for s in z["frame_ids"]]
-        fl = [bool(int(x)) for x in z["flags"]] + [False]
-        self.avg_reprojection, self.disable_automasking, self.no_ssim, self.v1_multiscale = fl[:4]
+        fl = [bool(int(x)) for x in z["flags"]] + [False, False]
+        self.avg_reprojection, self.disable_automasking, self.no_ssim, self.v1_multiscale, self.posecnn = fl[:5]
         self.B, _, self.H, self.W = z["in__color__0__0"].shape
         self.n_src = len(self.frame_ids) - 1
         self.n_id = 0 if self.disable_automasking else (1 if self.avg_reprojection else self.n_src)
@@ -37,7 +37,7 @@ class Golden:
         return O.OracleConfig(height=self.H, width=self.W, frame_ids=tuple(self.frame_ids),
                               avg_reprojection=self.avg_reprojection,
                               disable_automasking=self.disable_automasking, no_ssim=self.no_ssim,
-                              v1_multiscale=self.v1_multiscale, **kw)
+                              v1_multiscale=self.v1_multiscale, posecnn=self.posecnn, **kw)
 
     def t(self, key, dtype=torch.float32):
         return torch.from_numpy(np.asarray(self.z[key])).to(dtype)
@@ -87,6 +87,8 @@ def run_oracle(g: Golden, dtype=torch.float32, **cfgkw):
         T = O.transformation_from_parameters(lv[("axisangle", f)], lv[("translation", f)], invert=(f < 0))
         T.retain_grad()
         outs[("cam_T_cam", 0, f)] = T
+        outs[("axisangle", 0, f)] = lv[("axisangle", f)].reshape(-1, 1, 1, 3)
+        outs[("translation", 0, f)] = lv[("translation", f)].reshape(-1, 1, 1, 3)
     O.generate_images_pred(inputs, outs, cfg)
     for s in range(4):
         outs[("depth", 0, s)].retain_grad()

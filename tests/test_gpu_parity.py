@@ -37,7 +37,8 @@ def test_cuda_matches_reference_golden(name, rows):
             assert (m != z["idsel__%d" % s]).mean() <= 5e-4     # tiny fixtures: 1 flip of 7680 px = 1.3e-4
     # per-pixel (pre-aggregation) gradient, protocol P2
     a, c = 0.01, 9.99
-    for s in range(4):
+    # (under posecnn the disparity also acts through the per-scale T, outside the kernel's per-pixel map)
+    for s in range(4) if not g.posecnn else []:
         gd = r["side"][("grad_updisp", s)].cpu().numpy()
         d_s = g.t("disp__%d" % s)
         if not g.v1_multiscale:
@@ -49,7 +50,12 @@ def test_cuda_matches_reference_golden(name, rows):
     for s in range(4):
         assert rel_l2(r["leaves"][("disp", s)].grad.cpu(), z["grad_disp__%d" % s]) < 8e-2
     for f in g.frame_ids[1:]:
-        if f != "s":
+        if f == "s":
+            continue
+        if g.posecnn:
+            assert rel_l2(r["leaves"][("axisangle", f)].grad.cpu().reshape(-1), z["grad_axisangle__%s" % f].reshape(-1)) < 8e-2
+            assert rel_l2(r["leaves"][("translation", f)].grad.cpu().reshape(-1), z["grad_translation__%s" % f].reshape(-1)) < 8e-2
+        else:
             assert rel_l2(r["leaves"][("T", f)].grad.cpu(), z["grad_cam_T_cam__%s" % f]) < 8e-2
 
 

@@ -31,7 +31,8 @@ def test_oracle_matches_reference_golden(name):
     for f in g.frame_ids[1:]:
         if f == "s":
             continue
-        assert rel_l2(r["outs"][("cam_T_cam", 0, f)].grad, z["grad_cam_T_cam__%s" % f]) < 1e-4
+        if not g.posecnn:      # under posecnn T is rebuilt per scale from axisangle / translation
+            assert rel_l2(r["outs"][("cam_T_cam", 0, f)].grad, z["grad_cam_T_cam__%s" % f]) < 1e-4
         assert rel_l2(r["leaves"][("axisangle", f)].grad, z["grad_axisangle__%s" % f]) < 1e-3
         assert rel_l2(r["leaves"][("translation", f)].grad, z["grad_translation__%s" % f]) < 1e-3
 
