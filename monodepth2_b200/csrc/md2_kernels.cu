@@ -21,7 +21,10 @@
 
 namespace md2 {
 
-constexpr int kWarpsPerCta = 4;
+#ifndef MD2_WARPS_PER_CTA
+#define MD2_WARPS_PER_CTA 4
+#endif
+constexpr int kWarpsPerCta = MD2_WARPS_PER_CTA;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kSmoothPerThread = 4;
