@@ -8,9 +8,10 @@ from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 wl = sys.argv[3] if len(sys.argv) > 3 else "mono"
+kind = sys.argv[4] if len(sys.argv) > 4 else "iid"
 B, H, W = (12, 320, 1024) if wl == "hires" else (12, 192, 640)
 fids = [0, -1, 1, "s"] if wl == "stereo" else [0, -1, 1]
-inputs, outputs, pose, noise = make_batch(B, H, W, fids)
+inputs, outputs, pose, noise = make_batch(B, H, W, fids, kind=kind, seed=5 if kind == 'structured' else 0)
 dev = 'cuda:0'
 inputs = {k: v.to(dev) for k, v in inputs.items()}
 outs = {k: v.to(dev).requires_grad_(True) for k, v in outputs.items()}
@@ -25,4 +26,4 @@ for i in range(n):
     l = view_synthesis_loss(plan, inputs, outs, noise)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
-print(wl, "rows", rows, "ms/step %.4f" % ms, "frames/s %.0f" % (B / ms * 1e3), "loss", float(l["loss"].detach()))
+print(wl, kind, "rows", rows, "ms/step %.4f" % ms, "frames/s %.0f" % (B / ms * 1e3), "loss", float(l["loss"].detach()))
