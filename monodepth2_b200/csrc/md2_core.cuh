@@ -30,6 +30,15 @@
 #if defined(__CUDA_ARCH__)
 #define MD2_LD(p) __ldg(p)
 #define MD2_LD4(p) __ldg(reinterpret_cast<const float4*>(p))
+// streaming loads (read once per job: target row, disparity, identity loss, noise): do not allocate in
+// L1, which is kept for the data-dependent gathers
+#ifndef MD2_STREAM_ALLOC
+#define MD2_LDS1(p) md2::ld_stream(p)
+#define MD2_LDS4(p) md2::ld_stream4(p)
+#else
+#define MD2_LDS1(p) __ldg(p)
+#define MD2_LDS4(p) __ldg(reinterpret_cast<const float4*>(p))
+#endif
 #define MD2_FMUL(a, b) __fmul_rn(a, b)
 #define MD2_FADD(a, b) __fadd_rn(a, b)
 #define MD2_RCP(a) md2::rcp_nr(a)
@@ -47,6 +56,8 @@
 #define MD2_PREFETCH_L1(p) ((void)(p))
 #define MD2_LD(p) (*(p))
 #define MD2_LD4(p) (*reinterpret_cast<const md2::F4*>(p))
+#define MD2_LDS1(p) (*(p))
+#define MD2_LDS4(p) (*reinterpret_cast<const md2::F4*>(p))
 #define MD2_FMUL(a, b) md2::host_fmul(a, b)
 #define MD2_FADD(a, b) md2::host_fadd(a, b)
 #define MD2_RCP(a) (1.0f / (a))
@@ -66,6 +77,16 @@ MD2_HD F4 make_f4(float a, float b, float c, float d) { F4 r; r.x = a; r.y = b; 
 
 #if defined(__CUDA_ARCH__)
 // MUFU.RCP + one Newton step: <= 1 ulp, 3 instructions instead of the IEEE sequence
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float r;
+  asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ F4 ld_stream4(const float* p) {
+  F4 r;
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ float rcp_approx(float a) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
@@ -356,7 +377,7 @@ struct Stash {
 template <class C>
 MD2_HD void prefetch_row(Lane<C>& L, const WarpJob& J, int t) {
   const int tr = reflect_clamp(t, J.H);
-  L.ntg = MD2_LD4(J.tgt4 + 4 * (tr * J.W + L.xi));
+  L.ntg = MD2_LDS4(J.tgt4 + 4 * (tr * J.W + L.xi));
   if (J.s == 0) {
     L.nd[0] = MD2_LD(J.disp + tr * J.W + L.xi);
   } else {
@@ -464,9 +485,9 @@ MD2_HD void stage_a_issue(Lane<C>& L, const Params& P, const WarpJob& J, int t) 
     const int yw = t - 1;
     const int pix = (yw < 0 ? 0 : (yw >= J.H ? J.H - 1 : yw)) * J.W + L.xi;
 #pragma unroll
-    for (int f = 0; f < C::NSRC; ++f) L.idv[f] = MD2_LD(J.idl + f * J.plane + pix);
+    for (int f = 0; f < C::NSRC; ++f) L.idv[f] = MD2_LDS1(J.idl + f * J.plane + pix);
 #pragma unroll
-    for (int f = 0; f < C::NID; ++f) L.nzv[f] = MD2_LD(J.noise + f * J.plane + pix);
+    for (int f = 0; f < C::NID; ++f) L.nzv[f] = MD2_LDS1(J.noise + f * J.plane + pix);
   }
   const float sd = MD2_FADD(P.a_disp, MD2_FMUL(P.c_disp, D));
   const float z = MD2_RCP(sd);
