@@ -107,7 +107,10 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------- reference arm
-def oracle_step(B, H, W, frame_ids, avg, noauto, batch, threads):
+def oracle_step(B, H, W, frame_ids, avg, noauto, batch, threads, device=None):
+    """One fwd+bwd of the reference path (oracle port).  device=None: CPU, wall clock;
+    device=cuda: the same code on torch's CUDA kernels (the reference's PyTorch-CUDA path), the
+    batch must already be resident on the device."""
     from oracle import view_synthesis as O
     inputs, outputs, pose, noise = batch
     cfg = O.OracleConfig(height=H, width=W, frame_ids=tuple(frame_ids), avg_reprojection=avg,
@@ -125,10 +128,35 @@ def oracle_step(B, H, W, frame_ids, avg, noauto, batch, threads):
         outs[("cam_T_cam", 0, f)] = O.transformation_from_parameters(a, t, invert=(f < 0))
     ins = {k: v[:B] for k, v in inputs.items()}
     nz = [n[:B] for n in noise] if noise is not None else None
+    if device is not None:
+        torch.cuda.synchronize(device)
     t0 = time.perf_counter()
     losses = O.view_synthesis_loss(ins, outs, cfg, nz)
     losses["loss"].backward()
-    return time.perf_counter() - t0, float(losses["loss"])
+    if device is not None:
+        torch.cuda.synchronize(device)
+    return time.perf_counter() - t0, float(losses["loss"].detach())
+
+
+def batch_to(batch, dev):
+    inputs, outputs, pose, noise = batch
+    return ({k: v.to(dev) for k, v in inputs.items()}, {k: v.to(dev) for k, v in outputs.items()},
+            {f: (a.to(dev), t.to(dev)) for f, (a, t) in pose.items()},
+            [n.to(dev) for n in noise] if noise is not None else None)
+
+
+def torch_cuda_baseline(H, W, frame_ids, avg, noauto, batch, dev, reps=10):
+    """The reference's PyTorch-CUDA path (BASELINE.json configs[1]: "vs the reference's PyTorch CUDA
+    path"): the oracle port on torch's stock CUDA kernels, full batch, inputs resident in HBM."""
+    db = batch_to(batch, dev)
+    for _ in range(3):
+        oracle_step(BATCH, H, W, frame_ids, avg, noauto, db, 0, dev)
+    ts = [oracle_step(BATCH, H, W, frame_ids, avg, noauto, db, 0, dev)[0] for _ in range(reps)]
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return {"value": BATCH / med, "unit": UNIT, "ms_per_step": 1e3 * med, "best_ms": 1e3 * ts[0],
+            "kind": "port on torch CUDA kernels (oracle/view_synthesis.py, ~2.1k ATen launches per step)",
+            "sample": "%d full batches of %d frames, fwd+bwd, median" % (reps, BATCH)}
 
 
 def run_reference(args, wl):
@@ -393,6 +421,14 @@ def run_own(args, wl):
         cpu = {"value": n_fr / t_used, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "%d full batches of %d frames (oracle/view_synthesis.py, fwd+bwd)" % (reps, BATCH)}
 
+    tcb = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cb = host[0] if n_id > 0 else (host[0][0], host[0][1], host[0][2], None)
+        try:
+            tcb = torch_cuda_baseline(H, W, frame_ids, avg, noauto, cb, dev)
+        except Exception as e:      # a baseline leg must not take the bench line down
+            tcb = {"error": repr(e)[:200]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -403,7 +439,7 @@ def run_own(args, wl):
                        (nrot, int((h2d + n_id * BATCH * H * W * 4 * 4) / 1e6)),
                        "rows_per_segment": plan.problem(True).rows_per_segment or max(32, (H + 3) // 4), "loss": loss_val,
                        "launch": "plain C-ABI calls" if graphs is None else "CUDA-graph replay of the C-ABI call"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": cpu, "torch_cuda_baseline": tcb, "e2e": e2e,
             "gpu_launches": 7 * args.steps,
             "clocks": clocks,
         }

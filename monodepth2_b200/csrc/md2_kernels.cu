@@ -15,6 +15,7 @@
 // adjoint needs two rows later sit in a thread-private shared-memory ring.  No block-level
 // synchronisation, no tensor cores (the path is gather/stream work, BASELINE.json).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "md2_core.cuh"
 #include "md2_plan.h"
@@ -288,7 +289,12 @@ template <class C>
 static cudaError_t launch_march(const Params& P, cudaStream_t stream) {
   const int jobs = P.S * P.B * P.nseg * P.nband;
   const int grid = (jobs + kWarpsPerCta - 1) / kWarpsPerCta;
-  const size_t smem = (size_t)kThreads * C::SMEM4 * sizeof(float4);
+  size_t smem = (size_t)kThreads * C::SMEM4 * sizeof(float4);
+#ifdef MD2_DEV_KNOBS
+  // development knob: pad the dynamic shared memory to lower the number of resident warps per SM
+  static const int pad = getenv("MD2_PAD_SMEM") ? atoi(getenv("MD2_PAD_SMEM")) : 0;
+  smem += (size_t)pad;
+#endif
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(md2_march<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -52,6 +52,7 @@ class OracleConfig:
     disable_automasking: bool = False
     no_ssim: bool = False
     v1_multiscale: bool = False               # trainer.py:347-352,417-420: source_scale = scale
+    predictive_mask: bool = False             # trainer.py:447-459 (requires disable_automasking, trainer.py:90-92)
     posecnn: bool = False                     # trainer.py:366-375: translation scaled by the mean inverse depth
     # trainer.py:384-387 leaves align_corners unspecified -> False on torch >= 1.3.
     align_corners: bool = False
@@ -202,7 +203,16 @@ def compute_losses(inputs: Dict, outputs: Dict, cfg: OracleConfig,
         disp = outputs[("disp", s)]
         color = inputs[("color", 0, s)]
         reproj = torch.cat([reprojection_loss(outputs[("color", f, s)], target, cfg) for f in srcs], 1)
-        if cfg.avg_reprojection:
+        extra = 0
+        if cfg.disable_automasking and cfg.predictive_mask:
+            # trainer.py:447-459: per-source mask from the mask decoder, up-sampled like the disparity;
+            # weights the reprojection losses and is pushed towards 1 by 0.2 * BCE(mask, 1)
+            mask = outputs["predictive_mask"][("disp", s)]
+            if not cfg.v1_multiscale:
+                mask = F.interpolate(mask, [cfg.height, cfg.width], mode="bilinear", align_corners=False)
+            reproj = reproj * mask
+            extra = 0.2 * F.binary_cross_entropy(mask, torch.ones_like(mask))
+        if cfg.avg_reprojection:       # trainer.py:461-462 (after the mask weighting)
             reproj = reproj.mean(1, keepdim=True)
         if not cfg.disable_automasking:
             ident = torch.cat([reprojection_loss(inputs[("color", f, src_scale)], target, cfg) for f in srcs], 1)
@@ -220,7 +230,7 @@ def compute_losses(inputs: Dict, outputs: Dict, cfg: OracleConfig,
             to_optimise, idxs = torch.min(combined, dim=1)
         if not cfg.disable_automasking:
             outputs["identity_selection/{}".format(s)] = (idxs > ident.shape[1] - 1).to(disp.dtype)
-        loss = to_optimise.mean()
+        loss = to_optimise.mean() + extra
         mean_disp = disp.mean(2, True).mean(3, True)
         norm_disp = disp / (mean_disp + 1e-7)
         loss = loss + cfg.disparity_smoothness * smooth_loss(norm_disp, color) / (2 ** s)
