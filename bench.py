@@ -448,6 +448,106 @@ def run_own(args, wl):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------- full training step
+def run_train(args, wl):
+    """--mode train: nets + loss + backward + Adam (+ DDP all-reduce), batch 12 per GPU, synthetic
+    batches resident in HBM.  --impl own: fused loss; --impl reference: the
+    reference's PyTorch-CUDA loss path (oracle port on torch CUDA kernels) in the same harness."""
+    from benchmarks.train_step import Nets, TrainStep, parameter_count
+    from monodepth2_b200.synthetic import make_batch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --mode train needs a CUDA device")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    H, W, frame_ids, avg, noauto = WORKLOADS[wl]
+    n_src = len(frame_ids) - 1
+    torch.manual_seed(1234)                         # identical initial weights on every rank
+    nets = Nets(frame_ids, args.num_layers).to(dev)
+    n_params = parameter_count(nets)
+    model = nets
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        model = DDP(nets, device_ids=[local], gradient_as_bucket_view=True)
+
+    if args.impl == "reference":
+        from oracle import view_synthesis as O
+        cfg = O.OracleConfig(height=H, width=W, frame_ids=tuple(frame_ids), avg_reprojection=avg,
+                             disable_automasking=noauto)
+
+        def loss_fn(inputs, outputs):
+            return O.view_synthesis_loss(inputs, outputs, cfg, None)
+        pose_fn = O.transformation_from_parameters
+        loss_name = "reference PyTorch-CUDA loss path (oracle port)"
+    else:
+        from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
+        from monodepth2_b200.layers import transformation_from_parameters as pose_fn
+        plan = LossPlan(BATCH, H, W, frame_ids, avg_reprojection=avg, disable_automasking=noauto)
+
+        def loss_fn(inputs, outputs):
+            return view_synthesis_loss(plan, inputs, outputs)
+        loss_name = "fused md2_view_synthesis_loss"
+
+    nrot = 2
+    batches = []
+    for i in range(nrot):
+        inputs, _, _, _ = make_batch(BATCH, H, W, frame_ids, 4, seed=1000 * rank + i, kind="structured")
+        batches.append({k: v.to(dev) for k, v in inputs.items()})
+    step = TrainStep(model, frame_ids, loss_fn, pose_fn)
+    torch.backends.cudnn.benchmark = True
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(batches[i % nrot])
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(batches[i % nrot])
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    tt = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total = float(tt.item())
+    if rank == 0:
+        line = {
+            "impl": args.impl, "metric": "train steps/s (nets + view-synthesis loss + backward + Adam)",
+            "value": args.steps / (ms_total * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "frames_per_s": world * BATCH * args.steps / (ms_total * 1e-3),
+            "config": {"workload": wl, "mode": "train", "batch_per_gpu": BATCH, "global_batch": world * BATCH,
+                       "frame_ids": [str(f) for f in frame_ids], "scales": 4,
+                       "nets": "stand-in ResNet-%d encoder + depth decoder + pose encoder/decoder, %.2f M params, "
+                               "random init, fp32 (TF32 off)" % (args.num_layers, n_params / 1e6),
+                       "loss": loss_name, "parallelism": "ddp%d (NCCL all-reduce of %.1f MB of gradients)" %
+                       (world, n_params * 4 / 1e6) if world > 1 else "single GPU",
+                       "last_loss": float(loss.item())},
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -458,8 +558,13 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="rows per marching segment (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="plain C-ABI calls instead of CUDA-graph replay")
+    ap.add_argument("--mode", default="loss", choices=["loss", "train"],
+                    help="loss: the hot path alone (the contract metric); train: the full training step around it")
+    ap.add_argument("--num-layers", type=int, default=18, choices=[18, 50], help="--mode train: ResNet depth")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.mode == "train":
+        run_train(args, args.workload)
+    elif args.impl == "reference":
         run_reference(args, args.workload)
     else:
         run_own(args, args.workload)
