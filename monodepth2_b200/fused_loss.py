@@ -37,7 +37,7 @@ class LossPlan:
                  disparity_smoothness: float = 1e-3, avg_reprojection: bool = False,
                  disable_automasking: bool = False, align_corners: bool = False,
                  rows_per_segment: int = 0, no_ssim: bool = False, v1_multiscale: bool = False,
-                 posecnn: bool = False):
+                 posecnn: bool = False, predictive_mask: bool = False):
         if list(scales) != list(range(len(scales))):
             raise RuntimeError("scales must be 0..n-1, got %s" % (list(scales),))
         self.batch_size, self.height, self.width = int(batch_size), int(height), int(width)
@@ -55,6 +55,13 @@ class LossPlan:
         self.posecnn = bool(posecnn)
         if self.posecnn and self.v1_multiscale:
             raise RuntimeError("posecnn together with --v1_multiscale is not supported by the fused loss")
+        # --predictive_mask (trainer.py:447-459) needs --disable_automasking (trainer.py:90-92)
+        self.predictive_mask = bool(predictive_mask)
+        if self.predictive_mask and self.automask:
+            raise RuntimeError("When using predictive_mask, please disable automasking with --disable_automasking")
+        if self.predictive_mask and (self.v1_multiscale or self.posecnn):
+            raise RuntimeError("--predictive_mask together with --v1_multiscale / posecnn is not supported")
+        self._layer_modules = None
         self.n_src = len(self.src_ids)
         self.n_id = 0 if not self.automask else (1 if self.avg_reprojection else self.n_src)
         self.lib = _capi.load_library()
@@ -81,13 +88,12 @@ class LossPlan:
     @classmethod
     def from_opt(cls, opt, **kw) -> "LossPlan":
         """Build from a reference ``options.py`` namespace (after trainer.py:51-52 appended "s")."""
-        if getattr(opt, "predictive_mask", False):
-            raise RuntimeError("--predictive_mask is not supported by the fused loss yet")
         return cls(opt.batch_size, opt.height, opt.width, opt.frame_ids, opt.scales, opt.min_depth,
                    opt.max_depth, opt.disparity_smoothness, opt.avg_reprojection,
                    opt.disable_automasking, no_ssim=getattr(opt, "no_ssim", False),
                    v1_multiscale=getattr(opt, "v1_multiscale", False),
-                   posecnn=(getattr(opt, "pose_model_type", "separate_resnet") == "posecnn"), **kw)
+                   posecnn=(getattr(opt, "pose_model_type", "separate_resnet") == "posecnn"),
+                   predictive_mask=getattr(opt, "predictive_mask", False), **kw)
 
     def problem(self, want_grad: bool) -> Md2Problem:
         return Md2Problem(batch=self.batch_size, height=self.height, width=self.width,
@@ -213,6 +219,8 @@ def view_synthesis_loss(plan: LossPlan, inputs: Dict, outputs: Dict,
     ``side`` selects optional outputs: {"depth_scales": [...], "color_scales": [...], "mask_scales": [...]};
     the produced tensors are stored both in ``side`` and in ``outputs`` under the reference's keys.
     """
+    if plan.predictive_mask:
+        return _view_synthesis_loss_predictive_mask(plan, inputs, outputs, side)
     if plan.v1_multiscale:
         return _view_synthesis_loss_v1_multiscale(plan, inputs, outputs, noise, side)
     if plan.posecnn:
@@ -330,6 +338,56 @@ def _view_synthesis_loss_posecnn(plan: LossPlan, inputs: Dict, outputs: Dict, no
                 elif isinstance(k, str) and k.startswith("identity_selection/"):
                     side["identity_selection/{}".format(s)] = v
                     outputs["identity_selection/{}".format(s)] = v
+    losses["loss"] = total / len(plan.scales)
+    return losses
+
+
+def _view_synthesis_loss_predictive_mask(plan: LossPlan, inputs: Dict, outputs: Dict, side):
+    """--predictive_mask (trainer.py:447-459): the per-source mask of the mask decoder weights the
+    reprojection losses *before* the per-pixel minimum and is pushed towards 1 by 0.2 * BCE(mask, 1).
+    This ablation is not fused: it is composed from the per-layer sm_100a ops of ``layers.py``
+    (md2_disp_to_depth, md2_backproject_depth, md2_project3d, md2_grid_sample_border, md2_ssim,
+    md2_smooth_loss); the mask weighting, minimum, means and BCE are torch element-wise glue."""
+    import torch.nn.functional as F
+    from . import layers as L
+    B, H, W = plan.batch_size, plan.height, plan.width
+    if plan._layer_modules is None:
+        dev = inputs[("color", 0, 0)].device
+        plan._layer_modules = (L.BackprojectDepth(B, H, W).to(dev), L.Project3D(B, H, W).to(dev), L.SSIM().to(dev))
+    backproject, project, ssim = plan._layer_modules
+    target = inputs[("color", 0, 0)]
+    K, inv_K = inputs[("K", 0)], inputs[("inv_K", 0)]
+    losses: Dict[str, torch.Tensor] = {}
+    total = 0
+    for s in plan.scales:
+        disp = outputs[("disp", s)]
+        up = F.interpolate(disp, [H, W], mode="bilinear", align_corners=False) if s > 0 else disp
+        _, depth = L.disp_to_depth(up, plan.min_depth, plan.max_depth)
+        if side is not None and s in side.get("depth_scales", []):
+            side[("depth", 0, s)] = outputs[("depth", 0, s)] = depth.detach()
+        points = backproject(depth, inv_K)
+        rls = []
+        for f in plan.src_ids:
+            T = inputs["stereo_T"] if f == "s" else outputs[("cam_T_cam", 0, f)]
+            pred = L.grid_sample_border(inputs[("color", f, 0)], project(points, K, T), plan.align_corners)
+            if side is not None and s in side.get("color_scales", []):
+                side[("color", f, s)] = outputs[("color", f, s)] = pred.detach()
+            l1 = (target - pred).abs().mean(1, True)
+            rls.append(l1 if plan.no_ssim else 0.85 * ssim(pred, target).mean(1, True) + 0.15 * l1)
+        reproj = torch.cat(rls, 1)
+        mask = outputs["predictive_mask"][("disp", s)]
+        mask = F.interpolate(mask, [H, W], mode="bilinear", align_corners=False)
+        reproj = reproj * mask
+        loss = 0.2 * F.binary_cross_entropy(mask, torch.ones_like(mask))
+        if plan.avg_reprojection:
+            reproj = reproj.mean(1, True)
+        to_optimise = reproj if reproj.shape[1] == 1 else torch.min(reproj, dim=1)[0]
+        loss = loss + to_optimise.mean()
+        mean_disp = disp.mean(2, True).mean(3, True)
+        smooth = L.get_smooth_loss(disp / (mean_disp + 1e-7), inputs[("color", 0, s)])
+        loss = loss + plan.disparity_smoothness * smooth / (2 ** s)
+        losses["loss/{}".format(s)] = loss
+        total = total + loss
     losses["loss"] = total / len(plan.scales)
     return losses
 

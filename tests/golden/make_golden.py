@@ -46,6 +46,8 @@ CASES = {
                           flags=["--v1_multiscale"]),
     "posecnn": dict(B=2, H=48, W=80, frame_ids=[0, -1, 1], kind="structured", seed=10,
                     flags=["--pose_model_type", "posecnn"]),
+    "predictive_mask": dict(B=2, H=48, W=80, frame_ids=[0, -1, 1], kind="structured", seed=12,
+                            flags=["--disable_automasking", "--predictive_mask"]),
     "stereo_only": dict(B=2, H=32, W=64, frame_ids=[0], kind="structured", seed=7,
                         flags=["--use_stereo", "--frame_ids", "0"]),
 }
@@ -128,6 +130,15 @@ def run_reference(T, MonodepthOptions, case, dtype=torch.float32, batch=None):
         # generate_images_pred (trainer.py:366-375) rebuilds T from these
         outs[("axisangle", 0, f)] = a.reshape(-1, 1, 1, 3)
         outs[("translation", 0, f)] = t.reshape(-1, 1, 1, 3)
+    if opt.predictive_mask:
+        # what the mask decoder emits (trainer.py:96-98, 251-252): one sigmoid map per source and scale
+        gm = torch.Generator().manual_seed(1000 + case["seed"])
+        outs["predictive_mask"] = {}
+        for s in range(4):
+            m = torch.sigmoid(2.0 * torch.randn(case["B"], n_src, case["H"] >> s, case["W"] >> s, generator=gm))
+            m = m.to(dtype).requires_grad_(True)
+            leaves[("mask", s)] = m
+            outs["predictive_mask"][("disp", s)] = m
     me = build_self(T, opt, dtype)
     me.generate_images_pred(inputs, outs)
     for s in range(4):
@@ -141,10 +152,15 @@ def run_reference(T, MonodepthOptions, case, dtype=torch.float32, batch=None):
         assert tuple(z.shape) == tuple(shape), (z.shape, shape)
         return z
     torch.randn = fake_randn
+    # trainer.py:458 hard-codes `.cuda()` in the predictive-mask branch; on this CPU run it is made a
+    # no-op from outside (the reference source stays unmodified)
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
     try:
         losses = me.compute_losses(inputs, outs)
     finally:
         torch.randn = real_randn
+        torch.Tensor.cuda = real_cuda
     losses["loss"].backward()
     return dict(opt=opt, frame_ids=frame_ids, inputs=inputs, outs=outs, leaves=leaves,
                 losses=losses, noise=noise, n_id=n_id, pose=pose)
@@ -156,7 +172,8 @@ def pack(res):
     d["frame_ids"] = np.array([str(f) for f in fids])
     opt = res["opt"]
     d["flags"] = np.array([int(opt.avg_reprojection), int(opt.disable_automasking), int(opt.no_ssim),
-                           int(opt.v1_multiscale), int(opt.pose_model_type == "posecnn")])
+                           int(opt.v1_multiscale), int(opt.pose_model_type == "posecnn"),
+                           int(opt.predictive_mask)])
     for k, v in res["inputs"].items():
         name = "in__" + "__".join(str(x) for x in (k if isinstance(k, tuple) else (k,)))
         d[name] = v.detach().numpy()
@@ -169,6 +186,10 @@ def pack(res):
         key = "identity_selection/%d" % s
         if key in res["outs"]:
             d["idsel__%d" % s] = res["outs"][key].detach().numpy().astype(np.uint8)
+    for s in range(4):
+        if ("mask", s) in res["leaves"]:
+            d["mask__%d" % s] = res["leaves"][("mask", s)].detach().numpy()
+            d["grad_mask__%d" % s] = res["leaves"][("mask", s)].grad.numpy()
     d["loss"] = res["losses"]["loss"].detach().numpy()
     d["depth__0"] = res["outs"][("depth", 0, 0)].detach().numpy()
     for f in fids[1:]:
@@ -187,7 +208,10 @@ def pack(res):
 def main():
     torch.manual_seed(0)
     T, MonodepthOptions = import_reference()
+    only = sys.argv[1:]
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         res = run_reference(T, MonodepthOptions, case)
         d = pack(res)
         path = os.path.join(HERE, name + ".npz")

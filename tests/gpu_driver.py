@@ -8,7 +8,7 @@ def run_cuda(g, rows_per_segment=0, align_corners=False, want_grad=True, side_al
     plan = LossPlan(g.B, g.H, g.W, g.frame_ids, avg_reprojection=g.avg_reprojection,
                     disable_automasking=g.disable_automasking, align_corners=align_corners,
                     rows_per_segment=rows_per_segment, no_ssim=g.no_ssim, v1_multiscale=g.v1_multiscale,
-                    posecnn=g.posecnn)
+                    posecnn=g.posecnn, predictive_mask=g.predictive_mask)
     inputs = {k: v.to(dev) for k, v in g.inputs().items()}
     outs, leaves = {}, {}
     for s in range(4):
@@ -26,6 +26,12 @@ def run_cuda(g, rows_per_segment=0, align_corners=False, want_grad=True, side_al
             tr = g.t("translation__%s" % f).to(dev).reshape(-1, 1, 1, 3).requires_grad_(want_grad)
             outs[("axisangle", 0, f)], outs[("translation", 0, f)] = aa, tr
             leaves[("axisangle", f)], leaves[("translation", f)] = aa, tr
+    if g.predictive_mask:      # the mask decoder's outputs (trainer.py:251-252)
+        outs["predictive_mask"] = {}
+        for s in range(4):
+            m = g.t("mask__%d" % s).to(dev).requires_grad_(want_grad)
+            outs["predictive_mask"][("disp", s)] = m
+            leaves[("mask", s)] = m
     noise = [n.to(dev) for n in g.noise()] if g.n_id > 0 else None
     side = None
     if side_all:

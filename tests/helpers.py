@@ -27,8 +27,9 @@ class Golden:
         z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
         self.z = z
         self.frame_ids = [_fid(str(s)) for s in z["frame_ids"]]
-        fl = [bool(int(x)) for x in z["flags"]] + [False, False]
+        fl = [bool(int(x)) for x in z["flags"]] + [False, False, False]
         self.avg_reprojection, self.disable_automasking, self.no_ssim, self.v1_multiscale, self.posecnn = fl[:5]
+        self.predictive_mask = fl[5]
         self.B, _, self.H, self.W = z["in__color__0__0"].shape
         self.n_src = len(self.frame_ids) - 1
         self.n_id = 0 if self.disable_automasking else (1 if self.avg_reprojection else self.n_src)
@@ -37,7 +38,8 @@ class Golden:
         return O.OracleConfig(height=self.H, width=self.W, frame_ids=tuple(self.frame_ids),
                               avg_reprojection=self.avg_reprojection,
                               disable_automasking=self.disable_automasking, no_ssim=self.no_ssim,
-                              v1_multiscale=self.v1_multiscale, posecnn=self.posecnn, **kw)
+                              v1_multiscale=self.v1_multiscale, posecnn=self.posecnn,
+                              predictive_mask=self.predictive_mask, **kw)
 
     def t(self, key, dtype=torch.float32):
         return torch.from_numpy(np.asarray(self.z[key])).to(dtype)
@@ -65,6 +67,9 @@ class Golden:
         lv = {}
         for s in range(4):
             lv[("disp", s)] = self.t("disp__%d" % s, dtype).requires_grad_(True)
+        if self.predictive_mask:
+            for s in range(4):
+                lv[("mask", s)] = self.t("mask__%d" % s, dtype).requires_grad_(True)
         for f in self.frame_ids[1:]:
             if f == "s":
                 continue
@@ -89,6 +94,8 @@ def run_oracle(g: Golden, dtype=torch.float32, **cfgkw):
         outs[("cam_T_cam", 0, f)] = T
         outs[("axisangle", 0, f)] = lv[("axisangle", f)].reshape(-1, 1, 1, 3)
         outs[("translation", 0, f)] = lv[("translation", f)].reshape(-1, 1, 1, 3)
+    if g.predictive_mask:
+        outs["predictive_mask"] = {("disp", s): lv[("mask", s)] for s in range(4)}
     O.generate_images_pred(inputs, outs, cfg)
     for s in range(4):
         outs[("depth", 0, s)].retain_grad()

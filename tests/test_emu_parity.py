@@ -8,7 +8,7 @@ from helpers import Golden, golden_cases, rel_l2
 
 
 @pytest.mark.parametrize("rows", [16, 5])
-@pytest.mark.parametrize("name", [c for c in golden_cases() if c not in ("v1_multiscale", "posecnn")])  # composition is host-side
+@pytest.mark.parametrize("name", [c for c in golden_cases() if c not in ("v1_multiscale", "posecnn", "predictive_mask")])  # composition is host-side
 def test_emulated_kernels_match_reference_golden(name, rows):
     from emu_driver import run_emu
     g = Golden(name)

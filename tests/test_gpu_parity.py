@@ -38,7 +38,8 @@ def test_cuda_matches_reference_golden(name, rows):
     # per-pixel (pre-aggregation) gradient, protocol P2
     a, c = 0.01, 9.99
     # (under posecnn the disparity also acts through the per-scale T, outside the kernel's per-pixel map)
-    for s in range(4) if not g.posecnn else []:
+    # (--predictive_mask is composed from the per-layer ops and has no per-pixel debug map)
+    for s in range(4) if not (g.posecnn or g.predictive_mask) else []:
         gd = r["side"][("grad_updisp", s)].cpu().numpy()
         d_s = g.t("disp__%d" % s)
         if not g.v1_multiscale:
@@ -49,6 +50,8 @@ def test_cuda_matches_reference_golden(name, rows):
     # aggregated gradients: relL2 bounded (flips allowed, see test_full_size for the P3 protocol)
     for s in range(4):
         assert rel_l2(r["leaves"][("disp", s)].grad.cpu(), z["grad_disp__%d" % s]) < 8e-2
+        if g.predictive_mask:
+            assert rel_l2(r["leaves"][("mask", s)].grad.cpu(), z["grad_mask__%d" % s]) < 1e-3
     for f in g.frame_ids[1:]:
         if f == "s":
             continue

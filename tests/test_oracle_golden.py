@@ -28,6 +28,9 @@ def test_oracle_matches_reference_golden(name):
     for s in range(4):
         assert rel_l2(r["leaves"][("disp", s)].grad, z["grad_disp__%d" % s]) < 1e-4
         assert rel_l2(r["outs"][("depth", 0, s)].grad, z["grad_depth__%d" % s]) < 1e-4
+    if g.predictive_mask:
+        for s in range(4):
+            assert rel_l2(r["leaves"][("mask", s)].grad, z["grad_mask__%d" % s]) < 1e-4
     for f in g.frame_ids[1:]:
         if f == "s":
             continue
