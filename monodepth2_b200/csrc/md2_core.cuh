@@ -518,11 +518,25 @@ MD2_HD void stage_a_issue(Lane<C>& L, const Params& P, const WarpJob& J, int t) 
     });
     const int dx1 = (x0 + 1 < J.W) ? 4 : 0;                 // texel step to the east tap
     const int dy1 = (y0 + 1 < J.H) ? J.W * 4 : 0;           // texel step to the south tap
+#if defined(MD2_KO_GATHER) && MD2_KO_GATHER == 1
+    // timing knock-out (results invalid): coalesced taps at the lane's own pixel, address still data-dependent
+    const float* t00 = J.src4[f] + 4 * (tr * J.W + L.xi + (x0 >> 30) + (y0 >> 30));
+#else
     const float* t00 = J.src4[f] + 4 * (y0 * J.W + x0);
+#endif
+#if defined(MD2_KO_GATHER) && MD2_KO_GATHER == 2
+    // timing knock-out (results invalid): no memory access at all for the taps
+    L.tap[f][0] = make_f4(ixc * 1e-3f, iyc * 1e-3f, u * 1e-3f, 0.f);
+    L.tap[f][1] = make_f4(iyc * 1e-3f, u * 1e-3f, ixc * 1e-3f, (float)(dx1 + dy1));
+    L.tap[f][2] = make_f4(v * 1e-3f, ixc * 2e-3f, iyc * 1e-3f, 0.f);
+    L.tap[f][3] = make_f4(iyc * 2e-3f, v * 1e-3f, u * 2e-3f, 0.f);
+    (void)t00;
+#else
     L.tap[f][0] = MD2_LD4(t00);
     L.tap[f][1] = MD2_LD4(t00 + dx1);
     L.tap[f][2] = MD2_LD4(t00 + dy1);
     L.tap[f][3] = MD2_LD4(t00 + dy1 + dx1);
+#endif
     L.cu[f] = u; L.cv[f] = v;
     L.cwx[f] = ixc - fx0; L.cwy[f] = iyc - fy0;
     L.cgx[f] = mx ? P.sx * inv : 0.0f;

@@ -16,8 +16,10 @@
 // synchronisation, no tensor cores (the path is gather/stream work, BASELINE.json).
 #include <cuda_runtime.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "md2_core.cuh"
+#include "md2_pack2.cuh"
 #include "md2_plan.h"
 
 namespace md2 {
@@ -152,18 +154,25 @@ __global__ void md2_smooth_scalars(Params P) {
 }
 
 // ------------------------------------------------------------------ 5. the marching kernel
+#ifdef MD2_KO_SHFL   // timing knock-out (results invalid): no neighbour exchange
+#define MD2_SHUP(v) (v)
+#define MD2_SHDN(v) (v)
+#else
+#define MD2_SHUP(v) __shfl_up_sync(kFull, v, 1)
+#define MD2_SHDN(v) __shfl_down_sync(kFull, v, 1)
+#endif
 template <class C>
 __device__ __forceinline__ void exchange_and_stage_c(Lane<C>& L, const Params& P, const WarpJob& J, int t, int lane,
                                                      const Stash& st) {
   Xchg2<C> l2, r2;
-  l2.tag = __shfl_up_sync(kFull, L.tag, 1);
-  r2.tag = __shfl_down_sync(kFull, L.tag, 1);
+  l2.tag = MD2_SHUP(L.tag);
+  r2.tag = MD2_SHDN(L.tag);
 #pragma unroll
   for (int n = 0; n < C::NCS; ++n)
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      l2.coef[n][k] = C::NOSSIM ? 0.f : __shfl_up_sync(kFull, L.coef[n][k], 1);
-      r2.coef[n][k] = C::NOSSIM ? 0.f : __shfl_down_sync(kFull, L.coef[n][k], 1);
+      l2.coef[n][k] = C::NOSSIM ? 0.f : MD2_SHUP(L.coef[n][k]);
+      r2.coef[n][k] = C::NOSSIM ? 0.f : MD2_SHDN(L.coef[n][k]);
     }
   stage_c(L, P, J, t, lane, l2, r2, st);
 }
@@ -221,12 +230,12 @@ __global__ void MD2_MARCH_BOUNDS md2_march(Params P) {
     Xchg1<C> l1, r1;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      l1.tg[c] = __shfl_up_sync(kFull, L.tg[c], 1);
-      r1.tg[c] = __shfl_down_sync(kFull, L.tg[c], 1);
+      l1.tg[c] = MD2_SHUP(L.tg[c]);
+      r1.tg[c] = MD2_SHDN(L.tg[c]);
 #pragma unroll
       for (int f = 0; f < C::NSRC; ++f) {
-        l1.pr[f][c] = __shfl_up_sync(kFull, L.pr[f][c], 1);
-        r1.pr[f][c] = __shfl_down_sync(kFull, L.pr[f][c], 1);
+        l1.pr[f][c] = MD2_SHUP(L.pr[f][c]);
+        r1.pr[f][c] = MD2_SHDN(L.pr[f][c]);
       }
     }
     stage_b(L, P, J, t, lane, l1, r1);
@@ -240,6 +249,84 @@ __global__ void MD2_MARCH_BOUNDS md2_march(Params P) {
       if (!P.pose_grad[f]) continue;
       float dP[12];
       lane_dP(L, P, J, f, dP);
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const float v = warp_sum(dP[k]);
+        if (lane == 0) atomicAdd(&P.acc[acc_dP(P, J.b, f, k)], (double)v);
+      }
+    }
+  }
+}
+
+
+// Packed-fp32 form of md2_march for two sources (md2_pack2.cuh): same decomposition, same pipeline.
+template <class C>
+__device__ __forceinline__ void exchange_and_stage_c2(Lane2<C>& L, const Params& P, const WarpJob& J, int t, int lane,
+                                                      const Stash& st) {
+  Xchg2P<C> l2, r2;
+  l2.tag = MD2_SHUP(L.tag);
+  r2.tag = MD2_SHDN(L.tag);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    l2.cf[i] = C::NOSSIM ? bc(0.f) : p2(MD2_SHUP(L.cf[i].x), MD2_SHUP(L.cf[i].y));
+    r2.cf[i] = C::NOSSIM ? bc(0.f) : p2(MD2_SHDN(L.cf[i].x), MD2_SHDN(L.cf[i].y));
+    l2.cfb[i] = C::NOSSIM ? 0.f : MD2_SHUP(L.cfb[i]);
+    r2.cfb[i] = C::NOSSIM ? 0.f : MD2_SHDN(L.cfb[i]);
+  }
+  stage_c2(L, P, J, t, lane, l2, r2, st);
+}
+
+template <class C>
+__global__ void MD2_MARCH_BOUNDS md2_march2(Params P) {
+  static_assert(C::NSRC == 2 && !C::AVG, "packed form: two sources, per-pixel minimum");
+  extern __shared__ float4 smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
+  const int job = blockIdx.x * kWarpsPerCta + warp;
+  const int per_seg = P.S * P.nband;
+  const int per_b = P.nseg * per_seg;
+  if (job >= per_b * P.B) return;
+  const int jb = P.B - 1 - job / per_b;
+  const int r = job - (job / per_b) * per_b;
+  const int seg = r / per_seg;
+  const int r2 = r - seg * per_seg;
+  const int js = r2 / P.nband;
+  const int jy0 = seg * P.seg_rows;
+  const WarpJob J = make_job(P, js, jb, (r2 - js * P.nband) * kOwnCols, jy0, min(jy0 + P.seg_rows, P.H));
+
+  Stash st;
+  st.base = smem + threadIdx.x;
+  st.bring = nullptr;
+  st.stride = kThreads;
+
+  Lane2<C> L;
+  lane_init2(L, P, J, lane);
+  MD2_LOOP_UNROLL
+  for (int t = J.y0 - 2; t <= J.y1 + 1; ++t) {
+    stage_a_issue2(L, P, J, t);
+    if (C::GRAD && t > J.y0 - 2) exchange_and_stage_c2(L, P, J, t - 1, lane, st);
+    stage_a_finish2(L, P, J, t, st);
+    Xchg1P<C> l1, r1;
+    l1.tgrg = p2(MD2_SHUP(L.tgrg.x), MD2_SHUP(L.tgrg.y));
+    r1.tgrg = p2(MD2_SHDN(L.tgrg.x), MD2_SHDN(L.tgrg.y));
+    l1.tgb = MD2_SHUP(L.tgb);
+    r1.tgb = MD2_SHDN(L.tgb);
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      l1.pr[s] = p2(MD2_SHUP(L.pr[s].x), MD2_SHUP(L.pr[s].y));
+      r1.pr[s] = p2(MD2_SHDN(L.pr[s].x), MD2_SHDN(L.pr[s].y));
+    }
+    stage_b2(L, P, J, t, lane, l1, r1);
+  }
+  if (C::GRAD) exchange_and_stage_c2(L, P, J, J.y1 + 1, lane, st);
+  const float ls = warp_sum(L.loss);
+  if (lane == 0) atomicAdd(&P.acc[acc_photo(J.s)], (double)ls);
+  if (C::GRAD) {
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      if (!P.pose_grad[f]) continue;
+      float dP[12];
+      lane_dP2(L, P, J, f, dP);
 #pragma unroll
       for (int k = 0; k < 12; ++k) {
         const float v = warp_sum(dP[k]);
@@ -285,6 +372,19 @@ __global__ void md2_final(Params P) {
 }
 
 // ------------------------------------------------------------------ launcher
+// Which two-source instantiations use the packed-fp32 form (md2_pack2.cuh).  Default: forward-only calls
+// (measured faster), scalar form when gradients are wanted (measured faster).  MD2_PACK2=all / MD2_PACK2=off
+// in the environment force one form for every two-source call (A/B checks, tests/test_gpu_parity.py).
+static bool use_pack2(bool grad) {
+  static const int mode = [] {
+    const char* e = getenv("MD2_PACK2");
+    if (e && !strcmp(e, "all")) return 2;
+    if (e && !strcmp(e, "off")) return 0;
+    return 1;
+  }();
+  return mode == 2 || (mode == 1 && !grad);
+}
+
 template <class C>
 static cudaError_t launch_march(const Params& P, cudaStream_t stream) {
   const int jobs = P.S * P.B * P.nseg * P.nband;
@@ -298,6 +398,16 @@ static cudaError_t launch_march(const Params& P, cudaStream_t stream) {
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(md2_march<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+  }
+  if constexpr (C::NSRC == 2 && !C::AVG) {
+    if (use_pack2(C::GRAD)) {
+      if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(md2_march2<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+      }
+      md2_march2<C><<<grid, kThreads, smem, stream>>>(P);
+      return cudaGetLastError();
+    }
   }
   md2_march<C><<<grid, kThreads, smem, stream>>>(P);
   return cudaGetLastError();

@@ -87,3 +87,31 @@ def test_cuda_matches_host_emulator_of_the_same_source(name):
         if g.n_id > 0:
             m = r["side"]["identity_selection/%d" % s].cpu().numpy()
             assert (m != e["idsel"][s]).mean() <= 5e-4
+
+
+def test_packed_and_scalar_two_source_kernels_agree(tmp_path):
+    """md2_pack2.cuh (FFMA2 form, default for forward-only calls) against the scalar form on the same
+    inputs: same order of operations, so losses agree to rounding and per-pixel gradients almost everywhere."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    res = {}
+    for mode in ("all", "off"):
+        path = str(tmp_path / ("pack2_%s.npz" % mode))
+        env = dict(os.environ, MD2_PACK2=mode, PYTHONPATH=here + os.pathsep + os.path.dirname(here))
+        subprocess.run([sys.executable, os.path.join(here, "pack2_probe.py"), path], env=env, check=True, timeout=600)
+        res[mode] = np.load(path)
+    a, b = res["all"], res["off"]
+    assert sorted(a.files) == sorted(b.files)
+    for k in a.files:
+        if k.endswith("/loss") or k.endswith("/loss_nograd"):
+            np.testing.assert_allclose(a[k], b[k], rtol=2e-6)
+        elif "/idsel" in k:
+            assert (a[k] != b[k]).mean() <= 5e-4
+        elif "/color" in k:
+            np.testing.assert_allclose(a[k], b[k], atol=2e-6)
+        elif "/gup" in k:
+            assert frac_within(a[k], b[k], 1e-5) >= 0.999, k
+        else:
+            assert rel_l2(a[k], b[k]) < 2e-2, k
