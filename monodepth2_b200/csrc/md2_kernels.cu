@@ -337,37 +337,91 @@ __global__ void MD2_MARCH_BOUNDS md2_march2(Params P) {
 }
 
 // ------------------------------------------------------------------ 6. final
-// grad_disp_s = up-sampling adjoint of dD_s (K = 2^s threads per coarse pixel, each visiting
-// 2 fine rows x 2K fine columns, combined with shuffles) + smoothness adjoint; block (0,0,0)
-// also writes the losses and grad_T.
+// grad_disp_s (s >= 1) = adjoint of the bilinear up-sampling of dD_s (trainer.py:350-351) + smoothness
+// adjoint.  Separable, one pass over the fine map: a block owns kFinalFineRows fine rows x 256 fine columns;
+// pass 1, one thread per fine column (coalesced rows), folds the rows into the block's coarse rows with the
+// vertical weights and leaves them in shared memory; pass 2, one thread per coarse pixel, folds 2K columns
+// with the horizontal weights.  Every fine value is read ~1.1x (the gather form read it 4x).  Block 0 also
+// writes the losses and grad_T.  Scale 0 is finished by md2_march itself.
+constexpr int kFinalThreads = 256;
+constexpr int kFinalFineRows = 16;
+
+__host__ __device__ inline int final_tiles_x(int Ws, int K) { const int t = kFinalThreads / K - 1; return (Ws + t - 1) / t; }
+__host__ __device__ inline int final_tiles_y(int Hs, int K) { const int t = kFinalFineRows / K; return (Hs + t - 1) / t; }
+
 template <int K>
-__device__ __forceinline__ void final_scale(const Params& P, int s, int b) {
-  const float inv_m = __ldg(P.smsc + 2 * (s * P.B + b)), dterm = __ldg(P.smsc + 2 * (s * P.B + b) + 1);
+__device__ __forceinline__ void final_tile(const Params& P, int s, int b, int tx, int ty) {
+  constexpr int TXC = kFinalThreads / K - 1;     // coarse columns per block
+  constexpr int TYC = kFinalFineRows / K;        // coarse rows per block
+  constexpr int NR = (TYC + 1) * K;              // fine rows read per block
+  __shared__ float sm[TYC][kFinalThreads];
   const int Hs = P.H >> s, Ws = P.W >> s;
-  const int n = Hs * Ws;
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int cp = gid / K, j = gid % K;
-  const bool ok = cp < n;
-  float part = 0.f;
-  if (ok) part = (K == 1) ? __ldg(P.dD[s] + (size_t)b * n + cp) : upsample_adjoint_part<K>(P, s, b, cp / Ws, cp % Ws, j);
+  const int X0 = tx * TXC, Y0 = ty * TYC;
+  const float* dD = P.dD[s] + (size_t)b * P.H * P.W;
+  {
+    const int x = K * X0 - K / 2 + (int)threadIdx.x;
+    const int xc = x < 0 ? 0 : (x >= P.W ? P.W - 1 : x);
+    const int ylo = K * Y0 - K / 2;
+    float acc[TYC];
 #pragma unroll
-  for (int o = K / 2; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
-  if (ok && j == 0) P.grad_disp[s][(size_t)b * n + cp] = part + final_smooth_grad(P, s, b, cp, inv_m, dterm);
+    for (int l = 0; l < TYC; ++l) acc[l] = 0.f;
+    float v[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int y = ylo + r;
+      const int yc = y < 0 ? 0 : (y >= P.H ? P.H - 1 : y);
+      v[r] = __ldg(dD + yc * P.W + xc);
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      // fine row r is tap r - l*K of coarse row l, for the (at most two) rows l with 0 <= r - l*K < 2K
+#pragma unroll
+      for (int l = 0; l < TYC; ++l) {
+        const int i = r - l * K;
+        if (i >= 0 && i < 2 * K) acc[l] = fmaf(up_weight<K>(i, Y0 + l, Hs), v[r], acc[l]);
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < TYC; ++l) sm[l][threadIdx.x] = acc[l];
+  }
+  __syncthreads();
+  const float inv_m = __ldg(P.smsc + 2 * (s * P.B + b)), dterm = __ldg(P.smsc + 2 * (s * P.B + b) + 1);
+  for (int idx = threadIdx.x; idx < TYC * TXC; idx += kFinalThreads) {
+    const int l = idx / TXC, lx = idx - l * TXC;
+    const int X = X0 + lx, Y = Y0 + l;
+    if (X >= Ws || Y >= Hs) continue;
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2 * K; ++i) a = fmaf(up_weight<K>(i, X, Ws), sm[l][lx * K + i], a);
+    const int cp = Y * Ws + X;
+    P.grad_disp[s][(size_t)b * Hs * Ws + cp] = a + final_smooth_grad(P, s, b, cp, inv_m, dterm);
+  }
 }
 
-__global__ void md2_final(Params P) {
-  const int s = blockIdx.z + 1, b = blockIdx.y;      // scale 0 is finished by md2_march itself
-  if (blockIdx.x == 0 && b == 0 && blockIdx.z == 0) {
+__global__ void __launch_bounds__(kFinalThreads) md2_final(Params P) {
+  if (blockIdx.x == 0) {
     if (threadIdx.x == 0) final_scalars(P);
     if (P.want_grad && threadIdx.x < P.B * P.nsrc) final_grad_T(P, threadIdx.x / P.nsrc, threadIdx.x % P.nsrc);
   }
-  if (!P.want_grad || s >= P.S) return;
-  // scale s needs (H>>s)*(W>>s)*2^s = H*W / 2^s threads
-  if (blockIdx.x * blockDim.x >= (P.H * P.W) >> s) return;
-  switch (s) {
-    case 1: final_scale<2>(P, 1, b); break;
-    case 2: final_scale<4>(P, 2, b); break;
-    default: final_scale<8>(P, 3, b); break;
+  if (!P.want_grad) return;
+  // block -> (scale, sample, tile row, tile column), scale-major
+  int rem = blockIdx.x;
+  for (int s = 1; s < P.S; ++s) {
+    const int K = 1 << s;
+    const int ntx = final_tiles_x(P.W >> s, K), nty = final_tiles_y(P.H >> s, K);
+    const int n = ntx * nty * P.B;
+    if (rem < n) {
+      const int b = rem / (ntx * nty);
+      const int t = rem - b * ntx * nty;
+      const int ty = t / ntx, tx = t - ty * ntx;
+      switch (s) {
+        case 1: final_tile<2>(P, 1, b, tx, ty); break;
+        case 2: final_tile<4>(P, 2, b, tx, ty); break;
+        default: final_tile<8>(P, 3, b, tx, ty); break;
+      }
+      return;
+    }
+    rem -= n;
   }
 }
 
@@ -530,9 +584,11 @@ cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
   if (g_prof_on) cudaEventRecord(g_prof_ev[1], stream);
   // ---- scales >= 1: up-sampling adjoint + smoothness adjoint; losses; grad_T
   {
-    const int n1 = (P.H * P.W) >> 1;
-    dim3 grid((n1 + 255) / 256, P.B, P.S > 1 ? P.S - 1 : 1);
-    md2_final<<<grid, 256, 0, stream>>>(P);
+    int blocks = 0;
+    if (P.want_grad)
+      for (int s = 1; s < P.S; ++s)
+        blocks += final_tiles_x(P.W >> s, 1 << s) * final_tiles_y(P.H >> s, 1 << s) * P.B;
+    md2_final<<<blocks > 0 ? blocks : 1, kFinalThreads, 0, stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   return cudaSuccess;
