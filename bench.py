@@ -489,7 +489,7 @@ def run_train(args, wl):
         loss_name = "reference PyTorch-CUDA loss path (oracle port)"
     else:
         from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
-        from monodepth2_b200.layers import transformation_from_parameters as pose_fn
+        pose_fn = None          # the fused call takes the pose leaves and builds cam_T_cam itself
         plan = LossPlan(BATCH, H, W, frame_ids, avg_reprojection=avg, disable_automasking=noauto)
 
         def loss_fn(inputs, outputs):

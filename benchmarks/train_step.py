@@ -151,7 +151,7 @@ class TrainStep:
         colors = {f: inputs[("color", f, 0)] for f in self.frame_ids}       # color_aug = color copy
         outputs = self.nets(colors)
         for f in self.frame_ids[1:]:
-            if f == "s":
+            if f == "s" or self.pose_fn is None:     # pose_fn None: the loss builds T from the pose leaves itself
                 continue
             outputs[("cam_T_cam", 0, f)] = self.pose_fn(outputs[("axisangle", 0, f)][:, 0],
                                                         outputs[("translation", 0, f)][:, 0], f < 0)

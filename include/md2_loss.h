@@ -72,6 +72,18 @@ typedef struct md2_tensors {
   float *warped[MD2_MAX_SRC][MD2_MAX_SCALES]; /* outputs[("color",f,s)]    (B,3,H,W)     */
   float *identity_selection[MD2_MAX_SCALES];  /* outputs["identity_selection/s"] (B,H,W) */
   float *grad_depth_dbg[MD2_MAX_SCALES];      /* test hook: d loss / d upsampled disp_s (B,1,H,W) */
+  /* ---- optional pose leaves (replaces layers.py:28-103 transformation_from_parameters as called from
+   *      predict_poses, trainer.py:294-295): when axisangle[f] is non-NULL, T[f] is ignored and the call
+   *      builds T_f = transformation_from_parameters(axisangle, translation, invert) itself; with want_grad the
+   *      pose gradient is returned on the leaves.  3 floats per sample, pose_stride[f] floats between
+   *      samples (6 for the [:, 0] view of PoseDecoder's (B,2,1,3) output, pose_decoder.py:49-54). ---- */
+  const float *axisangle[MD2_MAX_SRC];
+  const float *translation[MD2_MAX_SRC];
+  int pose_stride[MD2_MAX_SRC];
+  int pose_invert[MD2_MAX_SRC];               /* frame_id < 0                                  */
+  float *cam_T_cam[MD2_MAX_SRC];              /* out: outputs[("cam_T_cam",0,f)] (B,4,4); NULL = internal scratch */
+  float *grad_axisangle[MD2_MAX_SRC];         /* out (B,3) */
+  float *grad_translation[MD2_MAX_SRC];       /* out (B,3) */
 } md2_tensors;
 
 int md2_version(void);

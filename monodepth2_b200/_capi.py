@@ -42,6 +42,13 @@ class Md2Tensors(C.Structure):
         ("warped", (C.c_void_p * MAX_SCALES) * MAX_SRC),
         ("identity_selection", C.c_void_p * MAX_SCALES),
         ("grad_depth_dbg", C.c_void_p * MAX_SCALES),
+        ("axisangle", C.c_void_p * MAX_SRC),
+        ("translation", C.c_void_p * MAX_SRC),
+        ("pose_stride", C.c_int * MAX_SRC),
+        ("pose_invert", C.c_int * MAX_SRC),
+        ("cam_T_cam", C.c_void_p * MAX_SRC),
+        ("grad_axisangle", C.c_void_p * MAX_SRC),
+        ("grad_translation", C.c_void_p * MAX_SRC),
     ]
 
 

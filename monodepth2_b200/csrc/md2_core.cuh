@@ -154,6 +154,14 @@ struct Params {
   const float* src[kMaxSrc];
   const float* Tm[kMaxSrc];
   int pose_grad[kMaxSrc];
+  // pose leaves (optional, per source): when aa[f] is set the call builds T_f itself
+  const float* aa[kMaxSrc];        // axisangle, 3 floats per sample, `pose_stride[f]` floats between samples
+  const float* tr[kMaxSrc];        // translation, same layout
+  int pose_stride[kMaxSrc];
+  int pose_invert[kMaxSrc];        // frame_id < 0 (trainer.py:294-295)
+  float* Tws[kMaxSrc];             // (B,4,4) workspace / output: the T built from the leaves
+  float* grad_aa[kMaxSrc];         // (B,3) d loss / d axisangle
+  float* grad_tr[kMaxSrc];         // (B,3) d loss / d translation
   const float* K;
   const float* invK;
   const float* disp[kMaxScales];
@@ -1267,11 +1275,90 @@ MD2_HD void pack_pixel(const Params& P, int img, int b, int p) {
   *reinterpret_cast<F4*>(out) = make_f4(MD2_LD(in), MD2_LD(in + plane), MD2_LD(in + 2 * plane), 0.f);
 }
 
+// ------------------------------------------------------------------ pose parameterisation
+// transformation_from_parameters (layers.py:28-45) = rot_from_axisangle (layers.py:64-103) and
+// get_translation_matrix (layers.py:48-61): T = Trans(t) R, or R^T Trans(-t) when `invert` (frame_id < 0,
+// trainer.py:294-295), in fp32 like the reference; and its adjoint (where the pose gradient leaves the path).
+struct Rod { float x, y, z, ca, sa, C, angle, a; };
+MD2_HD Rod rodrigues(const float* v, float R[3][3]) {
+  Rod r;
+  r.angle = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  r.a = r.angle + 1e-7f;
+  r.x = v[0] / r.a; r.y = v[1] / r.a; r.z = v[2] / r.a;
+  r.ca = cosf(r.angle); r.sa = sinf(r.angle); r.C = 1.f - r.ca;
+  const float x = r.x, y = r.y, z = r.z, ca = r.ca, sa = r.sa, C = r.C;
+  R[0][0] = x * x * C + ca; R[0][1] = x * y * C - z * sa; R[0][2] = z * x * C + y * sa;
+  R[1][0] = x * y * C + z * sa; R[1][1] = y * y * C + ca; R[1][2] = y * z * C - x * sa;
+  R[2][0] = z * x * C - y * sa; R[2][1] = y * z * C + x * sa; R[2][2] = z * z * C + ca;
+  return r;
+}
+// v, t: 3 floats each; o: 16 floats (row-major 4x4)
+MD2_HD void pose_to_matrix(const float* v, const float* t, int invert, float* o) {
+  float R[3][3];
+  rodrigues(v, R);
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) o[i * 4 + j] = invert ? R[j][i] : R[i][j];
+    // invert: R^T Trans(-t) -> last column = -R^T t ; else Trans(t) R -> last column = t
+    o[i * 4 + 3] = invert ? -(R[0][i] * t[0] + R[1][i] * t[1] + R[2][i] * t[2]) : t[i];
+  }
+  o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 1.f;
+}
+// g: d loss / d T (16 floats) -> gaa, gtr (3 floats each)
+MD2_HD void pose_to_matrix_backward(const float* g, const float* v, const float* t, int invert, float* gaa, float* gtr) {
+  float R[3][3];
+  const Rod r = rodrigues(v, R);
+  float gR[3][3], gt[3];
+  for (int i = 0; i < 3; ++i) {
+    gt[i] = 0.f;
+    for (int j = 0; j < 3; ++j) gR[i][j] = invert ? g[j * 4 + i] : g[i * 4 + j];
+  }
+  if (invert) {
+    // col_i = -sum_k R[k][i] t[k]
+    for (int i = 0; i < 3; ++i)
+      for (int k = 0; k < 3; ++k) { gR[k][i] -= g[i * 4 + 3] * t[k]; gt[k] -= g[i * 4 + 3] * R[k][i]; }
+  } else {
+    for (int i = 0; i < 3; ++i) gt[i] = g[i * 4 + 3];
+  }
+  const float x = r.x, y = r.y, z = r.z, sa = r.sa, C = r.C;
+  float gx = 0, gy = 0, gz = 0, gca = 0, gsa = 0, gC = 0;
+  // R00 = x x C + ca
+  gx += gR[0][0] * 2 * x * C; gC += gR[0][0] * x * x; gca += gR[0][0];
+  // R01 = x y C - z sa
+  gx += gR[0][1] * y * C; gy += gR[0][1] * x * C; gC += gR[0][1] * x * y; gz -= gR[0][1] * sa; gsa -= gR[0][1] * z;
+  // R02 = z x C + y sa
+  gz += gR[0][2] * x * C; gx += gR[0][2] * z * C; gC += gR[0][2] * z * x; gy += gR[0][2] * sa; gsa += gR[0][2] * y;
+  // R10 = x y C + z sa
+  gx += gR[1][0] * y * C; gy += gR[1][0] * x * C; gC += gR[1][0] * x * y; gz += gR[1][0] * sa; gsa += gR[1][0] * z;
+  // R11 = y y C + ca
+  gy += gR[1][1] * 2 * y * C; gC += gR[1][1] * y * y; gca += gR[1][1];
+  // R12 = y z C - x sa
+  gy += gR[1][2] * z * C; gz += gR[1][2] * y * C; gC += gR[1][2] * y * z; gx -= gR[1][2] * sa; gsa -= gR[1][2] * x;
+  // R20 = z x C - y sa
+  gz += gR[2][0] * x * C; gx += gR[2][0] * z * C; gC += gR[2][0] * z * x; gy -= gR[2][0] * sa; gsa -= gR[2][0] * y;
+  // R21 = y z C + x sa
+  gy += gR[2][1] * z * C; gz += gR[2][1] * y * C; gC += gR[2][1] * y * z; gx += gR[2][1] * sa; gsa += gR[2][1] * x;
+  // R22 = z z C + ca
+  gz += gR[2][2] * 2 * z * C; gC += gR[2][2] * z * z; gca += gR[2][2];
+  gca -= gC;                                   // C = 1 - ca
+  float gang = -r.sa * gca + r.ca * gsa;       // ca = cos(angle), sa = sin(angle)
+  // axis = v / a, a = angle + 1e-7
+  const float ga = -(gx * v[0] + gy * v[1] + gz * v[2]) / (r.a * r.a);
+  gang += ga;
+  float gv[3] = {gx / r.a, gy / r.a, gz / r.a};
+  if (r.angle > 0.f)
+    for (int k = 0; k < 3; ++k) gv[k] += gang * v[k] / r.angle;   // torch.norm backward (0 at the origin)
+  for (int k = 0; k < 3; ++k) { gaa[k] = gv[k]; gtr[k] = gt[k]; }
+}
+
 // ------------------------------------------------------------------ small per-element pieces
 // proj table: M = (K T)[:3,:3] * invK[:3,:3], p4 = (K T)[:3,3], in double then rounded once.
 MD2_HD void setup_projection(const Params& P, int b, int f) {
   const float* K = P.K + (size_t)b * 16;
-  const float* T = P.Tm[f] + (size_t)b * 16;
+  if (P.aa[f]) {     // T from the pose leaves, written where Tm[f] points (P.Tws[f])
+    pose_to_matrix(P.aa[f] + (size_t)b * P.pose_stride[f], P.tr[f] + (size_t)b * P.pose_stride[f], P.pose_invert[f],
+                   P.Tws[f] + (size_t)b * 16);
+  }
+  const float* T = (P.aa[f] ? P.Tws[f] : P.Tm[f]) + (size_t)b * 16;
   const float* iK = P.invK + (size_t)b * 16;
   double Pm[3][4];
   for (int i = 0; i < 3; ++i)
@@ -1413,15 +1500,22 @@ MD2_HD void final_scalars(const Params& P) {
 }
 MD2_HD void final_grad_T(const Params& P, int b, int f) {
   float* g = P.grad_T[f];
-  if (!g) return;
+  const bool leaves = P.aa[f] && P.grad_aa[f] && P.grad_tr[f];
+  if (!g && !leaves) return;
   const float* K = P.K + (size_t)b * 16;
+  float gT[16];
   for (int k = 0; k < 4; ++k)
     for (int j = 0; j < 4; ++j) {
       double a = 0.0;
       if (P.pose_grad[f])
         for (int i = 0; i < 3; ++i) a += (double)MD2_LD(K + i * 4 + k) * P.acc[acc_dP(P, b, f, i * 4 + j)];
-      g[(size_t)b * 16 + k * 4 + j] = (float)(a * (double)P.gscale);
+      gT[k * 4 + j] = (float)(a * (double)P.gscale);
     }
+  if (g)
+    for (int i = 0; i < 16; ++i) g[(size_t)b * 16 + i] = gT[i];
+  if (leaves)      // adjoint of transformation_from_parameters: the pose gradient leaves the path here
+    pose_to_matrix_backward(gT, P.aa[f] + (size_t)b * P.pose_stride[f], P.tr[f] + (size_t)b * P.pose_stride[f],
+                            P.pose_invert[f], P.grad_aa[f] + (size_t)b * 3, P.grad_tr[f] + (size_t)b * 3);
 }
 
 }  // namespace md2

@@ -6,6 +6,7 @@
 #include <math.h>
 
 #include "../../include/md2_loss.h"
+#include "md2_core.cuh"
 
 namespace {
 
@@ -321,85 +322,19 @@ __global__ void k_smooth_bwd(const float* __restrict__ gl, const float* __restri
 }
 
 // ---------------------------------------------------------------- pose -> 4x4 (layers.py:28-103)
-struct Rod { float x, y, z, ca, sa, C, angle, a; };
-__device__ __forceinline__ Rod rodrigues(const float* v, float R[3][3]) {
-  Rod r;
-  r.angle = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-  r.a = r.angle + 1e-7f;
-  r.x = v[0] / r.a; r.y = v[1] / r.a; r.z = v[2] / r.a;
-  r.ca = cosf(r.angle); r.sa = sinf(r.angle); r.C = 1.f - r.ca;
-  const float x = r.x, y = r.y, z = r.z, ca = r.ca, sa = r.sa, C = r.C;
-  R[0][0] = x * x * C + ca; R[0][1] = x * y * C - z * sa; R[0][2] = z * x * C + y * sa;
-  R[1][0] = x * y * C + z * sa; R[1][1] = y * y * C + ca; R[1][2] = y * z * C - x * sa;
-  R[2][0] = z * x * C - y * sa; R[2][1] = y * z * C + x * sa; R[2][2] = z * z * C + ca;
-  return r;
-}
+// (the per-sample arithmetic lives in md2_core.cuh: the fused call builds T from the pose leaves itself)
 __global__ void k_pose_to_matrix(const float* __restrict__ aa, const float* __restrict__ tr, int invert,
                                  float* __restrict__ T, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  float R[3][3];
-  rodrigues(aa + b * 3, R);
-  const float* t = tr + b * 3;
-  float* o = T + b * 16;
-  for (int i = 0; i < 3; ++i) {
-    for (int j = 0; j < 3; ++j) o[i * 4 + j] = invert ? R[j][i] : R[i][j];
-    // invert: R^T Trans(-t) -> last column = -R^T t ; else Trans(t) R -> last column = t
-    o[i * 4 + 3] = invert ? -(R[0][i] * t[0] + R[1][i] * t[1] + R[2][i] * t[2]) : t[i];
-  }
-  o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 1.f;
+  md2::pose_to_matrix(aa + b * 3, tr + b * 3, invert, T + b * 16);
 }
 __global__ void k_pose_to_matrix_bwd(const float* __restrict__ gT, const float* __restrict__ aa,
                                      const float* __restrict__ tr, int invert, float* __restrict__ gaa,
                                      float* __restrict__ gtr, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  float R[3][3];
-  const float* v = aa + b * 3;
-  const Rod r = rodrigues(v, R);
-  const float* t = tr + b * 3;
-  const float* g = gT + b * 16;
-  float gR[3][3], gt[3];
-  for (int i = 0; i < 3; ++i) {
-    gt[i] = 0.f;
-    for (int j = 0; j < 3; ++j) gR[i][j] = invert ? g[j * 4 + i] : g[i * 4 + j];
-  }
-  if (invert) {
-    // col_i = -sum_k R[k][i] t[k]
-    for (int i = 0; i < 3; ++i)
-      for (int k = 0; k < 3; ++k) { gR[k][i] -= g[i * 4 + 3] * t[k]; gt[k] -= g[i * 4 + 3] * R[k][i]; }
-  } else {
-    for (int i = 0; i < 3; ++i) gt[i] = g[i * 4 + 3];
-  }
-  const float x = r.x, y = r.y, z = r.z, ca = r.ca, sa = r.sa, C = r.C;
-  float gx = 0, gy = 0, gz = 0, gca = 0, gsa = 0, gC = 0;
-  // R00 = x x C + ca
-  gx += gR[0][0] * 2 * x * C; gC += gR[0][0] * x * x; gca += gR[0][0];
-  // R01 = x y C - z sa
-  gx += gR[0][1] * y * C; gy += gR[0][1] * x * C; gC += gR[0][1] * x * y; gz -= gR[0][1] * sa; gsa -= gR[0][1] * z;
-  // R02 = z x C + y sa
-  gz += gR[0][2] * x * C; gx += gR[0][2] * z * C; gC += gR[0][2] * z * x; gy += gR[0][2] * sa; gsa += gR[0][2] * y;
-  // R10 = x y C + z sa
-  gx += gR[1][0] * y * C; gy += gR[1][0] * x * C; gC += gR[1][0] * x * y; gz += gR[1][0] * sa; gsa += gR[1][0] * z;
-  // R11 = y y C + ca
-  gy += gR[1][1] * 2 * y * C; gC += gR[1][1] * y * y; gca += gR[1][1];
-  // R12 = y z C - x sa
-  gy += gR[1][2] * z * C; gz += gR[1][2] * y * C; gC += gR[1][2] * y * z; gx -= gR[1][2] * sa; gsa -= gR[1][2] * x;
-  // R20 = z x C - y sa
-  gz += gR[2][0] * x * C; gx += gR[2][0] * z * C; gC += gR[2][0] * z * x; gy -= gR[2][0] * sa; gsa -= gR[2][0] * y;
-  // R21 = y z C + x sa
-  gy += gR[2][1] * z * C; gz += gR[2][1] * y * C; gC += gR[2][1] * y * z; gx += gR[2][1] * sa; gsa += gR[2][1] * x;
-  // R22 = z z C + ca
-  gz += gR[2][2] * 2 * z * C; gC += gR[2][2] * z * z; gca += gR[2][2];
-  gca -= gC;                                   // C = 1 - ca
-  float gang = -r.sa * gca + r.ca * gsa;       // ca = cos(angle), sa = sin(angle)
-  // axis = v / a, a = angle + 1e-7
-  const float ga = -(gx * v[0] + gy * v[1] + gz * v[2]) / (r.a * r.a);
-  gang += ga;
-  float gv[3] = {gx / r.a, gy / r.a, gz / r.a};
-  if (r.angle > 0.f)
-    for (int k = 0; k < 3; ++k) gv[k] += gang * v[k] / r.angle;   // torch.norm backward (0 at the origin)
-  for (int k = 0; k < 3; ++k) { gaa[b * 3 + k] = gv[k]; gtr[b * 3 + k] = gt[k]; }
+  md2::pose_to_matrix_backward(gT + b * 16, aa + b * 3, tr + b * 3, invert, gaa + b * 3, gtr + b * 3);
 }
 
 }  // namespace

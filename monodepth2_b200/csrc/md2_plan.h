@@ -19,6 +19,7 @@ struct Layout {
   size_t proj_off, idloss_off, smsc_off;
   size_t tgt4_off, src4_off[kMaxSrc];
   size_t dD_off[kMaxScales], gn_off[kMaxScales];
+  size_t Tws_off[kMaxSrc];
   size_t total;
 };
 
@@ -46,6 +47,7 @@ inline Layout make_layout(const md2_problem* p) {
   off = align_up(off + L.acc_bytes, 256);
   L.proj_off = off; off = align_up(off + B * p->num_src * 12 * sizeof(float), 256);
   L.smsc_off = off; off = align_up(off + kMaxScales * B * 2 * sizeof(float), 256);
+  for (int f = 0; f < p->num_src; ++f) { L.Tws_off[f] = off; off = align_up(off + B * 16 * sizeof(float), 256); }
   L.idloss_off = off; off = align_up(off + B * p->num_src * H * W * sizeof(float), 256);
   L.tgt4_off = off; off = align_up(off + B * H * W * 4 * sizeof(float), 256);
   for (int f = 0; f < p->num_src; ++f) {
@@ -107,8 +109,22 @@ inline int fill_params(const md2_problem* p, const md2_tensors* t, void* workspa
   if (!t->target || !t->K || !t->inv_K || !t->losses) return MD2_ERR_INVALID_ARGUMENT;
   P->tgt = t->target; P->K = t->K; P->invK = t->inv_K;
   for (int f = 0; f < p->num_src; ++f) {
-    if (!t->source[f] || !t->T[f]) return MD2_ERR_INVALID_ARGUMENT;
-    P->src[f] = t->source[f]; P->Tm[f] = t->T[f];
+    if (!t->source[f]) return MD2_ERR_INVALID_ARGUMENT;
+    if (t->axisangle[f]) {          // T built in the call from the pose leaves
+      if (!t->translation[f] || t->pose_stride[f] < 3) return MD2_ERR_INVALID_ARGUMENT;
+      P->aa[f] = t->axisangle[f]; P->tr[f] = t->translation[f];
+      P->pose_stride[f] = t->pose_stride[f]; P->pose_invert[f] = t->pose_invert[f] ? 1 : 0;
+      P->Tws[f] = t->cam_T_cam[f] ? t->cam_T_cam[f] : (float*)(ws + L.Tws_off[f]);
+      P->Tm[f] = P->Tws[f];
+      if (p->want_grad && t->pose_requires_grad[f]) {
+        if (!t->grad_axisangle[f] || !t->grad_translation[f]) return MD2_ERR_INVALID_ARGUMENT;
+        P->grad_aa[f] = t->grad_axisangle[f]; P->grad_tr[f] = t->grad_translation[f];
+      }
+    } else {
+      if (!t->T[f]) return MD2_ERR_INVALID_ARGUMENT;
+      P->Tm[f] = t->T[f];
+    }
+    P->src[f] = t->source[f];
     P->pose_grad[f] = (t->pose_requires_grad[f] && p->want_grad) ? 1 : 0;
     P->grad_T[f] = p->want_grad ? t->grad_T[f] : nullptr;
   }

@@ -116,16 +116,22 @@ class LossPlan:
 
 
 class _ViewSynthesisLossFn(torch.autograd.Function):
-    """forward(plan, side, target, sources, K, inv_K, colors, noise, n_disp, *disps_and_Ts)"""
+    """forward(plan, side, target, sources, K, inv_K, colors, noise, pose_grad, pose_invert, *leaves)
+
+    leaves = S disparities, then per source the matrix T (B,4,4) *or* the axisangle leaf, then per source
+    the translation leaf (None for a source given as a matrix).  ``pose_invert[i]`` is None for a matrix
+    source, else the ``invert`` flag of transformation_from_parameters (frame_id < 0)."""
+
+    N_FIXED = 10
 
     @staticmethod
     def forward(ctx, plan: LossPlan, side: Optional[dict], target, sources, K, inv_K, colors, noise, pose_grad,
-                *leaves):
+                pose_invert, *leaves):
         S, F = len(plan.scales), plan.n_src
-        disps, Ts = leaves[:S], leaves[S:]
+        disps, firsts, seconds = leaves[:S], leaves[S:S + F], leaves[S + F:S + 2 * F]
         B, H, W = plan.batch_size, plan.height, plan.width
         dev = target.device
-        want_grad = any(ctx.needs_input_grad[9:])
+        want_grad = any(ctx.needs_input_grad[_ViewSynthesisLossFn.N_FIXED:])
         t = Md2Tensors()
         keep = []
 
@@ -133,14 +139,44 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
             keep.append(x)
             return x.data_ptr()
 
+        def pose_leaf(x, name):
+            # (B,3) / (B,1,3) view whose 3 components are adjacent; any batch stride (e.g. the [:, 0] view of
+            # PoseDecoder's (B,2,1,3) output, pose_decoder.py:49-54)
+            if not x.is_cuda or x.dtype != torch.float32:
+                raise RuntimeError("%s must be a CUDA float32 tensor" % name)
+            if x.numel() != B * 3 or x.shape[0] != B or x.shape[-1] != 3:
+                raise RuntimeError("%s has shape %s, expected (%d,1,3)" % (name, tuple(x.shape), B))
+            if x.stride(-1) != 1 or (B > 1 and x.stride(0) < 3):
+                x = x.contiguous()
+            return x, (x.stride(0) if B > 1 else 3)
+
         t.target = ptr(_check_f32_cuda(target, "target", (B, 3, H, W)))
+        cam_T = [None] * F
+        grad_first, grad_second = [None] * F, [None] * F
         for i in range(F):
             t.source[i] = ptr(_check_f32_cuda(sources[i], "source[%d]" % i, (B, 3, H, W)))
-            t.T[i] = ptr(_check_f32_cuda(Ts[i], "T[%d]" % i, (B, 4, 4)))
             t.pose_requires_grad[i] = int(bool(pose_grad[i]))
+            if pose_invert[i] is None:
+                t.T[i] = ptr(_check_f32_cuda(firsts[i], "T[%d]" % i, (B, 4, 4)))
+                if want_grad:
+                    grad_first[i] = torch.empty((B, 4, 4), dtype=torch.float32, device=dev)
+                    t.grad_T[i] = ptr(grad_first[i])
+            else:
+                aa, sa = pose_leaf(firsts[i], "axisangle[%d]" % i)
+                tr, st_ = pose_leaf(seconds[i], "translation[%d]" % i)
+                if sa != st_:
+                    tr = tr.contiguous(); aa = aa.contiguous(); sa = 3
+                t.axisangle[i], t.translation[i] = ptr(aa), ptr(tr)
+                t.pose_stride[i], t.pose_invert[i] = int(sa), int(bool(pose_invert[i]))
+                cam_T[i] = torch.empty((B, 4, 4), dtype=torch.float32, device=dev)
+                t.cam_T_cam[i] = ptr(cam_T[i])
+                if want_grad and pose_grad[i]:
+                    grad_first[i] = torch.empty((B, 3), dtype=torch.float32, device=dev)
+                    grad_second[i] = torch.empty((B, 3), dtype=torch.float32, device=dev)
+                    t.grad_axisangle[i], t.grad_translation[i] = ptr(grad_first[i]), ptr(grad_second[i])
         t.K = ptr(_check_f32_cuda(K, "K", (B, 4, 4)))
         t.inv_K = ptr(_check_f32_cuda(inv_K, "inv_K", (B, 4, 4)))
-        grad_disp, grad_T = [], []
+        grad_disp = []
         for s in range(S):
             hs, ws = H >> s, W >> s
             t.disp[s] = ptr(_check_f32_cuda(disps[s], "disp[%d]" % s, (B, 1, hs, ws)))
@@ -151,11 +187,6 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
                 g = torch.empty((B, 1, hs, ws), dtype=torch.float32, device=dev)
                 grad_disp.append(g)
                 t.grad_disp[s] = ptr(g)
-        if want_grad:
-            for i in range(F):
-                g = torch.empty((B, 4, 4), dtype=torch.float32, device=dev)
-                grad_T.append(g)
-                t.grad_T[i] = ptr(g)
         if side is not None:
             for s in side.get("depth_scales", []):
                 d = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
@@ -176,6 +207,7 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
                     gd = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
                     side[("grad_updisp", s)] = gd
                     t.grad_depth_dbg[s] = ptr(gd)
+            side["_cam_T_cam"] = cam_T
         losses = torch.empty(MAX_SCALES + 1, dtype=torch.float32, device=dev)
         t.losses = ptr(losses)
         ws_buf = plan.workspace(dev)
@@ -187,8 +219,12 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
         _capi.check(plan.lib, st, "md2_view_synthesis_loss")
         ctx.S, ctx.F = S, F
         ctx.pose_grad = list(pose_grad)
+        ctx.first_shapes = [tuple(x.shape) for x in firsts]
+        ctx.second_shapes = [tuple(x.shape) if x is not None else None for x in seconds]
+        ctx.have = [(grad_first[i] is not None, grad_second[i] is not None) for i in range(F)]
         if want_grad:
-            ctx.save_for_backward(*grad_disp, *grad_T)
+            ctx.save_for_backward(*grad_disp, *[g for g in grad_first if g is not None],
+                                  *[g for g in grad_second if g is not None])
         total = losses[0]
         per_scale = losses[1:1 + S]
         ctx.mark_non_differentiable(per_scale)
@@ -197,15 +233,23 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_total, _g_scales):
-        saved = ctx.saved_tensors
+        saved = list(ctx.saved_tensors)
         S, F = ctx.S, ctx.F
-        out = [None] * 9
+        n0 = _ViewSynthesisLossFn.N_FIXED
+        out = [None] * n0
         for s in range(S):
-            out.append(saved[s] * g_total if ctx.needs_input_grad[9 + s] else None)
+            out.append(saved[s] * g_total if ctx.needs_input_grad[n0 + s] else None)
+        firsts = iter(saved[S:S + sum(1 for h in ctx.have if h[0])])
+        seconds = iter(saved[S + sum(1 for h in ctx.have if h[0]):])
+        g1, g2 = [], []
         for i in range(F):
-            need = ctx.needs_input_grad[9 + S + i] and ctx.pose_grad[i]
-            out.append(saved[S + i] * g_total if need else None)
-        return tuple(out)
+            a = next(firsts) if ctx.have[i][0] else None
+            b = next(seconds) if ctx.have[i][1] else None
+            need1 = ctx.needs_input_grad[n0 + S + i] and ctx.pose_grad[i] and a is not None
+            need2 = ctx.needs_input_grad[n0 + S + F + i] and ctx.pose_grad[i] and b is not None
+            g1.append((a * g_total).reshape(ctx.first_shapes[i]) if need1 else None)
+            g2.append((b * g_total).reshape(ctx.second_shapes[i]) if need2 else None)
+        return tuple(out + g1 + g2)
 
 
 def view_synthesis_loss(plan: LossPlan, inputs: Dict, outputs: Dict,
@@ -231,21 +275,35 @@ def view_synthesis_loss(plan: LossPlan, inputs: Dict, outputs: Dict,
     sources = [inputs[("color", f, 0)] for f in plan.src_ids]
     colors = [inputs[("color", 0, s)] for s in plan.scales]
     disps = [outputs[("disp", s)] for s in plan.scales]
-    Ts, pose_grad = [], []
+    firsts, seconds, pose_grad, pose_invert = [], [], [], []
     for f in plan.src_ids:
         if f == "s":
-            Ts.append(inputs["stereo_T"])
-            pose_grad.append(False)
-        else:
+            firsts.append(inputs["stereo_T"]); seconds.append(None)
+            pose_grad.append(False); pose_invert.append(None)
+        elif ("cam_T_cam", 0, f) in outputs:
             T = outputs[("cam_T_cam", 0, f)]
-            Ts.append(T)
-            pose_grad.append(bool(T.requires_grad) and torch.is_grad_enabled())
+            firsts.append(T); seconds.append(None)
+            pose_grad.append(bool(T.requires_grad) and torch.is_grad_enabled()); pose_invert.append(None)
+        else:
+            # pose leaves straight from the pose network (trainer.py:289-295): T is built inside the call
+            #  and handed back as outputs[("cam_T_cam", 0, f)]
+            aa = outputs[("axisangle", 0, f)][:, 0]
+            tr = outputs[("translation", 0, f)][:, 0]
+            firsts.append(aa); seconds.append(tr)
+            pose_grad.append(bool(aa.requires_grad or tr.requires_grad) and torch.is_grad_enabled())
+            pose_invert.append(f < 0)
     if plan.n_id > 0 and noise is None:
         shape = (plan.batch_size, plan.n_id, plan.height, plan.width)
         noise = [torch.randn(shape, device=dev) for _ in plan.scales]
+    if side is None and any(pi is not None for pi in pose_invert):
+        side = {}
     total, per_scale = _ViewSynthesisLossFn.apply(plan, side, target, sources, inputs[("K", 0)],
-                                                  inputs[("inv_K", 0)], colors, noise, pose_grad,
-                                                  *disps, *Ts)
+                                                  inputs[("inv_K", 0)], colors, noise, pose_grad, pose_invert,
+                                                  *disps, *firsts, *seconds)
+    if side is not None:
+        for i, T in enumerate(side.pop("_cam_T_cam", [])):
+            if T is not None:
+                outputs[("cam_T_cam", 0, plan.src_ids[i])] = T
     losses = {"loss": total}
     for i, s in enumerate(plan.scales):
         losses["loss/{}".format(s)] = per_scale[i]

@@ -4,7 +4,8 @@ import torch
 from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
 
 
-def run_cuda(g, rows_per_segment=0, align_corners=False, want_grad=True, side_all=True, dev="cuda:0"):
+def run_cuda(g, rows_per_segment=0, align_corners=False, want_grad=True, side_all=True, dev="cuda:0",
+             pose_leaves=False):
     plan = LossPlan(g.B, g.H, g.W, g.frame_ids, avg_reprojection=g.avg_reprojection,
                     disable_automasking=g.disable_automasking, align_corners=align_corners,
                     rows_per_segment=rows_per_segment, no_ssim=g.no_ssim, v1_multiscale=g.v1_multiscale,
@@ -17,6 +18,18 @@ def run_cuda(g, rows_per_segment=0, align_corners=False, want_grad=True, side_al
         leaves[("disp", s)] = d
     for f in g.frame_ids[1:]:
         if f == "s":
+            continue
+        if pose_leaves:
+            # what PoseDecoder emits: (B,2,1,3), only [:, 0] is used (trainer.py:289-295); no cam_T_cam given,
+            # the fused call builds it from the leaves
+            aa = torch.zeros(g.B, 2, 1, 3)
+            tr = torch.zeros(g.B, 2, 1, 3)
+            aa[:, 0] = g.t("axisangle__%s" % f).reshape(g.B, 1, 3)
+            tr[:, 0] = g.t("translation__%s" % f).reshape(g.B, 1, 3)
+            aa = aa.to(dev).requires_grad_(want_grad)
+            tr = tr.to(dev).requires_grad_(want_grad)
+            outs[("axisangle", 0, f)], outs[("translation", 0, f)] = aa, tr
+            leaves[("axisangle", f)], leaves[("translation", f)] = aa, tr
             continue
         T = g.t("cam_T_cam__%s" % f).to(dev).requires_grad_(want_grad)
         outs[("cam_T_cam", 0, f)] = T

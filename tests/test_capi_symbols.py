@@ -36,7 +36,8 @@ def test_struct_layout_matches_header():
     assert C.sizeof(Md2Problem) == 14 * 4
     # 1 + 4 + 4 pointers, 4 ints, 2 + 3*4 + 1 + 4 + 4 + 4 + 16 + 4 + 4 pointers
     nptr = 1 + 4 + 4 + 2 + 12 + 1 + 4 + 4 + 4 + 16 + 4 + 4
-    assert C.sizeof(Md2Tensors) == nptr * 8 + 4 * 4
+    # pose leaves: 2*4 pointers, 2*4 ints, 3*4 pointers
+    assert C.sizeof(Md2Tensors) == nptr * 8 + 4 * 4 + (8 + 12) * 8 + 8 * 4
 
 
 def test_validation_without_gpu(lib):

@@ -115,3 +115,33 @@ def test_packed_and_scalar_two_source_kernels_agree(tmp_path):
             assert frac_within(a[k], b[k], 1e-5) >= 0.999, k
         else:
             assert rel_l2(a[k], b[k]) < 2e-2, k
+
+
+@pytest.mark.parametrize("name", ["mono_structured", "stereo_iid", "avg_reprojection"])
+def test_pose_leaves_built_inside_the_call(name):
+    """given axisangle / translation instead of cam_T_cam, the fused call builds T
+    (transformation_from_parameters, layers.py:28-45) and returns the pose gradient on the leaves."""
+    from gpu_driver import run_cuda
+    from monodepth2_b200 import layers as L
+    g = Golden(name)
+    z = g.z
+    r = run_cuda(g, pose_leaves=True)
+    assert abs(float(r["losses"]["loss"]) - float(z["loss"])) <= LOSS_RTOL * abs(float(z["loss"]))
+    m = run_cuda(g)                                   # matrix mode on the same inputs
+    for f in g.frame_ids[1:]:
+        if f == "s":
+            continue
+        np.testing.assert_allclose(r["outs"][("cam_T_cam", 0, f)].cpu().numpy(), z["cam_T_cam__%s" % f], atol=2e-6)
+        ga = r["leaves"][("axisangle", f)].grad.cpu()
+        gt = r["leaves"][("translation", f)].grad.cpu()
+        assert float(ga[:, 1].abs().max()) == 0.0 and float(gt[:, 1].abs().max()) == 0.0   # unused second frame
+        # against the reference's gradients (flips allowed) ...
+        assert rel_l2(ga[:, 0].reshape(-1), z["grad_axisangle__%s" % f].reshape(-1)) < 8e-2
+        assert rel_l2(gt[:, 0].reshape(-1), z["grad_translation__%s" % f].reshape(-1)) < 8e-2
+        # ... and against the matrix-mode gradient pushed through the per-layer pose op (same arithmetic)
+        aa = g.t("axisangle__%s" % f).to("cuda:0").reshape(g.B, 1, 3).requires_grad_(True)
+        tr = g.t("translation__%s" % f).to("cuda:0").reshape(g.B, 1, 3).requires_grad_(True)
+        T = L.transformation_from_parameters(aa, tr, f < 0)
+        T.backward(m["leaves"][("T", f)].grad)
+        assert rel_l2(ga[:, 0].reshape(-1), aa.grad.cpu().reshape(-1)) < 1e-5
+        assert rel_l2(gt[:, 0].reshape(-1), tr.grad.cpu().reshape(-1)) < 1e-5
