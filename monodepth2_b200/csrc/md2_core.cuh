@@ -187,14 +187,18 @@ struct Params {
 
 // accumulator layout (doubles)
 MD2_HD int acc_photo(int s) { return s; }
-MD2_HD int acc_smx(int s) { return kMaxScales + s; }
-MD2_HD int acc_smy(int s) { return 2 * kMaxScales + s; }
+// (slots [kMaxScales, 3 kMaxScales) are unused: the smoothness sums are kept per (scale, sample), see
+// acc_smx / acc_smy below, so that the blocks of md2_smooth do not all hit two addresses per scale)
 MD2_HD int acc_dispsum(const Params& P, int s, int b) { return 3 * kMaxScales + s * P.B + b; }
 MD2_HD int acc_dot(const Params& P, int s, int b) { return 3 * kMaxScales + kMaxScales * P.B + s * P.B + b; }
 MD2_HD int acc_dP(const Params& P, int b, int f, int k) {
   return 3 * kMaxScales + 2 * kMaxScales * P.B + (b * P.nsrc + f) * 12 + k;
 }
-MD2_HD int acc_count(const Params& P) { return 3 * kMaxScales + 2 * kMaxScales * P.B + P.B * P.nsrc * 12; }
+MD2_HD int acc_smx(const Params& P, int s, int b) {
+  return 3 * kMaxScales + 2 * kMaxScales * P.B + P.B * P.nsrc * 12 + 2 * (s * P.B + b);
+}
+MD2_HD int acc_smy(const Params& P, int s, int b) { return acc_smx(P, s, b) + 1; }
+MD2_HD int acc_count(const Params& P) { return 3 * kMaxScales + 4 * kMaxScales * P.B + P.B * P.nsrc * 12; }
 
 // One marching job (warp-uniform): a band of kOwnCols columns x rows [y0,y1) of sample b at
 // scale s, with every base pointer already offset to the sample so that per-pixel addressing
@@ -1490,8 +1494,9 @@ MD2_HD void final_scalars(const Params& P) {
   for (int s = 0; s < P.S; ++s) {
     const int Hs = P.H >> s, Ws = P.W >> s;
     const double photo = P.acc[acc_photo(s)] / ((double)P.B * P.H * P.W);
-    const double sm = P.acc[acc_smx(s)] / ((double)P.B * Hs * (Ws - 1)) +
-                      P.acc[acc_smy(s)] / ((double)P.B * (Hs - 1) * Ws);
+    double sx = 0.0, sy = 0.0;
+    for (int b = 0; b < P.B; ++b) { sx += P.acc[acc_smx(P, s, b)]; sy += P.acc[acc_smy(P, s, b)]; }
+    const double sm = sx / ((double)P.B * Hs * (Ws - 1)) + sy / ((double)P.B * (Hs - 1) * Ws);
     const double ls = photo + (double)P.smooth_w[s] * sm;
     P.losses[1 + s] = (float)ls;
     total += ls;

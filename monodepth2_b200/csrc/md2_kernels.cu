@@ -43,7 +43,7 @@ __global__ void md2_prologue(Params P) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nacc = acc_count(P);
   for (int i = tid; i < nacc; i += gridDim.x * blockDim.x) P.acc[i] = 0.0;
-  if (tid < P.B * P.nsrc) setup_projection(P, tid / P.nsrc, tid % P.nsrc);
+  for (int i = tid; i < P.B * P.nsrc; i += gridDim.x * blockDim.x) setup_projection(P, i / P.nsrc, i % P.nsrc);
 }
 
 // re-layout of target and sources to RGBx texels (one 16-byte load per bilinear tap later on)
@@ -106,6 +106,37 @@ __global__ void __launch_bounds__(kThreads) md2_identity(Params P) {
   }
 }
 
+// packed-fp32 form of the identity pass for two sources (md2_pack2.cuh)
+template <bool NOSSIM>
+__global__ void __launch_bounds__(kThreads) md2_identity2(Params P) {
+  const int lane = threadIdx.x & 31;
+  const int job = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const int njobs = P.B * P.nseg_id * P.nband_id;
+  if (job >= njobs) return;
+  const int band = job % P.nband_id;
+  const int seg = (job / P.nband_id) % P.nseg_id;
+  const int b = job / (P.nband_id * P.nseg_id);
+  const int y0 = seg * P.id_rows;
+  const int y1 = min(y0 + P.id_rows, P.H);
+  IdLane2 L;
+  id_init2(L, P, band * kIdCols, lane);
+  id_prefetch2(L, P, b, y0 - 1);
+  for (int t = y0 - 1; t <= y1; ++t) {
+    id_stage_a2(L, P, b, t, lane, y0, y1);
+    IdXchg2 lf, rt;
+    lf.tgrg = p2(__shfl_up_sync(kFull, L.tgrg.x, 1), __shfl_up_sync(kFull, L.tgrg.y, 1));
+    rt.tgrg = p2(__shfl_down_sync(kFull, L.tgrg.x, 1), __shfl_down_sync(kFull, L.tgrg.y, 1));
+    lf.tgb = __shfl_up_sync(kFull, L.tgb, 1);
+    rt.tgb = __shfl_down_sync(kFull, L.tgb, 1);
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      lf.pr[s] = p2(__shfl_up_sync(kFull, L.pr[s].x, 1), __shfl_up_sync(kFull, L.pr[s].y, 1));
+      rt.pr[s] = p2(__shfl_down_sync(kFull, L.pr[s].x, 1), __shfl_down_sync(kFull, L.pr[s].y, 1));
+    }
+    id_stage_b2<NOSSIM>(L, P, b, t, lane, y0, y1, lf, rt);
+  }
+}
+
 // ------------------------------------------------------------------ 4. smoothness
 __global__ void md2_smooth(Params P) {
   const int s = blockIdx.z, b = blockIdx.y;
@@ -135,8 +166,8 @@ __global__ void md2_smooth(Params P) {
     ey = warp_sum(l < nw ? part[1][l] : 0.f);
     dot = warp_sum(l < nw ? part[2][l] : 0.f);
     if (l == 0) {
-      atomicAdd(&P.acc[acc_smx(s)], (double)ex);
-      atomicAdd(&P.acc[acc_smy(s)], (double)ey);
+      atomicAdd(&P.acc[acc_smx(P, s, b)], (double)ex);
+      atomicAdd(&P.acc[acc_smy(P, s, b)], (double)ey);
       atomicAdd(&P.acc[acc_dot(P, s, b)], (double)dot);
     }
   }
@@ -401,7 +432,8 @@ __device__ __forceinline__ void final_tile(const Params& P, int s, int b, int tx
 __global__ void __launch_bounds__(kFinalThreads) md2_final(Params P) {
   if (blockIdx.x == 0) {
     if (threadIdx.x == 0) final_scalars(P);
-    if (P.want_grad && threadIdx.x < P.B * P.nsrc) final_grad_T(P, threadIdx.x / P.nsrc, threadIdx.x % P.nsrc);
+    if (P.want_grad)
+      for (int i = threadIdx.x; i < P.B * P.nsrc; i += blockDim.x) final_grad_T(P, i / P.nsrc, i % P.nsrc);
   }
   if (!P.want_grad) return;
   // block -> (scale, sample, tile row, tile column), scale-major
@@ -429,15 +461,16 @@ __global__ void __launch_bounds__(kFinalThreads) md2_final(Params P) {
 // Which two-source instantiations use the packed-fp32 form (md2_pack2.cuh).  Default: forward-only calls
 // (measured faster), scalar form when gradients are wanted (measured faster).  MD2_PACK2=all / MD2_PACK2=off
 // in the environment force one form for every two-source call (A/B checks, tests/test_gpu_parity.py).
-static bool use_pack2(bool grad) {
+static int pack2_mode() {
   static const int mode = [] {
     const char* e = getenv("MD2_PACK2");
     if (e && !strcmp(e, "all")) return 2;
     if (e && !strcmp(e, "off")) return 0;
     return 1;
   }();
-  return mode == 2 || (mode == 1 && !grad);
+  return mode;
 }
+static bool use_pack2(bool grad) { return pack2_mode() == 2 || (pack2_mode() == 1 && !grad); }
 
 template <class C>
 static cudaError_t launch_march(const Params& P, cudaStream_t stream) {
@@ -487,6 +520,13 @@ static cudaError_t launch_march_ns(const Params& P, cudaStream_t stream) {
 }
 template <int NSRC>
 static void launch_identity_ns(const Params& P, int grid, cudaStream_t stream) {
+  if constexpr (NSRC == 2) {
+    if (pack2_mode() != 0) {      // the identity pass is forward-only: packed form unless MD2_PACK2=off
+      if (P.no_ssim) md2_identity2<true><<<grid, kThreads, 0, stream>>>(P);
+      else md2_identity2<false><<<grid, kThreads, 0, stream>>>(P);
+      return;
+    }
+  }
   if (P.no_ssim) md2_identity<NSRC, true><<<grid, kThreads, 0, stream>>>(P);
   else md2_identity<NSRC, false><<<grid, kThreads, 0, stream>>>(P);
 }
@@ -553,7 +593,7 @@ cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
     dim3 grid2((n0 + 256 * kSmoothPerThread - 1) / (256 * kSmoothPerThread), P.B, P.S);
     md2_smooth<<<grid2, 256, 0, side->stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    md2_smooth_scalars<<<1, 64, 0, side->stream>>>(P);
+    md2_smooth_scalars<<<(P.S * P.B + 63) / 64, 64, 0, side->stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   if ((e = cudaEventRecord(side->join, side->stream)) != cudaSuccess) return e;

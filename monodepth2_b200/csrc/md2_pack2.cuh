@@ -497,6 +497,123 @@ __device__ __forceinline__ void lane_dP2(const Lane2<C>& L, const Params& P, con
   for (int i = 0; i < 3; ++i) dP[i * 4 + 3] = f ? L.S3[i].y : L.S3[i].x;
 }
 
+// ------------------------------------------------------------------ identity pass, two sources (see id_stage_a / id_stage_b)
+struct IdLane2 {
+  int x, xi;
+  bool colok;
+  P2 H1[3][3], H2[3][3];
+  P2 HYrg1[2], HYrg2[2];
+  float HYb1[2], HYb2[2];
+  P2 pr1[3], tgrg1;
+  float tgb1;
+  P2 pr[3], tgrg;
+  float tgb;
+  float npr[2][3], ntg[3];        // next row, in flight
+};
+struct IdXchg2 {
+  P2 pr[3];
+  P2 tgrg;
+  float tgb;
+};
+
+__device__ __forceinline__ void id_init2(IdLane2& L, const Params& P, int x0, int lane) {
+  L.x = x0 - 1 + lane;
+  L.colok = (L.x >= 0) && (L.x < P.W);
+  L.xi = reflect_clamp(L.x, P.W);
+  const P2 z2 = bc(0.f);
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { L.H1[s][k] = z2; L.H2[s][k] = z2; }
+    L.pr1[s] = z2; L.pr[s] = z2;
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) { L.HYrg1[k] = z2; L.HYrg2[k] = z2; L.HYb1[k] = 0.f; L.HYb2[k] = 0.f; }
+  L.tgrg1 = z2; L.tgrg = z2; L.tgb1 = 0.f; L.tgb = 0.f;
+}
+
+__device__ __forceinline__ void id_prefetch2(IdLane2& L, const Params& P, int b, int t) {
+  const int tr = reflect_clamp(t, P.H);
+  const int plane = P.H * P.W;
+  const int off = b * 3 * plane + tr * P.W + L.xi;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    L.ntg[c] = MD2_LD(P.tgt + off + c * plane);
+    L.npr[0][c] = MD2_LD(P.src[0] + off + c * plane);
+    L.npr[1][c] = MD2_LD(P.src[1] + off + c * plane);
+  }
+}
+
+__device__ __forceinline__ void id_stage_a2(IdLane2& L, const Params& P, int b, int t, int lane, int y0, int y1) {
+  const int tr = reflect_clamp(t, P.H);
+  const int plane = P.H * P.W;
+  const bool own = L.colok && t >= y0 && t < y1 && lane >= 1 && lane <= kIdCols;
+  const int o4 = 4 * (b * plane + tr * P.W + L.xi);
+  const float tg[3] = {L.ntg[0], L.ntg[1], L.ntg[2]};
+  const float p0[3] = {L.npr[0][0], L.npr[0][1], L.npr[0][2]}, p1[3] = {L.npr[1][0], L.npr[1][1], L.npr[1][2]};
+  L.tgrg = p2(tg[0], tg[1]); L.tgb = tg[2];
+  L.pr[0] = p2(p0[0], p0[1]); L.pr[1] = p2(p1[0], p1[1]); L.pr[2] = p2(p0[2], p1[2]);
+  id_prefetch2(L, P, b, t + 1);
+  if (own) {
+    *reinterpret_cast<F4*>(P.tgt4 + o4) = make_f4(tg[0], tg[1], tg[2], 0.f);
+    *reinterpret_cast<F4*>(P.src4[0] + o4) = make_f4(p0[0], p0[1], p0[2], 0.f);
+    *reinterpret_cast<F4*>(P.src4[1] + o4) = make_f4(p1[0], p1[1], p1[2], 0.f);
+  }
+}
+
+template <bool NOSSIM>
+__device__ __forceinline__ void id_stage_b2(IdLane2& L, const Params& P, int b, int t, int lane, int y0, int y1,
+                                            const IdXchg2& lf, const IdXchg2& rt) {
+  const int yw = t - 1;
+  P2 H0[3][3], HYrg0[2];
+  float HYb0[2];
+  HYrg0[0] = add2(add2(lf.tgrg, L.tgrg), rt.tgrg);
+  HYrg0[1] = fma2(rt.tgrg, rt.tgrg, fma2(L.tgrg, L.tgrg, mul2(lf.tgrg, lf.tgrg)));
+  HYb0[0] = lf.tgb + L.tgb + rt.tgb;
+  HYb0[1] = fmaf(rt.tgb, rt.tgb, fmaf(L.tgb, L.tgb, lf.tgb * lf.tgb));
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    const P2 yl = (s < 2) ? lf.tgrg : bc(lf.tgb), yc = (s < 2) ? L.tgrg : bc(L.tgb), yr = (s < 2) ? rt.tgrg : bc(rt.tgb);
+    const P2 xl = lf.pr[s], xc = L.pr[s], xr = rt.pr[s];
+    H0[s][0] = add2(add2(xl, xc), xr);
+    H0[s][1] = fma2(xr, xr, fma2(xc, xc, mul2(xl, xl)));
+    H0[s][2] = fma2(xr, yr, fma2(xc, yc, mul2(xl, yl)));
+  }
+  const bool own = L.colok && yw >= y0 && yw < y1 && lane >= 1 && lane <= kIdCols;
+  if (own) {
+    const size_t plane = (size_t)P.H * P.W;
+    P2 S[3];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      S[s] = bc(0.f);
+      if (!NOSSIM) {
+        const P2 vy0 = (s < 2) ? add2(L.HYrg2[0], HYrg0[0]) : bc(L.HYb2[0] + HYb0[0]);
+        const P2 vy1 = (s < 2) ? add2(L.HYrg2[1], HYrg0[1]) : bc(L.HYb2[1] + HYb0[1]);
+        S[s] = ssim_window2(add2(L.H2[s][0], H0[s][0]), add2(L.H2[s][1], H0[s][1]), add2(L.H2[s][2], H0[s][2]), vy0, vy1, nullptr);
+      }
+    }
+    const P2 e0 = sub2(L.tgrg1, L.pr1[0]), e1 = sub2(L.tgrg1, L.pr1[1]), e2 = sub2(bc(L.tgb1), L.pr1[2]);
+    const float ss0 = ((0.f + S[0].x) + S[0].y) + S[2].x, ss1 = ((0.f + S[1].x) + S[1].y) + S[2].y;
+    const float l10 = ((0.f + fabsf(e0.x)) + fabsf(e0.y)) + fabsf(e2.x);
+    const float l11 = ((0.f + fabsf(e1.x)) + fabsf(e1.y)) + fabsf(e2.y);
+    float* o = P.idloss + ((size_t)b * 2) * plane + (size_t)yw * P.W + L.xi;
+    o[0] = NOSSIM ? l10 * (1.0f / 3.0f) : fmaf(0.85f / 3.0f, ss0, (0.15f / 3.0f) * l10);
+    o[plane] = NOSSIM ? l11 * (1.0f / 3.0f) : fmaf(0.85f / 3.0f, ss1, (0.15f / 3.0f) * l11);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    L.HYrg2[k] = add2(L.HYrg1[k], HYrg0[k]); L.HYrg1[k] = HYrg0[k];
+    L.HYb2[k] = L.HYb1[k] + HYb0[k]; L.HYb1[k] = HYb0[k];
+  }
+  L.tgrg1 = L.tgrg; L.tgb1 = L.tgb;
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { L.H2[s][k] = add2(L.H1[s][k], H0[s][k]); L.H1[s][k] = H0[s][k]; }
+    L.pr1[s] = L.pr[s];
+  }
+}
+
 }  // namespace md2
 
 #endif  // __CUDACC__

@@ -42,7 +42,7 @@ inline Layout make_layout(const md2_problem* p) {
   memset(&L, 0, sizeof(L));
   const size_t B = p->batch, H = p->height, W = p->width;
   size_t off = 0;
-  const size_t nacc = 3 * kMaxScales + 2 * kMaxScales * B + B * p->num_src * 12;
+  const size_t nacc = 3 * kMaxScales + 4 * kMaxScales * B + B * p->num_src * 12;   // = acc_count()
   L.acc_off = off; L.acc_bytes = nacc * sizeof(double);
   off = align_up(off + L.acc_bytes, 256);
   L.proj_off = off; off = align_up(off + B * p->num_src * 12 * sizeof(float), 256);

@@ -171,8 +171,8 @@ extern "C" int md2_emu_view_synthesis_loss(const md2_problem* p, const md2_tenso
         float e0, e1, g;
         smooth_pixel(P, s, b, i / Ws, i % Ws, inv_m, e0, e1, g);
         P.gn[s][(size_t)b * n + i] = g;
-        P.acc[acc_smx(s)] += e0;
-        P.acc[acc_smy(s)] += e1;
+        P.acc[acc_smx(P, s, b)] += e0;
+        P.acc[acc_smy(P, s, b)] += e1;
         P.acc[acc_dot(P, s, b)] += (double)g * P.disp[s][(size_t)b * n + i];
       }
     }

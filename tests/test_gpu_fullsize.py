@@ -160,6 +160,35 @@ def test_other_baseline_configs_loss_parity(wl):
             assert rel_l2(outs[("cam_T_cam", 0, f)].grad.cpu(), g32[("T", f)].grad) < 5e-2
 
 
+def test_large_batch_small_images():
+    """Batch sizes beyond the round-1 benchmarks (the per-(scale, sample) scalar kernels and the pose epilogue
+    must cover every sample): B=40, mono+stereo, against the live oracle."""
+    from monodepth2_b200.synthetic import make_batch
+    from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
+    B, H, W = 40, 32, 64
+    fids = [0, -1, 1, "s"]
+    batch = make_batch(B, H, W, fids, 4, 41, "structured")
+    inputs, outputs, pose, noise = batch
+    l32, o32, g32 = _oracle(batch, fids, torch.float32)
+    plan = LossPlan(B, H, W, fids)
+    ins = {k: v.to(DEV) for k, v in inputs.items()}
+    outs = {k: v.to(DEV).requires_grad_(True) for k, v in outputs.items()}
+    lk = view_synthesis_loss(plan, ins, outs, [n.to(DEV) for n in noise])
+    lk["loss"].backward()
+    for key in ["loss"] + ["loss/%d" % s for s in range(4)]:
+        ref = float(l32[key].detach())
+        assert abs(float(lk[key].detach()) - ref) <= 1e-5 * abs(ref), key
+    for s in range(4):
+        g, r = outs[("disp", s)].grad.cpu(), g32[("disp", s)].grad
+        assert rel_l2(g, r) < 0.1, s
+        per_sample = ((g - r).flatten(1).norm(dim=1) / (r.flatten(1).norm(dim=1) + 1e-30))
+        assert float(per_sample.max()) < 0.5, (s, per_sample)          # no sample left without its gradient
+    for f in (-1, 1):
+        g, r = outs[("cam_T_cam", 0, f)].grad.cpu(), g32[("T", f)].grad
+        per_sample = ((g - r).flatten(1).norm(dim=1) / (r.flatten(1).norm(dim=1) + 1e-30))
+        assert float(per_sample.max()) < 0.5, (f, per_sample)
+
+
 @pytest.mark.parametrize("shape", [(1, 40, 72), (3, 64, 200), (2, 32, 32)])
 def test_odd_shapes_and_align_corners_true(shape):
     """Protocol P6 (align_corners=True, the torch-0.4.1 behaviour the reference was written for) and
