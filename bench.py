@@ -26,6 +26,16 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+# stdout carries exactly ONE line, the JSON result: everything else that libraries print on fd 1 (e.g. the
+# "NCCL version ..." banner) is sent to stderr while the benchmark runs
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+
+
 WORKLOADS = {
     # name: (H, W, frame_ids, avg_reprojection, disable_automasking)
     "mono_640x192_b12": (192, 640, [0, -1, 1], False, False),
@@ -196,7 +206,7 @@ def run_reference(args, wl):
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------- own arm
@@ -443,7 +453,7 @@ def run_own(args, wl):
             "gpu_launches": 7 * args.steps,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -543,7 +553,7 @@ def run_train(args, wl):
                        "last_loss": float(loss.item())},
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -30,7 +30,6 @@ namespace md2 {
 constexpr int kWarpsPerCta = MD2_WARPS_PER_CTA;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kSmoothPerThread = 4;
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -138,38 +137,117 @@ __global__ void __launch_bounds__(kThreads) md2_identity2(Params P) {
 }
 
 // ------------------------------------------------------------------ 4. smoothness
-__global__ void md2_smooth(Params P) {
-  const int s = blockIdx.z, b = blockIdx.y;
-  const int Hs = P.H >> s, Ws = P.W >> s;
-  const int n = Hs * Ws;
-  if (blockIdx.x * blockDim.x >= n) return;                      // uniform per block
-  __shared__ float sh_inv_m;
-  if (threadIdx.x == 0) sh_inv_m = 1.0f / ((float)(P.acc[acc_dispsum(P, s, b)] / (double)n) + 1e-7f);
-  __syncthreads();
-  const float inv_m = sh_inv_m;
+// Edge-aware smoothness (layers.py:202-215 on the mean-normalised disparity, trainer.py:486-487): value and
+// numerator gradient gn, all scales.  A warp owns 32 columns x kSmoothRows rows of one (scale, sample) and marches
+// down: the current row lives in registers, the next row is loaded once, so every edge is evaluated ONCE (its
+// weight exp(-|dI|) and sign serve both of its end points: right neighbour by shuffle, upper neighbour from
+// the previous step) instead of once per end point.  Same per-edge arithmetic as smooth_pixel (md2_core.cuh).
+constexpr int kSmoothRows = 16;
+constexpr int kSmoothWarps = 4;
+__host__ __device__ inline int smooth_bands(int Ws) { return (Ws + 31) / 32; }
+__host__ __device__ inline int smooth_segs(int Hs) { return (Hs + kSmoothRows - 1) / kSmoothRows; }
+
+struct SmoothPx { float raw, n, i0, i1, i2; };
+__device__ __forceinline__ SmoothPx smooth_load(const float* d, const float* im, int plane, int p, float inv_m) {
+  SmoothPx r;
+  r.raw = __ldg(d + p);
+  r.n = r.raw * inv_m;
+  r.i0 = __ldg(im + p); r.i1 = __ldg(im + plane + p); r.i2 = __ldg(im + 2 * plane + p);
+  return r;
+}
+// edge between `a` (first end) and `q`: |n_a - n_q| w  and  sign(n_a - n_q) w
+__device__ __forceinline__ void smooth_edge(const SmoothPx& a, const SmoothPx& q, float& e, float& sw) {
+  const float g = fabsf(a.i0 - q.i0) + fabsf(a.i1 - q.i1) + fabsf(a.i2 - q.i2);
+  const float w = md2_exp_neg(g * (1.0f / 3.0f));
+  const float df = a.n - q.n;
+  e = fabsf(df) * w;
+  sw = (df > 0.f) ? w : ((df < 0.f) ? -w : 0.f);
+}
+
+__global__ void __launch_bounds__(kSmoothWarps * 32) md2_smooth(Params P) {
+  const int lane = threadIdx.x & 31;
+  int rem = blockIdx.x * kSmoothWarps + (threadIdx.x >> 5);
+  int s = 0;
+  for (; s < P.S; ++s) {
+    const int n = smooth_bands(P.W >> s) * smooth_segs(P.H >> s) * P.B;
+    if (rem < n) break;
+    rem -= n;
+  }
+  if (s >= P.S) return;
+  const int Hs = P.H >> s, Ws = P.W >> s, plane = Hs * Ws;
+  const int nb = smooth_bands(Ws), ns = smooth_segs(Hs);
+  const int b = rem / (nb * ns);
+  const int r = rem - b * nb * ns;
+  const int seg = r / nb, band = r - seg * nb;
+  float inv_m = 0.f;
+  if (lane == 0) inv_m = 1.0f / ((float)(P.acc[acc_dispsum(P, s, b)] / (double)plane) + 1e-7f);
+  inv_m = __shfl_sync(kFull, inv_m, 0);
+  const float* d = P.disp[s] + (size_t)b * plane;
+  const float* im = P.color[s] + (size_t)b * 3 * plane;
+  float* gn = P.gn[s] + (size_t)b * plane;
+  const float inx = 1.0f / ((float)P.B * (float)Hs * (float)(Ws - 1));
+  const float iny = 1.0f / ((float)P.B * (float)(Hs - 1) * (float)Ws);
+  const int x = band * 32 + lane;
+  const bool xok = x < Ws;
+  const int xc = xok ? x : Ws - 1;
+  const bool has_rt = x + 1 < Ws;
+  // pixel beyond the band that only the first / last lane needs: the left neighbour of lane 0, the right
+  // neighbour of lane 31 (loaded one row ahead like the band itself)
+  const bool side_lane = (lane == 0 && x > 0) || (lane == 31 && has_rt);
+  const int xs = (lane == 0) ? x - 1 : x + 1;
+  const int y0 = seg * kSmoothRows, y1 = min(y0 + kSmoothRows, Hs);
+  auto row = [&](int y) { return (y < Hs ? y : Hs - 1) * Ws; };
+  SmoothPx cur = smooth_load(d, im, plane, row(y0) + xc, inv_m);
+  SmoothPx nxt = smooth_load(d, im, plane, row(y0 + 1) + xc, inv_m);
+  SmoothPx side = cur, side_nxt = cur;
+  if (side_lane) { side = smooth_load(d, im, plane, row(y0) + xs, inv_m); side_nxt = smooth_load(d, im, plane, row(y0 + 1) + xs, inv_m); }
+  float sy_up = 0.f;                       // sign * weight of the edge to the row above
+  if (y0 > 0) {
+    const SmoothPx up = smooth_load(d, im, plane, (y0 - 1) * Ws + xc, inv_m);
+    float e;
+    smooth_edge(up, cur, e, sy_up);
+  }
   float ex = 0.f, ey = 0.f, dot = 0.f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    float e0, e1, g;
-    smooth_pixel(P, s, b, i / Ws, i % Ws, inv_m, e0, e1, g);
-    P.gn[s][(size_t)b * n + i] = g;
-    ex += e0; ey += e1;
-    dot = fmaf(g, __ldg(P.disp[s] + (size_t)b * n + i), dot);
+  for (int y = y0; y < y1; ++y) {
+    // rows y and y+1 are in registers; put row y+2 in flight
+    const SmoothPx nn = smooth_load(d, im, plane, row(y + 2) + xc, inv_m);
+    SmoothPx side_nn = side_nxt;
+    if (side_lane) side_nn = smooth_load(d, im, plane, row(y + 2) + xs, inv_m);
+    const bool has_dn = y + 1 < Hs;
+    // right neighbour: next lane, or the side pixel at the end of the band
+    SmoothPx rt;
+    rt.n = __shfl_down_sync(kFull, cur.n, 1); rt.i0 = __shfl_down_sync(kFull, cur.i0, 1);
+    rt.i1 = __shfl_down_sync(kFull, cur.i1, 1); rt.i2 = __shfl_down_sync(kFull, cur.i2, 1);
+    if (lane == 31) rt = side;
+    float e_x = 0.f, sx = 0.f, e_y = 0.f, sy = 0.f;
+    if (has_rt) smooth_edge(cur, rt, e_x, sx);
+    if (has_dn) smooth_edge(cur, nxt, e_y, sy);
+    // left neighbour's edge towards this pixel: previous lane, or recomputed from the side pixel
+    float sxl = __shfl_up_sync(kFull, sx, 1);
+    if (lane == 0) {
+      sxl = 0.f;
+      if (x > 0) { float e; smooth_edge(side, cur, e, sxl); }
+    }
+    if (xok) {
+      // d(sum_x/Nx + sum_y/Ny) / d n(p): +sign*w for the edges this pixel starts, -sign*w for those it ends
+      float g = 0.f;
+      g += inx * sx;
+      g += inx * (-sxl);
+      g += iny * sy;
+      g += iny * (-sy_up);
+      gn[y * Ws + x] = g;
+      ex += e_x; ey += e_y;
+      dot = fmaf(g, cur.raw, dot);
+    }
+    sy_up = sy;
+    cur = nxt; nxt = nn;
+    side = side_nxt; side_nxt = side_nn;
   }
   ex = warp_sum(ex); ey = warp_sum(ey); dot = warp_sum(dot);
-  __shared__ float part[3][32];
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) { part[0][w] = ex; part[1][w] = ey; part[2][w] = dot; }
-  __syncthreads();
-  if (w == 0) {
-    const int nw = blockDim.x >> 5;
-    ex = warp_sum(l < nw ? part[0][l] : 0.f);
-    ey = warp_sum(l < nw ? part[1][l] : 0.f);
-    dot = warp_sum(l < nw ? part[2][l] : 0.f);
-    if (l == 0) {
-      atomicAdd(&P.acc[acc_smx(P, s, b)], (double)ex);
-      atomicAdd(&P.acc[acc_smy(P, s, b)], (double)ey);
-      atomicAdd(&P.acc[acc_dot(P, s, b)], (double)dot);
-    }
+  if (lane == 0) {
+    atomicAdd(&P.acc[acc_smx(P, s, b)], (double)ex);
+    atomicAdd(&P.acc[acc_smy(P, s, b)], (double)ey);
+    atomicAdd(&P.acc[acc_dot(P, s, b)], (double)dot);
   }
 }
 
@@ -590,8 +668,9 @@ cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
     dim3 grid((n0 + 256 * 8 - 1) / (256 * 8), P.B, P.S);
     md2_disp_mean<<<grid, 256, 0, side->stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    dim3 grid2((n0 + 256 * kSmoothPerThread - 1) / (256 * kSmoothPerThread), P.B, P.S);
-    md2_smooth<<<grid2, 256, 0, side->stream>>>(P);
+    int sjobs = 0;
+    for (int s = 0; s < P.S; ++s) sjobs += smooth_bands(P.W >> s) * smooth_segs(P.H >> s) * P.B;
+    md2_smooth<<<(sjobs + kSmoothWarps - 1) / kSmoothWarps, kSmoothWarps * 32, 0, side->stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     md2_smooth_scalars<<<(P.S * P.B + 63) / 64, 64, 0, side->stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;

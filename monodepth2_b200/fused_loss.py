@@ -327,8 +327,10 @@ def _view_synthesis_loss_v1_multiscale(plan: LossPlan, inputs: Dict, outputs: Di
             ins[("color", f, 0)] = inputs[("color", f, s)]
         outs = {("disp", 0): outputs[("disp", s)]}
         for f in plan.src_ids:
-            if f != "s":
-                outs[("cam_T_cam", 0, f)] = outputs[("cam_T_cam", 0, f)]
+            if f != "s":       # the matrix if the caller built it, else the pose leaves (T is then built in the call)
+                for key in (("cam_T_cam", 0, f), ("axisangle", 0, f), ("translation", 0, f)):
+                    if key in outputs:
+                        outs[key] = outputs[key]
         sub_side = None
         if side is not None:
             sub_side = {k: ([0] if s in side.get(k, []) else []) for k in
