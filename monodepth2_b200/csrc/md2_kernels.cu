@@ -120,6 +120,8 @@ __global__ void __launch_bounds__(kThreads) md2_identity2(Params P) {
   IdLane2 L;
   id_init2(L, P, band * kIdCols, lane);
   id_prefetch2(L, P, b, y0 - 1);
+  id_shift2(L);
+  id_prefetch2(L, P, b, y0);
   for (int t = y0 - 1; t <= y1; ++t) {
     id_stage_a2(L, P, b, t, lane, y0, y1);
     IdXchg2 lf, rt;

@@ -508,7 +508,8 @@ struct IdLane2 {
   float tgb1;
   P2 pr[3], tgrg;
   float tgb;
-  float npr[2][3], ntg[3];        // next row, in flight
+  float npr[2][3], ntg[3];        // row t+1, in flight
+  float n2pr[2][3], n2tg[3];      // row t+2, in flight (the pass is bound by bytes in flight, not by issue)
 };
 struct IdXchg2 {
   P2 pr[3];
@@ -532,16 +533,21 @@ __device__ __forceinline__ void id_init2(IdLane2& L, const Params& P, int x0, in
   L.tgrg1 = z2; L.tgrg = z2; L.tgb1 = 0.f; L.tgb = 0.f;
 }
 
+// issue the planar loads of row t into the far prefetch slot (consumed two steps later)
 __device__ __forceinline__ void id_prefetch2(IdLane2& L, const Params& P, int b, int t) {
   const int tr = reflect_clamp(t, P.H);
   const int plane = P.H * P.W;
   const int off = b * 3 * plane + tr * P.W + L.xi;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    L.ntg[c] = MD2_LD(P.tgt + off + c * plane);
-    L.npr[0][c] = MD2_LD(P.src[0] + off + c * plane);
-    L.npr[1][c] = MD2_LD(P.src[1] + off + c * plane);
+    L.n2tg[c] = MD2_LD(P.tgt + off + c * plane);
+    L.n2pr[0][c] = MD2_LD(P.src[0] + off + c * plane);
+    L.n2pr[1][c] = MD2_LD(P.src[1] + off + c * plane);
   }
+}
+__device__ __forceinline__ void id_shift2(IdLane2& L) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { L.ntg[c] = L.n2tg[c]; L.npr[0][c] = L.n2pr[0][c]; L.npr[1][c] = L.n2pr[1][c]; }
 }
 
 __device__ __forceinline__ void id_stage_a2(IdLane2& L, const Params& P, int b, int t, int lane, int y0, int y1) {
@@ -553,7 +559,8 @@ __device__ __forceinline__ void id_stage_a2(IdLane2& L, const Params& P, int b, 
   const float p0[3] = {L.npr[0][0], L.npr[0][1], L.npr[0][2]}, p1[3] = {L.npr[1][0], L.npr[1][1], L.npr[1][2]};
   L.tgrg = p2(tg[0], tg[1]); L.tgb = tg[2];
   L.pr[0] = p2(p0[0], p0[1]); L.pr[1] = p2(p1[0], p1[1]); L.pr[2] = p2(p0[2], p1[2]);
-  id_prefetch2(L, P, b, t + 1);
+  id_shift2(L);
+  id_prefetch2(L, P, b, t + 2);
   if (own) {
     *reinterpret_cast<F4*>(P.tgt4 + o4) = make_f4(tg[0], tg[1], tg[2], 0.f);
     *reinterpret_cast<F4*>(P.src4[0] + o4) = make_f4(p0[0], p0[1], p0[2], 0.f);
