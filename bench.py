@@ -217,6 +217,7 @@ class DeviceBatch:
         from monodepth2_b200._capi import Md2Tensors, MAX_SCALES
         inputs, outputs, pose, noise = batch
         self.keep = []
+        self.noise = []
         t = Md2Tensors()
 
         def put(x):
@@ -245,6 +246,7 @@ class DeviceBatch:
             t.color[s] = put(inputs[("color", 0, s)])
             if plan.n_id > 0:
                 t.noise[s] = put(noise[s])
+                self.noise.append(self.keep[-1])
             g = torch.empty((B, 1, H >> s, W >> s), device=dev)
             self.grad_disp.append(g)
             t.grad_disp[s] = g.data_ptr()
@@ -334,6 +336,31 @@ def run_own(args, wl):
     ms_total = float(tt.item())
     value = world * BATCH * args.steps / (ms_total * 1e-3)
     loss_val = float(devb[(args.steps - 1) % nrot].losses[0].item())
+
+    # ---- the same loop with the tie-break noise of trainer.py:468-469 drawn inside the timed region
+    # (torch.randn into the resident noise buffers, once per scale, as the public API does); reported beside
+    # `value`, whose noise tensors are inputs that are already resident like every other input
+    ms_noise = None
+    if n_id > 0:
+        noise_bufs = [b.noise for b in devb]
+
+        def step_with_noise(i):
+            for t in noise_bufs[i % nrot]:
+                t.normal_()
+            step(i)
+        for i in range(3):
+            step_with_noise(i)
+        barrier()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record(stream)
+        for i in range(args.steps):
+            step_with_noise(i)
+        n1.record(stream)
+        barrier()
+        tn = torch.tensor([n0.elapsed_time(n1)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+        ms_noise = float(tn.item())
 
     # ---- roofline of the dominant kernel (md2_march): per-launch CUDA events, live
     lib.md2_profile_enable(1)
@@ -448,7 +475,10 @@ def run_own(args, wl):
                        "scales": 4, "l2": "inputs larger than L2: %d rotating batches of ~%d MB each" %
                        (nrot, int((h2d + n_id * BATCH * H * W * 4 * 4) / 1e6)),
                        "rows_per_segment": plan.problem(True).rows_per_segment or max(32, (H + 3) // 4), "loss": loss_val,
-                       "launch": "plain C-ABI calls" if graphs is None else "CUDA-graph replay of the C-ABI call"},
+                       "launch": "plain C-ABI calls" if graphs is None else "CUDA-graph replay of the C-ABI call",
+                       "noise": "tie-break noise tensors are resident inputs of the timed call; "
+                                "value_with_noise_draw times the same loop with 4 torch.randn draws per step"},
+            "value_with_noise_draw": (world * BATCH * args.steps / (ms_noise * 1e-3)) if ms_noise else None,
             "roofline": roofline, "cpu_baseline": cpu, "torch_cuda_baseline": tcb, "e2e": e2e,
             "gpu_launches": 7 * args.steps,
             "clocks": clocks,
