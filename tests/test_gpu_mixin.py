@@ -1,0 +1,92 @@
+"""FusedLossMixin the way INTEGRATION.md section 2 uses it: an object with the reference's `opt` namespace calls
+generate_images_pred(inputs, outputs) then compute_losses(inputs, outputs) (trainer.py:257-258) and
+losses["loss"].backward() (trainer.py:208); the tie-break noise comes from the CUDA generator as in
+trainer.py:468-469, so seeding it reproduces the oracle's draws.  Also the logging-step side outputs
+(`md2_side`) and the no_grad validation mode (trainer.py:330-331)."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_l2
+from oracle import view_synthesis as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _opt(B, H, W, frame_ids, **kw):
+    d = dict(batch_size=B, height=H, width=W, frame_ids=list(frame_ids), scales=[0, 1, 2, 3], min_depth=0.1,
+             max_depth=100.0, disparity_smoothness=1e-3, avg_reprojection=False, disable_automasking=False,
+             no_ssim=False, v1_multiscale=False, predictive_mask=False, pose_model_type="separate_resnet")
+    d.update(kw)
+    return SimpleNamespace(**d)
+
+
+def _trainer(opt):
+    from monodepth2_b200.fused_loss import FusedLossMixin
+
+    class T(FusedLossMixin):
+        def __init__(self, opt):
+            self.opt = opt
+    return T(opt)
+
+
+@pytest.mark.parametrize("fids,kw", [([0, -1, 1], {}), ([0, -1, 1, "s"], {}), ([0, -1, 1], {"avg_reprojection": True})])
+def test_mixin_matches_oracle_with_generator_noise(fids, kw):
+    from monodepth2_b200.synthetic import make_batch
+    B, H, W = 3, 64, 96
+    inputs, outputs, pose, _ = make_batch(B, H, W, fids, 4, 51, "structured")
+    n_src = len(fids) - 1
+    n_id = 1 if kw.get("avg_reprojection") else n_src
+    t = _trainer(_opt(B, H, W, fids, **kw))
+    t.md2_side = {"depth_scales": [0], "color_scales": [0], "mask_scales": [0, 1, 2, 3]}
+    ins = {k: v.to(DEV) for k, v in inputs.items()}
+    outs = {k: v.to(DEV).requires_grad_(True) for k, v in outputs.items()}
+    leaves = dict(outs)
+    torch.manual_seed(123)
+    t.generate_images_pred(ins, outs)
+    losses = t.compute_losses(ins, outs)
+    losses["loss"].backward()
+    assert sorted(losses) == ["loss", "loss/0", "loss/1", "loss/2", "loss/3"]
+    # the same four draws, in the same order, for the oracle
+    torch.manual_seed(123)
+    noise = [torch.randn((B, n_id, H, W), device=DEV).cpu() for _ in range(4)]
+    cfg = O.OracleConfig(height=H, width=W, frame_ids=tuple(fids), **kw)
+    o_outs = {k: v.clone().requires_grad_(True) for k, v in outputs.items()}
+    o_leaves = dict(o_outs)
+    o_losses = O.view_synthesis_loss(dict(inputs), o_outs, cfg, noise)
+    o_losses["loss"].backward()
+    for k in losses:
+        ref = float(o_losses[k].detach())
+        assert abs(float(losses[k].detach()) - ref) <= 1e-5 * abs(ref), k
+    for k in leaves:
+        assert rel_l2(leaves[k].grad.cpu(), o_leaves[k].grad) < 0.1, k
+    # what Trainer.log / compute_depth_losses read on logging steps (trainer.py:504,553-572)
+    np.testing.assert_allclose(outs[("depth", 0, 0)].cpu().numpy(), o_outs[("depth", 0, 0)].detach().numpy(), rtol=2e-6)
+    for f in fids[1:]:
+        np.testing.assert_allclose(outs[("color", f, 0)].cpu().numpy(), o_outs[("color", f, 0)].detach().numpy(), atol=5e-5)
+    for s in range(4):
+        m = outs["identity_selection/%d" % s].cpu()
+        assert m.shape == (B, H, W)
+        assert float((m != o_outs["identity_selection/%d" % s]).float().mean()) <= 1e-3
+
+
+def test_mixin_under_no_grad_is_forward_only():
+    from monodepth2_b200.synthetic import make_batch
+    B, H, W, fids = 2, 48, 80, [0, -1, 1]
+    inputs, outputs, pose, _ = make_batch(B, H, W, fids, 4, 52, "structured")
+    t = _trainer(_opt(B, H, W, fids))
+    ins = {k: v.to(DEV) for k, v in inputs.items()}
+    outs = {k: v.to(DEV).requires_grad_(True) for k, v in outputs.items()}
+    with torch.no_grad():                      # Trainer.val, trainer.py:330-331
+        torch.manual_seed(5)
+        t.generate_images_pred(ins, outs)
+        l0 = t.compute_losses(ins, outs)
+    assert not l0["loss"].requires_grad
+    torch.manual_seed(5)
+    t.generate_images_pred(ins, outs)
+    l1 = t.compute_losses(ins, outs)
+    assert l1["loss"].requires_grad
+    assert abs(float(l0["loss"]) - float(l1["loss"].detach())) <= 2e-6 * abs(float(l0["loss"]))
