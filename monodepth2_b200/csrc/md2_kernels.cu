@@ -14,7 +14,9 @@
 // warp shuffles, vertical neighbours live in registers (rolling 3-row sums), the values the
 // adjoint needs two rows later sit in a thread-private shared-memory ring.  No block-level
 // synchronisation, no tensor cores (the path is gather/stream work, BASELINE.json).
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -136,6 +138,141 @@ __global__ void __launch_bounds__(kThreads) md2_identity2(Params P) {
     }
     id_stage_b2<NOSSIM>(L, P, b, t, lane, y0, y1, lf, rt);
   }
+}
+
+// ------------------------------------------------------------------ 3b. identity pass, TMA-staged
+// The identity pass is a streaming stencil: every input byte is used by a 3x3 window and nothing is
+// data-dependent, so the tile a CTA needs is a box.  One elected thread arms an mbarrier and issues three
+// cp.async.bulk.tensor (TMA) loads - target, source 0, source 1, each a box of kTmaBoxW x kTmaBoxH x 3 channels of
+// the planar (B*3, H, W) tensor including the 1-pixel halo - the CTA waits on the barrier, mirrors the halo of
+// border tiles in shared memory (TMA fills out-of-bounds elements with zeros, ReflectionPad2d(1) wants the
+// mirror image, layers.py:235-236) and marches the rows out of shared memory: a lane owns one column and reads
+// its left / right neighbours from the tile (no warp halo, no shuffles, all 32 lanes productive).  Two CTAs per
+// SM (2 x 86 KB of tiles) overlap one CTA's loads with the other's arithmetic.  Used for two sources when the
+// row pitch is a multiple of 16 bytes; otherwise md2_identity / md2_identity2 run.
+constexpr int kTmaCols = 128, kTmaRows = 16;                  // pixels a CTA owns
+constexpr int kTmaPadX = 4;      // the box starts 4 columns left of the tile: TMA needs a 16-byte aligned inner start
+constexpr int kTmaBoxW = kTmaCols + 2 * kTmaPadX, kTmaBoxH = kTmaRows + 2;   // (x0 - 1 faults with "illegal instruction")
+constexpr int kTmaImgFloats = ((3 * kTmaBoxH * kTmaBoxW * 4 + 127) / 128) * 32;   // one image's tile, 128-byte multiple
+constexpr int kTmaSmemBytes = 3 * kTmaImgFloats * 4 + 16;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+struct IdTensorMaps { CUtensorMap tgt, src0, src1; };
+
+template <bool NOSSIM>
+__global__ void __launch_bounds__(kTmaCols) md2_identity_tma(Params P, const __grid_constant__ IdTensorMaps maps) {
+  extern __shared__ __align__(128) float tile[];
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(tile + 3 * kTmaImgFloats);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * kTmaCols, y0 = blockIdx.y * kTmaRows, b = blockIdx.z;
+  const int y1 = min(y0 + kTmaRows, P.H);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned bytes = 3u * 3u * kTmaBoxH * kTmaBoxW * 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    const CUtensorMap* m[3] = {&maps.tgt, &maps.src0, &maps.src1};
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"(smem_u32(tile + i * kTmaImgFloats)), "l"(m[i]), "r"(x0 - kTmaPadX), "r"(y0 - 1), "r"(b * 3), "r"(smem_u32(bar))
+          : "memory");
+  }
+  {   // every thread waits for the bytes to land (phase 0)
+    unsigned done = 0, spins = 0;
+    while (!done) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(smem_u32(bar)) : "memory");
+      if (!done && ++spins > (1u << 24)) __trap();      // a descriptor fault must not turn into a hang
+    }
+  }
+  // mirror the halo of border tiles: columns first, then rows (so that the corners come out right)
+  auto at = [&](int img, int c, int r, int col) -> float& { return tile[img * kTmaImgFloats + (c * kTmaBoxH + r) * kTmaBoxW + col]; };
+  const int cl = (x0 == 0) ? kTmaPadX - 1 : -1;                           // tile column of x = -1
+  const int cr = (P.W - x0 + kTmaPadX <= kTmaBoxW - 1) ? P.W - x0 + kTmaPadX : -1;   // tile column of x = W
+  if (cl >= 0 || cr >= 0) {
+    for (int i = threadIdx.x; i < 9 * kTmaBoxH; i += blockDim.x) {
+      const int img = i / (3 * kTmaBoxH), c = (i / kTmaBoxH) % 3, r = i % kTmaBoxH;
+      if (cl >= 0) at(img, c, r, cl) = at(img, c, r, cl + 2);
+      if (cr >= 2) at(img, c, r, cr) = at(img, c, r, cr - 2);
+    }
+    __syncthreads();
+  }
+  const int rt_ = (y0 == 0) ? 0 : -1;                                     // tile row of y = -1
+  const int rb = (P.H - y0 + 1 <= kTmaBoxH - 1 && P.H >= y0) ? P.H - y0 + 1 : -1;   // tile row of y = H
+  if (rt_ >= 0 || rb >= 0) {
+    for (int i = threadIdx.x; i < 9 * kTmaBoxW; i += blockDim.x) {
+      const int img = i / (3 * kTmaBoxW), c = (i / kTmaBoxW) % 3, col = i % kTmaBoxW;
+      if (rt_ >= 0) at(img, c, 0, col) = at(img, c, 2, col);
+      if (rb >= 2) at(img, c, rb, col) = at(img, c, rb - 2, col);
+    }
+    __syncthreads();
+  }
+  IdLane2 L;
+  id_init2(L, P, 0, 0);
+  L.x = x0 + warp * 32 + lane;
+  L.colok = L.x < P.W;
+  L.xi = L.colok ? L.x : P.W - 1;
+  const int col = warp * 32 + lane + kTmaPadX;                            // tile column of this lane's pixel
+  const int plane = P.H * P.W;
+  for (int r = 0; r < kTmaBoxH; ++r) {
+    const int t = y0 - 1 + r;
+    if (t > y1) break;
+    float v[3][3][3];                                                     // [image][channel][left, centre, right]
+#pragma unroll
+    for (int img = 0; img < 3; ++img)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* row = &at(img, c, r, col);
+        v[img][c][0] = row[-1]; v[img][c][1] = row[0]; v[img][c][2] = row[1];
+      }
+    IdXchg2 lf, rt;
+    lf.tgrg = p2(v[0][0][0], v[0][1][0]); lf.tgb = v[0][2][0];
+    rt.tgrg = p2(v[0][0][2], v[0][1][2]); rt.tgb = v[0][2][2];
+    L.tgrg = p2(v[0][0][1], v[0][1][1]); L.tgb = v[0][2][1];
+    lf.pr[0] = p2(v[1][0][0], v[1][1][0]); lf.pr[1] = p2(v[2][0][0], v[2][1][0]); lf.pr[2] = p2(v[1][2][0], v[2][2][0]);
+    rt.pr[0] = p2(v[1][0][2], v[1][1][2]); rt.pr[1] = p2(v[2][0][2], v[2][1][2]); rt.pr[2] = p2(v[1][2][2], v[2][2][2]);
+    L.pr[0] = p2(v[1][0][1], v[1][1][1]); L.pr[1] = p2(v[2][0][1], v[2][1][1]); L.pr[2] = p2(v[1][2][1], v[2][2][1]);
+    if (L.colok && t >= y0 && t < y1) {                                   // RGBx texels for the marching kernel
+      const int o4 = 4 * (b * plane + t * P.W + L.x);
+      *reinterpret_cast<float4*>(P.tgt4 + o4) = make_float4(v[0][0][1], v[0][1][1], v[0][2][1], 0.f);
+      *reinterpret_cast<float4*>(P.src4[0] + o4) = make_float4(v[1][0][1], v[1][1][1], v[1][2][1], 0.f);
+      *reinterpret_cast<float4*>(P.src4[1] + o4) = make_float4(v[2][0][1], v[2][1][1], v[2][2][1], 0.f);
+    }
+    id_stage_b2<NOSSIM>(L, P, b, t, lane, y0, y1, lf, rt, 0, 31);
+  }
+}
+
+// host: tensor map of a planar (B*3, H, W) fp32 image tensor with the identity pass's box
+typedef CUresult (*md2_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static md2_encode_tiled_fn get_encode_tiled() {
+  static md2_encode_tiled_fn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (md2_encode_tiled_fn)p;
+  }();
+  return fn;
+}
+static bool make_image_map(CUtensorMap* m, const float* base, int B, int H, int W) {
+  md2_encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * 3};
+  const cuuint64_t gstride[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+  const cuuint32_t box[3] = {kTmaBoxW, kTmaBoxH, 3};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // ------------------------------------------------------------------ 4. smoothness
@@ -601,6 +738,25 @@ static cudaError_t launch_march_ns(const Params& P, cudaStream_t stream) {
 template <int NSRC>
 static void launch_identity_ns(const Params& P, int grid, cudaStream_t stream) {
   if constexpr (NSRC == 2) {
+    // TMA-staged form: two sources, production-sized images whose row pitch is a multiple of 16 bytes, base
+    // pointers 16-byte aligned (cuTensorMapEncodeTiled's requirements).  MD2_IDENTITY_TMA=0 disables it.
+    static const bool tma_on = !(getenv("MD2_IDENTITY_TMA") && atoi(getenv("MD2_IDENTITY_TMA")) == 0);
+    const bool aligned = (((uintptr_t)P.tgt | (uintptr_t)P.src[0] | (uintptr_t)P.src[1]) & 15) == 0;
+    if (tma_on && pack2_mode() != 0 && aligned && P.W % 4 == 0 && P.W >= kTmaBoxW && P.H >= kTmaBoxH) {
+      IdTensorMaps maps;
+      if (make_image_map(&maps.tgt, P.tgt, P.B, P.H, P.W) && make_image_map(&maps.src0, P.src[0], P.B, P.H, P.W) &&
+          make_image_map(&maps.src1, P.src[1], P.B, P.H, P.W)) {
+        const dim3 g((P.W + kTmaCols - 1) / kTmaCols, (P.H + kTmaRows - 1) / kTmaRows, P.B);
+        if (P.no_ssim) {
+          cudaFuncSetAttribute(md2_identity_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+          md2_identity_tma<true><<<g, kTmaCols, kTmaSmemBytes, stream>>>(P, maps);
+        } else {
+          cudaFuncSetAttribute(md2_identity_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+          md2_identity_tma<false><<<g, kTmaCols, kTmaSmemBytes, stream>>>(P, maps);
+        }
+        return;
+      }
+    }
     if (pack2_mode() != 0) {      // the identity pass is forward-only: packed form unless MD2_PACK2=off
       if (P.no_ssim) md2_identity2<true><<<grid, kThreads, 0, stream>>>(P);
       else md2_identity2<false><<<grid, kThreads, 0, stream>>>(P);

@@ -570,7 +570,7 @@ __device__ __forceinline__ void id_stage_a2(IdLane2& L, const Params& P, int b, 
 
 template <bool NOSSIM>
 __device__ __forceinline__ void id_stage_b2(IdLane2& L, const Params& P, int b, int t, int lane, int y0, int y1,
-                                            const IdXchg2& lf, const IdXchg2& rt) {
+                                            const IdXchg2& lf, const IdXchg2& rt, int lane_lo = 1, int lane_hi = kIdCols) {
   const int yw = t - 1;
   P2 H0[3][3], HYrg0[2];
   float HYb0[2];
@@ -586,7 +586,7 @@ __device__ __forceinline__ void id_stage_b2(IdLane2& L, const Params& P, int b, 
     H0[s][1] = fma2(xr, xr, fma2(xc, xc, mul2(xl, xl)));
     H0[s][2] = fma2(xr, yr, fma2(xc, yc, mul2(xl, yl)));
   }
-  const bool own = L.colok && yw >= y0 && yw < y1 && lane >= 1 && lane <= kIdCols;
+  const bool own = L.colok && yw >= y0 && yw < y1 && lane >= lane_lo && lane <= lane_hi;
   if (own) {
     const size_t plane = (size_t)P.H * P.W;
     P2 S[3];
