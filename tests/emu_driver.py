@@ -40,7 +40,8 @@ class DebugSink(C.Structure):
                 ("smoff", C.c_long * 4)]
 
 
-def run_emu(g, want_grad=True, rows_per_segment=0, align_corners=False, side_outputs=True, decisions=False):
+def run_emu(g, want_grad=True, rows_per_segment=0, align_corners=False, side_outputs=True, decisions=False,
+            pose_leaves=False):
     """Run the emulator on a Golden fixture; returns dict of numpy outputs."""
     lib = C.CDLL(build_emu())
     lib.md2_emu_workspace_bytes.argtypes = [C.POINTER(Md2Problem), C.POINTER(C.c_size_t)]
@@ -68,6 +69,20 @@ def run_emu(g, want_grad=True, rows_per_segment=0, align_corners=False, side_out
         if f == "s":
             t.T[i] = _ptr(arr(z["in__stereo_T"]))
             t.pose_requires_grad[i] = 0
+        elif pose_leaves:
+            # the pose leaves as PoseDecoder lays them out: (B,2,1,3), only [:, 0] used -> stride 6
+            aa = np.zeros((B, 2, 1, 3), np.float32); tr = np.zeros((B, 2, 1, 3), np.float32)
+            aa[:, 0] = np.asarray(z["axisangle__%s" % f]).reshape(B, 1, 3)
+            tr[:, 0] = np.asarray(z["translation__%s" % f]).reshape(B, 1, 3)
+            t.axisangle[i], t.translation[i] = _ptr(arr(aa)), _ptr(arr(tr))
+            t.pose_stride[i], t.pose_invert[i] = 6, int(f < 0)
+            t.pose_requires_grad[i] = 1
+            out.setdefault("cam_T_cam", {})[f] = np.zeros((B, 4, 4), np.float32)
+            out.setdefault("grad_axisangle", {})[f] = np.zeros((B, 3), np.float32)
+            out.setdefault("grad_translation", {})[f] = np.zeros((B, 3), np.float32)
+            t.cam_T_cam[i] = _ptr(out["cam_T_cam"][f])
+            t.grad_axisangle[i] = _ptr(out["grad_axisangle"][f])
+            t.grad_translation[i] = _ptr(out["grad_translation"][f])
         else:
             t.T[i] = _ptr(arr(z["cam_T_cam__%s" % f]))
             t.pose_requires_grad[i] = 1

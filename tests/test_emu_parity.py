@@ -33,3 +33,28 @@ def test_emulator_forward_only():
     g = Golden("mono_iid")
     o = run_emu(g, want_grad=False, side_outputs=False)
     assert abs(o["losses"][0] - float(g.z["loss"])) <= 1e-5 * abs(float(g.z["loss"]))
+
+
+@pytest.mark.parametrize("name", ["mono_structured", "stereo_iid"])
+def test_emulator_pose_leaves(name):
+    """The in-call pose construction on the host build of the same source: T built from
+    axisangle / translation equals the reference's cam_T_cam, and the pose gradient on the leaves equals the
+    matrix-mode gradient pushed through the oracle's transformation_from_parameters."""
+    import torch
+    from emu_driver import run_emu
+    from oracle import view_synthesis as O
+    g = Golden(name)
+    z = g.z
+    o = run_emu(g, pose_leaves=True, rows_per_segment=16)
+    m = run_emu(g, rows_per_segment=16)
+    assert abs(o["losses"][0] - float(z["loss"])) <= 1e-5 * abs(float(z["loss"]))
+    for f in g.frame_ids[1:]:
+        if f == "s":
+            continue
+        np.testing.assert_allclose(o["cam_T_cam"][f], z["cam_T_cam__%s" % f], atol=2e-6)
+        np.testing.assert_allclose(o["grad_T"][f], m["grad_T"][f], rtol=1e-5, atol=1e-9)
+        aa = torch.from_numpy(np.asarray(z["axisangle__%s" % f])).reshape(g.B, 1, 3).requires_grad_(True)
+        tr = torch.from_numpy(np.asarray(z["translation__%s" % f])).reshape(g.B, 1, 3).requires_grad_(True)
+        O.transformation_from_parameters(aa, tr, f < 0).backward(torch.from_numpy(m["grad_T"][f]))
+        assert rel_l2(o["grad_axisangle"][f].reshape(-1), aa.grad.reshape(-1)) < 1e-4
+        assert rel_l2(o["grad_translation"][f].reshape(-1), tr.grad.reshape(-1)) < 1e-5
