@@ -160,6 +160,34 @@ def test_other_baseline_configs_loss_parity(wl):
             assert rel_l2(outs[("cam_T_cam", 0, f)].grad.cpu(), g32[("T", f)].grad) < 5e-2
 
 
+@pytest.mark.parametrize("shape", [(1, 24, 136), (2, 40, 200), (2, 56, 264), (1, 32, 384)])
+@pytest.mark.parametrize("no_ssim", [False, True])
+def test_tma_identity_pass_sizes(shape, no_ssim):
+    """Sizes that take the TMA-staged identity pass (two sources, W >= 136 and a multiple of 4, H >= 18): the
+    smallest eligible image, partial right / bottom tiles, tiles whose mirrored halo column or row falls in the
+    padding of the box; with SSIM and --no_ssim.  Loss parity + identity-selection masks against the live oracle."""
+    from monodepth2_b200.synthetic import make_batch
+    from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
+    B, H, W = shape
+    fids = [0, -1, 1]
+    batch = make_batch(B, H, W, fids, 4, 61, "structured")
+    inputs, outputs, pose, noise = batch
+    l32, o32, g32 = _oracle(batch, fids, torch.float32, no_ssim=no_ssim)
+    plan = LossPlan(B, H, W, fids, no_ssim=no_ssim)
+    ins = {k: v.to(DEV) for k, v in inputs.items()}
+    outs = {k: v.to(DEV).requires_grad_(True) for k, v in outputs.items()}
+    side = {"mask_scales": [0, 1, 2, 3]}
+    lk = view_synthesis_loss(plan, ins, outs, [n.to(DEV) for n in noise], side)
+    lk["loss"].backward()
+    for key in ["loss"] + ["loss/%d" % s for s in range(4)]:
+        ref = float(l32[key].detach())
+        assert abs(float(lk[key].detach()) - ref) <= 1e-5 * abs(ref), key
+    for s in range(4):
+        m = side["identity_selection/%d" % s].cpu()
+        assert float((m != o32["identity_selection/%d" % s]).float().mean()) <= 2e-3, s
+        assert rel_l2(outs[("disp", s)].grad.cpu(), g32[("disp", s)].grad) < 0.25, s
+
+
 def test_large_batch_small_images():
     """Batch sizes beyond the round-1 benchmarks (the per-(scale, sample) scalar kernels and the pose epilogue
     must cover every sample): B=40, mono+stereo, against the live oracle."""
