@@ -147,10 +147,13 @@ __global__ void __launch_bounds__(kThreads) md2_identity2(Params P) {
 // the planar (B*3, H, W) tensor including the 1-pixel halo - the CTA waits on the barrier, mirrors the halo of
 // border tiles in shared memory (TMA fills out-of-bounds elements with zeros, ReflectionPad2d(1) wants the
 // mirror image, layers.py:235-236) and marches the rows out of shared memory: a lane owns one column and reads
-// its left / right neighbours from the tile (no warp halo, no shuffles, all 32 lanes productive).  Two CTAs per
-// SM (2 x 86 KB of tiles) overlap one CTA's loads with the other's arithmetic.  Used for two sources when the
+// its left / right neighbours from the tile (no warp halo, no shuffles, all 32 lanes productive).  Four CTAs per
+// SM (4 x 48 KB of tiles) overlap the loads of some CTAs with the arithmetic of the others.  Used for two sources when the
 // row pitch is a multiple of 16 bytes; otherwise md2_identity / md2_identity2 run.
-constexpr int kTmaCols = 128, kTmaRows = 16;                  // pixels a CTA owns
+#ifndef MD2_TMA_ROWS
+#define MD2_TMA_ROWS 8     // measured (whole step, 640x192 x 12): 8 rows 0.486 ms, 12 rows 0.487 ms, 16 rows 0.491 ms
+#endif
+constexpr int kTmaCols = 128, kTmaRows = MD2_TMA_ROWS;        // pixels a CTA owns
 constexpr int kTmaPadX = 4;      // the box starts 4 columns left of the tile: TMA needs a 16-byte aligned inner start
 constexpr int kTmaBoxW = kTmaCols + 2 * kTmaPadX, kTmaBoxH = kTmaRows + 2;   // (x0 - 1 faults with "illegal instruction")
 constexpr int kTmaImgFloats = ((3 * kTmaBoxH * kTmaBoxW * 4 + 127) / 128) * 32;   // one image's tile, 128-byte multiple
