@@ -1221,7 +1221,7 @@ MD2_HD void id_stage_a(IdLane<NSRC>& L, const Params& P, int b, int t, int lane,
 
 template <int NSRC, bool NOSSIM = false>
 MD2_HD void id_stage_b(IdLane<NSRC>& L, const Params& P, int b, int t, int lane, int y0, int y1,
-                       const IdXchg<NSRC>& lf, const IdXchg<NSRC>& rt) {
+                       const IdXchg<NSRC>& lf, const IdXchg<NSRC>& rt, int lane_lo = 1, int lane_hi = kIdCols) {
   const int yw = t - 1;
   float H0[NSRC][3][3], HY0[3][2];
 #pragma unroll
@@ -1237,7 +1237,7 @@ MD2_HD void id_stage_b(IdLane<NSRC>& L, const Params& P, int b, int t, int lane,
       H0[f][c][2] = fmaf(xr, yr, fmaf(xc, yc, xl * yl));
     }
   }
-  const bool own = L.colok && yw >= y0 && yw < y1 && lane >= 1 && lane <= kIdCols;
+  const bool own = L.colok && yw >= y0 && yw < y1 && lane >= lane_lo && lane <= lane_hi;
   if (own) {
     const size_t plane = (size_t)P.H * P.W;
 #pragma unroll

@@ -157,16 +157,17 @@ constexpr int kTmaCols = 128, kTmaRows = MD2_TMA_ROWS;        // pixels a CTA ow
 constexpr int kTmaPadX = 4;      // the box starts 4 columns left of the tile: TMA needs a 16-byte aligned inner start
 constexpr int kTmaBoxW = kTmaCols + 2 * kTmaPadX, kTmaBoxH = kTmaRows + 2;   // (x0 - 1 faults with "illegal instruction")
 constexpr int kTmaImgFloats = ((3 * kTmaBoxH * kTmaBoxW * 4 + 127) / 128) * 32;   // one image's tile, 128-byte multiple
-constexpr int kTmaSmemBytes = 3 * kTmaImgFloats * 4 + 16;
+constexpr int tma_smem_bytes(int nsrc) { return (1 + nsrc) * kTmaImgFloats * 4 + 16; }
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-struct IdTensorMaps { CUtensorMap tgt, src0, src1; };
+struct IdTensorMaps { CUtensorMap img[1 + 3]; };     // target, then the sources
 
-template <bool NOSSIM>
+template <int NSRC, bool NOSSIM>
 __global__ void __launch_bounds__(kTmaCols) md2_identity_tma(Params P, const __grid_constant__ IdTensorMaps maps) {
+  constexpr int NIMG = 1 + NSRC;
   extern __shared__ __align__(128) float tile[];
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(tile + 3 * kTmaImgFloats);
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(tile + NIMG * kTmaImgFloats);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x0 = blockIdx.x * kTmaCols, y0 = blockIdx.y * kTmaRows, b = blockIdx.z;
   const int y1 = min(y0 + kTmaRows, P.H);
@@ -176,14 +177,14 @@ __global__ void __launch_bounds__(kTmaCols) md2_identity_tma(Params P, const __g
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned bytes = 3u * 3u * kTmaBoxH * kTmaBoxW * 4u;
+    const unsigned bytes = (unsigned)NIMG * 3u * kTmaBoxH * kTmaBoxW * 4u;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    const CUtensorMap* m[3] = {&maps.tgt, &maps.src0, &maps.src1};
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < NIMG; ++i)
       asm volatile(
           "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-          ::"r"(smem_u32(tile + i * kTmaImgFloats)), "l"(m[i]), "r"(x0 - kTmaPadX), "r"(y0 - 1), "r"(b * 3), "r"(smem_u32(bar))
+          ::"r"(smem_u32(tile + i * kTmaImgFloats)), "l"(&maps.img[i]), "r"(x0 - kTmaPadX), "r"(y0 - 1), "r"(b * 3),
+            "r"(smem_u32(bar))
           : "memory");
   }
   {   // every thread waits for the bytes to land (phase 0)
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(kTmaCols) md2_identity_tma(Params P, const __g
   const int cl = (x0 == 0) ? kTmaPadX - 1 : -1;                           // tile column of x = -1
   const int cr = (P.W - x0 + kTmaPadX <= kTmaBoxW - 1) ? P.W - x0 + kTmaPadX : -1;   // tile column of x = W
   if (cl >= 0 || cr >= 0) {
-    for (int i = threadIdx.x; i < 9 * kTmaBoxH; i += blockDim.x) {
+    for (int i = threadIdx.x; i < NIMG * 3 * kTmaBoxH; i += blockDim.x) {
       const int img = i / (3 * kTmaBoxH), c = (i / kTmaBoxH) % 3, r = i % kTmaBoxH;
       if (cl >= 0) at(img, c, r, cl) = at(img, c, r, cl + 2);
       if (cr >= 2) at(img, c, r, cr) = at(img, c, r, cr - 2);
@@ -209,45 +210,59 @@ __global__ void __launch_bounds__(kTmaCols) md2_identity_tma(Params P, const __g
   const int rt_ = (y0 == 0) ? 0 : -1;                                     // tile row of y = -1
   const int rb = (P.H - y0 + 1 <= kTmaBoxH - 1 && P.H >= y0) ? P.H - y0 + 1 : -1;   // tile row of y = H
   if (rt_ >= 0 || rb >= 0) {
-    for (int i = threadIdx.x; i < 9 * kTmaBoxW; i += blockDim.x) {
+    for (int i = threadIdx.x; i < NIMG * 3 * kTmaBoxW; i += blockDim.x) {
       const int img = i / (3 * kTmaBoxW), c = (i / kTmaBoxW) % 3, col = i % kTmaBoxW;
       if (rt_ >= 0) at(img, c, 0, col) = at(img, c, 2, col);
       if (rb >= 2) at(img, c, rb, col) = at(img, c, rb - 2, col);
     }
     __syncthreads();
   }
-  IdLane2 L;
-  id_init2(L, P, 0, 0);
-  L.x = x0 + warp * 32 + lane;
-  L.colok = L.x < P.W;
-  L.xi = L.colok ? L.x : P.W - 1;
+  const int x = x0 + warp * 32 + lane;
+  const bool colok = x < P.W;
   const int col = warp * 32 + lane + kTmaPadX;                            // tile column of this lane's pixel
   const int plane = P.H * P.W;
+  // NSRC == 2: packed-fp32 arithmetic (md2_pack2.cuh); otherwise the scalar stage of md2_core.cuh
+  IdLane2 L2;
+  IdLane<NSRC> L1;
+  if constexpr (NSRC == 2) { id_init2(L2, P, 0, 0); L2.x = x; L2.colok = colok; L2.xi = colok ? x : P.W - 1; }
+  else { id_init(L1, P, 0, 0); L1.x = x; L1.colok = colok; L1.xi = colok ? x : P.W - 1; }
   for (int r = 0; r < kTmaBoxH; ++r) {
     const int t = y0 - 1 + r;
     if (t > y1) break;
-    float v[3][3][3];                                                     // [image][channel][left, centre, right]
+    float v[NIMG][3][3];                                                  // [image][channel][left, centre, right]
 #pragma unroll
-    for (int img = 0; img < 3; ++img)
+    for (int img = 0; img < NIMG; ++img)
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float* row = &at(img, c, r, col);
         v[img][c][0] = row[-1]; v[img][c][1] = row[0]; v[img][c][2] = row[1];
       }
-    IdXchg2 lf, rt;
-    lf.tgrg = p2(v[0][0][0], v[0][1][0]); lf.tgb = v[0][2][0];
-    rt.tgrg = p2(v[0][0][2], v[0][1][2]); rt.tgb = v[0][2][2];
-    L.tgrg = p2(v[0][0][1], v[0][1][1]); L.tgb = v[0][2][1];
-    lf.pr[0] = p2(v[1][0][0], v[1][1][0]); lf.pr[1] = p2(v[2][0][0], v[2][1][0]); lf.pr[2] = p2(v[1][2][0], v[2][2][0]);
-    rt.pr[0] = p2(v[1][0][2], v[1][1][2]); rt.pr[1] = p2(v[2][0][2], v[2][1][2]); rt.pr[2] = p2(v[1][2][2], v[2][2][2]);
-    L.pr[0] = p2(v[1][0][1], v[1][1][1]); L.pr[1] = p2(v[2][0][1], v[2][1][1]); L.pr[2] = p2(v[1][2][1], v[2][2][1]);
-    if (L.colok && t >= y0 && t < y1) {                                   // RGBx texels for the marching kernel
-      const int o4 = 4 * (b * plane + t * P.W + L.x);
+    if (colok && t >= y0 && t < y1) {                                     // RGBx texels for the marching kernel
+      const int o4 = 4 * (b * plane + t * P.W + x);
       *reinterpret_cast<float4*>(P.tgt4 + o4) = make_float4(v[0][0][1], v[0][1][1], v[0][2][1], 0.f);
-      *reinterpret_cast<float4*>(P.src4[0] + o4) = make_float4(v[1][0][1], v[1][1][1], v[1][2][1], 0.f);
-      *reinterpret_cast<float4*>(P.src4[1] + o4) = make_float4(v[2][0][1], v[2][1][1], v[2][2][1], 0.f);
+#pragma unroll
+      for (int f = 0; f < NSRC; ++f)
+        *reinterpret_cast<float4*>(P.src4[f] + o4) = make_float4(v[1 + f][0][1], v[1 + f][1][1], v[1 + f][2][1], 0.f);
     }
-    id_stage_b2<NOSSIM>(L, P, b, t, lane, y0, y1, lf, rt, 0, 31);
+    if constexpr (NSRC == 2) {
+      IdXchg2 lf, rt;
+      lf.tgrg = p2(v[0][0][0], v[0][1][0]); lf.tgb = v[0][2][0];
+      rt.tgrg = p2(v[0][0][2], v[0][1][2]); rt.tgb = v[0][2][2];
+      L2.tgrg = p2(v[0][0][1], v[0][1][1]); L2.tgb = v[0][2][1];
+      lf.pr[0] = p2(v[1][0][0], v[1][1][0]); lf.pr[1] = p2(v[2][0][0], v[2][1][0]); lf.pr[2] = p2(v[1][2][0], v[2][2][0]);
+      rt.pr[0] = p2(v[1][0][2], v[1][1][2]); rt.pr[1] = p2(v[2][0][2], v[2][1][2]); rt.pr[2] = p2(v[1][2][2], v[2][2][2]);
+      L2.pr[0] = p2(v[1][0][1], v[1][1][1]); L2.pr[1] = p2(v[2][0][1], v[2][1][1]); L2.pr[2] = p2(v[1][2][1], v[2][2][1]);
+      id_stage_b2<NOSSIM>(L2, P, b, t, lane, y0, y1, lf, rt, 0, 31);
+    } else {
+      IdXchg<NSRC> lf, rt;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        lf.tg[c] = v[0][c][0]; L1.tg[c] = v[0][c][1]; rt.tg[c] = v[0][c][2];
+#pragma unroll
+        for (int f = 0; f < NSRC; ++f) { lf.pr[f][c] = v[1 + f][c][0]; L1.pr[f][c] = v[1 + f][c][1]; rt.pr[f][c] = v[1 + f][c][2]; }
+      }
+      id_stage_b<NSRC, NOSSIM>(L1, P, b, t, lane, y0, y1, lf, rt, 0, 31);
+    }
   }
 }
 
@@ -740,26 +755,32 @@ static cudaError_t launch_march_ns(const Params& P, cudaStream_t stream) {
 }
 template <int NSRC>
 static void launch_identity_ns(const Params& P, int grid, cudaStream_t stream) {
-  if constexpr (NSRC == 2) {
-    // TMA-staged form: two sources, production-sized images whose row pitch is a multiple of 16 bytes, base
-    // pointers 16-byte aligned (cuTensorMapEncodeTiled's requirements).  MD2_IDENTITY_TMA=0 disables it.
+  {
+    // TMA-staged form: production-sized images whose row pitch is a multiple of 16 bytes, base pointers 16-byte
+    // aligned (cuTensorMapEncodeTiled's requirements).  MD2_IDENTITY_TMA=0 disables it.
     static const bool tma_on = !(getenv("MD2_IDENTITY_TMA") && atoi(getenv("MD2_IDENTITY_TMA")) == 0);
-    const bool aligned = (((uintptr_t)P.tgt | (uintptr_t)P.src[0] | (uintptr_t)P.src[1]) & 15) == 0;
-    if (tma_on && pack2_mode() != 0 && aligned && P.W % 4 == 0 && P.W >= kTmaBoxW && P.H >= kTmaBoxH) {
+    uintptr_t bits = (uintptr_t)P.tgt;
+    for (int f = 0; f < NSRC; ++f) bits |= (uintptr_t)P.src[f];
+    if (tma_on && pack2_mode() != 0 && (bits & 15) == 0 && P.W % 4 == 0 && P.W >= kTmaBoxW && P.H >= kTmaBoxH) {
       IdTensorMaps maps;
-      if (make_image_map(&maps.tgt, P.tgt, P.B, P.H, P.W) && make_image_map(&maps.src0, P.src[0], P.B, P.H, P.W) &&
-          make_image_map(&maps.src1, P.src[1], P.B, P.H, P.W)) {
+      bool ok = make_image_map(&maps.img[0], P.tgt, P.B, P.H, P.W);
+      for (int f = 0; f < NSRC && ok; ++f) ok = make_image_map(&maps.img[1 + f], P.src[f], P.B, P.H, P.W);
+      for (int f = NSRC; f < 3; ++f) maps.img[1 + f] = maps.img[0];
+      if (ok) {
         const dim3 g((P.W + kTmaCols - 1) / kTmaCols, (P.H + kTmaRows - 1) / kTmaRows, P.B);
+        const int smem = tma_smem_bytes(NSRC);
         if (P.no_ssim) {
-          cudaFuncSetAttribute(md2_identity_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
-          md2_identity_tma<true><<<g, kTmaCols, kTmaSmemBytes, stream>>>(P, maps);
+          cudaFuncSetAttribute(md2_identity_tma<NSRC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+          md2_identity_tma<NSRC, true><<<g, kTmaCols, smem, stream>>>(P, maps);
         } else {
-          cudaFuncSetAttribute(md2_identity_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
-          md2_identity_tma<false><<<g, kTmaCols, kTmaSmemBytes, stream>>>(P, maps);
+          cudaFuncSetAttribute(md2_identity_tma<NSRC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+          md2_identity_tma<NSRC, false><<<g, kTmaCols, smem, stream>>>(P, maps);
         }
         return;
       }
     }
+  }
+  if constexpr (NSRC == 2) {
     if (pack2_mode() != 0) {      // the identity pass is forward-only: packed form unless MD2_PACK2=off
       if (P.no_ssim) md2_identity2<true><<<grid, kThreads, 0, stream>>>(P);
       else md2_identity2<false><<<grid, kThreads, 0, stream>>>(P);

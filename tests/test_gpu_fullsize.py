@@ -160,16 +160,17 @@ def test_other_baseline_configs_loss_parity(wl):
             assert rel_l2(outs[("cam_T_cam", 0, f)].grad.cpu(), g32[("T", f)].grad) < 5e-2
 
 
-@pytest.mark.parametrize("shape", [(1, 24, 136), (2, 40, 200), (2, 56, 264), (1, 32, 384)])
+@pytest.mark.parametrize("shape,fids", [((1, 24, 136), [0, -1, 1]), ((2, 40, 200), [0, -1, 1]), ((2, 56, 264), [0, -1, 1]),
+                                        ((1, 32, 384), [0, -1, 1]), ((2, 40, 200), [0, 1]), ((2, 40, 200), [0, -1, 1, "s"]),
+                                        ((1, 24, 136), [0, "s"])])
 @pytest.mark.parametrize("no_ssim", [False, True])
-def test_tma_identity_pass_sizes(shape, no_ssim):
-    """Sizes that take the TMA-staged identity pass (two sources, W >= 136 and a multiple of 4, H >= 18): the
+def test_tma_identity_pass_sizes(shape, fids, no_ssim):
+    """Sizes that take the TMA-staged identity pass (1-3 sources, W >= 136 and a multiple of 4, H >= 10): the
     smallest eligible image, partial right / bottom tiles, tiles whose mirrored halo column or row falls in the
     padding of the box; with SSIM and --no_ssim.  Loss parity + identity-selection masks against the live oracle."""
     from monodepth2_b200.synthetic import make_batch
     from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
     B, H, W = shape
-    fids = [0, -1, 1]
     batch = make_batch(B, H, W, fids, 4, 61, "structured")
     inputs, outputs, pose, noise = batch
     l32, o32, g32 = _oracle(batch, fids, torch.float32, no_ssim=no_ssim)
