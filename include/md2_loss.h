@@ -94,7 +94,12 @@ int md2_loss_workspace_bytes(const md2_problem *p, size_t *bytes);
 
 /* Fused replacement for Trainer.generate_images_pred (trainer.py:341-391) followed by
  * Trainer.compute_losses (trainer.py:407-496) and, when want_grad, the adjoint that
- * losses["loss"].backward() (trainer.py:208) propagates to disp_s and cam_T_cam. */
+ * losses["loss"].backward() (trainer.py:208) propagates to disp_s and cam_T_cam.
+ * Threading: the library keeps one internal side stream and event pair per device (the small smoothness
+ * kernels overlap the identity pass on it; fork/join by events, so the caller's stream order and CUDA-graph
+ * capture of `stream` are preserved).  Calls for the same device must not be issued concurrently from several
+ * host threads; one process per GPU (the reference's model, and DDP's) needs no locking.  `workspace` may be
+ * reused by successive calls on the same stream; two calls in flight on different streams need two workspaces. */
 int md2_view_synthesis_loss(const md2_problem *p, const md2_tensors *t,
                             void *workspace, size_t workspace_bytes, void *stream);
 
