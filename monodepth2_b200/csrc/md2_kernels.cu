@@ -299,7 +299,10 @@ static bool make_image_map(CUtensorMap* m, const float* base, int B, int H, int 
 // down: the current row lives in registers, the next row is loaded once, so every edge is evaluated ONCE (its
 // weight exp(-|dI|) and sign serve both of its end points: right neighbour by shuffle, upper neighbour from
 // the previous step) instead of once per end point.  Same per-edge arithmetic as smooth_pixel (md2_core.cuh).
-constexpr int kSmoothRows = 16;
+#ifndef MD2_SMOOTH_ROWS
+#define MD2_SMOOTH_ROWS 16
+#endif
+constexpr int kSmoothRows = MD2_SMOOTH_ROWS;
 constexpr int kSmoothWarps = 4;
 __host__ __device__ inline int smooth_bands(int Ws) { return (Ws + 31) / 32; }
 __host__ __device__ inline int smooth_segs(int Hs) { return (Hs + kSmoothRows - 1) / kSmoothRows; }
