@@ -477,7 +477,7 @@ def run_own(args, wl):
             "config": {"workload": wl, "batch_per_gpu": BATCH, "frame_ids": [str(f) for f in frame_ids],
                        "scales": 4, "l2": "inputs larger than L2: %d rotating batches of ~%d MB each" %
                        (nrot, int((h2d + n_id * BATCH * H * W * 4 * 4) / 1e6)),
-                       "rows_per_segment": plan.problem(True).rows_per_segment or max(32, (H + 3) // 4), "loss": loss_val,
+                       "rows_per_segment": plan.problem(True).rows_per_segment or "library default (wave-quantisation model)", "loss": loss_val,
                        "launch": "plain C-ABI calls" if graphs is None else "CUDA-graph replay of the C-ABI call",
                        "noise": "tie-break noise tensors are resident inputs of the timed call; "
                                 "value_with_noise_draw times the same loop with 4 torch.randn draws per step"},

@@ -62,12 +62,25 @@ inline Layout make_layout(const md2_problem* p) {
 }
 
 inline int default_seg_rows(const md2_problem* p) {
-  // default: a quarter of the image height (48 rows at 192, 80 at 320), measured optimum of the
-  // wave-quantisation vs halo-row trade-off on B200 (profiles/r01_optimization_log.md)
-  int r = p->rows_per_segment > 0 ? p->rows_per_segment : (p->height + 3) / 4;
-  if (r < 32) r = 32;
-  if (r > p->height) r = p->height;
-  return r;
+  // Rows marched per warp job.  A job marches r + 4 rows (2 halo rows each side) and the kernel runs in waves of
+  // 148 SMs x 8 warps (12 for the forward-only instantiations): minimise waves x (r + 4) over r = ceil(H / n).
+  // Measured on B200 (profiles/r01_optimization_log.md): 640x192 x 12: 96 rows 0.474 ms, 64 rows 0.480 ms,
+  // 48 rows 0.486 ms per step; 1024x320: 160 rows 1.170 ms, 80 rows 1.185 ms, 107 rows 1.251 ms.
+  if (p->rows_per_segment > 0) return p->rows_per_segment < p->height ? p->rows_per_segment : p->height;
+  const long slots = 148L * (p->want_grad ? 8 : 12);
+  const long nband = (p->width + kOwnCols - 1) / kOwnCols;
+  int best_r = p->height;
+  long best_cost = -1;
+  // (n = 1, one job per band, is excluded when the image is tall enough to split: measured 0.654 ms at 640x192
+  // although the model rates it best - all warps then stream the same image rows in lock step)
+  for (int n = (p->height >= 48 ? 2 : 1); n <= 8; ++n) {
+    const int r = (p->height + n - 1) / n;
+    if (n > 1 && r < 24) break;
+    const long jobs = (long)p->num_scales * p->batch * nband * ((p->height + r - 1) / r);
+    const long cost = ((jobs + slots - 1) / slots) * (r + 4);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_r = r; }
+  }
+  return best_r;
 }
 
 // Fills `P`.  Returns MD2_OK or an error when required tensors are missing.
