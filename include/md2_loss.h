@@ -84,6 +84,16 @@ typedef struct md2_tensors {
   float *cam_T_cam[MD2_MAX_SRC];              /* out: outputs[("cam_T_cam",0,f)] (B,4,4); NULL = internal scratch */
   float *grad_axisangle[MD2_MAX_SRC];         /* out (B,3) */
   float *grad_translation[MD2_MAX_SRC];       /* out (B,3) */
+  /* ---- optional uint8 images (what MonoDataset holds before ToTensor, datasets/mono_dataset.py:106-109,
+   *      156-185): when target_u8 is non-NULL the call reads the frames as bytes and converts them with
+   *      x / 255 (bit-identical to torchvision's ToTensor) where it would have read the float images;
+   *      target / source[] / color[] are then ignored and may be NULL.  Layout: u8_hwc != 0: (B,H,W,3)
+   *      interleaved (numpy view of the PIL image), else (B,3,H,W) planar.  color_u8[0] may be NULL
+   *      (= target_u8).  A quarter of the host-to-device bytes of the float entry. ---- */
+  const unsigned char *target_u8;
+  const unsigned char *source_u8[MD2_MAX_SRC];
+  const unsigned char *color_u8[MD2_MAX_SCALES];
+  int u8_hwc;
 } md2_tensors;
 
 int md2_version(void);

@@ -49,6 +49,10 @@ class Md2Tensors(C.Structure):
         ("cam_T_cam", C.c_void_p * MAX_SRC),
         ("grad_axisangle", C.c_void_p * MAX_SRC),
         ("grad_translation", C.c_void_p * MAX_SRC),
+        ("target_u8", C.c_void_p),
+        ("source_u8", C.c_void_p * MAX_SRC),
+        ("color_u8", C.c_void_p * MAX_SCALES),
+        ("u8_hwc", C.c_int),
     ]
 
 

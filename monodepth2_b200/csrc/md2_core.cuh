@@ -162,6 +162,13 @@ struct Params {
   float* Tws[kMaxSrc];             // (B,4,4) workspace / output: the T built from the leaves
   float* grad_aa[kMaxSrc];         // (B,3) d loss / d axisangle
   float* grad_tr[kMaxSrc];         // (B,3) d loss / d translation
+  // uint8 image inputs (optional, md2_tensors::target_u8 ...): what the dataloader holds before ToTensor
+  // (datasets/mono_dataset.py:106-109); converted with x / 255 (IEEE division = torchvision's ToTensor) where
+  // the float images would have been read.  u8_hwc: (B,H,W,3) interleaved, else (B,3,H,W) planar.
+  const unsigned char* tgt8;
+  const unsigned char* src8[kMaxSrc];
+  const unsigned char* color8[kMaxScales];
+  int u8_hwc;
   const float* K;
   const float* invK;
   const float* disp[kMaxScales];
@@ -199,6 +206,22 @@ MD2_HD int acc_smx(const Params& P, int s, int b) {
 }
 MD2_HD int acc_smy(const Params& P, int s, int b) { return acc_smx(P, s, b) + 1; }
 MD2_HD int acc_count(const Params& P) { return 3 * kMaxScales + 4 * kMaxScales * P.B + P.B * P.nsrc * 12; }
+
+// ToTensor (torchvision.transforms.functional.to_tensor): uint8 -> float32, then .div(255)
+MD2_HD float u8_unit(unsigned char v) { return MD2_DIV((float)v, 255.0f); }
+// channel c of pixel `pix` (= y * w + x) of sample b of a 3-channel image given as float planar NCHW (`f32`)
+// or, when `u8` is set, as uint8 (planar or interleaved); `plane` = h * w of that image
+MD2_HD float load_px(const float* f32, const unsigned char* u8, int hwc, int b, int c, int plane, int pix) {
+  if (u8) {
+    const size_t o = hwc ? ((size_t)b * plane + pix) * 3 + c : ((size_t)b * 3 + c) * plane + pix;
+#if defined(__CUDA_ARCH__)
+    return u8_unit(__ldg(u8 + o));
+#else
+    return u8_unit(u8[o]);
+#endif
+  }
+  return MD2_LD(f32 + ((size_t)b * 3 + c) * plane + pix);
+}
 
 // One marching job (warp-uniform): a band of kOwnCols columns x rows [y0,y1) of sample b at
 // scale s, with every base pointer already offset to the sample so that per-pixel addressing
@@ -377,13 +400,17 @@ MD2_HD int ring_slot(int t) { return ((t % kRing) + kRing) % kRing; }
 
 // thread-private stash of 16-byte fields: element (slot, field) of this lane; consecutive
 // lanes are 16 bytes apart, so 128-bit shared accesses are conflict-free
-struct Stash {
+template <int R>
+struct StashT {
+  static constexpr int kDepth = R;   // rows kept in the ring
   F4* base;
   F4* bring;      // ring of 2 rows x NB4 fields (backward box sums), only when Cfg::BSMEM
   int stride;     // threads sharing the ring (lane stride of one field)
+  MD2_HD int slot(int t) const { return ((t % R) + R) % R; }
   MD2_HD F4& at(int slot, int field, int nfields) const { return base[(slot * nfields + field) * stride]; }
   MD2_HD F4& b(int slot, int field, int nfields) const { return bring[(slot * nfields + field) * stride]; }
 };
+typedef StashT<kRing> Stash;
 
 // issue the loads of row `t`'s target texel and disparity taps (consumed one step later)
 template <class C>
@@ -460,8 +487,8 @@ MD2_HD void lane_init(Lane<C>& L, const Params& P, const WarpJob& J, int lane) {
 }
 
 // zero the shared-memory ring of backward box sums at the start of a job
-template <class C>
-MD2_HD void bring_reset(const Stash& st) {
+template <class C, class ST>
+MD2_HD void bring_reset(const ST& st) {
   if (C::BSMEM) {
 #pragma unroll
     for (int i = 0; i < 2 * C::NB4; ++i) st.bring[i * st.stride] = make_f4(0.f, 0.f, 0.f, 0.f);
@@ -477,7 +504,20 @@ MD2_HD void bring_reset(const Stash& st) {
 // loads per source and the loads of the following row (target, disparity) and of the identity
 // loss / noise of window row t-1.  Nothing here waits for memory: the caller runs the adjoint of
 // an earlier row (stage_c) while the gather is in flight.
+// identity loss + tie-break noise of window row t-1 (consumed by stage_b of step t)
 template <class C>
+MD2_HD void load_identity_row(Lane<C>& L, const WarpJob& J, int t) {
+  if (C::AUTOMASK) {
+    const int yw = t - 1;
+    const int pix = (yw < 0 ? 0 : (yw >= J.H ? J.H - 1 : yw)) * J.W + L.xi;
+#pragma unroll
+    for (int f = 0; f < C::NSRC; ++f) L.idv[f] = MD2_LDS1(J.idl + f * J.plane + pix);
+#pragma unroll
+    for (int f = 0; f < C::NID; ++f) L.nzv[f] = MD2_LDS1(J.noise + f * J.plane + pix);
+  }
+}
+
+template <class C, bool WITH_ID = true>
 MD2_HD void stage_a_issue(Lane<C>& L, const Params& P, const WarpJob& J, int t) {
   const int tr = reflect_clamp(t, J.H);
   L.ctg = L.ntg;
@@ -493,14 +533,7 @@ MD2_HD void stage_a_issue(Lane<C>& L, const Params& P, const WarpJob& J, int t) 
     D = l0 * top + l1 * bot;
   }
   prefetch_row(L, J, t + 1);
-  if (C::AUTOMASK) {
-    const int yw = t - 1;
-    const int pix = (yw < 0 ? 0 : (yw >= J.H ? J.H - 1 : yw)) * J.W + L.xi;
-#pragma unroll
-    for (int f = 0; f < C::NSRC; ++f) L.idv[f] = MD2_LDS1(J.idl + f * J.plane + pix);
-#pragma unroll
-    for (int f = 0; f < C::NID; ++f) L.nzv[f] = MD2_LDS1(J.noise + f * J.plane + pix);
-  }
+  if (WITH_ID) load_identity_row(L, J, t);
   const float sd = MD2_FADD(P.a_disp, MD2_FMUL(P.c_disp, D));
   const float z = MD2_RCP(sd);
   L.cz = z;
@@ -558,15 +591,17 @@ MD2_HD void stage_a_issue(Lane<C>& L, const Params& P, const WarpJob& J, int t) 
 
 // stage_a_finish: the taps have arrived; interpolate pred and its derivatives, export pr/tg for
 // the neighbour exchange and stash what the adjoint of row t needs later.
-template <class C>
-MD2_HD void stage_a_finish(Lane<C>& L, const Params& P, const WarpJob& J, int t, const Stash& st) {
-  const int slot = ring_slot(t);
+// PUBLISH: the row's target / pred fields go to the ring even without gradients (the role-specialised
+// kernel hands rows from warp to warp through it)
+template <class C, class ST, bool PUBLISH = C::GRAD>
+MD2_HD void stage_a_finish(Lane<C>& L, const Params& P, const WarpJob& J, int t, const ST& st) {
+  const int slot = st.slot(t);
   const F4 tg4 = L.ctg;
   const float z = L.cz;
   const bool own = (t >= J.y0) && (t < J.y1) && (L.x >= J.x0) && (L.x < J.x0 + kOwnCols) && L.colok;
   L.tg[0] = tg4.x; L.tg[1] = tg4.y; L.tg[2] = tg4.z;
   if (J.depth && own) J.depth[t * J.W + L.xi] = z;
-  if (C::GRAD) st.at(slot, 0, C::STASH4) = make_f4(tg4.x, tg4.y, tg4.z, z);
+  if (PUBLISH) st.at(slot, 0, C::STASH4) = make_f4(tg4.x, tg4.y, tg4.z, z);
 #pragma unroll
   for (int f = 0; f < C::NSRC; ++f) {
     const F4 nw = L.tap[f][0], ne = L.tap[f][1], sw = L.tap[f][2], se = L.tap[f][3];
@@ -591,8 +626,8 @@ MD2_HD void stage_a_finish(Lane<C>& L, const Params& P, const WarpJob& J, int t,
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) L.pr[f][c] = pr[c];
+    if (PUBLISH) st.at(slot, 1 + 3 * f, C::STASH4) = make_f4(pr[0], pr[1], pr[2], L.cu[f]);
     if (C::GRAD) {
-      st.at(slot, 1 + 3 * f, C::STASH4) = make_f4(pr[0], pr[1], pr[2], L.cu[f]);
       st.at(slot, 2 + 3 * f, C::STASH4) = make_f4(dxp[0], dxp[1], dxp[2], L.cv[f]);
       st.at(slot, 3 + 3 * f, C::STASH4) = make_f4(dyp[0], dyp[1], dyp[2], 0.f);
     }
@@ -892,9 +927,9 @@ MD2_HD void stage_b(Lane<C>& L, const Params& P, const WarpJob& J, int t, int la
 // Adjoint for pixel row t-2: 3x3 box adjoint of the coefficient maps (with the fold
 // of the reflection ring), d loss/d pred, grid-sample and projection
 // adjoints (A.3).  Writes d loss / d D for owned pixels and accumulates the pose sums.
-template <class C>
+template <class C, class ST>
 MD2_HD void stage_c_divergent(Lane<C>& L, const Params& P, const WarpJob& J, int t, int lane,
-                    const Xchg2<C>& lf, const Xchg2<C>& rt, const Stash& st) {
+                    const Xchg2<C>& lf, const Xchg2<C>& rt, const ST& st) {
   const int yp = t - 2;
   const float wl = (L.x == 1) ? 2.0f : 1.0f;
   const float wr = (L.x == P.W - 2) ? 2.0f : 1.0f;
@@ -933,7 +968,7 @@ MD2_HD void stage_c_divergent(Lane<C>& L, const Params& P, const WarpJob& J, int
     }
     const float wu = (yp == 1) ? 2.0f : 1.0f;
     const float wd = (yp == P.H - 2) ? 2.0f : 1.0f;
-    const int slot = ring_slot(yp);
+    const int slot = st.slot(yp);
     const F4 s0 = st.at(slot, 0, C::STASH4);
     const float tg[3] = {s0.x, s0.y, s0.z};
     const float z = s0.w;
@@ -1003,9 +1038,9 @@ MD2_HD void stage_c_divergent(Lane<C>& L, const Params& P, const WarpJob& J, int
   L.tag1 = L.tag;
 }
 
-template <class C>
+template <class C, class ST>
 MD2_HD void stage_c_straight(Lane<C>& L, const Params& P, const WarpJob& J, int t, int lane,
-                    const Xchg2<C>& lf, const Xchg2<C>& rt, const Stash& st) {
+                    const Xchg2<C>& lf, const Xchg2<C>& rt, const ST& st) {
   const int yp = t - 2;
   const float wl = (L.x == 1) ? 2.0f : 1.0f;
   const float wr = (L.x == P.W - 2) ? 2.0f : 1.0f;
@@ -1045,7 +1080,7 @@ MD2_HD void stage_c_straight(Lane<C>& L, const Params& P, const WarpJob& J, int 
     }
     const float wu = (yp == 1) ? 2.0f : 1.0f;
     const float wd = (yp == P.H - 2) ? 2.0f : 1.0f;
-    const int slot = ring_slot(yp);
+    const int slot = st.slot(yp);
     const F4 s0 = st.at(slot, 0, C::STASH4);
     const float tg[3] = {s0.x, s0.y, s0.z};
     const float z = s0.w;
@@ -1119,9 +1154,9 @@ MD2_HD void stage_c_straight(Lane<C>& L, const Params& P, const WarpJob& J, int 
   L.tag1 = L.tag;
 }
 
-template <class C>
+template <class C, class ST>
 MD2_HD void stage_c(Lane<C>& L, const Params& P, const WarpJob& J, int t, int lane,
-                    const Xchg2<C>& lf, const Xchg2<C>& rt, const Stash& st) {
+                    const Xchg2<C>& lf, const Xchg2<C>& rt, const ST& st) {
   if (C::STRAIGHT) stage_c_straight(L, P, J, t, lane, lf, rt, st);
   else stage_c_divergent(L, P, J, t, lane, lf, rt, st);
 }
@@ -1186,13 +1221,13 @@ template <int NSRC>
 MD2_HD void id_prefetch(IdLane<NSRC>& L, const Params& P, int b, int t) {
   const int tr = reflect_clamp(t, P.H);
   const int plane = P.H * P.W;
-  const int off = b * 3 * plane + tr * P.W + L.xi;
+  const int pix = tr * P.W + L.xi;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) L.ntg[c] = MD2_LD(P.tgt + off + c * plane);
+  for (int c = 0; c < 3; ++c) L.ntg[c] = load_px(P.tgt, P.tgt8, P.u8_hwc, b, c, plane, pix);
 #pragma unroll
   for (int f = 0; f < NSRC; ++f)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) L.npr[f][c] = MD2_LD(P.src[f] + off + c * plane);
+    for (int c = 0; c < 3; ++c) L.npr[f][c] = load_px(P.src[f], P.src8[f], P.u8_hwc, b, c, plane, pix);
 }
 
 // Consumes row t of the planar NCHW target / sources (prefetched one step earlier), puts row t+1 in
@@ -1273,10 +1308,12 @@ MD2_HD void id_stage_b(IdLane<NSRC>& L, const Params& P, int b, int t, int lane,
 
 // Re-layout of one pixel of image `img` (0 = target, 1+f = source f) from planar NCHW to RGBx.
 MD2_HD void pack_pixel(const Params& P, int img, int b, int p) {
-  const size_t plane = (size_t)P.H * P.W;
-  const float* in = (img == 0 ? P.tgt : P.src[img - 1]) + (size_t)b * 3 * plane + p;
+  const int plane = P.H * P.W;
+  const float* in = (img == 0 ? P.tgt : P.src[img - 1]);
+  const unsigned char* in8 = (img == 0 ? P.tgt8 : P.src8[img - 1]);
   float* out = (img == 0 ? P.tgt4 : P.src4[img - 1]) + ((size_t)b * plane + p) * 4;
-  *reinterpret_cast<F4*>(out) = make_f4(MD2_LD(in), MD2_LD(in + plane), MD2_LD(in + 2 * plane), 0.f);
+  *reinterpret_cast<F4*>(out) = make_f4(load_px(in, in8, P.u8_hwc, b, 0, plane, p), load_px(in, in8, P.u8_hwc, b, 1, plane, p),
+                                        load_px(in, in8, P.u8_hwc, b, 2, plane, p), 0.f);
 }
 
 // ------------------------------------------------------------------ pose parameterisation
@@ -1397,16 +1434,16 @@ MD2_HD void smooth_pixel(const Params& P, int s, int b, int y, int x, float inv_
   const int Hs = P.H >> s, Ws = P.W >> s;
   const size_t plane = (size_t)Hs * Ws;
   const float* d = P.disp[s] + (size_t)b * plane;
-  const float* im = P.color[s] + (size_t)b * 3 * plane;
   const size_t p = (size_t)y * Ws + x;
   const float inx = 1.0f / ((float)P.B * (float)Hs * (float)(Ws - 1));
   const float iny = 1.0f / ((float)P.B * (float)(Hs - 1) * (float)Ws);
   const float n0 = MD2_LD(d + p) * inv_m;
-  const float i0 = MD2_LD(im + p), i1 = MD2_LD(im + plane + p), i2 = MD2_LD(im + 2 * plane + p);
+  auto px = [&](int c, size_t q) { return load_px(P.color[s], P.color8[s], P.u8_hwc, b, c, (int)plane, (int)q); };
+  const float i0 = px(0, p), i1 = px(1, p), i2 = px(2, p);
   float gn = 0.f, ex = 0.f, ey = 0.f;
   // one edge between this pixel and the neighbour at offset `o`; `fwd` = this pixel is the first end
   auto edge = [&](size_t q, bool fwd, float scale, float& e_out) {
-    const float g = fabsf(i0 - MD2_LD(im + q)) + fabsf(i1 - MD2_LD(im + plane + q)) + fabsf(i2 - MD2_LD(im + 2 * plane + q));
+    const float g = fabsf(i0 - px(0, q)) + fabsf(i1 - px(1, q)) + fabsf(i2 - px(2, q));
     const float w = md2_exp_neg(g * (1.0f / 3.0f));
     const float df = n0 - MD2_LD(d + q) * inv_m;          // n(this) - n(neighbour)
     MD2_DBG(if (fwd) {

@@ -39,6 +39,10 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+}  // namespace md2
+#include "md2_roles.cuh"
+namespace md2 {
+
 // ------------------------------------------------------------------ 1. prologue
 __global__ void md2_prologue(Params P) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -308,11 +312,19 @@ __host__ __device__ inline int smooth_bands(int Ws) { return (Ws + 31) / 32; }
 __host__ __device__ inline int smooth_segs(int Hs) { return (Hs + kSmoothRows - 1) / kSmoothRows; }
 
 struct SmoothPx { float raw, n, i0, i1, i2; };
-__device__ __forceinline__ SmoothPx smooth_load(const float* d, const float* im, int plane, int p, float inv_m) {
+// the colour image of one (scale, sample): float planar, or uint8 planar / interleaved (Params::color8)
+struct SmoothImg { const float* f32; const unsigned char* u8; int hwc; };
+__device__ __forceinline__ SmoothPx smooth_load(const float* d, const SmoothImg& im, int plane, int p, float inv_m) {
   SmoothPx r;
   r.raw = __ldg(d + p);
   r.n = r.raw * inv_m;
-  r.i0 = __ldg(im + p); r.i1 = __ldg(im + plane + p); r.i2 = __ldg(im + 2 * plane + p);
+  if (im.u8) {
+    const unsigned char* q = im.u8 + (im.hwc ? 3 * p : p);
+    const int cs = im.hwc ? 1 : plane;
+    r.i0 = u8_unit(__ldg(q)); r.i1 = u8_unit(__ldg(q + cs)); r.i2 = u8_unit(__ldg(q + 2 * cs));
+  } else {
+    r.i0 = __ldg(im.f32 + p); r.i1 = __ldg(im.f32 + plane + p); r.i2 = __ldg(im.f32 + 2 * plane + p);
+  }
   return r;
 }
 // edge between `a` (first end) and `q`: |n_a - n_q| w  and  sign(n_a - n_q) w
@@ -343,7 +355,10 @@ __global__ void __launch_bounds__(kSmoothWarps * 32) md2_smooth(Params P) {
   if (lane == 0) inv_m = 1.0f / ((float)(P.acc[acc_dispsum(P, s, b)] / (double)plane) + 1e-7f);
   inv_m = __shfl_sync(kFull, inv_m, 0);
   const float* d = P.disp[s] + (size_t)b * plane;
-  const float* im = P.color[s] + (size_t)b * 3 * plane;
+  SmoothImg im;
+  im.f32 = P.color[s] ? P.color[s] + (size_t)b * 3 * plane : nullptr;
+  im.u8 = P.color8[s] ? P.color8[s] + (size_t)b * 3 * plane : nullptr;
+  im.hwc = P.u8_hwc;
   float* gn = P.gn[s] + (size_t)b * plane;
   const float inx = 1.0f / ((float)P.B * (float)Hs * (float)(Ws - 1));
   const float iny = 1.0f / ((float)P.B * (float)(Hs - 1) * (float)Ws);
@@ -696,6 +711,7 @@ __global__ void __launch_bounds__(kFinalThreads) md2_final(Params P) {
 }
 
 // ------------------------------------------------------------------ launcher
+
 // Which two-source instantiations use the packed-fp32 form (md2_pack2.cuh).  Default: forward-only calls
 // (measured faster), scalar form when gradients are wanted (measured faster).  MD2_PACK2=all / MD2_PACK2=off
 // in the environment force one form for every two-source call (A/B checks, tests/test_gpu_parity.py).
@@ -710,8 +726,40 @@ static int pack2_mode() {
 }
 static bool use_pack2(bool grad) { return pack2_mode() == 2 || (pack2_mode() == 1 && !grad); }
 
+// Which form of the marching kernel runs.  Default: the role-specialised kernel (md2_roles.cuh).
+// MD2_MARCH=warp selects the round-1 one-warp-per-band kernels (md2_march / md2_march2) for A/B checks.
+static int march_mode() {
+  static const int mode = [] {
+    const char* e = getenv("MD2_MARCH");
+    if (e && !strcmp(e, "warp")) return 0;
+    return 1;
+  }();
+  return mode;
+}
+
+template <class C0>
+static cudaError_t launch_march_roles(const Params& P, cudaStream_t stream) {
+  typedef RoleOf<C0> C;
+  typedef RoleCfg<C> RC;
+  const int jobs = P.S * P.B * P.nseg * P.nband;
+  const size_t smem = (size_t)RC::SMEM_F4 * sizeof(float4);
+  if constexpr (C::NSRC == 2 && !C::AVG) {
+    if (pack2_mode() != 0) {          // packed-fp32 roles unless MD2_PACK2=off
+      static cudaError_t attr2 = cudaFuncSetAttribute(md2_march_roles<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (attr2 != cudaSuccess) return attr2;
+      md2_march_roles<C, true><<<jobs, RC::THREADS, smem, stream>>>(P);
+      return cudaGetLastError();
+    }
+  }
+  static cudaError_t attr = cudaFuncSetAttribute(md2_march_roles<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (attr != cudaSuccess) return attr;
+  md2_march_roles<C, false><<<jobs, RC::THREADS, smem, stream>>>(P);
+  return cudaGetLastError();
+}
+
 template <class C>
 static cudaError_t launch_march(const Params& P, cudaStream_t stream) {
+  if (march_mode() == 1) return launch_march_roles<C>(P, stream);
   const int jobs = P.S * P.B * P.nseg * P.nband;
   const int grid = (jobs + kWarpsPerCta - 1) / kWarpsPerCta;
   size_t smem = (size_t)kThreads * C::SMEM4 * sizeof(float4);
@@ -764,7 +812,7 @@ static void launch_identity_ns(const Params& P, int grid, cudaStream_t stream) {
     static const bool tma_on = !(getenv("MD2_IDENTITY_TMA") && atoi(getenv("MD2_IDENTITY_TMA")) == 0);
     uintptr_t bits = (uintptr_t)P.tgt;
     for (int f = 0; f < NSRC; ++f) bits |= (uintptr_t)P.src[f];
-    if (tma_on && pack2_mode() != 0 && (bits & 15) == 0 && P.W % 4 == 0 && P.W >= kTmaBoxW && P.H >= kTmaBoxH) {
+    if (tma_on && !P.tgt8 && pack2_mode() != 0 && (bits & 15) == 0 && P.W % 4 == 0 && P.W >= kTmaBoxW && P.H >= kTmaBoxH) {
       IdTensorMaps maps;
       bool ok = make_image_map(&maps.img[0], P.tgt, P.B, P.H, P.W);
       for (int f = 0; f < NSRC && ok; ++f) ok = make_image_map(&maps.img[1 + f], P.src[f], P.B, P.H, P.W);

@@ -193,6 +193,18 @@ __device__ __forceinline__ void lane_init2(Lane2<C>& L, const Params& P, const W
 
 // ------------------------------------------------------------------ stage A (see stage_a_issue / stage_a_finish)
 template <class C>
+__device__ __forceinline__ void load_identity_row2(Lane2<C>& L, const WarpJob& J, int t) {
+  if (C::AUTOMASK) {
+    const int yw = t - 1;
+    const int pix = (yw < 0 ? 0 : (yw >= J.H ? J.H - 1 : yw)) * J.W + L.xi;
+    L.idv[0] = MD2_LDS1(J.idl + pix);
+    L.idv[1] = MD2_LDS1(J.idl + J.plane + pix);
+    L.nzv[0] = MD2_LDS1(J.noise + pix);
+    L.nzv[1] = MD2_LDS1(J.noise + J.plane + pix);
+  }
+}
+
+template <class C, bool WITH_ID = true>
 __device__ __forceinline__ void stage_a_issue2(Lane2<C>& L, const Params& P, const WarpJob& J, int t) {
   const int tr = reflect_clamp(t, J.H);
   L.ctg = L.ntg;
@@ -208,14 +220,7 @@ __device__ __forceinline__ void stage_a_issue2(Lane2<C>& L, const Params& P, con
     D = l0 * top + l1 * bot;
   }
   prefetch_row2(L, J, t + 1);
-  if (C::AUTOMASK) {
-    const int yw = t - 1;
-    const int pix = (yw < 0 ? 0 : (yw >= J.H ? J.H - 1 : yw)) * J.W + L.xi;
-    L.idv[0] = MD2_LDS1(J.idl + pix);
-    L.idv[1] = MD2_LDS1(J.idl + J.plane + pix);
-    L.nzv[0] = MD2_LDS1(J.noise + pix);
-    L.nzv[1] = MD2_LDS1(J.noise + J.plane + pix);
-  }
+  if (WITH_ID) load_identity_row2(L, J, t);
   const float sd = MD2_FADD(P.a_disp, MD2_FMUL(P.c_disp, D));
   const float z = MD2_RCP(sd);
   L.cz = z;
@@ -255,16 +260,16 @@ __device__ __forceinline__ void stage_a_issue2(Lane2<C>& L, const Params& P, con
   }
 }
 
-template <class C>
-__device__ __forceinline__ void stage_a_finish2(Lane2<C>& L, const Params& P, const WarpJob& J, int t, const Stash& st) {
-  const int slot = ring_slot(t);
+template <class C, class ST, bool PUBLISH = C::GRAD>
+__device__ __forceinline__ void stage_a_finish2(Lane2<C>& L, const Params& P, const WarpJob& J, int t, const ST& st) {
+  const int slot = st.slot(t);
   const F4 tg4 = L.ctg;
   const float z = L.cz;
   const bool own = (t >= J.y0) && (t < J.y1) && (L.x >= J.x0) && (L.x < J.x0 + kOwnCols) && L.colok;
   L.tgrg = p2(tg4.x, tg4.y);
   L.tgb = tg4.z;
   if (J.depth && own) J.depth[t * J.W + L.xi] = z;
-  if (C::GRAD) st.at(slot, 0, C::STASH4) = make_f4(tg4.x, tg4.y, tg4.z, z);
+  if (PUBLISH) st.at(slot, 0, C::STASH4) = make_f4(tg4.x, tg4.y, tg4.z, z);
   float prb[2];
 #pragma unroll
   for (int f = 0; f < 2; ++f) {
@@ -292,8 +297,8 @@ __device__ __forceinline__ void stage_a_finish2(Lane2<C>& L, const Params& P, co
     }
     L.pr[f] = pr2;
     prb[f] = pb;
+    if (PUBLISH) st.at(slot, 1 + 3 * f, C::STASH4) = make_f4(pr2.x, pr2.y, pb, f ? L.cu.y : L.cu.x);
     if (C::GRAD) {
-      st.at(slot, 1 + 3 * f, C::STASH4) = make_f4(pr2.x, pr2.y, pb, f ? L.cu.y : L.cu.x);
       st.at(slot, 2 + 3 * f, C::STASH4) = make_f4(dxp2.x, dxp2.y, dxb, f ? L.cv.y : L.cv.x);
       st.at(slot, 3 + 3 * f, C::STASH4) = make_f4(dyp2.x, dyp2.y, dyb, 0.f);
     }
@@ -394,9 +399,9 @@ __device__ __forceinline__ void stage_b2(Lane2<C>& L, const Params& P, const War
 }
 
 // ------------------------------------------------------------------ stage C (see stage_c_divergent)
-template <class C>
+template <class C, class ST>
 __device__ __forceinline__ void stage_c2(Lane2<C>& L, const Params& P, const WarpJob& J, int t, int lane,
-                                         const Xchg2P<C>& lf, const Xchg2P<C>& rt, const Stash& st) {
+                                         const Xchg2P<C>& lf, const Xchg2P<C>& rt, const ST& st) {
   const int yp = t - 2;
   const float wl = (L.x == 1) ? 2.0f : 1.0f;
   const float wr = (L.x == P.W - 2) ? 2.0f : 1.0f;
@@ -421,7 +426,7 @@ __device__ __forceinline__ void stage_c2(Lane2<C>& L, const Params& P, const War
     const P2 (&B1b)[3] = L.B1b, (&B2b)[3] = L.B2b;
     const float wu = (yp == 1) ? 2.0f : 1.0f;
     const float wd = (yp == P.H - 2) ? 2.0f : 1.0f;
-    const int slot = ring_slot(yp);
+    const int slot = st.slot(yp);
     const F4 s0 = st.at(slot, 0, C::STASH4);
     const P2 tgrg = p2(s0.x, s0.y);
     const float tgb = s0.z, z = s0.w;
@@ -537,12 +542,12 @@ __device__ __forceinline__ void id_init2(IdLane2& L, const Params& P, int x0, in
 __device__ __forceinline__ void id_prefetch2(IdLane2& L, const Params& P, int b, int t) {
   const int tr = reflect_clamp(t, P.H);
   const int plane = P.H * P.W;
-  const int off = b * 3 * plane + tr * P.W + L.xi;
+  const int pix = tr * P.W + L.xi;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    L.n2tg[c] = MD2_LD(P.tgt + off + c * plane);
-    L.n2pr[0][c] = MD2_LD(P.src[0] + off + c * plane);
-    L.n2pr[1][c] = MD2_LD(P.src[1] + off + c * plane);
+    L.n2tg[c] = load_px(P.tgt, P.tgt8, P.u8_hwc, b, c, plane, pix);
+    L.n2pr[0][c] = load_px(P.src[0], P.src8[0], P.u8_hwc, b, c, plane, pix);
+    L.n2pr[1][c] = load_px(P.src[1], P.src8[1], P.u8_hwc, b, c, plane, pix);
   }
 }
 __device__ __forceinline__ void id_shift2(IdLane2& L) {

@@ -133,10 +133,12 @@ inline int fill_params(const md2_problem* p, const md2_tensors* t, void* workspa
     P->id_rows = best_r;
   }
   P->nseg_id = (p->height + P->id_rows - 1) / P->id_rows;
-  if (!t->target || !t->K || !t->inv_K || !t->losses) return MD2_ERR_INVALID_ARGUMENT;
-  P->tgt = t->target; P->K = t->K; P->invK = t->inv_K;
+  const bool u8 = t->target_u8 != nullptr;
+  if ((!u8 && !t->target) || !t->K || !t->inv_K || !t->losses) return MD2_ERR_INVALID_ARGUMENT;
+  P->tgt = u8 ? nullptr : t->target; P->K = t->K; P->invK = t->inv_K;
+  P->tgt8 = t->target_u8; P->u8_hwc = t->u8_hwc ? 1 : 0;
   for (int f = 0; f < p->num_src; ++f) {
-    if (!t->source[f]) return MD2_ERR_INVALID_ARGUMENT;
+    if (u8 ? !t->source_u8[f] : !t->source[f]) return MD2_ERR_INVALID_ARGUMENT;
     if (t->axisangle[f]) {          // T built in the call from the pose leaves
       if (!t->translation[f] || t->pose_stride[f] < 3) return MD2_ERR_INVALID_ARGUMENT;
       P->aa[f] = t->axisangle[f]; P->tr[f] = t->translation[f];
@@ -151,15 +153,17 @@ inline int fill_params(const md2_problem* p, const md2_tensors* t, void* workspa
       if (!t->T[f]) return MD2_ERR_INVALID_ARGUMENT;
       P->Tm[f] = t->T[f];
     }
-    P->src[f] = t->source[f];
+    P->src[f] = u8 ? nullptr : t->source[f];
+    P->src8[f] = u8 ? t->source_u8[f] : nullptr;
     P->pose_grad[f] = (t->pose_requires_grad[f] && p->want_grad) ? 1 : 0;
     P->grad_T[f] = p->want_grad ? t->grad_T[f] : nullptr;
   }
   for (int s = 0; s < p->num_scales; ++s) {
-    if (!t->disp[s] || !t->color[s]) return MD2_ERR_INVALID_ARGUMENT;
+    const unsigned char* c8 = u8 ? (t->color_u8[s] ? t->color_u8[s] : (s == 0 ? t->target_u8 : nullptr)) : nullptr;
+    if (!t->disp[s] || (u8 ? !c8 : !t->color[s])) return MD2_ERR_INVALID_ARGUMENT;
     if (P->automask && !t->noise[s]) return MD2_ERR_INVALID_ARGUMENT;
     if (p->want_grad && !t->grad_disp[s]) return MD2_ERR_INVALID_ARGUMENT;
-    P->disp[s] = t->disp[s]; P->color[s] = t->color[s]; P->noise[s] = t->noise[s];
+    P->disp[s] = t->disp[s]; P->color[s] = u8 ? nullptr : t->color[s]; P->color8[s] = c8; P->noise[s] = t->noise[s];
     P->grad_disp[s] = t->grad_disp[s];
     P->depth[s] = t->depth[s];
     P->idsel[s] = t->identity_selection[s];

@@ -29,6 +29,15 @@ def _check_f32_cuda(t: torch.Tensor, name: str, shape=None) -> torch.Tensor:
     return t.contiguous()
 
 
+def _check_u8_cuda(t: torch.Tensor, name: str, B: int, H: int, W: int, hwc: bool) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (the fused loss has no CPU path)" % name)
+    shape = (B, H, W, 3) if hwc else (B, 3, H, W)
+    if t.dtype != torch.uint8 or tuple(t.shape) != shape:
+        raise RuntimeError("%s must be uint8 of shape %s, got %s %s" % (name, shape, t.dtype, tuple(t.shape)))
+    return t.contiguous()
+
+
 class LossPlan:
     """Static description of one loss configuration (mirrors the ``opt`` flags the path reads)."""
 
@@ -150,11 +159,22 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
                 x = x.contiguous()
             return x, (x.stride(0) if B > 1 else 3)
 
-        t.target = ptr(_check_f32_cuda(target, "target", (B, 3, H, W)))
+        # uint8 frames (what the dataloader holds before ToTensor, mono_dataset.py:106-109): (B,H,W,3) or
+        # (B,3,H,W); converted with x / 255 inside the kernels, a quarter of the host-to-device bytes
+        u8 = target.dtype == torch.uint8
+        hwc = u8 and target.dim() == 4 and target.shape[-1] == 3 and target.shape[1] != 3
+        if u8:
+            t.target_u8 = ptr(_check_u8_cuda(target, "target", B, H, W, hwc))
+            t.u8_hwc = int(hwc)
+        else:
+            t.target = ptr(_check_f32_cuda(target, "target", (B, 3, H, W)))
         cam_T = [None] * F
         grad_first, grad_second = [None] * F, [None] * F
         for i in range(F):
-            t.source[i] = ptr(_check_f32_cuda(sources[i], "source[%d]" % i, (B, 3, H, W)))
+            if u8:
+                t.source_u8[i] = ptr(_check_u8_cuda(sources[i], "source[%d]" % i, B, H, W, hwc))
+            else:
+                t.source[i] = ptr(_check_f32_cuda(sources[i], "source[%d]" % i, (B, 3, H, W)))
             t.pose_requires_grad[i] = int(bool(pose_grad[i]))
             if pose_invert[i] is None:
                 t.T[i] = ptr(_check_f32_cuda(firsts[i], "T[%d]" % i, (B, 4, 4)))
@@ -180,7 +200,10 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
         for s in range(S):
             hs, ws = H >> s, W >> s
             t.disp[s] = ptr(_check_f32_cuda(disps[s], "disp[%d]" % s, (B, 1, hs, ws)))
-            t.color[s] = ptr(_check_f32_cuda(colors[s], "color[%d]" % s, (B, 3, hs, ws)))
+            if u8:
+                t.color_u8[s] = ptr(_check_u8_cuda(colors[s], "color[%d]" % s, B, hs, ws, hwc))
+            else:
+                t.color[s] = ptr(_check_f32_cuda(colors[s], "color[%d]" % s, (B, 3, hs, ws)))
             if plan.n_id > 0:
                 t.noise[s] = ptr(_check_f32_cuda(noise[s], "noise[%d]" % s, (B, plan.n_id, H, W)))
             if want_grad:
@@ -453,13 +476,20 @@ def _view_synthesis_loss_predictive_mask(plan: LossPlan, inputs: Dict, outputs: 
 
 
 class FusedLossMixin:
-    """Mix into (or bind onto) the reference ``Trainer``: overrides only the two hot-path methods.
+    """Mix into (or bind onto) the reference ``Trainer``: overrides the two hot-path methods and makes the
+    two consumers of their side outputs (``log`` and ``compute_depth_losses``) materialise
+    what they read.
 
         class FusedTrainer(FusedLossMixin, Trainer): pass
+        FusedTrainer(opts).train()
 
-    ``self.opt`` must be the reference options namespace.  Set ``self.md2_side`` to e.g.
-    ``{"depth_scales": [0], "color_scales": [0], "mask_scales": [0, 1, 2, 3]}`` on logging steps to
-    materialise what ``Trainer.log`` / ``compute_depth_losses`` read.
+    ``self.opt`` must be the reference options namespace.  The training call itself produces no side outputs.
+    ``Trainer.run_epoch`` decides to log only *after* ``process_batch`` (trainer.py:213-227), so the side outputs
+    are produced on demand: when ``log`` / ``compute_depth_losses`` (also reached through ``val``) find
+    ``outputs[("depth", 0, 0)]``, ``outputs[("color", f, 0)]`` or ``outputs["identity_selection/s"]`` missing,
+    one extra forward-only fused call (same inputs, same tie-break noise as the training call) fills them in.
+    Setting ``self.md2_side`` (e.g. ``{"depth_scales": [0], "color_scales": [0], "mask_scales": [0, 1, 2, 3]}``)
+    makes every call produce them eagerly instead.
     """
 
     md2_side: Optional[dict] = None
@@ -468,8 +498,47 @@ class FusedLossMixin:
     def generate_images_pred(self, inputs, outputs):
         if self._md2_plan is None:
             self._md2_plan = LossPlan.from_opt(self.opt)
+        plan = self._md2_plan
         side = dict(self.md2_side) if self.md2_side else None
-        outputs["_md2_losses"] = view_synthesis_loss(self._md2_plan, inputs, outputs, side=side)
+        noise = None
+        if plan.n_id > 0 and not (plan.predictive_mask or plan.v1_multiscale or plan.posecnn):
+            # drawn here exactly as view_synthesis_loss would (one torch.randn per scale, in scale order,
+            # trainer.py:468-469) and kept so that a later on-demand side-output call sees the same masks
+            shape = (plan.batch_size, plan.n_id, plan.height, plan.width)
+            noise = [torch.randn(shape, device=inputs[("color", 0, 0)].device) for _ in plan.scales]
+            outputs["_md2_noise"] = noise
+        outputs["_md2_losses"] = view_synthesis_loss(plan, inputs, outputs, noise=noise, side=side)
 
     def compute_losses(self, inputs, outputs):
         return outputs.pop("_md2_losses")
+
+    def _md2_materialise(self, inputs, outputs, depth=False, color=False, masks=False):
+        """Fill in the side outputs ``log`` / ``compute_depth_losses`` read, if the training call did not."""
+        plan = self._md2_plan
+        if plan is None:
+            return
+        scales = list(plan.scales)
+        side = {}
+        if depth and ("depth", 0, 0) not in outputs:
+            side["depth_scales"] = [0]
+        if color and any(("color", f, 0) not in outputs for f in plan.src_ids):
+            side["color_scales"] = [0]
+        if masks and plan.automask and any("identity_selection/{}".format(s) not in outputs for s in scales):
+            side["mask_scales"] = scales
+        if not side:
+            return
+        with torch.no_grad():
+            outs = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in outputs.items()
+                    if not (isinstance(k, str) and k.startswith("_md2"))}
+            view_synthesis_loss(plan, inputs, outs, noise=outputs.get("_md2_noise"), side=side)
+        for k, v in outs.items():
+            if k not in outputs:
+                outputs[k] = v
+
+    def compute_depth_losses(self, inputs, outputs, losses):
+        self._md2_materialise(inputs, outputs, depth=True)
+        return super().compute_depth_losses(inputs, outputs, losses)
+
+    def log(self, mode, inputs, outputs, losses):
+        self._md2_materialise(inputs, outputs, color=True, masks=True)
+        return super().log(mode, inputs, outputs, losses)

@@ -40,9 +40,17 @@ class DebugSink(C.Structure):
                 ("smoff", C.c_long * 4)]
 
 
+def quantise_u8(a):
+    """float image in [0,1] -> the uint8 image a dataloader would hold before ToTensor"""
+    return np.clip(np.rint(np.asarray(a, np.float64) * 255.0), 0, 255).astype(np.uint8)
+
+
 def run_emu(g, want_grad=True, rows_per_segment=0, align_corners=False, side_outputs=True, decisions=False,
-            pose_leaves=False):
-    """Run the emulator on a Golden fixture; returns dict of numpy outputs."""
+            pose_leaves=False, u8=None):
+    """Run the emulator on a Golden fixture; returns dict of numpy outputs.
+
+    u8: None (float images as stored), "f32" (float images = ToTensor of the quantised uint8 frames),
+    "chw" / "hwc" (the quantised uint8 frames through the uint8 entry, planar / interleaved)."""
     lib = C.CDLL(build_emu())
     lib.md2_emu_workspace_bytes.argtypes = [C.POINTER(Md2Problem), C.POINTER(C.c_size_t)]
     lib.md2_emu_view_synthesis_loss.argtypes = [C.POINTER(Md2Problem), C.POINTER(Md2Tensors), C.c_void_p, C.c_size_t]
@@ -61,11 +69,24 @@ def run_emu(g, want_grad=True, rows_per_segment=0, align_corners=False, side_out
         keep.append(a)
         return a
 
+    def img(key):
+        """(float pointer, uint8 pointer) of one image tensor under the requested entry"""
+        a = z[key]
+        if u8 is None:
+            return _ptr(arr(a)), None
+        q = quantise_u8(a)
+        if u8 == "f32":      # torchvision ToTensor: uint8 -> float32, .div(255)
+            return _ptr(arr(q.astype(np.float32) / np.float32(255.0))), None
+        q = np.ascontiguousarray(q.transpose(0, 2, 3, 1) if u8 == "hwc" else q)
+        keep.append(q)
+        return None, _ptr(q)
+
     t = Md2Tensors()
-    t.target = _ptr(arr(z["in__color__0__0"]))
+    t.target, t.target_u8 = img("in__color__0__0")
+    t.u8_hwc = int(u8 == "hwc")
     out = {"grad_T": {}, "warped": {}}
     for i, f in enumerate(srcs):
-        t.source[i] = _ptr(arr(z["in__color__%s__0" % f]))
+        t.source[i], t.source_u8[i] = img("in__color__%s__0" % f)
         if f == "s":
             t.T[i] = _ptr(arr(z["in__stereo_T"]))
             t.pose_requires_grad[i] = 0
@@ -94,7 +115,7 @@ def run_emu(g, want_grad=True, rows_per_segment=0, align_corners=False, side_out
     out["grad_disp"], out["grad_updisp"], out["idsel"], out["depth"] = [], [], [], []
     for s in range(4):
         t.disp[s] = _ptr(arr(z["disp__%d" % s]))
-        t.color[s] = _ptr(arr(z["in__color__0__%d" % s]))
+        t.color[s], t.color_u8[s] = img("in__color__0__%d" % s)
         if g.n_id > 0:
             t.noise[s] = _ptr(arr(z["noise__%d" % s][:, :g.n_id]))
         gd = np.zeros((B, 1, H >> s, W >> s), np.float32)

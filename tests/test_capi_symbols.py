@@ -31,13 +31,26 @@ def test_header_symbols_all_exported(lib):
         assert hasattr(lib, s), "libmd2loss.so does not export %s" % s
 
 
-def test_struct_layout_matches_header():
+def test_struct_layout_matches_header(tmp_path):
+    """sizeof / offsetof of every field of the header's structs, as gcc lays them out, against the ctypes mirror."""
+    import subprocess
     from monodepth2_b200._capi import Md2Problem, Md2Tensors
-    assert C.sizeof(Md2Problem) == 14 * 4
-    # 1 + 4 + 4 pointers, 4 ints, 2 + 3*4 + 1 + 4 + 4 + 4 + 16 + 4 + 4 pointers
-    nptr = 1 + 4 + 4 + 2 + 12 + 1 + 4 + 4 + 4 + 16 + 4 + 4
-    # pose leaves: 2*4 pointers, 2*4 ints, 3*4 pointers
-    assert C.sizeof(Md2Tensors) == nptr * 8 + 4 * 4 + (8 + 12) * 8 + 8 * 4
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "md2_loss.h"', 'int main(void) {',
+             'printf("md2_problem %zu\\n", sizeof(md2_problem));', 'printf("md2_tensors %zu\\n", sizeof(md2_tensors));']
+    for cname, cls in (("md2_problem", Md2Problem), ("md2_tensors", Md2Tensors)):
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    assert int(got["md2_problem"]) == C.sizeof(Md2Problem)
+    assert int(got["md2_tensors"]) == C.sizeof(Md2Tensors)
+    for cname, cls in (("md2_problem", Md2Problem), ("md2_tensors", Md2Tensors)):
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
 
 
 def test_validation_without_gpu(lib):

@@ -90,3 +90,67 @@ def test_mixin_under_no_grad_is_forward_only():
     l1 = t.compute_losses(ins, outs)
     assert l1["loss"].requires_grad
     assert abs(float(l0["loss"]) - float(l1["loss"].detach())) <= 2e-6 * abs(float(l0["loss"]))
+
+
+def test_logging_step_materialises_side_outputs_on_demand():
+    """Trainer.run_epoch decides to log after process_batch (trainer.py:213-227), so log() and
+    compute_depth_losses() must find outputs[("depth",0,0)], ("color",f,0) and "identity_selection/s" although the
+    training call produced none.  The base class below reads exactly the keys trainer.py:504,553-572 read."""
+    from monodepth2_b200.fused_loss import FusedLossMixin
+    from monodepth2_b200.synthetic import make_batch
+    B, H, W, fids = 2, 48, 80, [0, -1, 1]
+    seen = {}
+
+    class RefLike:
+        def compute_depth_losses(self, inputs, outputs, losses):
+            seen["depth"] = outputs[("depth", 0, 0)]                       # trainer.py:504
+
+        def log(self, mode, inputs, outputs, losses):
+            for f in self.opt.frame_ids[1:]:
+                seen[("color", f)] = outputs[("color", f, 0)]              # trainer.py:561-563
+            for s in self.opt.scales:
+                seen[("mask", s)] = outputs["identity_selection/{}".format(s)]   # trainer.py:570-572
+
+    class T(FusedLossMixin, RefLike):
+        def __init__(self, opt):
+            self.opt = opt
+
+    def step(eager):
+        inputs, outputs, pose, _ = make_batch(B, H, W, fids, 4, 53, "structured")
+        t = T(_opt(B, H, W, fids))
+        if eager:
+            t.md2_side = {"depth_scales": [0], "color_scales": [0], "mask_scales": [0, 1, 2, 3]}
+        ins = {k: v.to(DEV) for k, v in inputs.items()}
+        outs = {k: v.to(DEV).requires_grad_(True) for k, v in outputs.items()}
+        torch.manual_seed(7)
+        t.generate_images_pred(ins, outs)
+        losses = t.compute_losses(ins, outs)
+        losses["loss"].backward()
+        return t, ins, outs, losses
+
+    t, ins, outs, losses = step(eager=False)
+    assert ("depth", 0, 0) not in outs and "identity_selection/0" not in outs
+    seen.clear()
+    t.compute_depth_losses(ins, outs, losses)
+    t.log("train", ins, outs, losses)
+    lazy = {k: v.clone() for k, v in seen.items()}
+    t2, ins2, outs2, losses2 = step(eager=True)
+    seen.clear()
+    t2.compute_depth_losses(ins2, outs2, losses2)
+    t2.log("train", ins2, outs2, losses2)
+    assert abs(float(losses["loss"].detach()) - float(losses2["loss"].detach())) <= 1e-7 * abs(float(losses2["loss"].detach()))
+    assert sorted(map(str, lazy)) == sorted(map(str, seen))
+    for k in seen:
+        assert torch.equal(lazy[k], seen[k]), k                            # same noise -> same masks, same images
+    # and the validation path (trainer.py:320-339: no_grad, then compute_depth_losses + log)
+    with torch.no_grad():
+        inputs, outputs, pose, _ = make_batch(B, H, W, fids, 4, 54, "structured")
+        tv = T(_opt(B, H, W, fids))
+        insv = {k: v.to(DEV) for k, v in inputs.items()}
+        outsv = {k: v.to(DEV) for k, v in outputs.items()}
+        tv.generate_images_pred(insv, outsv)
+        lv = tv.compute_losses(insv, outsv)
+        seen.clear()
+        tv.compute_depth_losses(insv, outsv, lv)
+        tv.log("val", insv, outsv, lv)
+        assert seen["depth"].shape == (B, 1, H, W) and seen[("mask", 3)].shape == (B, H, W)
