@@ -45,6 +45,7 @@ WORKLOADS = {
     "mono_640x192_b12_disable_automasking": (192, 640, [0, -1, 1], False, True),
 }
 BATCH = 12
+L2_NOTE = "GPU arm: 4 rotating batches of ~110 MB each, together larger than the 126 MB L2 (no flush); the reference arm runs on the CPU"
 METRIC = "reproj-loss fwd+bwd frames/s"
 UNIT = "frames/s"
 
@@ -203,8 +204,9 @@ def run_reference(args, wl):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": wl, "batch_per_gpu": BATCH, "frame_ids": [str(f) for f in frame_ids],
-                   "scales": 4, "device": "cpu (reference --no_cuda path, oracle port)"},
+        "config": {"workload": wl, "batch_per_gpu": BATCH, "frame_ids": [str(f) for f in frame_ids], "scales": 4,
+                   "l2": L2_NOTE},
+        "notes": {"device": "cpu (reference --no_cuda path, oracle port: oracle/view_synthesis.py)"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -258,6 +260,54 @@ class DeviceBatch:
         self.t = t
 
 
+class PublicStep:
+    """One rotating batch driven through the PUBLIC call: view_synthesis_loss(plan, inputs, outputs) with the
+    tie-break noise drawn inside (torch.randn, trainer.py:468-469) + losses["loss"].backward() through the
+    autograd wrapper, captured once in a CUDA graph and replayed (tests/test_gpu_parity.py shows capture
+    replays identically)."""
+
+    def __init__(self, plan, batch, dev):
+        from monodepth2_b200.fused_loss import view_synthesis_loss
+        inputs, outputs, pose, noise = batch
+        self.plan, self.fn = plan, view_synthesis_loss
+        self.ins = {k: v.to(dev) for k, v in inputs.items()}
+        self.leaves = {k: v.to(dev).requires_grad_(True) for k, v in outputs.items()}
+        self.graph, self.loss = None, None
+
+    def run(self):
+        for v in self.leaves.values():
+            v.grad = None
+        losses = self.fn(self.plan, self.ins, dict(self.leaves))
+        losses["loss"].backward()
+        return losses["loss"].detach()
+
+    def capture(self):
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.run()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        for v in self.leaves.values():
+            v.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self.run()
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.loss = self.run()
+
+
+def quantise_u8(x):
+    """float frame in [0,1] -> the uint8 frame a dataloader holds before ToTensor, interleaved (B,H,W,3)"""
+    return (x * 255.0).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+
+
 def run_own(args, wl):
     from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
     from monodepth2_b200.synthetic import make_batch
@@ -283,35 +333,8 @@ def run_own(args, wl):
     nrot = 4        # rotating batches: ~110 MB each, together larger than the 126 MB L2
     host = [make_batch(BATCH, H, W, frame_ids, 4, seed=1000 * rank + i, kind="iid", n_id=max(n_id, 1))
             for i in range(nrot)]
-    devb = [DeviceBatch(plan, b, dev) for b in host]
-    ws = plan.workspace(dev)
-    prob = plan.problem(True)
     stream = torch.cuda.current_stream()
     sptr = C.c_void_p(stream.cuda_stream)
-
-    def launch(i, stream_ptr):
-        st = lib.md2_view_synthesis_loss(C.byref(prob), C.byref(devb[i % nrot].t), ws.data_ptr(), ws.numel(), stream_ptr)
-        if st != 0:
-            _capi.check(lib, st, "md2_view_synthesis_loss")
-
-    # One CUDA graph per rotating batch: the 6 launches (and the fork/join of the library's side
-    # stream) of a step are captured once and replayed, which removes the CPU launch gaps.
-    graphs = None
-    if not args.no_graph:
-        launch(0, sptr)                       # creates the library's side stream / events outside capture
-        torch.cuda.synchronize()
-        graphs = []
-        for i in range(nrot):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                launch(i, C.c_void_p(torch.cuda.current_stream().cuda_stream))
-            graphs.append(g)
-
-    def step(i):
-        if graphs is not None:
-            graphs[i % nrot].replay()
-        else:
-            launch(i, sptr)
 
     def barrier():
         torch.cuda.synchronize()
@@ -319,53 +342,62 @@ def run_own(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: K steps, inputs resident in HBM, CUDA events, max over ranks
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(args.steps):
-        step(i)
-    e1.record(stream)
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop()
-    tt = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_total = float(tt.item())
-    value = world * BATCH * args.steps / (ms_total * 1e-3)
-    loss_val = float(devb[(args.steps - 1) % nrot].losses[0].item())
-
-    # ---- the same loop with the tie-break noise of trainer.py:468-469 drawn inside the timed region
-    # (torch.randn into the resident noise buffers, once per scale, as the public API does); reported beside
-    # `value`, whose noise tensors are inputs that are already resident like every other input
-    ms_noise = None
-    if n_id > 0:
-        noise_bufs = [b.noise for b in devb]
-
-        def step_with_noise(i):
-            for t in noise_bufs[i % nrot]:
-                t.normal_()
-            step(i)
-        for i in range(3):
-            step_with_noise(i)
+    def timed(step_fn, steps, warmup, sample_clocks=False):
+        """warm-up, barrier, K steps between CUDA events on the launching stream, max over ranks"""
+        for i in range(warmup):
+            step_fn(i)
         barrier()
-        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0.record(stream)
-        for i in range(args.steps):
-            step_with_noise(i)
-        n1.record(stream)
+        sampler = None
+        if sample_clocks:
+            sampler = ClockSampler(local)
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            step_fn(i)
+        e1.record(stream)
         barrier()
-        tn = torch.tensor([n0.elapsed_time(n1)], device=dev, dtype=torch.float64)
+        clocks = sampler.stop() if sampler else None
+        tt = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if dist is not None:
-            dist.all_reduce(tn, op=dist.ReduceOp.MAX)
-        ms_noise = float(tn.item())
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()), clocks
 
-    # ---- roofline of the dominant kernel (md2_march): per-launch CUDA events, live
+    # ---- value: the public call (noise drawn inside, autograd wrapper and backward() included), inputs resident
+    # in HBM, one CUDA graph per rotating batch
+    pub = [PublicStep(plan, b, dev) for b in host]
+    if not args.no_graph:
+        for p in pub:
+            p.capture()
+    ms_total, clocks = timed(lambda i: pub[i % nrot].step(), args.steps, max(args.warmup, 3), sample_clocks=True)
+    value = world * BATCH * args.steps / (ms_total * 1e-3)
+    loss_val = float(pub[(args.steps - 1) % nrot].loss.item())
+
+    # ---- the raw C-ABI call with pre-drawn noise tensors (round 1's headline; kept as an extra key): what the
+    # library itself costs without the 4 torch.randn draws and the autograd wrapper
+    devb = [DeviceBatch(plan, b, dev) for b in host]
+    ws = plan.workspace(dev)
+    prob = plan.problem(True)
+
+    def launch(i, stream_ptr):
+        st = lib.md2_view_synthesis_loss(C.byref(prob), C.byref(devb[i % nrot].t), ws.data_ptr(), ws.numel(), stream_ptr)
+        if st != 0:
+            _capi.check(lib, st, "md2_view_synthesis_loss")
+
+    graphs = None
+    if not args.no_graph:
+        launch(0, sptr)
+        torch.cuda.synchronize()
+        graphs = []
+        for i in range(nrot):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                launch(i, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            graphs.append(g)
+    ms_cabi, _ = timed((lambda i: graphs[i % nrot].replay()) if graphs else (lambda i: launch(i, sptr)),
+                       args.steps, 3)
+
+    # ---- roofline of the dominant kernel (md2_march_roles): per-launch CUDA events, live
     lib.md2_profile_enable(1)
     march = []
     for i in range(min(args.steps, 20)):
@@ -383,28 +415,32 @@ def run_own(args, wl):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "march_traffic.json"))).get(wl)
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "md2_march", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "md2_march_roles", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": a_alg, "kernel_ms": march_ms,
                 "frac_of_8TBs_nominal": achieved / 8000.0,
                 "whole_step_achieved": a_alg / (ms_total / args.steps * 1e-3) / 1e9}
 
-    # ---- e2e: public API, pinned host inputs copied every step, loss read back every step
+    # ---- e2e: public API through the uint8 entry; every step's inputs are copied from pinned host memory
+    # (frames as the uint8 the dataloader holds before ToTensor, mono_dataset.py:106-109; disparities / poses /
+    # intrinsics as fp32) and every step's loss is read back
     pinned = []
     for b in host[:2]:
         inputs, outputs, pose, noise = b
-        # exactly the tensors the path reads: source and target frames at scale 0,
-        # the target pyramid for the smoothness term, K / inv_K / stereo_T; disparities and poses
-        need = [("color", f, 0) for f in frame_ids] + [("color", 0, s) for s in range(1, 4)] + \
-               [("K", 0), ("inv_K", 0)] + (["stereo_T"] if "s" in frame_ids else [])
-        pin_in = {k: inputs[k].pin_memory() for k in need}
+        pin_in = {}
+        for f in frame_ids:
+            pin_in[("color", f, 0)] = quantise_u8(inputs[("color", f, 0)]).pin_memory()
+        for s_ in range(1, 4):
+            pin_in[("color", 0, s_)] = quantise_u8(inputs[("color", 0, s_)]).pin_memory()
+        for k in [("K", 0), ("inv_K", 0)] + (["stereo_T"] if "s" in frame_ids else []):
+            pin_in[k] = inputs[k].pin_memory()
         pin_out = {k: v.pin_memory() for k, v in outputs.items()}
         pinned.append((pin_in, pin_out))
-    h2d = sum(v.numel() * 4 for v in pinned[0][0].values()) + sum(v.numel() * 4 for v in pinned[0][1].values())
+    h2d = sum(v.numel() * v.element_size() for v in pinned[0][0].values()) + \
+        sum(v.numel() * v.element_size() for v in pinned[0][1].values())
 
-    # The H2D copy of step i+1 is enqueued on a copy stream before step i computes (double
-    # buffering, what a training input pipeline does); every step's inputs are still copied from
-    # pinned host memory inside the timed region and every step's loss is read back.
+    # The H2D copy of step i+1 is enqueued on a copy stream before step i computes (double buffering, what a
+    # training input pipeline does); every step's inputs are still copied inside the timed region.
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream()
 
@@ -443,7 +479,9 @@ def run_own(args, wl):
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = {"value": world * BATCH * n_e2e / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": 4, "steps": n_e2e, "pipeline": "H2D of step i+1 overlaps compute of step i"}
+           "d2h_bytes_per_step": 4, "steps": n_e2e, "pipeline": "H2D of step i+1 overlaps compute of step i",
+           "entry": "uint8 frames (B,H,W,3) + uint8 target pyramid, converted in-kernel (x/255 = ToTensor); fp32 "
+                    "disparities, cam_T_cam, K, inv_K"}
 
     # ---- CPU baseline (oracle port) on rank 0 at N=1, bounded sample
     cpu = None
@@ -469,22 +507,37 @@ def run_own(args, wl):
         except Exception as e:      # a baseline leg must not take the bench line down
             tcb = {"error": repr(e)[:200]}
 
+    # ---- the caller of the path: full training step (nets + loss + backward + Adam, DDP all-reduce at N > 1),
+    # so that the per-N records carry a training curve (BASELINE.json: "train steps/s at 1-8 GPUs")
+    train = None
+    if not args.no_train:
+        del pub, devb, graphs
+        torch.cuda.empty_cache()
+        try:
+            train = train_record(args, wl, dev, dist, rank, world, steps=min(args.steps, 10), warmup=3)
+        except Exception as e:
+            train = {"error": repr(e)[:300]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl, "batch_per_gpu": BATCH, "frame_ids": [str(f) for f in frame_ids],
-                       "scales": 4, "l2": "inputs larger than L2: %d rotating batches of ~%d MB each" %
-                       (nrot, int((h2d + n_id * BATCH * H * W * 4 * 4) / 1e6)),
+            # `config` names the workload and is identical in both arms; everything about how this arm ran is in `notes`
+            "config": {"workload": wl, "batch_per_gpu": BATCH, "frame_ids": [str(f) for f in frame_ids], "scales": 4,
+                       "l2": L2_NOTE},
+            "notes": {"device": "cuda (B200)",
                        "rows_per_segment": plan.problem(True).rows_per_segment or "library default (wave-quantisation model)", "loss": loss_val,
-                       "launch": "plain C-ABI calls" if graphs is None else "CUDA-graph replay of the C-ABI call",
-                       "noise": "tie-break noise tensors are resident inputs of the timed call; "
-                                "value_with_noise_draw times the same loop with 4 torch.randn draws per step"},
-            "value_with_noise_draw": (world * BATCH * args.steps / (ms_noise * 1e-3)) if ms_noise else None,
+                       "launch": ("eager public calls" if args.no_graph else "CUDA-graph replay of the public call") +
+                                 ": view_synthesis_loss(plan, inputs, outputs) + losses['loss'].backward(); the 4 "
+                                 "torch.randn tie-break draws of trainer.py:468-469 and the autograd wrapper are inside "
+                                 "the timed region"},
+            "value_cabi_predrawn_noise": world * BATCH * args.steps / (ms_cabi * 1e-3),
+            "ms_per_step_cabi_predrawn_noise": ms_cabi / args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "torch_cuda_baseline": tcb, "e2e": e2e,
             "gpu_launches": 7 * args.steps,
             "clocks": clocks,
+            "train": train,
         }
         emit(line)
     if dist is not None:
@@ -492,36 +545,25 @@ def run_own(args, wl):
 
 
 # ------------------------------------------------------------------------------- full training step
-def run_train(args, wl):
-    """--mode train: nets + loss + backward + Adam (+ DDP all-reduce), batch 12 per GPU, synthetic
-    batches resident in HBM.  --impl own: fused loss; --impl reference: the
-    reference's PyTorch-CUDA loss path (oracle port on torch CUDA kernels) in the same harness."""
+def train_record(args, wl, dev, dist, rank, world, steps, warmup, impl="own", num_layers=18):
+    """nets + loss + backward + Adam (+ DDP all-reduce), batch 12 per GPU, synthetic batches resident in HBM
+    (the caller is Trainer.run_epoch / process_batch, trainer.py:193-260).  Returns the
+    record; the max over ranks of the CUDA-event time is taken like for the loss path."""
+    import contextlib
     from benchmarks.train_step import Nets, TrainStep, parameter_count
     from monodepth2_b200.synthetic import make_batch
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py --mode train needs a CUDA device")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-
     H, W, frame_ids, avg, noauto = WORKLOADS[wl]
-    n_src = len(frame_ids) - 1
     torch.manual_seed(1234)                         # identical initial weights on every rank
-    nets = Nets(frame_ids, args.num_layers).to(dev)
+    nets = Nets(frame_ids, num_layers).to(dev)
     n_params = parameter_count(nets)
     model = nets
     if world > 1:
         from torch.nn.parallel import DistributedDataParallel as DDP
-        model = DDP(nets, device_ids=[local], gradient_as_bucket_view=True)
+        model = DDP(nets, device_ids=[dev.index], gradient_as_bucket_view=True, bucket_cap_mb=args.bucket_mb,
+                    static_graph=True)
 
-    if args.impl == "reference":
+    if impl == "reference":
         from oracle import view_synthesis as O
         cfg = O.OracleConfig(height=H, width=W, frame_ids=tuple(frame_ids), avg_reprojection=avg,
                              disable_automasking=noauto)
@@ -553,40 +595,68 @@ def run_train(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
-        step(batches[i % nrot])
-    barrier()
-    sampler = ClockSampler(local)
+    def run(n, w, ctx):
+        with ctx():
+            for i in range(w):
+                step(batches[i % nrot])
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            loss = None
+            for i in range(n):
+                loss = step(batches[i % nrot])
+            e1.record()
+            barrier()
+        tt = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()) / n, loss
+
+    sampler = ClockSampler(dev.index)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        loss = step(batches[i % nrot])
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms, loss = run(steps, max(warmup, 3), contextlib.nullcontext)
     clocks = sampler.stop()
-    tt = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_total = float(tt.item())
+    rec = {
+        "impl": impl, "metric": "train steps/s (nets + view-synthesis loss + backward + Adam)",
+        "value": 1e3 / ms, "unit": "steps/s", "n_gpus": world, "steps": steps, "ms_per_step": ms,
+        "frames_per_s": world * BATCH * 1e3 / ms, "gradient_bytes": n_params * 4,
+        "config": {"workload": wl, "mode": "train", "batch_per_gpu": BATCH, "global_batch": world * BATCH,
+                   "frame_ids": [str(f) for f in frame_ids], "scales": 4,
+                   "nets": "stand-in ResNet-%d encoder + depth decoder + pose encoder/decoder, %.2f M params, "
+                           "random init, fp32 (TF32 off)" % (num_layers, n_params / 1e6),
+                   "loss": loss_name, "parallelism": ("ddp%d (NCCL all-reduce of %.1f MB of gradients, bucket_cap_mb=%d, "
+                                                      "static_graph, gradient_as_bucket_view)" %
+                                                      (world, n_params * 4 / 1e6, args.bucket_mb)) if world > 1 else "single GPU",
+                   "last_loss": float(loss.item())},
+        "clocks": clocks,
+    }
+    if world > 1:
+        # the same step without the gradient all-reduce (DDP no_sync): what the collective leaves exposed
+        ms_local, _ = run(steps, 2, model.no_sync)
+        rec["ms_per_step_no_allreduce"] = ms_local
+        rec["exposed_allreduce_ms"] = ms - ms_local
+    return rec
+
+
+def run_train(args, wl):
+    """--mode train: the training-step record alone (--impl own: fused loss; --impl reference: the reference's
+    PyTorch-CUDA loss path in the same harness)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --mode train needs a CUDA device")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    rec = train_record(args, wl, dev, dist, rank, world, args.steps, args.warmup, args.impl, args.num_layers)
     if rank == 0:
-        line = {
-            "impl": args.impl, "metric": "train steps/s (nets + view-synthesis loss + backward + Adam)",
-            "value": args.steps / (ms_total * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "frames_per_s": world * BATCH * args.steps / (ms_total * 1e-3),
-            "config": {"workload": wl, "mode": "train", "batch_per_gpu": BATCH, "global_batch": world * BATCH,
-                       "frame_ids": [str(f) for f in frame_ids], "scales": 4,
-                       "nets": "stand-in ResNet-%d encoder + depth decoder + pose encoder/decoder, %.2f M params, "
-                               "random init, fp32 (TF32 off)" % (args.num_layers, n_params / 1e6),
-                       "loss": loss_name, "parallelism": "ddp%d (NCCL all-reduce of %.1f MB of gradients)" %
-                       (world, n_params * 4 / 1e6) if world > 1 else "single GPU",
-                       "last_loss": float(loss.item())},
-            "clocks": clocks,
-        }
-        emit(line)
+        rec.update({"warmup": max(args.warmup, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "f32", "data": "synthetic"})
+        emit(rec)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -604,6 +674,8 @@ def main():
     ap.add_argument("--mode", default="loss", choices=["loss", "train"],
                     help="loss: the hot path alone (the contract metric); train: the full training step around it")
     ap.add_argument("--num-layers", type=int, default=18, choices=[18, 50], help="--mode train: ResNet depth")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step sub-record of the default mode")
+    ap.add_argument("--bucket-mb", type=int, default=25, help="DDP bucket_cap_mb of the training-step record")
     args = ap.parse_args()
     if args.mode == "train":
         run_train(args, args.workload)

@@ -171,6 +171,20 @@ int md2_pose_to_matrix_backward(const float *grad_T, const float *axisangle, con
                                 int invert, float *grad_axisangle, float *grad_translation,
                                 int batch, void *stream);
 
+/* ---- colour pyramid on the GPU: replaces the per-frame host work of
+ * MonoDataset.preprocess, datasets/mono_dataset.py:57,82-86,98-103 - torchvision Resize with
+ * Image.ANTIALIAS on PIL images = PIL.Image.resize(size, LANCZOS), scale i built from scale i-1.
+ * Byte-exact with Pillow's 8-bit fixed-point resample (Resample.c); coefficient tables are computed on the host
+ * and uploaded when the plan is created (synchronous; do it once, outside CUDA-graph capture). ---- */
+typedef struct md2_resize_plan md2_resize_plan;
+int md2_resize_plan_create(int in_h, int in_w, int out_h, int out_w, md2_resize_plan **plan);
+void md2_resize_plan_destroy(md2_resize_plan *plan);
+/* bytes of device scratch one call needs (the uint8 temporary of the horizontal pass) */
+int md2_resize_scratch_bytes(const md2_resize_plan *plan, int batch, size_t *bytes);
+/* in: (B,in_h,in_w,3) when hwc != 0, else (B,3,in_h,in_w); out: same layout at (out_h,out_w). */
+int md2_resize_lanczos_u8(const md2_resize_plan *plan, const unsigned char *in, unsigned char *out,
+                          void *scratch, size_t scratch_bytes, int batch, int hwc, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,7 +14,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 # development knobs: MD2_LIB_NAME / MD2_NVCC_DEFS build an experimental variant next to the product library
 LIB = os.path.join(LIB_DIR, os.environ.get("MD2_LIB_NAME", "libmd2loss.so"))
 EXTRA_DEFS = os.environ.get("MD2_NVCC_DEFS", "").split()
-SOURCES = ["md2_kernels.cu", "md2_ops.cu", "md2_capi.cu"]
+SOURCES = ["md2_kernels.cu", "md2_ops.cu", "md2_capi.cu", "md2_pyramid.cu"]
 HEADERS = ["md2_core.cuh", "md2_pack2.cuh", "md2_roles.cuh", "md2_plan.h", os.path.join("..", "..", "include", "md2_loss.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -64,5 +64,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+DEBUG_LIB = os.path.join(LIB_DIR, "libmd2loss_dbg.so")
+
+
+def build_debug(force: bool = False) -> str:
+    """libmd2loss_dbg.so: the same sources with -DMD2_DBG_DEVICE -DMD2_BOUNDS_CHECK (decision export and
+    index checks inside the kernels, include/md2_debug.h).  Test infrastructure; built in a child process
+    because the library name and the defines are module-level settings."""
+    env = dict(os.environ, MD2_LIB_NAME="libmd2loss_dbg.so", MD2_NVCC_DEFS="-DMD2_DBG_DEVICE -DMD2_BOUNDS_CHECK")
+    subprocess.check_call([sys.executable, "-m", "monodepth2_b200.build"] + (["--force"] if force else []),
+                          cwd=os.path.dirname(HERE), env=env, stdout=subprocess.DEVNULL)
+    return DEBUG_LIB
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--debug" in sys.argv:
+        print(build_debug(force="--force" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -6,6 +6,10 @@
 #include "md2_plan.h"
 
 namespace md2 {
+#if defined(MD2_DBG_DEVICE) || defined(MD2_BOUNDS_CHECK)
+cudaError_t debug_set_sink(const DebugSink* host_copy);
+cudaError_t debug_oob_count(unsigned long long* count, int reset);
+#endif
 cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream);
 cudaError_t profile_enable(bool on);
 cudaError_t profile_march_ms(float* ms);
@@ -56,5 +60,16 @@ int md2_profile_march_ms(float* ms) {
   if (!ms) return MD2_ERR_INVALID_ARGUMENT;
   return md2::profile_march_ms(ms) == cudaSuccess ? MD2_OK : MD2_ERR_CUDA;
 }
+
+#if defined(MD2_DBG_DEVICE) || defined(MD2_BOUNDS_CHECK)
+/* debug build only (libmd2loss_dbg.so, include/md2_debug.h): decision export + bounds-check counter */
+int md2_debug_set_sink(const void* sink) {
+  return md2::debug_set_sink((const md2::DebugSink*)sink) == cudaSuccess ? MD2_OK : MD2_ERR_CUDA;
+}
+int md2_debug_oob_count(unsigned long long* count, int reset) {
+  if (!count) return MD2_ERR_INVALID_ARGUMENT;
+  return md2::debug_oob_count(count, reset) == cudaSuccess ? MD2_OK : MD2_ERR_CUDA;
+}
+#endif
 
 }  // extern "C"

@@ -99,16 +99,26 @@ __device__ __forceinline__ float rcp_nr(float a) {
 }
 #endif
 
+#if defined(__CUDACC__)
+// 16-byte asynchronous copy global -> shared (LDGSTS); tracked by the async-group counters, not by the scoreboard
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
+
 #if !defined(__CUDA_ARCH__)
 // keep the host compiler from contracting these into an fma
 inline float host_fmul(float a, float b) { volatile float r = a * b; return r; }
 inline float host_fadd(float a, float b) { volatile float r = a + b; return r; }
 #endif
 
-#if !defined(__CUDACC__)
-// Host-emulator-only export of the discrete decisions the kernels take (bilinear cell + clip
-// masks, per-pixel winner, SSIM clamp-live bits, L1 / smoothness signs).  Used by the
-// decision-locked fp64 test (protocol P4); never compiled into the CUDA build.
+// Export of the discrete decisions the kernels take (bilinear cell + clip masks, per-pixel winner, SSIM
+// clamp-live bits, L1 / smoothness signs) for the decision-locked fp64 test (protocol P4).
+// Two builds have it: the host emulator (g++), and the debug build of the CUDA library
+// (-DMD2_DBG_DEVICE, libmd2loss_dbg.so, tests only); the product library compiles MD2_DBG to nothing.
 struct DebugSink {
   int B, H, W, S, nsrc;
   short* x0;            // [S][B][nsrc][H][W]
@@ -121,11 +131,33 @@ struct DebugSink {
   signed char* smy;
   long smoff[4];
 };
+#if !defined(__CUDACC__)
 inline DebugSink*& debug_sink() { static DebugSink* g = nullptr; return g; }
-inline unsigned char*& dbg_live_slot() { static unsigned char* p = nullptr; return p; }   // where ssim_window puts its live bit
-#define MD2_DBG(stmt) do { if (md2::debug_sink()) { md2::DebugSink& D = *md2::debug_sink(); stmt; } } while (0)
+#define MD2_DBG_ON 1
+#define MD2_DBG(...) do { if (md2::debug_sink()) { md2::DebugSink& D = *md2::debug_sink(); __VA_ARGS__; } } while (0)
+#elif defined(MD2_DBG_DEVICE)
+static __device__ DebugSink g_dbg_sink;      // all-null = off; set by md2_debug_set_sink (md2_kernels.cu)
+#define MD2_DBG_ON 1
+#if defined(__CUDA_ARCH__)
+#define MD2_DBG(...) do { if (md2::g_dbg_sink.x0) { md2::DebugSink& D = md2::g_dbg_sink; __VA_ARGS__; } } while (0)
 #else
-#define MD2_DBG(stmt) do { } while (0)
+#define MD2_DBG(...) do { } while (0)
+#endif
+#else
+#define MD2_DBG_ON 0
+#define MD2_DBG(...) do { } while (0)
+#endif
+
+// Debug build only (-DMD2_BOUNDS_CHECK): every index the marching path uses for a global load / store is
+// checked against the extent of its tensor; violations are counted (md2_debug_oob_count), the access is skipped
+// by clamping.  compute-sanitizer is closed on the pool this was developed on; this is its stand-in.
+#if defined(MD2_BOUNDS_CHECK) && defined(__CUDACC__)
+static __device__ unsigned long long g_oob_count;
+#endif
+#if defined(MD2_BOUNDS_CHECK) && defined(__CUDA_ARCH__)
+#define MD2_CHK(idx, n) do { if ((unsigned)(idx) >= (unsigned)(n)) atomicAdd(&md2::g_oob_count, 1ULL); } while (0)
+#else
+#define MD2_CHK(idx, n) do { } while (0)
 #endif
 
 constexpr int kMaxScales = 4;
@@ -149,6 +181,7 @@ struct Params {
   float gscale;              // 1/(S*B*H*W) [* 1/nsrc under avg_reprojection]
   float smooth_w[kMaxScales];  // disparity_smoothness / 2^s
   int seg_rows, nseg, nband, nband_id;
+  int nsm;                   // SMs of the device (role rotation of the role-specialised kernel)
   int id_rows, nseg_id;      // row segments of the (much lighter) identity pass
   const float* tgt;
   const float* src[kMaxSrc];
@@ -310,7 +343,8 @@ struct Cfg {
 //   81 d1 = sx^2 + sy^2 + 81 C1      81 d2 = 9 (sxx + syy) - sx^2 - sy^2 + 81 C2
 // When `coef` is non-null it receives -0.5*live*(alpha, beta, gamma) with
 // d(n/d)/dx_j = alpha + beta*x_j + gamma*y_j for every x_j of the window.
-MD2_HD float ssim_window(float sx, float sxx, float sxy, float sy, float syy, float* coef, bool valid = true) {
+MD2_HD float ssim_window(float sx, float sxx, float sxy, float sy, float syy, float* coef, bool valid = true,
+                         unsigned char* live_out = nullptr) {
   const float c1 = 81.0f * kSsimC1, c2 = 81.0f * kSsimC2;
   const float pxy = sx * sy;
   const float pp = fmaf(sx, sx, sy * sy);
@@ -325,7 +359,7 @@ MD2_HD float ssim_window(float sx, float sxx, float sxy, float sy, float syy, fl
   const float S = fminf(fmaxf(raw, 0.0f), 1.0f);
   if (coef) {
     const bool live = (raw >= 0.0f) && (raw <= 1.0f);
-    MD2_DBG((void)D; if (dbg_live_slot()) *dbg_live_slot() = live ? 1 : 0;);
+    if (MD2_DBG_ON && live_out) *live_out = live ? 1 : 0;
     const float k = (live && valid) ? -0.5f : 0.0f;
     const float QD = Q * invD;                       // N / D^2
     const float alpha = 2.0f * (sy * (n2 - n1) * invD - sx * (d2 - d1) * QD);
@@ -346,6 +380,18 @@ MD2_HD int reflect_clamp(int i, int n) {
 }
 
 // ------------------------------------------------------------------ lane state
+// What stage_a_issue hands to stage_a_finish: the gather of one row in flight.  A separate struct so that a
+// caller can keep two rows in flight (role A of the role-specialised kernel).
+template <class C>
+struct Flight {
+  F4 tap[C::NSRC][4];                           // nw, ne, sw, se texels
+  float cz;                                     // depth
+  float cu[C::NSRC], cv[C::NSRC];               // projected pixel coordinates
+  float cwx[C::NSRC], cwy[C::NSRC];             // bilinear weights
+  float cgx[C::NSRC], cgy[C::NSRC];             // clip mask * d(ix,iy)/d(u,v) / den
+  F4 ctg;                                       // target texel of the row
+};
+
 template <class C>
 struct Lane {
   // constants of the job
@@ -361,12 +407,7 @@ struct Lane {
   F4 ntg;                 // target texel of row t+1
   float nd[4];            // disparity taps of row t+1 (d00,d01,d10,d11; scale 0: d00 only)
   // gather of the current row, in flight between stage_a_issue and stage_a_finish
-  F4 tap[C::NSRC][4];                           // nw, ne, sw, se texels
-  float cz;                                     // depth
-  float cu[C::NSRC], cv[C::NSRC];               // projected pixel coordinates
-  float cwx[C::NSRC], cwy[C::NSRC];             // bilinear weights
-  float cgx[C::NSRC], cgy[C::NSRC];             // clip mask * d(ix,iy)/d(u,v) / den
-  F4 ctg;                                       // target texel of the current row
+  Flight<C> fl;
   // identity loss + noise of the current window row (loaded at the top of the step)
   float idv[C::NSRC], nzv[C::NSRC];
   // forward rolling state (horizontal 3-sums of the two previous rows)
@@ -413,10 +454,11 @@ struct StashT {
 typedef StashT<kRing> Stash;
 
 // issue the loads of row `t`'s target texel and disparity taps (consumed one step later)
-template <class C>
+template <class C, bool WITH_TG = true>
 MD2_HD void prefetch_row(Lane<C>& L, const WarpJob& J, int t) {
   const int tr = reflect_clamp(t, J.H);
-  L.ntg = MD2_LDS4(J.tgt4 + 4 * (tr * J.W + L.xi));
+  MD2_CHK(tr * J.W + L.xi, J.plane);
+  if (WITH_TG) L.ntg = MD2_LDS4(J.tgt4 + 4 * (tr * J.W + L.xi));
   if (J.s == 0) {
     L.nd[0] = MD2_LD(J.disp + tr * J.W + L.xi);
   } else {
@@ -426,6 +468,7 @@ MD2_HD void prefetch_row(Lane<C>& L, const WarpJob& J, int t) {
     const int y1 = y0 + ((y0 < J.Hs - 1) ? 1 : 0);
     const float* r0 = J.disp + y0 * J.Ws;
     const float* r1 = J.disp + y1 * J.Ws;
+    MD2_CHK(y0 * J.Ws + L.ux0, J.Hs * J.Ws); MD2_CHK(y1 * J.Ws + L.ux1, J.Hs * J.Ws);
     L.nd[0] = MD2_LD(r0 + L.ux0); L.nd[1] = MD2_LD(r0 + L.ux1);
     L.nd[2] = MD2_LD(r1 + L.ux0); L.nd[3] = MD2_LD(r1 + L.ux1);
   }
@@ -510,6 +553,7 @@ MD2_HD void load_identity_row(Lane<C>& L, const WarpJob& J, int t) {
   if (C::AUTOMASK) {
     const int yw = t - 1;
     const int pix = (yw < 0 ? 0 : (yw >= J.H ? J.H - 1 : yw)) * J.W + L.xi;
+    MD2_CHK(pix, J.plane);
 #pragma unroll
     for (int f = 0; f < C::NSRC; ++f) L.idv[f] = MD2_LDS1(J.idl + f * J.plane + pix);
 #pragma unroll
@@ -517,10 +561,18 @@ MD2_HD void load_identity_row(Lane<C>& L, const WarpJob& J, int t) {
   }
 }
 
-template <class C, bool WITH_ID = true>
-MD2_HD void stage_a_issue(Lane<C>& L, const Params& P, const WarpJob& J, int t) {
+// ROW_STEP: distance to the row this warp handles next (its target / disparity loads are put in flight here)
+// TG_DIRECT: the target texel of row t is loaded here, straight into the slot stage_a_finish reads (it is not
+// needed before), instead of being prefetched one step ahead and moved: a move placed after the gather issue
+// waits on the gather's scoreboard (role kernel, measured: 10 % of all stall samples on that one MOV)
+// ASYNC (CUDA only): the taps are copied by cp.async (LDGSTS) into `tapdst` ([source][tap][lane] 16-byte fields of
+// shared memory) instead of being loaded into F.tap; the caller commits / waits for the group.
+template <class C, bool WITH_ID = true, int ROW_STEP = 1, bool TG_DIRECT = false, bool ASYNC = false>
+MD2_HD void stage_a_issue(Lane<C>& L, Flight<C>& F, const Params& P, const WarpJob& J, int t, F4* tapdst = nullptr) {
   const int tr = reflect_clamp(t, J.H);
-  L.ctg = L.ntg;
+  MD2_CHK(tr * J.W + L.xi, J.plane);
+  if (TG_DIRECT) F.ctg = MD2_LDS4(J.tgt4 + 4 * (tr * J.W + L.xi));
+  else F.ctg = L.ntg;
   float D;
   if (J.s == 0) {
     D = L.nd[0];
@@ -532,11 +584,11 @@ MD2_HD void stage_a_issue(Lane<C>& L, const Params& P, const WarpJob& J, int t) 
     const float bot = L.ul0 * L.nd[2] + L.ul1 * L.nd[3];
     D = l0 * top + l1 * bot;
   }
-  prefetch_row(L, J, t + 1);
+  if (ROW_STEP > 0) prefetch_row<C, !TG_DIRECT>(L, J, t + ROW_STEP);     // ROW_STEP 0: the caller prefetches
   if (WITH_ID) load_identity_row(L, J, t);
   const float sd = MD2_FADD(P.a_disp, MD2_FMUL(P.c_disp, D));
   const float z = MD2_RCP(sd);
-  L.cz = z;
+  F.cz = z;
   const float yf = (float)tr;
 #pragma unroll
   for (int f = 0; f < C::NSRC; ++f) {
@@ -571,22 +623,38 @@ MD2_HD void stage_a_issue(Lane<C>& L, const Params& P, const WarpJob& J, int t) 
 #endif
 #if defined(MD2_KO_GATHER) && MD2_KO_GATHER == 2
     // timing knock-out (results invalid): no memory access at all for the taps
-    L.tap[f][0] = make_f4(ixc * 1e-3f, iyc * 1e-3f, u * 1e-3f, 0.f);
-    L.tap[f][1] = make_f4(iyc * 1e-3f, u * 1e-3f, ixc * 1e-3f, (float)(dx1 + dy1));
-    L.tap[f][2] = make_f4(v * 1e-3f, ixc * 2e-3f, iyc * 1e-3f, 0.f);
-    L.tap[f][3] = make_f4(iyc * 2e-3f, v * 1e-3f, u * 2e-3f, 0.f);
+    F.tap[f][0] = make_f4(ixc * 1e-3f, iyc * 1e-3f, u * 1e-3f, 0.f);
+    F.tap[f][1] = make_f4(iyc * 1e-3f, u * 1e-3f, ixc * 1e-3f, (float)(dx1 + dy1));
+    F.tap[f][2] = make_f4(v * 1e-3f, ixc * 2e-3f, iyc * 1e-3f, 0.f);
+    F.tap[f][3] = make_f4(iyc * 2e-3f, v * 1e-3f, u * 2e-3f, 0.f);
     (void)t00;
 #else
-    L.tap[f][0] = MD2_LD4(t00);
-    L.tap[f][1] = MD2_LD4(t00 + dx1);
-    L.tap[f][2] = MD2_LD4(t00 + dy1);
-    L.tap[f][3] = MD2_LD4(t00 + dy1 + dx1);
+    MD2_CHK(y0 * J.W + x0, J.plane); MD2_CHK(y0 * J.W + x0 + (dx1 + dy1) / 4, J.plane);
+#if defined(__CUDA_ARCH__)
+    if (ASYNC) {
+      cp_async16(tapdst + (f * 4 + 0) * kLanes, t00);
+      cp_async16(tapdst + (f * 4 + 1) * kLanes, t00 + dx1);
+      cp_async16(tapdst + (f * 4 + 2) * kLanes, t00 + dy1);
+      cp_async16(tapdst + (f * 4 + 3) * kLanes, t00 + dy1 + dx1);
+    } else
 #endif
-    L.cu[f] = u; L.cv[f] = v;
-    L.cwx[f] = ixc - fx0; L.cwy[f] = iyc - fy0;
-    L.cgx[f] = mx ? P.sx * inv : 0.0f;
-    L.cgy[f] = my ? P.sy * inv : 0.0f;
+    {
+      F.tap[f][0] = MD2_LD4(t00);
+      F.tap[f][1] = MD2_LD4(t00 + dx1);
+      F.tap[f][2] = MD2_LD4(t00 + dy1);
+      F.tap[f][3] = MD2_LD4(t00 + dy1 + dx1);
+    }
+#endif
+    F.cu[f] = u; F.cv[f] = v;
+    F.cwx[f] = ixc - fx0; F.cwy[f] = iyc - fy0;
+    F.cgx[f] = mx ? P.sx * inv : 0.0f;
+    F.cgy[f] = my ? P.sy * inv : 0.0f;
   }
+}
+
+template <class C, bool WITH_ID = true, int ROW_STEP = 1, bool TG_DIRECT = false>
+MD2_HD void stage_a_issue(Lane<C>& L, const Params& P, const WarpJob& J, int t) {
+  stage_a_issue<C, WITH_ID, ROW_STEP, TG_DIRECT, false>(L, L.fl, P, J, t);
 }
 
 // stage_a_finish: the taps have arrived; interpolate pred and its derivatives, export pr/tg for
@@ -594,18 +662,19 @@ MD2_HD void stage_a_issue(Lane<C>& L, const Params& P, const WarpJob& J, int t) 
 // PUBLISH: the row's target / pred fields go to the ring even without gradients (the role-specialised
 // kernel hands rows from warp to warp through it)
 template <class C, class ST, bool PUBLISH = C::GRAD>
-MD2_HD void stage_a_finish(Lane<C>& L, const Params& P, const WarpJob& J, int t, const ST& st) {
+MD2_HD void stage_a_finish(Lane<C>& L, const Flight<C>& F, const Params& P, const WarpJob& J, int t, const ST& st) {
   const int slot = st.slot(t);
-  const F4 tg4 = L.ctg;
-  const float z = L.cz;
+  const F4 tg4 = F.ctg;
+  const float z = F.cz;
   const bool own = (t >= J.y0) && (t < J.y1) && (L.x >= J.x0) && (L.x < J.x0 + kOwnCols) && L.colok;
   L.tg[0] = tg4.x; L.tg[1] = tg4.y; L.tg[2] = tg4.z;
+  if (own) MD2_CHK(t * J.W + L.xi, J.plane);
   if (J.depth && own) J.depth[t * J.W + L.xi] = z;
   if (PUBLISH) st.at(slot, 0, C::STASH4) = make_f4(tg4.x, tg4.y, tg4.z, z);
 #pragma unroll
   for (int f = 0; f < C::NSRC; ++f) {
-    const F4 nw = L.tap[f][0], ne = L.tap[f][1], sw = L.tap[f][2], se = L.tap[f][3];
-    const float wx = L.cwx[f], wy = L.cwy[f], gxs = L.cgx[f], gys = L.cgy[f];
+    const F4 nw = F.tap[f][0], ne = F.tap[f][1], sw = F.tap[f][2], se = F.tap[f][3];
+    const float wx = F.cwx[f], wy = F.cwy[f], gxs = F.cgx[f], gys = F.cgy[f];
     float pr[3], dxp[3], dyp[3];
     {
       const float nwc[3] = {nw.x, nw.y, nw.z}, nec[3] = {ne.x, ne.y, ne.z};
@@ -626,12 +695,17 @@ MD2_HD void stage_a_finish(Lane<C>& L, const Params& P, const WarpJob& J, int t,
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) L.pr[f][c] = pr[c];
-    if (PUBLISH) st.at(slot, 1 + 3 * f, C::STASH4) = make_f4(pr[0], pr[1], pr[2], L.cu[f]);
+    if (PUBLISH) st.at(slot, 1 + 3 * f, C::STASH4) = make_f4(pr[0], pr[1], pr[2], F.cu[f]);
     if (C::GRAD) {
-      st.at(slot, 2 + 3 * f, C::STASH4) = make_f4(dxp[0], dxp[1], dxp[2], L.cv[f]);
+      st.at(slot, 2 + 3 * f, C::STASH4) = make_f4(dxp[0], dxp[1], dxp[2], F.cv[f]);
       st.at(slot, 3 + 3 * f, C::STASH4) = make_f4(dyp[0], dyp[1], dyp[2], 0.f);
     }
   }
+}
+
+template <class C, class ST, bool PUBLISH = C::GRAD>
+MD2_HD void stage_a_finish(Lane<C>& L, const Params& P, const WarpJob& J, int t, const ST& st) {
+  stage_a_finish<C, ST, PUBLISH>(L, L.fl, P, J, t, st);
 }
 
 // ------------------------------------------------------------------ stage B
@@ -717,6 +791,7 @@ MD2_HD void stage_b_divergent(Lane<C>& L, const Params& P, const WarpJob& J, int
     }
     if (own_win) {
       L.loss += best;
+      MD2_CHK(yw * J.W + L.xi, J.plane);
       if (C::AUTOMASK && J.idsel) J.idsel[yw * J.W + L.xi] = (tag >= 0) ? 1.0f : 0.0f;
     }
     if (C::GRAD && !C::NOSSIM && tag >= 0) {
@@ -726,10 +801,10 @@ MD2_HD void stage_b_divergent(Lane<C>& L, const Params& P, const WarpJob& J, int
 #pragma unroll
           for (int c = 0; c < 3; ++c)
           {
-            MD2_DBG(dbg_live_slot() = (L.colok && yw >= 0 && yw < J.H)
+            unsigned char* lp = nullptr;
+            MD2_DBG(lp = (L.colok && yw >= 0 && yw < J.H)
                         ? &D.live[(((((long)J.s * D.B + J.b) * D.nsrc + f) * 3 + c) * D.H + yw) * D.W + L.x] : nullptr;);
-            ssim_window(V[f][c][0], V[f][c][1], V[f][c][2], VY[c][0], VY[c][1], &L.coef[f][c * 3]);
-            MD2_DBG(dbg_live_slot() = nullptr;);
+            ssim_window(V[f][c][0], V[f][c][1], V[f][c][2], VY[c][0], VY[c][1], &L.coef[f][c * 3], true, lp);
           }
       } else {
         // select the winner's window sums without dynamic register indexing
@@ -746,10 +821,10 @@ MD2_HD void stage_b_divergent(Lane<C>& L, const Params& P, const WarpJob& J, int
 #pragma unroll
         for (int c = 0; c < 3; ++c)
         {
-          MD2_DBG(dbg_live_slot() = (tag >= 0 && L.colok && yw >= 0 && yw < J.H)
+          unsigned char* lp = nullptr;
+          MD2_DBG(lp = (tag >= 0 && L.colok && yw >= 0 && yw < J.H)
                       ? &D.live[(((((long)J.s * D.B + J.b) * D.nsrc + tag) * 3 + c) * D.H + yw) * D.W + L.x] : nullptr;);
-          ssim_window(W3[c][0], W3[c][1], W3[c][2], VY[c][0], VY[c][1], &L.coef[0][c * 3]);
-          MD2_DBG(dbg_live_slot() = nullptr;);
+          ssim_window(W3[c][0], W3[c][1], W3[c][2], VY[c][0], VY[c][1], &L.coef[0][c * 3], true, lp);
         }
       }
     }
@@ -853,6 +928,7 @@ MD2_HD void stage_b_straight(Lane<C>& L, const Params& P, const WarpJob& J, int 
     }
     tag = win_ok ? tag : -1;
     L.loss += own_win ? best : 0.0f;
+    if (own_win) MD2_CHK(yw * J.W + L.xi, J.plane);
     if (C::AUTOMASK && J.idsel && own_win) J.idsel[yw * J.W + L.xi] = (tag >= 0) ? 1.0f : 0.0f;
     if (C::GRAD && !C::NOSSIM) {
       const bool valid = tag >= 0;
@@ -862,10 +938,10 @@ MD2_HD void stage_b_straight(Lane<C>& L, const Params& P, const WarpJob& J, int 
 #pragma unroll
           for (int c = 0; c < 3; ++c)
           {
-            MD2_DBG(dbg_live_slot() = (L.colok && yw >= 0 && yw < J.H)
+            unsigned char* lp = nullptr;
+            MD2_DBG(lp = (valid && L.colok && yw >= 0 && yw < J.H)
                         ? &D.live[(((((long)J.s * D.B + J.b) * D.nsrc + f) * 3 + c) * D.H + yw) * D.W + L.x] : nullptr;);
-            ssim_window(V[f][c][0], V[f][c][1], V[f][c][2], VY[c][0], VY[c][1], &L.coef[f][c * 3], valid);
-            MD2_DBG(dbg_live_slot() = nullptr;);
+            ssim_window(V[f][c][0], V[f][c][1], V[f][c][2], VY[c][0], VY[c][1], &L.coef[f][c * 3], valid, lp);
           }
       } else {
         // select the winner's window sums without dynamic register indexing
@@ -882,10 +958,10 @@ MD2_HD void stage_b_straight(Lane<C>& L, const Params& P, const WarpJob& J, int 
 #pragma unroll
         for (int c = 0; c < 3; ++c)
         {
-          MD2_DBG(dbg_live_slot() = (tag >= 0 && L.colok && yw >= 0 && yw < J.H)
+          unsigned char* lp = nullptr;
+          MD2_DBG(lp = (tag >= 0 && L.colok && yw >= 0 && yw < J.H)
                       ? &D.live[(((((long)J.s * D.B + J.b) * D.nsrc + tag) * 3 + c) * D.H + yw) * D.W + L.x] : nullptr;);
-          ssim_window(W3[c][0], W3[c][1], W3[c][2], VY[c][0], VY[c][1], &L.coef[0][c * 3], valid);
-          MD2_DBG(dbg_live_slot() = nullptr;);
+          ssim_window(W3[c][0], W3[c][1], W3[c][2], VY[c][0], VY[c][1], &L.coef[0][c * 3], valid, lp);
         }
       }
     } else {
@@ -1014,6 +1090,7 @@ MD2_HD void stage_c_divergent(Lane<C>& L, const Params& P, const WarpJob& J, int
     }
     // d depth / d D = -c * z^2  (layers.py:23-24)
     const float dD = -P.c_disp * z * z * dzsum * P.gscale;
+    MD2_CHK(yp * J.W + L.xi, J.plane);
     J.dD[yp * J.W + L.xi] = dD;
     if (J.s == 0)   // up-sampling is the identity at scale 0: finish grad_disp_0 here (A.4 + A.3)
       J.gd0[yp * J.W + L.xi] = dD + J.sm_w * (MD2_LD(J.gn0 + yp * J.W + L.xi) * J.sm_inv_m - J.sm_dterm);
@@ -1129,6 +1206,7 @@ MD2_HD void stage_c_straight(Lane<C>& L, const Params& P, const WarpJob& J, int 
     // d depth / d D = -c * z^2  (layers.py:23-24)
     const float dD = -P.c_disp * z * z * dzsum * P.gscale;
     if (own) {
+      MD2_CHK(yp * J.W + L.xi, J.plane);
       J.dD[yp * J.W + L.xi] = dD;
       if (J.s == 0)   // up-sampling is the identity at scale 0: finish grad_disp_0 here (A.4 + A.3)
         J.gd0[yp * J.W + L.xi] = dD + J.sm_w * (MD2_LD(J.gn0 + yp * J.W + L.xi) * J.sm_inv_m - J.sm_dterm);

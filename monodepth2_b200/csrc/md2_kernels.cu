@@ -397,6 +397,12 @@ __global__ void __launch_bounds__(kSmoothWarps * 32) md2_smooth(Params P) {
     float e_x = 0.f, sx = 0.f, e_y = 0.f, sy = 0.f;
     if (has_rt) smooth_edge(cur, rt, e_x, sx);
     if (has_dn) smooth_edge(cur, nxt, e_y, sy);
+    MD2_DBG(if (xok) {       // signs of the smoothness differences (decision export, debug build only)
+      const long o = D.smoff[s] + (long)b * plane + (long)y * Ws + x;
+      const float dx = cur.n - rt.n, dy = cur.n - nxt.n;
+      if (has_rt) D.smx[o] = (signed char)(dx > 0.f ? 1 : (dx < 0.f ? -1 : 0));
+      if (has_dn) D.smy[o] = (signed char)(dy > 0.f ? 1 : (dy < 0.f ? -1 : 0));
+    });
     // left neighbour's edge towards this pixel: previous lane, or recomputed from the side pixel
     float sxl = __shfl_up_sync(kFull, sx, 1);
     if (lane == 0) {
@@ -404,6 +410,7 @@ __global__ void __launch_bounds__(kSmoothWarps * 32) md2_smooth(Params P) {
       if (x > 0) { float e; smooth_edge(side, cur, e, sxl); }
     }
     if (xok) {
+      MD2_CHK(y * Ws + x, plane);
       // d(sum_x/Nx + sum_y/Ny) / d n(p): +sign*w for the edges this pixel starts, -sign*w for those it ends
       float g = 0.f;
       g += inx * sx;
@@ -716,6 +723,9 @@ __global__ void __launch_bounds__(kFinalThreads) md2_final(Params P) {
 // (measured faster), scalar form when gradients are wanted (measured faster).  MD2_PACK2=all / MD2_PACK2=off
 // in the environment force one form for every two-source call (A/B checks, tests/test_gpu_parity.py).
 static int pack2_mode() {
+#ifdef MD2_DBG_DEVICE
+  return 0;      // the decision export lives in the scalar stage functions
+#endif
   static const int mode = [] {
     const char* e = getenv("MD2_PACK2");
     if (e && !strcmp(e, "all")) return 2;
@@ -732,16 +742,45 @@ static int march_mode() {
   static const int mode = [] {
     const char* e = getenv("MD2_MARCH");
     if (e && !strcmp(e, "warp")) return 0;
+    if (e && !strcmp(e, "flow")) return 2;
     return 1;
   }();
   return mode;
 }
 
+static int device_sm_count() {
+  static const int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1)
+      v = 148;
+    return v;
+  }();
+  return n;
+}
+
 template <class C0>
-static cudaError_t launch_march_roles(const Params& P, cudaStream_t stream) {
+static cudaError_t launch_march_roles(const Params& P0, cudaStream_t stream) {
   typedef RoleOf<C0> C;
   typedef RoleCfg<C> RC;
+  Params P = P0;
+  P.nsm = device_sm_count();
   const int jobs = P.S * P.B * P.nseg * P.nband;
+  if (march_mode() == 2) {           // MD2_MARCH=flow: free-running roles (experimental, measured 2.4x slower)
+    typedef FlowCfg<C> FC;
+    const size_t fsmem = (size_t)FC::SMEM_F4 * sizeof(float4);
+    if constexpr (C::NSRC == 2 && !C::AVG) {
+      if (pack2_mode() != 0) {
+        static cudaError_t a2 = cudaFuncSetAttribute(md2_march_flow<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+        if (a2 != cudaSuccess) return a2;
+        md2_march_flow<C, true><<<jobs, FC::THREADS, fsmem, stream>>>(P);
+        return cudaGetLastError();
+      }
+    }
+    static cudaError_t a1 = cudaFuncSetAttribute(md2_march_flow<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+    if (a1 != cudaSuccess) return a1;
+    md2_march_flow<C, false><<<jobs, FC::THREADS, fsmem, stream>>>(P);
+    return cudaGetLastError();
+  }
   const size_t smem = (size_t)RC::SMEM_F4 * sizeof(float4);
   if constexpr (C::NSRC == 2 && !C::AVG) {
     if (pack2_mode() != 0) {          // packed-fp32 roles unless MD2_PACK2=off
@@ -759,7 +798,7 @@ static cudaError_t launch_march_roles(const Params& P, cudaStream_t stream) {
 
 template <class C>
 static cudaError_t launch_march(const Params& P, cudaStream_t stream) {
-  if (march_mode() == 1) return launch_march_roles<C>(P, stream);
+  if (march_mode() != 0) return launch_march_roles<C>(P, stream);
   const int jobs = P.S * P.B * P.nseg * P.nband;
   const int grid = (jobs + kWarpsPerCta - 1) / kWarpsPerCta;
   size_t smem = (size_t)kThreads * C::SMEM4 * sizeof(float4);
@@ -945,5 +984,36 @@ cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
   }
   return cudaSuccess;
 }
+
+#if defined(MD2_DBG_DEVICE) || defined(MD2_BOUNDS_CHECK)
+// debug build only (include/md2_debug.h)
+cudaError_t debug_set_sink(const DebugSink* host_copy) {
+#ifdef MD2_DBG_DEVICE
+  DebugSink z;
+  memset(&z, 0, sizeof(z));
+  return cudaMemcpyToSymbol(g_dbg_sink, host_copy ? host_copy : &z, sizeof(DebugSink));
+#else
+  (void)host_copy;
+  return cudaErrorNotSupported;
+#endif
+}
+__global__ void md2_oob_rw(unsigned long long* out, int reset) {
+#if defined(MD2_BOUNDS_CHECK)
+  if (out) *out = g_oob_count;
+  if (reset) g_oob_count = 0ULL;
+#else
+  if (out) *out = ~0ULL;
+#endif
+}
+cudaError_t debug_oob_count(unsigned long long* count, int reset) {
+  unsigned long long* d = nullptr;
+  cudaError_t e = cudaMalloc((void**)&d, sizeof(*d));
+  if (e != cudaSuccess) return e;
+  md2_oob_rw<<<1, 1>>>(d, reset);
+  e = cudaMemcpy(count, d, sizeof(*d), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e;
+}
+#endif
 
 }  // namespace md2

@@ -79,6 +79,13 @@ __device__ __forceinline__ P2 ssim_window2(P2 sx, P2 sxx, P2 sxy, P2 sy, P2 syy,
 }
 
 // ------------------------------------------------------------------ lane state (two sources)
+struct Flight2 {                   // see Flight (md2_core.cuh)
+  F4 tap[2][4];
+  float cz;
+  P2 cu, cv, cwx, cwy, cgx, cgy;   // over the two sources
+  F4 ctg;
+};
+
 template <class C>
 struct Lane2 {
   int x, xi;
@@ -88,10 +95,7 @@ struct Lane2 {
   float ul0, ul1;
   F4 ntg;
   float nd[4];
-  F4 tap[2][4];
-  float cz;
-  P2 cu, cv, cwx, cwy, cgx, cgy;   // over the two sources
-  F4 ctg;
+  Flight2 fl;                      // gather of the current row, in flight between issue and finish
   float idv[2], nzv[2];
   // forward rolling state: [slot][x, xx, xy]; target: (r,g) pair and scalar b, [y, yy]
   P2 H1[3][3], H2[3][3];
@@ -125,10 +129,10 @@ struct Xchg2P {
   int tag;
 };
 
-template <class C>
+template <class C, bool WITH_TG = true>
 __device__ __forceinline__ void prefetch_row2(Lane2<C>& L, const WarpJob& J, int t) {
   const int tr = reflect_clamp(t, J.H);
-  L.ntg = MD2_LDS4(J.tgt4 + 4 * (tr * J.W + L.xi));
+  if (WITH_TG) L.ntg = MD2_LDS4(J.tgt4 + 4 * (tr * J.W + L.xi));
   if (J.s == 0) {
     L.nd[0] = MD2_LD(J.disp + tr * J.W + L.xi);
   } else {
@@ -204,10 +208,11 @@ __device__ __forceinline__ void load_identity_row2(Lane2<C>& L, const WarpJob& J
   }
 }
 
-template <class C, bool WITH_ID = true>
-__device__ __forceinline__ void stage_a_issue2(Lane2<C>& L, const Params& P, const WarpJob& J, int t) {
+template <class C, bool WITH_ID = true, int ROW_STEP = 1, bool TG_DIRECT = false, bool ASYNC = false>
+__device__ __forceinline__ void stage_a_issue2(Lane2<C>& L, Flight2& F, const Params& P, const WarpJob& J, int t, F4* tapdst = nullptr) {
   const int tr = reflect_clamp(t, J.H);
-  L.ctg = L.ntg;
+  if (TG_DIRECT) F.ctg = MD2_LDS4(J.tgt4 + 4 * (tr * J.W + L.xi));
+  else F.ctg = L.ntg;
   float D;
   if (J.s == 0) {
     D = L.nd[0];
@@ -219,11 +224,11 @@ __device__ __forceinline__ void stage_a_issue2(Lane2<C>& L, const Params& P, con
     const float bot = L.ul0 * L.nd[2] + L.ul1 * L.nd[3];
     D = l0 * top + l1 * bot;
   }
-  prefetch_row2(L, J, t + 1);
+  if (ROW_STEP > 0) prefetch_row2<C, !TG_DIRECT>(L, J, t + ROW_STEP);
   if (WITH_ID) load_identity_row2(L, J, t);
   const float sd = MD2_FADD(P.a_disp, MD2_FMUL(P.c_disp, D));
   const float z = MD2_RCP(sd);
-  L.cz = z;
+  F.cz = z;
   const float yf = (float)tr;
   const P2 q0 = fma2(L.qb[0], bc(yf), L.qa[0]);
   const P2 q1 = fma2(L.qb[1], bc(yf), L.qa[1]);
@@ -243,28 +248,40 @@ __device__ __forceinline__ void stage_a_issue2(Lane2<C>& L, const Params& P, con
   const P2 fx0 = p2(floorf(ixc.x), floorf(ixc.y));
   const P2 fy0 = p2(floorf(iyc.x), floorf(iyc.y));
   const P2 gx = mul2(bc(P.sx), inv), gy = mul2(bc(P.sy), inv);
-  L.cu = u; L.cv = v;
-  L.cwx = sub2(ixc, fx0); L.cwy = sub2(iyc, fy0);
-  L.cgx = p2(((ix.x > 0.0f) && (ix.x < P.wmax)) ? gx.x : 0.0f, ((ix.y > 0.0f) && (ix.y < P.wmax)) ? gx.y : 0.0f);
-  L.cgy = p2(((iy.x > 0.0f) && (iy.x < P.hmax)) ? gy.x : 0.0f, ((iy.y > 0.0f) && (iy.y < P.hmax)) ? gy.y : 0.0f);
+  F.cu = u; F.cv = v;
+  F.cwx = sub2(ixc, fx0); F.cwy = sub2(iyc, fy0);
+  F.cgx = p2(((ix.x > 0.0f) && (ix.x < P.wmax)) ? gx.x : 0.0f, ((ix.y > 0.0f) && (ix.y < P.wmax)) ? gx.y : 0.0f);
+  F.cgy = p2(((iy.x > 0.0f) && (iy.x < P.hmax)) ? gy.x : 0.0f, ((iy.y > 0.0f) && (iy.y < P.hmax)) ? gy.y : 0.0f);
 #pragma unroll
   for (int f = 0; f < 2; ++f) {
     const int x0 = (int)(f ? fx0.y : fx0.x), y0 = (int)(f ? fy0.y : fy0.x);
     const int dx1 = (x0 + 1 < J.W) ? 4 : 0;
     const int dy1 = (y0 + 1 < J.H) ? J.W * 4 : 0;
     const float* t00 = J.src4[f] + 4 * (y0 * J.W + x0);
-    L.tap[f][0] = MD2_LD4(t00);
-    L.tap[f][1] = MD2_LD4(t00 + dx1);
-    L.tap[f][2] = MD2_LD4(t00 + dy1);
-    L.tap[f][3] = MD2_LD4(t00 + dy1 + dx1);
+    if (ASYNC) {
+      cp_async16(tapdst + (f * 4 + 0) * kLanes, t00);
+      cp_async16(tapdst + (f * 4 + 1) * kLanes, t00 + dx1);
+      cp_async16(tapdst + (f * 4 + 2) * kLanes, t00 + dy1);
+      cp_async16(tapdst + (f * 4 + 3) * kLanes, t00 + dy1 + dx1);
+    } else {
+      F.tap[f][0] = MD2_LD4(t00);
+      F.tap[f][1] = MD2_LD4(t00 + dx1);
+      F.tap[f][2] = MD2_LD4(t00 + dy1);
+      F.tap[f][3] = MD2_LD4(t00 + dy1 + dx1);
+    }
   }
 }
 
+template <class C, bool WITH_ID = true, int ROW_STEP = 1, bool TG_DIRECT = false>
+__device__ __forceinline__ void stage_a_issue2(Lane2<C>& L, const Params& P, const WarpJob& J, int t) {
+  stage_a_issue2<C, WITH_ID, ROW_STEP, TG_DIRECT, false>(L, L.fl, P, J, t);
+}
+
 template <class C, class ST, bool PUBLISH = C::GRAD>
-__device__ __forceinline__ void stage_a_finish2(Lane2<C>& L, const Params& P, const WarpJob& J, int t, const ST& st) {
+__device__ __forceinline__ void stage_a_finish2(Lane2<C>& L, const Flight2& F, const Params& P, const WarpJob& J, int t, const ST& st) {
   const int slot = st.slot(t);
-  const F4 tg4 = L.ctg;
-  const float z = L.cz;
+  const F4 tg4 = F.ctg;
+  const float z = F.cz;
   const bool own = (t >= J.y0) && (t < J.y1) && (L.x >= J.x0) && (L.x < J.x0 + kOwnCols) && L.colok;
   L.tgrg = p2(tg4.x, tg4.y);
   L.tgb = tg4.z;
@@ -273,9 +290,9 @@ __device__ __forceinline__ void stage_a_finish2(Lane2<C>& L, const Params& P, co
   float prb[2];
 #pragma unroll
   for (int f = 0; f < 2; ++f) {
-    const F4 nw = L.tap[f][0], ne = L.tap[f][1], sw = L.tap[f][2], se = L.tap[f][3];
-    const float wx = f ? L.cwx.y : L.cwx.x, wy = f ? L.cwy.y : L.cwy.x;
-    const float gxs = f ? L.cgx.y : L.cgx.x, gys = f ? L.cgy.y : L.cgy.x;
+    const F4 nw = F.tap[f][0], ne = F.tap[f][1], sw = F.tap[f][2], se = F.tap[f][3];
+    const float wx = f ? F.cwx.y : F.cwx.x, wy = f ? F.cwy.y : F.cwy.x;
+    const float gxs = f ? F.cgx.y : F.cgx.x, gys = f ? F.cgy.y : F.cgy.x;
     // channels (r,g) as a pair
     const P2 nw2 = p2(nw.x, nw.y), ne2 = p2(ne.x, ne.y), sw2 = p2(sw.x, sw.y), se2 = p2(se.x, se.y);
     const P2 dn2 = sub2(ne2, nw2), ds2 = sub2(se2, sw2);
@@ -297,13 +314,18 @@ __device__ __forceinline__ void stage_a_finish2(Lane2<C>& L, const Params& P, co
     }
     L.pr[f] = pr2;
     prb[f] = pb;
-    if (PUBLISH) st.at(slot, 1 + 3 * f, C::STASH4) = make_f4(pr2.x, pr2.y, pb, f ? L.cu.y : L.cu.x);
+    if (PUBLISH) st.at(slot, 1 + 3 * f, C::STASH4) = make_f4(pr2.x, pr2.y, pb, f ? F.cu.y : F.cu.x);
     if (C::GRAD) {
-      st.at(slot, 2 + 3 * f, C::STASH4) = make_f4(dxp2.x, dxp2.y, dxb, f ? L.cv.y : L.cv.x);
+      st.at(slot, 2 + 3 * f, C::STASH4) = make_f4(dxp2.x, dxp2.y, dxb, f ? F.cv.y : F.cv.x);
       st.at(slot, 3 + 3 * f, C::STASH4) = make_f4(dyp2.x, dyp2.y, dyb, 0.f);
     }
   }
   L.pr[2] = p2(prb[0], prb[1]);
+}
+
+template <class C, class ST, bool PUBLISH = C::GRAD>
+__device__ __forceinline__ void stage_a_finish2(Lane2<C>& L, const Params& P, const WarpJob& J, int t, const ST& st) {
+  stage_a_finish2<C, ST, PUBLISH>(L, L.fl, P, J, t, st);
 }
 
 // ------------------------------------------------------------------ stage B (see stage_b_divergent)

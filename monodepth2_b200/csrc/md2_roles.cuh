@@ -5,19 +5,24 @@
 // per image row (measured in round 1: a warp alone needs ~3 250 cycles per row for 1 183
 // instructions; the kernel is bound by that latency, not by issue slots or bandwidth).
 //
-// Here the same per-lane arithmetic (md2_core.cuh, unchanged) is split over three warps that work on
-// the SAME band of 32 columns, one image row apart, and hand rows to each other through shared
-// memory:
+// Here the same per-lane arithmetic (md2_core.cuh / md2_pack2.cuh, unchanged) is split over warps that
+// work on the SAME band of 32 columns, a few image rows apart, and hand rows to each other through
+// shared memory:
 //   role A  stage_a_issue + stage_a_finish of row t      (disparity -> depth -> projection -> gather ->
-//           interpolation); publishes the row (target, pred, d pred / d (ix,iy), u, v, z) in a ring
+//           interpolation); publishes the row (target, pred, d pred / d (ix,iy), u, v, z) in a ring.
+//           Rows are independent in this stage, so it is dealt to kRoleAWarps warps round-robin; each of
+//           them issues the gather of its next row, crosses the CTA barrier, and only then interpolates:
+//           the gather latency is covered by the other warps' work.
 //   role B  stage_b of row t-1   (window sums, SSIM + L1, per-pixel minimum / automask, loss, the
 //           SSIM-adjoint coefficients of the winner); reads its own and its neighbours' row from the
-//           ring (no shuffles), publishes coefficients + winner in a second ring
+//           ring (no shuffles), publishes coefficients + winner in a second ring; its streamed inputs
+//           (identity loss, tie-break noise) are loaded two rows ahead
 //   role C  stage_c of row t-2   (3x3 box adjoint, d loss / d pred, grid-sample and projection
 //           adjoints, d loss / d disparity, pose sums)
-// One CTA = one band = 3 warps (2 without gradients), one bar.sync per image row.  Each warp carries
-// only its own role's rolling state, so the kernel fits 4-5 CTAs (12-15 warps) per SM, and the three
-// dependent chains of a row run concurrently on different warps instead of back to back in one.
+// One CTA = one band, one bar.sync per image row.  Each warp carries only its own role's rolling
+// state (126-168 registers instead of 240-255, no spills with 1-3 sources), so 16 warps are resident per
+// SM instead of 8, and the dependent chains of a row run concurrently on different warps instead of back
+// to back in one.
 #pragma once
 
 #include "md2_core.cuh"
@@ -28,6 +33,13 @@ namespace md2 {
 #ifndef MD2_ROLE_MIN_CTAS
 #define MD2_ROLE_MIN_CTAS 4
 #endif
+#ifndef MD2_ROLE_A_WARPS
+#define MD2_ROLE_A_WARPS 2
+#endif
+constexpr int kRoleAWarps = MD2_ROLE_A_WARPS;
+#ifndef MD2_ROLE_MIN_CTAS3
+#define MD2_ROLE_MIN_CTAS3 3      // three and more sources: 168 registers, no spills (4 CTAs: 128 registers, 0.4 KB of spills)
+#endif
 
 // the role kernel keeps the backward box sums of every source count in registers (role C has room)
 template <class C0>
@@ -37,12 +49,18 @@ struct RoleOf : C0 {
 
 template <class C>
 struct RoleCfg {
-  static constexpr int NROLES = C::GRAD ? 3 : 2;
+  static constexpr int NA = kRoleAWarps;                          // warps sharing role A
+  static constexpr int NROLES = NA + (C::GRAD ? 2 : 1);
   static constexpr int THREADS = 32 * NROLES;
   static constexpr int RING = C::GRAD ? 5 : 2;                   // rows in flight: A writes t, B reads t-1, C reads t-4
+  static constexpr int MIN_CTAS = (C::NSRC >= 3 && C::GRAD) ? MD2_ROLE_MIN_CTAS3 : MD2_ROLE_MIN_CTAS;
   static constexpr int NCF4 = (9 * C::NCS + 1 + 3) / 4;          // coefficient sets + winner tag, 16-byte fields
   static constexpr int STASH_F4 = RING * C::STASH4 * 32;
-  static constexpr int SMEM_F4 = STASH_F4 + (C::GRAD ? 2 * NCF4 * 32 : 0);
+  static constexpr int COEF_F4 = C::GRAD ? 2 * NCF4 * 32 : 0;
+  // NA == 1: role A keeps two rows of bilinear taps in flight through cp.async (LDGSTS) into this buffer
+  static constexpr int TAPROW_F4 = C::NSRC * 4 * 32;
+  static constexpr int TAP_F4 = (NA == 1) ? 2 * TAPROW_F4 : 0;
+  static constexpr int SMEM_F4 = STASH_F4 + COEF_F4 + TAP_F4;
 };
 
 template <int NT>
@@ -50,20 +68,122 @@ __device__ __forceinline__ void role_sync() {
   asm volatile("bar.sync 0, %0;" ::"r"(NT) : "memory");
 }
 
-// ---- role A: rows t0 .. t1
+// ---- role A, warp k of NA: rows t0 + k, t0 + k + NA, ...  Row t must be in the ring before the barrier that
+// ends period (t - t0); its gather is issued NA - 1 barriers earlier (NA == 1: in the same period).
+// NA == 1: one warp, two rows in flight.  The gather of row t+1 is issued (cp.async into shared memory: completion is
+// tracked by the async-group counter, so the wait for row t does not also wait for row t+1, which a register
+// destination sharing one scoreboard with it would) before row t is interpolated; the loop is unrolled by two so that
+// the two Flight records alternate without moves.
 template <class C, class ST>
-__device__ __forceinline__ void role_a(const Params& P, const WarpJob& J, int lane, const ST& st, int t0, int t1, int nit) {
+__device__ __forceinline__ void role_a_async(const Params& P, const WarpJob& J, int lane, const ST& st, F4* tapbuf,
+                                             int t0, int t1, int nit) {
+  typedef RoleCfg<C> RC;
   Lane<C> L;
   lane_init(L, P, J, lane);
-#pragma unroll 1
-  for (int i = 0; i < nit; ++i) {
-    const int t = t0 + i;
+  Flight<C> F[2];
+  stage_a_issue<C, false, 0, true, true>(L, F[0], P, J, t0, tapbuf);
+  cp_async_commit();
+  prefetch_row<C, false>(L, J, t0 + 1);
+  auto half = [&](int t, Flight<C>& Fc, Flight<C>& Fn, F4* bufc, F4* bufn) {
+    if (t + 1 <= t1) stage_a_issue<C, false, 0, true, true>(L, Fn, P, J, t + 1, bufn);
+    cp_async_commit();
     if (t <= t1) {
-      stage_a_issue<C, false>(L, P, J, t);
-      stage_a_finish<C, ST, true>(L, P, J, t, st);
+      cp_async_wait<1>();
+#pragma unroll
+      for (int f = 0; f < C::NSRC; ++f)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) Fc.tap[f][q] = bufc[(f * 4 + q) * kLanes];
+      stage_a_finish<C, ST, true>(L, Fc, P, J, t, st);
+      prefetch_row<C, false>(L, J, t + 2);
+    }
+    role_sync<RC::THREADS>();
+  };
+#pragma unroll 1
+  for (int p = 0; p < nit; p += 2) {
+    half(t0 + p, F[0], F[1], tapbuf, tapbuf + RC::TAPROW_F4);
+    if (p + 1 < nit) half(t0 + p + 1, F[1], F[0], tapbuf + RC::TAPROW_F4, tapbuf);
+  }
+  cp_async_wait<0>();
+}
+
+template <class C, class ST>
+__device__ __forceinline__ void role_a(const Params& P, const WarpJob& J, int lane, int k, const ST& st, int t0, int t1, int nit) {
+  constexpr int NA = RoleCfg<C>::NA;
+  Lane<C> L;
+  lane_init(L, P, J, lane);
+  // NA > 1: the disparity taps of a warp's next row are put in flight in its FINISH phase and consumed in its next
+  // ISSUE phase, one barrier later (a load issued in the phase that still consumes the previous instance of the
+  // same load shares its scoreboard with it: measured as long-scoreboard stalls right after the issue)
+  if (NA > 1) {
+    prefetch_row<C, false>(L, J, t0 + k);
+    if (k < NA - 1) {
+      stage_a_issue<C, false, 0, true>(L, P, J, t0 + k);
+      prefetch_row<C, false>(L, J, t0 + k + NA);
+    }
+  }
+#pragma unroll 1
+  for (int p = 0; p < nit; ++p) {
+    const int t = t0 + p;
+    if (NA == 1) {
+      if (t <= t1) {
+        stage_a_issue<C, false, 1, true>(L, P, J, t);
+        stage_a_finish<C, ST, true>(L, P, J, t, st);
+      }
+    } else {
+      int ph = (p - k) % NA;
+      ph = ph < 0 ? ph + NA : ph;
+      if (ph == 0) {
+        if (t <= t1) {
+          stage_a_finish<C, ST, true>(L, P, J, t, st);
+          if (t >= t0 + NA - 1) prefetch_row<C, false>(L, J, t + NA);    // (the prologue did it for the first rows)
+        }
+      } else if (ph == 1) {
+        if (t + NA - 1 <= t1) stage_a_issue<C, false, 0, true>(L, P, J, t + NA - 1);
+      }
     }
     role_sync<RoleCfg<C>::THREADS>();
   }
+}
+
+// ---- role B, one row: reads its own and its neighbours' row t from the ring, stage_b, publishes the
+// coefficients + winner into the 16-byte fields at `o`
+template <class C, class ST>
+__device__ __forceinline__ void b_step(Lane<C>& L, const Params& P, const WarpJob& J, int lane, const ST& st, F4* o,
+                                       int t, int ol, int orr) {
+  typedef RoleCfg<C> RC;
+  const int slot = st.slot(t);
+  Xchg1<C> lf, rt;
+  {
+    const F4* p = &st.at(slot, 0, C::STASH4);
+    const F4 c = p[0], l = p[ol], r = p[orr];
+    L.tg[0] = c.x; L.tg[1] = c.y; L.tg[2] = c.z;
+    lf.tg[0] = l.x; lf.tg[1] = l.y; lf.tg[2] = l.z;
+    rt.tg[0] = r.x; rt.tg[1] = r.y; rt.tg[2] = r.z;
+  }
+#pragma unroll
+  for (int f = 0; f < C::NSRC; ++f) {
+    const F4* p = &st.at(slot, 1 + 3 * f, C::STASH4);
+    const F4 c = p[0], l = p[ol], r = p[orr];
+    L.pr[f][0] = c.x; L.pr[f][1] = c.y; L.pr[f][2] = c.z;
+    lf.pr[f][0] = l.x; lf.pr[f][1] = l.y; lf.pr[f][2] = l.z;
+    rt.pr[f][0] = r.x; rt.pr[f][1] = r.y; rt.pr[f][2] = r.z;
+  }
+  stage_b(L, P, J, t, lane, lf, rt);
+  if (C::GRAD) {
+    float v[4 * RC::NCF4];
+#pragma unroll
+    for (int k = 0; k < 4 * RC::NCF4; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int n = 0; n < C::NCS; ++n)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) v[n * 9 + k] = L.coef[n][k];
+    v[9 * C::NCS] = __int_as_float(L.tag);
+#pragma unroll
+    for (int k = 0; k < RC::NCF4; ++k) o[k * 32] = make_f4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  }
+  // identity loss / noise of the NEXT row are put in flight after this row's values have been consumed: a load
+  // issued before their last use would share its scoreboard with them
+  load_identity_row(L, J, t + 1);
 }
 
 // ---- role B: window rows; row t of the ring was written one step earlier
@@ -75,86 +195,47 @@ __device__ __forceinline__ void role_b(const Params& P, const WarpJob& J, int la
   lane_init(L, P, J, lane);
   // neighbour offsets in the ring (the edge lanes read themselves: their windows are never used)
   const int ol = (lane > 0) ? -1 : 0, orr = (lane < 31) ? 1 : 0;
+  load_identity_row(L, J, t0);
 #pragma unroll 1
   for (int i = 0; i < nit; ++i) {
     const int t = t0 + i - 1;
-    if (i >= 1 && t <= t1) {
-      load_identity_row(L, J, t);
-      const int slot = st.slot(t);
-      Xchg1<C> lf, rt;
-      {
-        const F4* p = &st.at(slot, 0, C::STASH4);
-        const F4 c = p[0], l = p[ol], r = p[orr];
-        L.tg[0] = c.x; L.tg[1] = c.y; L.tg[2] = c.z;
-        lf.tg[0] = l.x; lf.tg[1] = l.y; lf.tg[2] = l.z;
-        rt.tg[0] = r.x; rt.tg[1] = r.y; rt.tg[2] = r.z;
-      }
-#pragma unroll
-      for (int f = 0; f < C::NSRC; ++f) {
-        const F4* p = &st.at(slot, 1 + 3 * f, C::STASH4);
-        const F4 c = p[0], l = p[ol], r = p[orr];
-        L.pr[f][0] = c.x; L.pr[f][1] = c.y; L.pr[f][2] = c.z;
-        lf.pr[f][0] = l.x; lf.pr[f][1] = l.y; lf.pr[f][2] = l.z;
-        rt.pr[f][0] = r.x; rt.pr[f][1] = r.y; rt.pr[f][2] = r.z;
-      }
-      stage_b(L, P, J, t, lane, lf, rt);
-      if (C::GRAD) {
-        float v[4 * RC::NCF4];
-#pragma unroll
-        for (int k = 0; k < 4 * RC::NCF4; ++k) v[k] = 0.f;
-#pragma unroll
-        for (int n = 0; n < C::NCS; ++n)
-#pragma unroll
-          for (int k = 0; k < 9; ++k) v[n * 9 + k] = L.coef[n][k];
-        v[9 * C::NCS] = __int_as_float(L.tag);
-        F4* o = cring + (t & 1) * RC::NCF4 * 32;
-#pragma unroll
-        for (int k = 0; k < RC::NCF4; ++k) o[k * 32] = make_f4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-      }
-    }
+    if (i >= 1 && t <= t1) b_step(L, P, J, lane, st, cring + (t & 1) * RC::NCF4 * 32, t, ol, orr);
     role_sync<RC::THREADS>();
   }
   const float ls = warp_sum(L.loss);
   if (lane == 0) atomicAdd(&P.acc[acc_photo(J.s)], (double)ls);
 }
 
-// ---- role C: adjoint rows; the coefficients of step t were written one step earlier
+// ---- role C, one row: reads its own and its neighbours' coefficients of step t from `q`, stage_c
 template <class C, class ST>
-__device__ __forceinline__ void role_c(const Params& P, const WarpJob& J, int lane, const ST& st, const F4* cring,
-                                       int t0, int t1, int nit) {
+__device__ __forceinline__ void c_step(Lane<C>& L, const Params& P, const WarpJob& J, int lane, const ST& st, const F4* q,
+                                       int t, int ol, int orr) {
   typedef RoleCfg<C> RC;
-  Lane<C> L;
-  lane_init(L, P, J, lane);
-  const int ol = (lane > 0) ? -1 : 0, orr = (lane < 31) ? 1 : 0;
-#pragma unroll 1
-  for (int i = 0; i < nit; ++i) {
-    const int t = t0 + i - 2;
-    if (i >= 2) {
-      const F4* q = cring + (t & 1) * RC::NCF4 * 32;
-      float vc[4 * RC::NCF4], vl[4 * RC::NCF4], vr[4 * RC::NCF4];
+  float vc[4 * RC::NCF4], vl[4 * RC::NCF4], vr[4 * RC::NCF4];
 #pragma unroll
-      for (int k = 0; k < RC::NCF4; ++k) {
-        const F4 c = q[k * 32], l = q[k * 32 + ol], r = q[k * 32 + orr];
-        vc[4 * k] = c.x; vc[4 * k + 1] = c.y; vc[4 * k + 2] = c.z; vc[4 * k + 3] = c.w;
-        vl[4 * k] = l.x; vl[4 * k + 1] = l.y; vl[4 * k + 2] = l.z; vl[4 * k + 3] = l.w;
-        vr[4 * k] = r.x; vr[4 * k + 1] = r.y; vr[4 * k + 2] = r.z; vr[4 * k + 3] = r.w;
-      }
-      Xchg2<C> lf, rt;
-#pragma unroll
-      for (int n = 0; n < C::NCS; ++n)
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          L.coef[n][k] = vc[n * 9 + k];
-          lf.coef[n][k] = vl[n * 9 + k];
-          rt.coef[n][k] = vr[n * 9 + k];
-        }
-      L.tag = __float_as_int(vc[9 * C::NCS]);
-      lf.tag = __float_as_int(vl[9 * C::NCS]);
-      rt.tag = __float_as_int(vr[9 * C::NCS]);
-      stage_c(L, P, J, t, lane, lf, rt, st);
-    }
-    role_sync<RC::THREADS>();
+  for (int k = 0; k < RC::NCF4; ++k) {
+    const F4 c = q[k * 32], l = q[k * 32 + ol], r = q[k * 32 + orr];
+    vc[4 * k] = c.x; vc[4 * k + 1] = c.y; vc[4 * k + 2] = c.z; vc[4 * k + 3] = c.w;
+    vl[4 * k] = l.x; vl[4 * k + 1] = l.y; vl[4 * k + 2] = l.z; vl[4 * k + 3] = l.w;
+    vr[4 * k] = r.x; vr[4 * k + 1] = r.y; vr[4 * k + 2] = r.z; vr[4 * k + 3] = r.w;
   }
+  Xchg2<C> lf, rt;
+#pragma unroll
+  for (int n = 0; n < C::NCS; ++n)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      L.coef[n][k] = vc[n * 9 + k];
+      lf.coef[n][k] = vl[n * 9 + k];
+      rt.coef[n][k] = vr[n * 9 + k];
+    }
+  L.tag = __float_as_int(vc[9 * C::NCS]);
+  lf.tag = __float_as_int(vl[9 * C::NCS]);
+  rt.tag = __float_as_int(vr[9 * C::NCS]);
+  stage_c(L, P, J, t, lane, lf, rt, st);
+}
+
+template <class C>
+__device__ __forceinline__ void c_reduce(const Lane<C>& L, const Params& P, const WarpJob& J, int lane) {
 #pragma unroll
   for (int f = 0; f < C::NSRC; ++f) {
     if (!P.pose_grad[f]) continue;
@@ -168,24 +249,120 @@ __device__ __forceinline__ void role_c(const Params& P, const WarpJob& J, int la
   }
 }
 
+// ---- role C: adjoint rows; the coefficients of step t were written one step earlier
+template <class C, class ST>
+__device__ __forceinline__ void role_c(const Params& P, const WarpJob& J, int lane, const ST& st, const F4* cring,
+                                       int t0, int t1, int nit) {
+  typedef RoleCfg<C> RC;
+  Lane<C> L;
+  lane_init(L, P, J, lane);
+  const int ol = (lane > 0) ? -1 : 0, orr = (lane < 31) ? 1 : 0;
+#pragma unroll 1
+  for (int i = 0; i < nit; ++i) {
+    const int t = t0 + i - 2;
+    if (i >= 2) c_step(L, P, J, lane, st, cring + (t & 1) * RC::NCF4 * 32, t, ol, orr);
+    role_sync<RC::THREADS>();
+  }
+  c_reduce(L, P, J, lane);
+}
+
 // ------------------------------------------------------------------ packed-fp32 roles (two sources, per-pixel minimum)
 // Same three roles over the f32x2 stage functions of md2_pack2.cuh (FFMA2 / FADD2 / FMUL2): the scalar FP32
 // instructions issue at one per two cycles per scheduler on this part, and role B is the longest of the three
 // (494 instructions per row, 312 of them on the fma pipe); packed over the two sources it comes down to the size
 // of the other two.
 template <class C, class ST>
-__device__ __forceinline__ void role_a2(const Params& P, const WarpJob& J, int lane, const ST& st, int t0, int t1, int nit) {
+__device__ __forceinline__ void role_a2_async(const Params& P, const WarpJob& J, int lane, const ST& st, F4* tapbuf,
+                                              int t0, int t1, int nit) {
+  typedef RoleCfg<C> RC;
   Lane2<C> L;
   lane_init2(L, P, J, lane);
-#pragma unroll 1
-  for (int i = 0; i < nit; ++i) {
-    const int t = t0 + i;
+  Flight2 F[2];
+  stage_a_issue2<C, false, 0, true, true>(L, F[0], P, J, t0, tapbuf);
+  cp_async_commit();
+  prefetch_row2<C, false>(L, J, t0 + 1);
+  auto half = [&](int t, Flight2& Fc, Flight2& Fn, F4* bufc, F4* bufn) {
+    if (t + 1 <= t1) stage_a_issue2<C, false, 0, true, true>(L, Fn, P, J, t + 1, bufn);
+    cp_async_commit();
     if (t <= t1) {
-      stage_a_issue2<C, false>(L, P, J, t);
-      stage_a_finish2<C, ST, true>(L, P, J, t, st);
+      cp_async_wait<1>();
+#pragma unroll
+      for (int f = 0; f < 2; ++f)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) Fc.tap[f][q] = bufc[(f * 4 + q) * kLanes];
+      stage_a_finish2<C, ST, true>(L, Fc, P, J, t, st);
+      prefetch_row2<C, false>(L, J, t + 2);
+    }
+    role_sync<RC::THREADS>();
+  };
+#pragma unroll 1
+  for (int p = 0; p < nit; p += 2) {
+    half(t0 + p, F[0], F[1], tapbuf, tapbuf + RC::TAPROW_F4);
+    if (p + 1 < nit) half(t0 + p + 1, F[1], F[0], tapbuf + RC::TAPROW_F4, tapbuf);
+  }
+  cp_async_wait<0>();
+}
+
+template <class C, class ST>
+__device__ __forceinline__ void role_a2(const Params& P, const WarpJob& J, int lane, int k, const ST& st, int t0, int t1, int nit) {
+  constexpr int NA = RoleCfg<C>::NA;
+  Lane2<C> L;
+  lane_init2(L, P, J, lane);
+  if (NA > 1) {
+    prefetch_row2<C, false>(L, J, t0 + k);
+    if (k < NA - 1) {
+      stage_a_issue2<C, false, 0, true>(L, P, J, t0 + k);
+      prefetch_row2<C, false>(L, J, t0 + k + NA);
+    }
+  }
+#pragma unroll 1
+  for (int p = 0; p < nit; ++p) {
+    const int t = t0 + p;
+    if (NA == 1) {
+      if (t <= t1) {
+        stage_a_issue2<C, false, 1, true>(L, P, J, t);
+        stage_a_finish2<C, ST, true>(L, P, J, t, st);
+      }
+    } else {
+      int ph = (p - k) % NA;
+      ph = ph < 0 ? ph + NA : ph;
+      if (ph == 0) {
+        if (t <= t1) {
+          stage_a_finish2<C, ST, true>(L, P, J, t, st);
+          if (t >= t0 + NA - 1) prefetch_row2<C, false>(L, J, t + NA);
+        }
+      } else if (ph == 1) {
+        if (t + NA - 1 <= t1) stage_a_issue2<C, false, 0, true>(L, P, J, t + NA - 1);
+      }
     }
     role_sync<RoleCfg<C>::THREADS>();
   }
+}
+
+template <class C, class ST>
+__device__ __forceinline__ void b_step2(Lane2<C>& L, const Params& P, const WarpJob& J, int lane, const ST& st, F4* o,
+                                        int t, int ol, int orr) {
+  const int slot = st.slot(t);
+  Xchg1P<C> lf, rt;
+  const F4* p0 = &st.at(slot, 0, C::STASH4);
+  const F4* p1 = &st.at(slot, 1, C::STASH4);
+  const F4* p2_ = &st.at(slot, 4, C::STASH4);
+  const F4 tc = p0[0], tl = p0[ol], tr = p0[orr];
+  const F4 ac = p1[0], al = p1[ol], ar = p1[orr];          // source 0: pred (r,g,b), u
+  const F4 bc_ = p2_[0], bl = p2_[ol], br = p2_[orr];      // source 1
+  L.tgrg = p2(tc.x, tc.y); L.tgb = tc.z;
+  lf.tgrg = p2(tl.x, tl.y); lf.tgb = tl.z;
+  rt.tgrg = p2(tr.x, tr.y); rt.tgb = tr.z;
+  L.pr[0] = p2(ac.x, ac.y); L.pr[1] = p2(bc_.x, bc_.y); L.pr[2] = p2(ac.z, bc_.z);
+  lf.pr[0] = p2(al.x, al.y); lf.pr[1] = p2(bl.x, bl.y); lf.pr[2] = p2(al.z, bl.z);
+  rt.pr[0] = p2(ar.x, ar.y); rt.pr[1] = p2(br.x, br.y); rt.pr[2] = p2(ar.z, br.z);
+  stage_b2(L, P, J, t, lane, lf, rt);
+  if (C::GRAD) {
+    o[0] = make_f4(L.cf[0].x, L.cf[0].y, L.cf[1].x, L.cf[1].y);
+    o[32] = make_f4(L.cf[2].x, L.cf[2].y, L.cfb[0], L.cfb[1]);
+    o[64] = make_f4(L.cfb[2], __int_as_float(L.tag), 0.f, 0.f);
+  }
+  load_identity_row2(L, J, t + 1);
 }
 
 template <class C, class ST>
@@ -195,33 +372,11 @@ __device__ __forceinline__ void role_b2(const Params& P, const WarpJob& J, int l
   Lane2<C> L;
   lane_init2(L, P, J, lane);
   const int ol = (lane > 0) ? -1 : 0, orr = (lane < 31) ? 1 : 0;
+  load_identity_row2(L, J, t0);
 #pragma unroll 1
   for (int i = 0; i < nit; ++i) {
     const int t = t0 + i - 1;
-    if (i >= 1 && t <= t1) {
-      load_identity_row2(L, J, t);
-      const int slot = st.slot(t);
-      Xchg1P<C> lf, rt;
-      const F4* p0 = &st.at(slot, 0, C::STASH4);
-      const F4* p1 = &st.at(slot, 1, C::STASH4);
-      const F4* p2_ = &st.at(slot, 4, C::STASH4);
-      const F4 tc = p0[0], tl = p0[ol], tr = p0[orr];
-      const F4 ac = p1[0], al = p1[ol], ar = p1[orr];          // source 0: pred (r,g,b), u
-      const F4 bc_ = p2_[0], bl = p2_[ol], br = p2_[orr];      // source 1
-      L.tgrg = p2(tc.x, tc.y); L.tgb = tc.z;
-      lf.tgrg = p2(tl.x, tl.y); lf.tgb = tl.z;
-      rt.tgrg = p2(tr.x, tr.y); rt.tgb = tr.z;
-      L.pr[0] = p2(ac.x, ac.y); L.pr[1] = p2(bc_.x, bc_.y); L.pr[2] = p2(ac.z, bc_.z);
-      lf.pr[0] = p2(al.x, al.y); lf.pr[1] = p2(bl.x, bl.y); lf.pr[2] = p2(al.z, bl.z);
-      rt.pr[0] = p2(ar.x, ar.y); rt.pr[1] = p2(br.x, br.y); rt.pr[2] = p2(ar.z, br.z);
-      stage_b2(L, P, J, t, lane, lf, rt);
-      if (C::GRAD) {
-        F4* o = cring + (t & 1) * RC::NCF4 * 32;
-        o[0] = make_f4(L.cf[0].x, L.cf[0].y, L.cf[1].x, L.cf[1].y);
-        o[32] = make_f4(L.cf[2].x, L.cf[2].y, L.cfb[0], L.cfb[1]);
-        o[64] = make_f4(L.cfb[2], __int_as_float(L.tag), 0.f, 0.f);
-      }
-    }
+    if (i >= 1 && t <= t1) b_step2(L, P, J, lane, st, cring + (t & 1) * RC::NCF4 * 32, t, ol, orr);
     role_sync<RC::THREADS>();
   }
   const float ls = warp_sum(L.loss);
@@ -229,30 +384,22 @@ __device__ __forceinline__ void role_b2(const Params& P, const WarpJob& J, int l
 }
 
 template <class C, class ST>
-__device__ __forceinline__ void role_c2(const Params& P, const WarpJob& J, int lane, const ST& st, const F4* cring,
-                                        int t0, int t1, int nit) {
-  typedef RoleCfg<C> RC;
-  Lane2<C> L;
-  lane_init2(L, P, J, lane);
-  const int ol = (lane > 0) ? -1 : 0, orr = (lane < 31) ? 1 : 0;
+__device__ __forceinline__ void c_step2(Lane2<C>& L, const Params& P, const WarpJob& J, int lane, const ST& st, const F4* q,
+                                        int t, int ol, int orr) {
   auto unpack = [](const F4& a, const F4& b, const F4& c, P2* cf, float* cfb, int& tag) {
     cf[0] = p2(a.x, a.y); cf[1] = p2(a.z, a.w); cf[2] = p2(b.x, b.y);
     cfb[0] = b.z; cfb[1] = b.w; cfb[2] = c.x;
     tag = __float_as_int(c.y);
   };
-#pragma unroll 1
-  for (int i = 0; i < nit; ++i) {
-    const int t = t0 + i - 2;
-    if (i >= 2) {
-      const F4* q = cring + (t & 1) * RC::NCF4 * 32;
-      Xchg2P<C> lf, rt;
-      unpack(q[0], q[32], q[64], L.cf, L.cfb, L.tag);
-      unpack(q[ol], q[32 + ol], q[64 + ol], lf.cf, lf.cfb, lf.tag);
-      unpack(q[orr], q[32 + orr], q[64 + orr], rt.cf, rt.cfb, rt.tag);
-      stage_c2(L, P, J, t, lane, lf, rt, st);
-    }
-    role_sync<RC::THREADS>();
-  }
+  Xchg2P<C> lf, rt;
+  unpack(q[0], q[32], q[64], L.cf, L.cfb, L.tag);
+  unpack(q[ol], q[32 + ol], q[64 + ol], lf.cf, lf.cfb, lf.tag);
+  unpack(q[orr], q[32 + orr], q[64 + orr], rt.cf, rt.cfb, rt.tag);
+  stage_c2(L, P, J, t, lane, lf, rt, st);
+}
+
+template <class C>
+__device__ __forceinline__ void c_reduce2(const Lane2<C>& L, const Params& P, const WarpJob& J, int lane) {
 #pragma unroll
   for (int f = 0; f < 2; ++f) {
     if (!P.pose_grad[f]) continue;
@@ -266,12 +413,31 @@ __device__ __forceinline__ void role_c2(const Params& P, const WarpJob& J, int l
   }
 }
 
+template <class C, class ST>
+__device__ __forceinline__ void role_c2(const Params& P, const WarpJob& J, int lane, const ST& st, const F4* cring,
+                                        int t0, int t1, int nit) {
+  typedef RoleCfg<C> RC;
+  Lane2<C> L;
+  lane_init2(L, P, J, lane);
+  const int ol = (lane > 0) ? -1 : 0, orr = (lane < 31) ? 1 : 0;
+#pragma unroll 1
+  for (int i = 0; i < nit; ++i) {
+    const int t = t0 + i - 2;
+    if (i >= 2) c_step2(L, P, J, lane, st, cring + (t & 1) * RC::NCF4 * 32, t, ol, orr);
+    role_sync<RC::THREADS>();
+  }
+  c_reduce2(L, P, J, lane);
+}
+
 template <class C, bool PACKED>
-__global__ void __launch_bounds__(RoleCfg<C>::THREADS, MD2_ROLE_MIN_CTAS) md2_march_roles(Params P) {
+__global__ void __launch_bounds__(RoleCfg<C>::THREADS, RoleCfg<C>::MIN_CTAS) md2_march_roles(Params P) {
   static_assert(!PACKED || (C::NSRC == 2 && !C::AVG), "packed form: two sources, per-pixel minimum");
   typedef RoleCfg<C> RC;
   extern __shared__ float4 smem[];
   const int lane = threadIdx.x & 31;
+  // (measured: rotating the warp -> role map from CTA to CTA changes nothing; the hardware does not pin a CTA's
+  // warp i to scheduler i % 4 in a way that would pile one role onto one scheduler: per-scheduler issue counts of
+  // one launch are within +-10 %)
   const int role = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
   // same job order as md2_march (sample-major, segment, scale, band; last sample first), one job per CTA
   const int job = blockIdx.x;
@@ -290,16 +456,189 @@ __global__ void __launch_bounds__(RoleCfg<C>::THREADS, MD2_ROLE_MIN_CTAS) md2_ma
   st.bring = nullptr;
   st.stride = 32;
   F4* cring = smem + RC::STASH_F4 + lane;
+  F4* tapbuf = smem + RC::STASH_F4 + RC::COEF_F4 + lane;
   const int t0 = J.y0 - 2, t1 = J.y1 + 1;
-  const int nit = (t1 - t0 + 1) + (RC::NROLES - 1);
+  const int nit = (t1 - t0 + 1) + (C::GRAD ? 2 : 1);
+  if constexpr (RC::NA == 1) {
+    if (role == 0) {
+      if constexpr (PACKED) role_a2_async<C>(P, J, lane, st, tapbuf, t0, t1, nit);
+      else role_a_async<C>(P, J, lane, st, tapbuf, t0, t1, nit);
+      return;
+    }
+  }
   if constexpr (PACKED) {
-    if (role == 0) role_a2<C>(P, J, lane, st, t0, t1, nit);
-    else if (role == 1) role_b2<C>(P, J, lane, st, cring, t0, t1, nit);
+    if (role < RC::NA) role_a2<C>(P, J, lane, role, st, t0, t1, nit);
+    else if (role == RC::NA) role_b2<C>(P, J, lane, st, cring, t0, t1, nit);
     else if (C::GRAD) role_c2<C>(P, J, lane, st, cring, t0, t1, nit);
   } else {
-    if (role == 0) role_a<C>(P, J, lane, st, t0, t1, nit);
-    else if (role == 1) role_b<C>(P, J, lane, st, cring, t0, t1, nit);
+    if (role < RC::NA) role_a<C>(P, J, lane, role, st, t0, t1, nit);
+    else if (role == RC::NA) role_b<C>(P, J, lane, st, cring, t0, t1, nit);
     else if (C::GRAD) role_c<C>(P, J, lane, st, cring, t0, t1, nit);
+  }
+}
+
+// ------------------------------------------------------------------ free-running roles
+// md2_march_roles above runs its warps in lock step (one bar.sync per image row): every warp waits for the
+// slowest role of every row, measured at ~35 % of every warp's time.  Here the same roles are decoupled: the rings
+// are deeper, and a warp waits only for the row it needs (a progress counter per role in shared memory, written by
+// lane 0 after a warp-level fence, polled by lane 0 of the consumer) or for the ring slot it wants to overwrite.
+//   A_k  rows t0 + k, t0 + k + NA, ...   issue + finish back to back (its gather latency is covered by the other
+//        warps); before writing ring slot(t): role C must be done with row t - RING (C reads row tC - 2)
+//   B    rows t0 .. t1 in order          needs row t from A_(t mod NA); coefficient slot(t): C done with t - CRING
+//   C    rows t0 .. t1 in order          needs the coefficients of row t from B (row t - 2 of the ring is then there)
+#ifndef MD2_FLOW_RING
+#define MD2_FLOW_RING 6
+#endif
+#ifndef MD2_FLOW_CRING
+#define MD2_FLOW_CRING 4
+#endif
+template <class C>
+struct FlowCfg {
+  static constexpr int NA = kRoleAWarps;
+  static constexpr int NROLES = NA + (C::GRAD ? 2 : 1);
+  static constexpr int THREADS = 32 * NROLES;
+  static constexpr int RING = MD2_FLOW_RING;
+  static constexpr int CRING = MD2_FLOW_CRING;
+  static constexpr int MIN_CTAS = RoleCfg<C>::MIN_CTAS;
+  static constexpr int NCF4 = RoleCfg<C>::NCF4;
+  static constexpr int STASH_F4 = RING * C::STASH4 * 32;
+  static constexpr int COEF_F4 = C::GRAD ? CRING * NCF4 * 32 : 0;
+  static constexpr int SMEM_F4 = STASH_F4 + COEF_F4 + 2;         // + 8 progress counters
+};
+
+struct Flow {
+  volatile int* prog;       // [0 .. NA-1]: last row role A_k published, [4]: role B, [5]: role C
+  __device__ __forceinline__ void wait_ge(int which, int v, int lane) const {
+    if (lane == 0) {
+      while (prog[which] < v) { }
+      __threadfence_block();
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ void publish(int which, int v, int lane) const {
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      prog[which] = v;
+    }
+  }
+};
+
+template <class C, bool PACKED>
+__global__ void __launch_bounds__(FlowCfg<C>::THREADS, FlowCfg<C>::MIN_CTAS) md2_march_flow(Params P) {
+  static_assert(!PACKED || (C::NSRC == 2 && !C::AVG), "packed form: two sources, per-pixel minimum");
+  typedef FlowCfg<C> FC;
+  constexpr int NA = FC::NA;
+  extern __shared__ float4 smem[];
+  const int lane = threadIdx.x & 31;
+  const int role = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
+  const int job = blockIdx.x;
+  const int per_seg = P.S * P.nband;
+  const int per_b = P.nseg * per_seg;
+  const int jb = P.B - 1 - job / per_b;
+  const int r = job - (job / per_b) * per_b;
+  const int seg = r / per_seg;
+  const int r2 = r - seg * per_seg;
+  const int js = r2 / P.nband;
+  const int jy0 = seg * P.seg_rows;
+  const WarpJob J = make_job(P, js, jb, (r2 - js * P.nband) * kOwnCols, jy0, min(jy0 + P.seg_rows, P.H));
+
+  StashT<FC::RING> st;
+  st.base = smem + lane;
+  st.bring = nullptr;
+  st.stride = 32;
+  F4* cring = smem + FC::STASH_F4 + lane;
+  Flow fl;
+  fl.prog = reinterpret_cast<volatile int*>(smem + FC::STASH_F4 + FC::COEF_F4);
+  const int t0 = J.y0 - 2, t1 = J.y1 + 1;
+  if (threadIdx.x < 8) fl.prog[threadIdx.x] = t0 - 1;
+  __syncthreads();
+  const int ol = (lane > 0) ? -1 : 0, orr = (lane < 31) ? 1 : 0;
+  // what the writer of ring slot(t) waits for: the last reader of row t - RING
+  constexpr int kLast = C::GRAD ? 5 : 4;               // counter of the last role of the chain
+  constexpr int kLag = C::GRAD ? 2 : 0;                // that role reads ring row (its t) - kLag
+
+  if (role < NA) {
+    const int k = role;
+    if constexpr (PACKED) {
+      Lane2<C> L;
+      lane_init2(L, P, J, lane);
+      prefetch_row2<C, false>(L, J, t0 + k);
+#pragma unroll 1
+      for (int t = t0 + k; t <= t1; t += NA) {
+        stage_a_issue2<C, false, NA, true>(L, P, J, t);
+        fl.wait_ge(kLast, t - FC::RING + kLag, lane);
+        stage_a_finish2<C, decltype(st), true>(L, P, J, t, st);
+        fl.publish(k, t, lane);
+      }
+    } else {
+      Lane<C> L;
+      lane_init(L, P, J, lane);
+      prefetch_row<C, false>(L, J, t0 + k);
+#pragma unroll 1
+      for (int t = t0 + k; t <= t1; t += NA) {
+        stage_a_issue<C, false, NA, true>(L, P, J, t);
+        fl.wait_ge(kLast, t - FC::RING + kLag, lane);
+        stage_a_finish<C, decltype(st), true>(L, P, J, t, st);
+        fl.publish(k, t, lane);
+      }
+    }
+  } else if (role == NA) {
+    if constexpr (PACKED) {
+      Lane2<C> L;
+      lane_init2(L, P, J, lane);
+      load_identity_row2(L, J, t0);
+#pragma unroll 1
+      for (int t = t0; t <= t1; ++t) {
+        int ka = (t - t0) % NA;
+        fl.wait_ge(ka, t, lane);
+        if (C::GRAD) fl.wait_ge(5, t - FC::CRING, lane);
+        int cs = (t - t0) % FC::CRING;
+        b_step2(L, P, J, lane, st, cring + cs * FC::NCF4 * 32, t, ol, orr);
+        fl.publish(4, t, lane);
+      }
+      const float ls = warp_sum(L.loss);
+      if (lane == 0) atomicAdd(&P.acc[acc_photo(J.s)], (double)ls);
+    } else {
+      Lane<C> L;
+      lane_init(L, P, J, lane);
+      load_identity_row(L, J, t0);
+#pragma unroll 1
+      for (int t = t0; t <= t1; ++t) {
+        int ka = (t - t0) % NA;
+        fl.wait_ge(ka, t, lane);
+        if (C::GRAD) fl.wait_ge(5, t - FC::CRING, lane);
+        int cs = (t - t0) % FC::CRING;
+        b_step(L, P, J, lane, st, cring + cs * FC::NCF4 * 32, t, ol, orr);
+        fl.publish(4, t, lane);
+      }
+      const float ls = warp_sum(L.loss);
+      if (lane == 0) atomicAdd(&P.acc[acc_photo(J.s)], (double)ls);
+    }
+  } else if (C::GRAD) {
+    if constexpr (PACKED) {
+      Lane2<C> L;
+      lane_init2(L, P, J, lane);
+#pragma unroll 1
+      for (int t = t0; t <= t1; ++t) {
+        fl.wait_ge(4, t, lane);
+        int cs = (t - t0) % FC::CRING;
+        c_step2(L, P, J, lane, st, cring + cs * FC::NCF4 * 32, t, ol, orr);
+        fl.publish(5, t, lane);
+      }
+      c_reduce2(L, P, J, lane);
+    } else {
+      Lane<C> L;
+      lane_init(L, P, J, lane);
+#pragma unroll 1
+      for (int t = t0; t <= t1; ++t) {
+        fl.wait_ge(4, t, lane);
+        int cs = (t - t0) % FC::CRING;
+        c_step(L, P, J, lane, st, cring + cs * FC::NCF4 * 32, t, ol, orr);
+        fl.publish(5, t, lane);
+      }
+      c_reduce(L, P, J, lane);
+    }
   }
 }
 

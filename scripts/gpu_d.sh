@@ -1,0 +1,13 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+L=monodepth2_b200/lib
+for v in a2c4 a1c5; do
+  MD2_LIB_PATH=$L/libmd2loss_$v.so python scripts/time_loss.py 0 30 mono
+  MD2_PACK2=off MD2_LIB_PATH=$L/libmd2loss_$v.so python scripts/time_loss.py 0 30 mono
+  MD2_LIB_PATH=$L/libmd2loss_$v.so python scripts/time_loss.py 0 30 hires
+  MD2_LIB_PATH=$L/libmd2loss_$v.so python scripts/time_loss.py 0 30 stereo
+done 2>&1 | grep -v Warning | tee gpurun_out/d_times.log
+CMD="python scripts/time_loss.py 0 3 mono"
+export MD2_LIB_PATH=$L/libmd2loss_a2c4.so
+$CMD > gpurun_out/d_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:md2_march -s 4 -c 1 -f -o gpurun_out/prof_d_march $CMD > gpurun_out/d_ncu.log 2>&1
+tail -2 gpurun_out/d_ncu.log

