@@ -171,6 +171,12 @@ int md2_pose_to_matrix_backward(const float *grad_T, const float *axisangle, con
                                 int invert, float *grad_axisangle, float *grad_translation,
                                 int batch, void *stream);
 
+/* autograd glue (trainer.py:208, losses["loss"].backward()): dst[i] = src[i] * (*scale) for n_tensors <=
+ * MD2_MAX_SCALE_TENSORS device tensors in one launch; `src`, `dst`, `numel` are HOST arrays, `scale` a device scalar. */
+#define MD2_MAX_SCALE_TENSORS 16
+int md2_scale_tensors(int n_tensors, const float *const *src, float *const *dst, const long long *numel,
+                      const float *scale, void *stream);
+
 /* ---- colour pyramid on the GPU: replaces the per-frame host work of
  * MonoDataset.preprocess, datasets/mono_dataset.py:57,82-86,98-103 - torchvision Resize with
  * Image.ANTIALIAS on PIL images = PIL.Image.resize(size, LANCZOS), scale i built from scale i-1.

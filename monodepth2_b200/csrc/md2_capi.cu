@@ -34,7 +34,6 @@ int md2_loss_workspace_bytes(const md2_problem* p, size_t* bytes) {
   if (!bytes) return MD2_ERR_INVALID_ARGUMENT;
   const int st = md2::validate(p);
   if (st != MD2_OK) return st;
-  if (p->num_src > 3) return MD2_ERR_UNSUPPORTED;
   *bytes = md2::make_layout(p).total;
   return MD2_OK;
 }
@@ -43,7 +42,6 @@ int md2_view_synthesis_loss(const md2_problem* p, const md2_tensors* t, void* wo
                             size_t workspace_bytes, void* stream) {
   int st = md2::validate(p);
   if (st != MD2_OK) return st;
-  if (p->num_src > 3) return MD2_ERR_UNSUPPORTED;
   if (workspace_bytes < md2::make_layout(p).total) return MD2_ERR_WORKSPACE_TOO_SMALL;
   md2::Params P;
   st = md2::fill_params(p, t, workspace, &P);

@@ -107,6 +107,25 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// mbarrier + TMA bulk copy (cp.async.bulk, UBLKCP in SASS): global -> shared, completion by transaction bytes
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+  }
+}
 #endif
 
 #if !defined(__CUDA_ARCH__)
@@ -278,6 +297,9 @@ struct WarpJob {
   float* idsel;
   float* depth;
   float* warped[kMaxSrc];
+  // role-specialised kernel, interior bands: the target texel row is put into the ring by a TMA bulk copy
+  // (field 0 of the slot = 32 consecutive RGBx texels) instead of being loaded and stored by every lane
+  int staged;
 };
 
 MD2_HD void smooth_scalars(const Params& P, int s, int b, float& inv_m, float& dterm);
@@ -307,6 +329,7 @@ MD2_HD WarpJob make_job(const Params& P, int s, int b, int x0, int y0, int y1) {
   }
   J.idsel = P.idsel[s] ? P.idsel[s] + boff : nullptr;
   J.depth = P.depth[s] ? P.depth[s] + boff : nullptr;
+  J.staged = 0;
   return J;
 }
 
@@ -447,7 +470,10 @@ struct StashT {
   F4* base;
   F4* bring;      // ring of 2 rows x NB4 fields (backward box sums), only when Cfg::BSMEM
   int stride;     // threads sharing the ring (lane stride of one field)
+  unsigned long long* tbar;   // WarpJob::staged: one mbarrier per slot, armed by the TMA copy of the target row
+  int t0;                     // first row of the job (the n-th use of a slot completes phase n of its mbarrier)
   MD2_HD int slot(int t) const { return ((t % R) + R) % R; }
+  MD2_HD unsigned parity(int t) const { return (unsigned)(((t - t0) / R) & 1); }
   MD2_HD F4& at(int slot, int field, int nfields) const { return base[(slot * nfields + field) * stride]; }
   MD2_HD F4& b(int slot, int field, int nfields) const { return bring[(slot * nfields + field) * stride]; }
 };
@@ -571,8 +597,10 @@ template <class C, bool WITH_ID = true, int ROW_STEP = 1, bool TG_DIRECT = false
 MD2_HD void stage_a_issue(Lane<C>& L, Flight<C>& F, const Params& P, const WarpJob& J, int t, F4* tapdst = nullptr) {
   const int tr = reflect_clamp(t, J.H);
   MD2_CHK(tr * J.W + L.xi, J.plane);
-  if (TG_DIRECT) F.ctg = MD2_LDS4(J.tgt4 + 4 * (tr * J.W + L.xi));
-  else F.ctg = L.ntg;
+  if (TG_DIRECT) {
+    if (J.staged) F.ctg = make_f4(0.f, 0.f, 0.f, 0.f);      // the row goes into the ring by TMA
+    else F.ctg = MD2_LDS4(J.tgt4 + 4 * (tr * J.W + L.xi));
+  } else F.ctg = L.ntg;
   float D;
   if (J.s == 0) {
     D = L.nd[0];
@@ -670,7 +698,8 @@ MD2_HD void stage_a_finish(Lane<C>& L, const Flight<C>& F, const Params& P, cons
   L.tg[0] = tg4.x; L.tg[1] = tg4.y; L.tg[2] = tg4.z;
   if (own) MD2_CHK(t * J.W + L.xi, J.plane);
   if (J.depth && own) J.depth[t * J.W + L.xi] = z;
-  if (PUBLISH) st.at(slot, 0, C::STASH4) = make_f4(tg4.x, tg4.y, tg4.z, z);
+  // WarpJob::staged: field 0 (the target texels) is written by the TMA copy of the row and by nobody else
+  if (PUBLISH && !J.staged) st.at(slot, 0, C::STASH4) = make_f4(tg4.x, tg4.y, tg4.z, 0.f);
 #pragma unroll
   for (int f = 0; f < C::NSRC; ++f) {
     const F4 nw = F.tap[f][0], ne = F.tap[f][1], sw = F.tap[f][2], se = F.tap[f][3];
@@ -698,7 +727,7 @@ MD2_HD void stage_a_finish(Lane<C>& L, const Flight<C>& F, const Params& P, cons
     if (PUBLISH) st.at(slot, 1 + 3 * f, C::STASH4) = make_f4(pr[0], pr[1], pr[2], F.cu[f]);
     if (C::GRAD) {
       st.at(slot, 2 + 3 * f, C::STASH4) = make_f4(dxp[0], dxp[1], dxp[2], F.cv[f]);
-      st.at(slot, 3 + 3 * f, C::STASH4) = make_f4(dyp[0], dyp[1], dyp[2], 0.f);
+      st.at(slot, 3 + 3 * f, C::STASH4) = make_f4(dyp[0], dyp[1], dyp[2], f == 0 ? z : 0.f);   // depth rides with source 0
     }
   }
 }
@@ -1047,7 +1076,7 @@ MD2_HD void stage_c_divergent(Lane<C>& L, const Params& P, const WarpJob& J, int
     const int slot = st.slot(yp);
     const F4 s0 = st.at(slot, 0, C::STASH4);
     const float tg[3] = {s0.x, s0.y, s0.z};
-    const float z = s0.w;
+    const float z = st.at(slot, 3, C::STASH4).w;
     const float yf = (float)yp;
     float dzsum = 0.f;
 #pragma unroll
@@ -1160,7 +1189,7 @@ MD2_HD void stage_c_straight(Lane<C>& L, const Params& P, const WarpJob& J, int 
     const int slot = st.slot(yp);
     const F4 s0 = st.at(slot, 0, C::STASH4);
     const float tg[3] = {s0.x, s0.y, s0.z};
-    const float z = s0.w;
+    const float z = st.at(slot, 3, C::STASH4).w;
     const float yf = (float)yp;
     float dzsum = 0.f;
 #pragma unroll

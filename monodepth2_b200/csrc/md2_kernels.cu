@@ -165,7 +165,7 @@ constexpr int tma_smem_bytes(int nsrc) { return (1 + nsrc) * kTmaImgFloats * 4 +
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-struct IdTensorMaps { CUtensorMap img[1 + 3]; };     // target, then the sources
+struct IdTensorMaps { CUtensorMap img[1 + kMaxSrc]; };     // target, then the sources
 
 template <int NSRC, bool NOSSIM>
 __global__ void __launch_bounds__(kTmaCols) md2_identity_tma(Params P, const __grid_constant__ IdTensorMaps maps) {
@@ -506,6 +506,7 @@ __global__ void MD2_MARCH_BOUNDS md2_march(Params P) {
   st.base = smem + threadIdx.x;
   st.bring = smem + kRing * C::STASH4 * kThreads + threadIdx.x;
   st.stride = kThreads;
+  st.tbar = nullptr; st.t0 = 0;
   bring_reset<C>(st);
 
   Lane<C> L;
@@ -589,6 +590,7 @@ __global__ void MD2_MARCH_BOUNDS md2_march2(Params P) {
   st.base = smem + threadIdx.x;
   st.bring = nullptr;
   st.stride = kThreads;
+  st.tbar = nullptr; st.t0 = 0;
 
   Lane2<C> L;
   lane_init2(L, P, J, lane);
@@ -765,6 +767,7 @@ static cudaError_t launch_march_roles(const Params& P0, cudaStream_t stream) {
   Params P = P0;
   P.nsm = device_sm_count();
   const int jobs = P.S * P.B * P.nseg * P.nband;
+#ifdef MD2_WITH_FLOW
   if (march_mode() == 2) {           // MD2_MARCH=flow: free-running roles (experimental, measured 2.4x slower)
     typedef FlowCfg<C> FC;
     const size_t fsmem = (size_t)FC::SMEM_F4 * sizeof(float4);
@@ -781,9 +784,11 @@ static cudaError_t launch_march_roles(const Params& P0, cudaStream_t stream) {
     md2_march_flow<C, false><<<jobs, FC::THREADS, fsmem, stream>>>(P);
     return cudaGetLastError();
   }
+#endif
   const size_t smem = (size_t)RC::SMEM_F4 * sizeof(float4);
-  if constexpr (C::NSRC == 2 && !C::AVG) {
-    if (pack2_mode() != 0) {          // packed-fp32 roles unless MD2_PACK2=off
+  if constexpr (C::NSRC == 2 && !C::AVG && (C::AUTOMASK || !C::GRAD)) {
+    if (pack2_mode() != 0) {          // packed-fp32 roles unless MD2_PACK2=off (--disable_automasking with
+                                      // gradients: the packed form spills 16 bytes under 128 registers, scalar fits)
       static cudaError_t attr2 = cudaFuncSetAttribute(md2_march_roles<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (attr2 != cudaSuccess) return attr2;
       md2_march_roles<C, true><<<jobs, RC::THREADS, smem, stream>>>(P);
@@ -798,7 +803,12 @@ static cudaError_t launch_march_roles(const Params& P0, cudaStream_t stream) {
 
 template <class C>
 static cudaError_t launch_march(const Params& P, cudaStream_t stream) {
-  if (march_mode() != 0) return launch_march_roles<C>(P, stream);
+#ifndef MD2_WITH_WARP_KERNELS
+  // the round-1 one-warp-per-band kernels (md2_march / md2_march2) are compiled only with -DMD2_WITH_WARP_KERNELS
+  // (A/B measurements); the product library holds the role-specialised kernels alone
+  return launch_march_roles<C>(P, stream);
+#else
+  if (march_mode() != 0 || C::NSRC > 3) return launch_march_roles<C>(P, stream);
   const int jobs = P.S * P.B * P.nseg * P.nband;
   const int grid = (jobs + kWarpsPerCta - 1) / kWarpsPerCta;
   size_t smem = (size_t)kThreads * C::SMEM4 * sizeof(float4);
@@ -823,6 +833,7 @@ static cudaError_t launch_march(const Params& P, cudaStream_t stream) {
   }
   md2_march<C><<<grid, kThreads, smem, stream>>>(P);
   return cudaGetLastError();
+#endif
 }
 
 template <int NSRC, bool NOSSIM>
@@ -855,7 +866,7 @@ static void launch_identity_ns(const Params& P, int grid, cudaStream_t stream) {
       IdTensorMaps maps;
       bool ok = make_image_map(&maps.img[0], P.tgt, P.B, P.H, P.W);
       for (int f = 0; f < NSRC && ok; ++f) ok = make_image_map(&maps.img[1 + f], P.src[f], P.B, P.H, P.W);
-      for (int f = NSRC; f < 3; ++f) maps.img[1 + f] = maps.img[0];
+      for (int f = NSRC; f < kMaxSrc; ++f) maps.img[1 + f] = maps.img[0];
       if (ok) {
         const dim3 g((P.W + kTmaCols - 1) / kTmaCols, (P.H + kTmaRows - 1) / kTmaRows, P.B);
         const int smem = tma_smem_bytes(NSRC);
@@ -955,7 +966,9 @@ cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
     switch (P.nsrc) {
       case 1: launch_identity_ns<1>(P, grid, stream); break;
       case 2: launch_identity_ns<2>(P, grid, stream); break;
-      default: launch_identity_ns<3>(P, grid, stream); break;
+      case 3: launch_identity_ns<3>(P, grid, stream); break;
+      case 4: launch_identity_ns<4>(P, grid, stream); break;
+      default: return cudaErrorInvalidValue;
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   } else {
@@ -969,7 +982,9 @@ cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
   switch (P.nsrc) {
     case 1: e = launch_march_ns<1>(P, stream); break;
     case 2: e = launch_march_ns<2>(P, stream); break;
-    default: e = launch_march_ns<3>(P, stream); break;
+    case 3: e = launch_march_ns<3>(P, stream); break;
+    case 4: e = launch_march_ns<4>(P, stream); break;
+    default: e = cudaErrorInvalidValue; break;
   }
   if (e != cudaSuccess) return e;
   if (g_prof_on) cudaEventRecord(g_prof_ev[1], stream);

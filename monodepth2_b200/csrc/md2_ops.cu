@@ -339,6 +339,27 @@ __global__ void k_pose_to_matrix_bwd(const float* __restrict__ gT, const float* 
 
 }  // namespace
 
+struct ScaleArgs {
+  const float* src[MD2_MAX_SCALE_TENSORS];
+  float* dst[MD2_MAX_SCALE_TENSORS];
+  long long start[MD2_MAX_SCALE_TENSORS + 1];
+  long long numel[MD2_MAX_SCALE_TENSORS];
+  int n;
+};
+__global__ void k_scale_tensors(ScaleArgs a, const float* __restrict__ scale) {
+  const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;      // 4 consecutive elements per thread
+  if (q >= a.start[a.n]) return;
+  int i = 0;
+  while (i + 1 < a.n && q >= a.start[i + 1]) ++i;
+  const long long j = q - a.start[i];
+  const float g = __ldg(scale);
+  const float* s = a.src[i];
+  float* d = a.dst[i];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (j + k < a.numel[i]) d[j + k] = __ldg(s + j + k) * g;
+}
+
 extern "C" {
 
 int md2_disp_to_depth(const float* disp, float min_depth, float max_depth, float* scaled_disp, float* depth,
@@ -462,6 +483,27 @@ int md2_pose_to_matrix_backward(const float* grad_T, const float* axisangle, con
     return MD2_ERR_INVALID_ARGUMENT;
   k_pose_to_matrix_bwd<<<blocks_for(batch), kT, 0, (cudaStream_t)stream>>>(grad_T, axisangle, translation, invert,
                                                                          grad_axisangle, grad_translation, batch);
+  return rc(cudaGetLastError());
+}
+
+/* autograd glue of the fused call: dst[i] = src[i] * (*scale) for up to MD2_MAX_SCALE_TENSORS tensors in ONE launch
+ * (the backward of the torch.autograd.Function multiplies every stored gradient by the incoming scalar gradient). */
+int md2_scale_tensors(int n_tensors, const float* const* src, float* const* dst, const long long* numel,
+                      const float* scale, void* stream) {
+  if (n_tensors < 1 || n_tensors > MD2_MAX_SCALE_TENSORS || !src || !dst || !numel || !scale) return MD2_ERR_INVALID_ARGUMENT;
+  ScaleArgs a;
+  long long total = 0;
+  for (int i = 0; i < n_tensors; ++i) {
+    if (!src[i] || !dst[i] || numel[i] < 0) return MD2_ERR_INVALID_ARGUMENT;
+    a.src[i] = src[i]; a.dst[i] = dst[i]; a.start[i] = total;
+    total += (numel[i] + 3) / 4 * 4;          // every tensor starts on a multiple of 4 of the flat index space
+  }
+  a.start[n_tensors] = total;
+  a.n = n_tensors;
+  for (int i = 0; i < n_tensors; ++i) a.numel[i] = numel[i];
+  if (total == 0) return MD2_OK;
+  const long long threads = total / 4;
+  k_scale_tensors<<<(unsigned)((threads + kT - 1) / kT), kT, 0, (cudaStream_t)stream>>>(a, scale);
   return rc(cudaGetLastError());
 }
 

@@ -211,8 +211,10 @@ __device__ __forceinline__ void load_identity_row2(Lane2<C>& L, const WarpJob& J
 template <class C, bool WITH_ID = true, int ROW_STEP = 1, bool TG_DIRECT = false, bool ASYNC = false>
 __device__ __forceinline__ void stage_a_issue2(Lane2<C>& L, Flight2& F, const Params& P, const WarpJob& J, int t, F4* tapdst = nullptr) {
   const int tr = reflect_clamp(t, J.H);
-  if (TG_DIRECT) F.ctg = MD2_LDS4(J.tgt4 + 4 * (tr * J.W + L.xi));
-  else F.ctg = L.ntg;
+  if (TG_DIRECT) {
+    if (J.staged) F.ctg = make_f4(0.f, 0.f, 0.f, 0.f);      // the row goes into the ring by TMA
+    else F.ctg = MD2_LDS4(J.tgt4 + 4 * (tr * J.W + L.xi));
+  } else F.ctg = L.ntg;
   float D;
   if (J.s == 0) {
     D = L.nd[0];
@@ -286,7 +288,7 @@ __device__ __forceinline__ void stage_a_finish2(Lane2<C>& L, const Flight2& F, c
   L.tgrg = p2(tg4.x, tg4.y);
   L.tgb = tg4.z;
   if (J.depth && own) J.depth[t * J.W + L.xi] = z;
-  if (PUBLISH) st.at(slot, 0, C::STASH4) = make_f4(tg4.x, tg4.y, tg4.z, z);
+  if (PUBLISH && !J.staged) st.at(slot, 0, C::STASH4) = make_f4(tg4.x, tg4.y, tg4.z, 0.f);   // see stage_a_finish
   float prb[2];
 #pragma unroll
   for (int f = 0; f < 2; ++f) {
@@ -317,7 +319,7 @@ __device__ __forceinline__ void stage_a_finish2(Lane2<C>& L, const Flight2& F, c
     if (PUBLISH) st.at(slot, 1 + 3 * f, C::STASH4) = make_f4(pr2.x, pr2.y, pb, f ? F.cu.y : F.cu.x);
     if (C::GRAD) {
       st.at(slot, 2 + 3 * f, C::STASH4) = make_f4(dxp2.x, dxp2.y, dxb, f ? F.cv.y : F.cv.x);
-      st.at(slot, 3 + 3 * f, C::STASH4) = make_f4(dyp2.x, dyp2.y, dyb, 0.f);
+      st.at(slot, 3 + 3 * f, C::STASH4) = make_f4(dyp2.x, dyp2.y, dyb, f == 0 ? z : 0.f);
     }
   }
   L.pr[2] = p2(prb[0], prb[1]);
@@ -451,7 +453,7 @@ __device__ __forceinline__ void stage_c2(Lane2<C>& L, const Params& P, const War
     const int slot = st.slot(yp);
     const F4 s0 = st.at(slot, 0, C::STASH4);
     const P2 tgrg = p2(s0.x, s0.y);
-    const float tgb = s0.z, z = s0.w;
+    const float tgb = s0.z, z = st.at(slot, 3, C::STASH4).w;
     const float yf = (float)yp;
     // channel b box adjoint, over the two sources
     const P2 Ab = fma2(bc(wu), B2b[0], fma2(bc(wd), B0b[0], B1b[0]));

@@ -30,11 +30,18 @@
 
 namespace md2 {
 
+// Measured on B200 (mono 640x192 x 12, md2_march_roles alone, profiles/r02_optimization_log.md):
+//   1 A warp, 5 CTAs per SM (126 registers)  0.366 ms      2 A warps, 4 CTAs (128 registers)  0.402 ms
+//   1 A warp, 4 CTAs (150 registers)         0.430 ms      3 A warps, 3 CTAs                  0.498 ms
+//   1 A warp + cp.async gather, 5 CTAs       0.388 ms      round-1 kernel (one warp per band) 0.419 ms
 #ifndef MD2_ROLE_MIN_CTAS
-#define MD2_ROLE_MIN_CTAS 4
+#define MD2_ROLE_MIN_CTAS 5
 #endif
 #ifndef MD2_ROLE_A_WARPS
-#define MD2_ROLE_A_WARPS 2
+#define MD2_ROLE_A_WARPS 1
+#endif
+#ifndef MD2_ROLE_ASYNC_TAPS
+#define MD2_ROLE_ASYNC_TAPS 0
 #endif
 constexpr int kRoleAWarps = MD2_ROLE_A_WARPS;
 #ifndef MD2_ROLE_MIN_CTAS3
@@ -53,19 +60,45 @@ struct RoleCfg {
   static constexpr int NROLES = NA + (C::GRAD ? 2 : 1);
   static constexpr int THREADS = 32 * NROLES;
   static constexpr int RING = C::GRAD ? 5 : 2;                   // rows in flight: A writes t, B reads t-1, C reads t-4
-  static constexpr int MIN_CTAS = (C::NSRC >= 3 && C::GRAD) ? MD2_ROLE_MIN_CTAS3 : MD2_ROLE_MIN_CTAS;
+  // register budget per instantiation (no spills anywhere): 4 sources 255, 3 sources or --avg_reprojection with
+  // gradients 168, everything else 128
+  static constexpr int MIN_CTAS = (C::NSRC >= 4) ? 2 : ((C::NSRC >= 3 || C::AVG) && C::GRAD) ? MD2_ROLE_MIN_CTAS3 : MD2_ROLE_MIN_CTAS;
+  // registers per thread such that MIN_CTAS CTAs fit an SM (64 K registers, allocation unit 8 per thread); given as
+  // __maxnreg__ rather than as the min-blocks argument of __launch_bounds__, under which ptxas picks 168 registers
+  // plus a few bytes of spills for the 3-source kernels although 224 would fit
+  static constexpr int MAXREG = ((65536 / (MIN_CTAS * THREADS)) / 8) * 8 > 255 ? 255 : ((65536 / (MIN_CTAS * THREADS)) / 8) * 8;
   static constexpr int NCF4 = (9 * C::NCS + 1 + 3) / 4;          // coefficient sets + winner tag, 16-byte fields
   static constexpr int STASH_F4 = RING * C::STASH4 * 32;
   static constexpr int COEF_F4 = C::GRAD ? 2 * NCF4 * 32 : 0;
   // NA == 1: role A keeps two rows of bilinear taps in flight through cp.async (LDGSTS) into this buffer
   static constexpr int TAPROW_F4 = C::NSRC * 4 * 32;
-  static constexpr int TAP_F4 = (NA == 1) ? 2 * TAPROW_F4 : 0;
-  static constexpr int SMEM_F4 = STASH_F4 + COEF_F4 + TAP_F4;
+  static constexpr bool ASYNC_TAPS = (NA == 1) && (MD2_ROLE_ASYNC_TAPS != 0);
+  static constexpr int TAP_F4 = ASYNC_TAPS ? 2 * TAPROW_F4 : 0;
+  static constexpr int BAR_F4 = (RING * 8 + 15) / 16;            // one mbarrier per ring slot (TMA-staged target row)
+  static constexpr int SMEM_F4 = STASH_F4 + COEF_F4 + TAP_F4 + BAR_F4;
 };
 
 template <int NT>
 __device__ __forceinline__ void role_sync() {
   asm volatile("bar.sync 0, %0;" ::"r"(NT) : "memory");
+}
+
+// Interior bands (WarpJob::staged): the 32 RGBx target texels of row t are one contiguous 512-byte run of the
+// texel array and field 0 of a ring slot is one contiguous 512-byte run of shared memory, so the row is staged by a
+// single TMA bulk copy (cp.async.bulk, UBLKCP) issued by one lane of role A; its completion is tracked by the
+// slot's mbarrier, which roles B and C wait on before they read the field.  No lane loads or stores the target.
+template <class C, class ST>
+__device__ __forceinline__ void stage_target_row(const WarpJob& J, const ST& st, int t, int lane) {
+  if (J.staged && lane == 0) {
+    const int tr = reflect_clamp(t, J.H);
+    const int slot = st.slot(t);
+    mbar_expect_tx(st.tbar + slot, 32 * 16);
+    tma_bulk_g2s(&st.at(slot, 0, C::STASH4), J.tgt4 + 4 * (tr * J.W + J.x0 - 2), 32 * 16, st.tbar + slot);
+  }
+}
+template <class C, class ST>
+__device__ __forceinline__ void wait_target_row(const WarpJob& J, const ST& st, int t) {
+  if (J.staged && t >= st.t0) mbar_wait(st.tbar + st.slot(t), st.parity(t));     // (rows before t0 are never staged)
 }
 
 // ---- role A, warp k of NA: rows t0 + k, t0 + k + NA, ...  Row t must be in the ring before the barrier that
@@ -88,6 +121,7 @@ __device__ __forceinline__ void role_a_async(const Params& P, const WarpJob& J, 
     if (t + 1 <= t1) stage_a_issue<C, false, 0, true, true>(L, Fn, P, J, t + 1, bufn);
     cp_async_commit();
     if (t <= t1) {
+      stage_target_row<C>(J, st, t, lane);
       cp_async_wait<1>();
 #pragma unroll
       for (int f = 0; f < C::NSRC; ++f)
@@ -126,6 +160,7 @@ __device__ __forceinline__ void role_a(const Params& P, const WarpJob& J, int la
     const int t = t0 + p;
     if (NA == 1) {
       if (t <= t1) {
+        stage_target_row<C>(J, st, t, lane);
         stage_a_issue<C, false, 1, true>(L, P, J, t);
         stage_a_finish<C, ST, true>(L, P, J, t, st);
       }
@@ -134,6 +169,7 @@ __device__ __forceinline__ void role_a(const Params& P, const WarpJob& J, int la
       ph = ph < 0 ? ph + NA : ph;
       if (ph == 0) {
         if (t <= t1) {
+          stage_target_row<C>(J, st, t, lane);
           stage_a_finish<C, ST, true>(L, P, J, t, st);
           if (t >= t0 + NA - 1) prefetch_row<C, false>(L, J, t + NA);    // (the prologue did it for the first rows)
         }
@@ -153,6 +189,7 @@ __device__ __forceinline__ void b_step(Lane<C>& L, const Params& P, const WarpJo
   typedef RoleCfg<C> RC;
   const int slot = st.slot(t);
   Xchg1<C> lf, rt;
+  wait_target_row<C>(J, st, t);
   {
     const F4* p = &st.at(slot, 0, C::STASH4);
     const F4 c = p[0], l = p[ol], r = p[orr];
@@ -231,6 +268,7 @@ __device__ __forceinline__ void c_step(Lane<C>& L, const Params& P, const WarpJo
   L.tag = __float_as_int(vc[9 * C::NCS]);
   lf.tag = __float_as_int(vl[9 * C::NCS]);
   rt.tag = __float_as_int(vr[9 * C::NCS]);
+  wait_target_row<C>(J, st, t - 2);
   stage_c(L, P, J, t, lane, lf, rt, st);
 }
 
@@ -285,6 +323,7 @@ __device__ __forceinline__ void role_a2_async(const Params& P, const WarpJob& J,
     if (t + 1 <= t1) stage_a_issue2<C, false, 0, true, true>(L, Fn, P, J, t + 1, bufn);
     cp_async_commit();
     if (t <= t1) {
+      stage_target_row<C>(J, st, t, lane);
       cp_async_wait<1>();
 #pragma unroll
       for (int f = 0; f < 2; ++f)
@@ -320,6 +359,7 @@ __device__ __forceinline__ void role_a2(const Params& P, const WarpJob& J, int l
     const int t = t0 + p;
     if (NA == 1) {
       if (t <= t1) {
+        stage_target_row<C>(J, st, t, lane);
         stage_a_issue2<C, false, 1, true>(L, P, J, t);
         stage_a_finish2<C, ST, true>(L, P, J, t, st);
       }
@@ -328,6 +368,7 @@ __device__ __forceinline__ void role_a2(const Params& P, const WarpJob& J, int l
       ph = ph < 0 ? ph + NA : ph;
       if (ph == 0) {
         if (t <= t1) {
+          stage_target_row<C>(J, st, t, lane);
           stage_a_finish2<C, ST, true>(L, P, J, t, st);
           if (t >= t0 + NA - 1) prefetch_row2<C, false>(L, J, t + NA);
         }
@@ -344,6 +385,7 @@ __device__ __forceinline__ void b_step2(Lane2<C>& L, const Params& P, const Warp
                                         int t, int ol, int orr) {
   const int slot = st.slot(t);
   Xchg1P<C> lf, rt;
+  wait_target_row<C>(J, st, t);
   const F4* p0 = &st.at(slot, 0, C::STASH4);
   const F4* p1 = &st.at(slot, 1, C::STASH4);
   const F4* p2_ = &st.at(slot, 4, C::STASH4);
@@ -395,7 +437,43 @@ __device__ __forceinline__ void c_step2(Lane2<C>& L, const Params& P, const Warp
   unpack(q[0], q[32], q[64], L.cf, L.cfb, L.tag);
   unpack(q[ol], q[32 + ol], q[64 + ol], lf.cf, lf.cfb, lf.tag);
   unpack(q[orr], q[32 + orr], q[64 + orr], rt.cf, rt.cfb, rt.tag);
+  wait_target_row<C>(J, st, t - 2);
   stage_c2(L, P, J, t, lane, lf, rt, st);
+}
+
+// scalar stage_c fed from the packed coefficient layout of b_step2 (the packed stage_c2 needs a few registers more
+// than the 128 that five CTAs per SM leave: 44 bytes of spills; the scalar one fits)
+template <class C, class ST>
+__device__ __forceinline__ void c_step_from_packed(Lane<C>& L, const Params& P, const WarpJob& J, int lane, const ST& st,
+                                                   const F4* q, int t, int ol, int orr) {
+  static_assert(C::NCS == 1, "per-pixel minimum");
+  auto unpack = [](const F4& a, const F4& b, const F4& c, float* coef, int& tag) {
+    coef[0] = a.x; coef[3] = a.y; coef[1] = a.z; coef[4] = a.w; coef[2] = b.x; coef[5] = b.y;
+    coef[6] = b.z; coef[7] = b.w; coef[8] = c.x;
+    tag = __float_as_int(c.y);
+  };
+  Xchg2<C> lf, rt;
+  unpack(q[0], q[32], q[64], L.coef[0], L.tag);
+  unpack(q[ol], q[32 + ol], q[64 + ol], lf.coef[0], lf.tag);
+  unpack(q[orr], q[32 + orr], q[64 + orr], rt.coef[0], rt.tag);
+  wait_target_row<C>(J, st, t - 2);
+  stage_c(L, P, J, t, lane, lf, rt, st);
+}
+
+template <class C, class ST>
+__device__ __forceinline__ void role_c_from_packed(const Params& P, const WarpJob& J, int lane, const ST& st, const F4* cring,
+                                                   int t0, int t1, int nit) {
+  typedef RoleCfg<C> RC;
+  Lane<C> L;
+  lane_init(L, P, J, lane);
+  const int ol = (lane > 0) ? -1 : 0, orr = (lane < 31) ? 1 : 0;
+#pragma unroll 1
+  for (int i = 0; i < nit; ++i) {
+    const int t = t0 + i - 2;
+    if (i >= 2) c_step_from_packed(L, P, J, lane, st, cring + (t & 1) * RC::NCF4 * 32, t, ol, orr);
+    role_sync<RC::THREADS>();
+  }
+  c_reduce(L, P, J, lane);
 }
 
 template <class C>
@@ -429,8 +507,13 @@ __device__ __forceinline__ void role_c2(const Params& P, const WarpJob& J, int l
   c_reduce2(L, P, J, lane);
 }
 
+#ifdef MD2_ROLE_USE_MINBLOCKS
+#define MD2_ROLE_BOUNDS(C) __launch_bounds__(RoleCfg<C>::THREADS, RoleCfg<C>::MIN_CTAS)
+#else
+#define MD2_ROLE_BOUNDS(C) __launch_bounds__(RoleCfg<C>::THREADS) __maxnreg__(RoleCfg<C>::MAXREG)
+#endif
 template <class C, bool PACKED>
-__global__ void __launch_bounds__(RoleCfg<C>::THREADS, RoleCfg<C>::MIN_CTAS) md2_march_roles(Params P) {
+__global__ void MD2_ROLE_BOUNDS(C) md2_march_roles(Params P) {
   static_assert(!PACKED || (C::NSRC == 2 && !C::AVG), "packed form: two sources, per-pixel minimum");
   typedef RoleCfg<C> RC;
   extern __shared__ float4 smem[];
@@ -449,17 +532,29 @@ __global__ void __launch_bounds__(RoleCfg<C>::THREADS, RoleCfg<C>::MIN_CTAS) md2
   const int r2 = r - seg * per_seg;
   const int js = r2 / P.nband;
   const int jy0 = seg * P.seg_rows;
-  const WarpJob J = make_job(P, js, jb, (r2 - js * P.nband) * kOwnCols, jy0, min(jy0 + P.seg_rows, P.H));
+  WarpJob J = make_job(P, js, jb, (r2 - js * P.nband) * kOwnCols, jy0, min(jy0 + P.seg_rows, P.H));
+  // bands whose 32 lanes all lie inside the image: the target row is staged by TMA (others read reflected columns)
+#ifndef MD2_ROLE_NO_TMA
+  J.staged = (J.x0 - 2 >= 0) && (J.x0 + 30 <= J.W);
+#endif
 
   StashT<RC::RING> st;
   st.base = smem + lane;
   st.bring = nullptr;
   st.stride = 32;
+  st.tbar = reinterpret_cast<unsigned long long*>(smem + RC::STASH_F4 + RC::COEF_F4 + RC::TAP_F4);
   F4* cring = smem + RC::STASH_F4 + lane;
   F4* tapbuf = smem + RC::STASH_F4 + RC::COEF_F4 + lane;
   const int t0 = J.y0 - 2, t1 = J.y1 + 1;
+  st.t0 = t0;
   const int nit = (t1 - t0 + 1) + (C::GRAD ? 2 : 1);
-  if constexpr (RC::NA == 1) {
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < RC::RING; ++i) mbar_init(st.tbar + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if constexpr (RC::ASYNC_TAPS) {
     if (role == 0) {
       if constexpr (PACKED) role_a2_async<C>(P, J, lane, st, tapbuf, t0, t1, nit);
       else role_a_async<C>(P, J, lane, st, tapbuf, t0, t1, nit);
@@ -469,7 +564,11 @@ __global__ void __launch_bounds__(RoleCfg<C>::THREADS, RoleCfg<C>::MIN_CTAS) md2
   if constexpr (PACKED) {
     if (role < RC::NA) role_a2<C>(P, J, lane, role, st, t0, t1, nit);
     else if (role == RC::NA) role_b2<C>(P, J, lane, st, cring, t0, t1, nit);
+#ifdef MD2_ROLE_PACKED_C
     else if (C::GRAD) role_c2<C>(P, J, lane, st, cring, t0, t1, nit);
+#else
+    else if (C::GRAD) role_c_from_packed<C>(P, J, lane, st, cring, t0, t1, nit);
+#endif
   } else {
     if (role < RC::NA) role_a<C>(P, J, lane, role, st, t0, t1, nit);
     else if (role == RC::NA) role_b<C>(P, J, lane, st, cring, t0, t1, nit);
@@ -547,6 +646,8 @@ __global__ void __launch_bounds__(FlowCfg<C>::THREADS, FlowCfg<C>::MIN_CTAS) md2
   st.base = smem + lane;
   st.bring = nullptr;
   st.stride = 32;
+  st.tbar = nullptr;
+  st.t0 = J.y0 - 2;
   F4* cring = smem + FC::STASH_F4 + lane;
   Flow fl;
   fl.prog = reinterpret_cast<volatile int*>(smem + FC::STASH_F4 + FC::COEF_F4);

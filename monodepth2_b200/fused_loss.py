@@ -241,6 +241,7 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
                                                   C.c_void_p(stream))
         _capi.check(plan.lib, st, "md2_view_synthesis_loss")
         ctx.S, ctx.F = S, F
+        ctx.lib = plan.lib
         ctx.pose_grad = list(pose_grad)
         ctx.first_shapes = [tuple(x.shape) for x in firsts]
         ctx.second_shapes = [tuple(x.shape) if x is not None else None for x in seconds]
@@ -259,20 +260,35 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
         saved = list(ctx.saved_tensors)
         S, F = ctx.S, ctx.F
         n0 = _ViewSynthesisLossFn.N_FIXED
-        out = [None] * n0
+        # every stored gradient times the incoming scalar, all tensors in ONE launch (md2_scale_tensors)
+        want = []           # (slot in the result tuple, stored gradient, shape)
         for s in range(S):
-            out.append(saved[s] * g_total if ctx.needs_input_grad[n0 + s] else None)
+            if ctx.needs_input_grad[n0 + s]:
+                want.append((n0 + s, saved[s], saved[s].shape))
         firsts = iter(saved[S:S + sum(1 for h in ctx.have if h[0])])
         seconds = iter(saved[S + sum(1 for h in ctx.have if h[0]):])
-        g1, g2 = [], []
         for i in range(F):
             a = next(firsts) if ctx.have[i][0] else None
             b = next(seconds) if ctx.have[i][1] else None
-            need1 = ctx.needs_input_grad[n0 + S + i] and ctx.pose_grad[i] and a is not None
-            need2 = ctx.needs_input_grad[n0 + S + F + i] and ctx.pose_grad[i] and b is not None
-            g1.append((a * g_total).reshape(ctx.first_shapes[i]) if need1 else None)
-            g2.append((b * g_total).reshape(ctx.second_shapes[i]) if need2 else None)
-        return tuple(out + g1 + g2)
+            if ctx.needs_input_grad[n0 + S + i] and ctx.pose_grad[i] and a is not None:
+                want.append((n0 + S + i, a, ctx.first_shapes[i]))
+            if ctx.needs_input_grad[n0 + S + F + i] and ctx.pose_grad[i] and b is not None:
+                want.append((n0 + S + F + i, b, ctx.second_shapes[i]))
+        out = [None] * (n0 + S + 2 * F)
+        if want:
+            n = len(want)
+            res = [torch.empty_like(w[1]) for w in want]
+            g = g_total.detach().to(torch.float32).contiguous()
+            src = (C.c_void_p * n)(*[w[1].data_ptr() for w in want])
+            dst = (C.c_void_p * n)(*[r.data_ptr() for r in res])
+            cnt = (C.c_longlong * n)(*[w[1].numel() for w in want])
+            with torch.cuda.device(g.device):
+                st = ctx.lib.md2_scale_tensors(n, src, dst, cnt, g.data_ptr(),
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            _capi.check(ctx.lib, st, "md2_scale_tensors")
+            for w, r in zip(want, res):
+                out[w[0]] = r.reshape(w[2])
+        return tuple(out)
 
 
 def view_synthesis_loss(plan: LossPlan, inputs: Dict, outputs: Dict,
@@ -473,6 +489,64 @@ def _view_synthesis_loss_predictive_mask(plan: LossPlan, inputs: Dict, outputs: 
         total = total + loss
     losses["loss"] = total / len(plan.scales)
     return losses
+
+
+class GraphedLoss:
+    """``view_synthesis_loss`` + ``backward()`` for a fixed plan, captured once in a CUDA graph over static device
+    buffers - what a training loop with static shapes does to get rid of the launch and Python overhead of the
+    eager call (the reference's own loop is eager; its ~2 100 launches per step are launch-bound).
+
+        g = GraphedLoss(plan, inputs, outputs)     # device tensors shaped like every later step's; captures
+        g.load(inputs, outputs)                    # copies a step's tensors (pinned host or device) into the buffers
+        loss = g.run()                             # replays; g.loss / g.grads[key] are the static results
+
+    ``inputs`` holds the tensors the path reads (``("color", f, 0)`` float or uint8, ``("color", 0, s)``, ``("K", 0)``,
+    ``("inv_K", 0)``, ``"stereo_T"``), ``outputs`` the leaves (``("disp", s)`` and ``("cam_T_cam", 0, f)`` or the pose
+    leaves).  The tie-break noise is drawn inside the graph by ``torch.randn`` from the default CUDA generator
+    (graph-safe), so every replay draws fresh noise as trainer.py:468-469 does.
+    """
+
+    def __init__(self, plan: LossPlan, inputs: Dict, outputs: Dict, warmup: int = 2):
+        dev = inputs[("color", 0, 0)].device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedLoss needs CUDA tensors (there is no CPU path)")
+        self.plan = plan
+        self.inputs = {k: torch.empty_like(v, device=dev).copy_(v) for k, v in inputs.items() if torch.is_tensor(v)}
+        self.leaves = {k: torch.empty_like(v, device=dev).copy_(v).requires_grad_(True)
+                       for k, v in outputs.items() if torch.is_tensor(v)}
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._step()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        for v in self.leaves.values():
+            v.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.losses = self._step()
+        self.loss = self.losses["loss"].detach()
+        self.grads = {k: v.grad for k, v in self.leaves.items()}
+
+    def _step(self):
+        for v in self.leaves.values():
+            v.grad = None
+        losses = view_synthesis_loss(self.plan, self.inputs, dict(self.leaves))
+        losses["loss"].backward()
+        return losses
+
+    def load(self, inputs: Dict, outputs: Dict) -> None:
+        with torch.no_grad():
+            for k, dst in self.inputs.items():
+                dst.copy_(inputs[k], non_blocking=True)
+            for k, dst in self.leaves.items():
+                dst.copy_(outputs[k], non_blocking=True)
+
+    def run(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.loss
 
 
 class FusedLossMixin:

@@ -102,6 +102,9 @@ def make_batch(batch: int = 12, height: int = 192, width: int = 640,
         hi = base.amax(dim=(1, 2, 3), keepdim=True)
         base = (base - lo) / (hi - lo)
         shift = {0: 0, -1: 3, 1: -3, "s": 6}
+        for f in frame_ids:                       # further temporal neighbours (--frame_ids 0 -2 -1 1 2): 3 px per frame
+            if f not in shift:
+                shift[f] = -3 * f
         for f in frame_ids:
             x0 = 32 + shift[f]
             frame = base[:, :, 32:32 + H, x0:x0 + W].contiguous()

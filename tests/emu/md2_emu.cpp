@@ -59,6 +59,7 @@ static void emu_march(const Params& P) {
             st[l].base = ring.data() + l;
             st[l].bring = ring.data() + 32 * kRing * C::STASH4 + l;
             st[l].stride = 32;
+            st[l].tbar = nullptr; st[l].t0 = 0;
             bring_reset<C>(st[l]);
           }
           auto run_c = [&](int t) {
@@ -136,7 +137,6 @@ extern "C" int md2_emu_view_synthesis_loss(const md2_problem* p, const md2_tenso
                                            size_t workspace_bytes) {
   int st = validate(p);
   if (st != MD2_OK) return st;
-  if (p->num_src > 3) return MD2_ERR_UNSUPPORTED;
   if (workspace_bytes < make_layout(p).total) return MD2_ERR_WORKSPACE_TOO_SMALL;
   Params P;
   st = fill_params(p, t, workspace, &P);
@@ -159,7 +159,8 @@ extern "C" int md2_emu_view_synthesis_loss(const md2_problem* p, const md2_tenso
     }
   // 3. identity
   if (P.automask) {
-    if (P.nsrc == 1) emu_identity<1>(P); else if (P.nsrc == 2) emu_identity<2>(P); else emu_identity<3>(P);
+    if (P.nsrc == 1) emu_identity<1>(P); else if (P.nsrc == 2) emu_identity<2>(P); else if (P.nsrc == 3) emu_identity<3>(P);
+    else emu_identity<4>(P);
   }
   // 4. smoothness
   for (int s = 0; s < P.S; ++s)
@@ -179,7 +180,8 @@ extern "C" int md2_emu_view_synthesis_loss(const md2_problem* p, const md2_tenso
   for (int s = 0; s < P.S; ++s)
     for (int b = 0; b < P.B; ++b) smooth_scalars(P, s, b, P.smsc[2 * (s * P.B + b)], P.smsc[2 * (s * P.B + b) + 1]);
   // 5. march
-  if (P.nsrc == 1) emu_march_n<1>(P); else if (P.nsrc == 2) emu_march_n<2>(P); else emu_march_n<3>(P);
+  if (P.nsrc == 1) emu_march_n<1>(P); else if (P.nsrc == 2) emu_march_n<2>(P); else if (P.nsrc == 3) emu_march_n<3>(P);
+  else emu_march_n<4>(P);
   // 6. final
   final_scalars(P);
   if (P.want_grad) {

@@ -48,6 +48,8 @@ CASES = {
                     flags=["--pose_model_type", "posecnn"]),
     "predictive_mask": dict(B=2, H=48, W=80, frame_ids=[0, -1, 1], kind="structured", seed=12,
                             flags=["--disable_automasking", "--predictive_mask"]),
+    # four source frames (options.py:80-84 takes any --frame_ids; the maximum the C ABI supports: MD2_MAX_SRC)
+    "five_frames": dict(B=2, H=32, W=64, frame_ids=[0, -2, -1, 1, 2], kind="structured", seed=13, flags=[]),
     "stereo_only": dict(B=2, H=32, W=64, frame_ids=[0], kind="structured", seed=7,
                         flags=["--use_stereo", "--frame_ids", "0"]),
 }

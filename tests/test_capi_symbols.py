@@ -62,8 +62,10 @@ def test_validation_without_gpu(lib):
     assert 30e6 < n.value < 200e6
     bad = Md2Problem(batch=12, height=190, width=640, num_scales=4, num_src=2, min_depth=0.1, max_depth=100.0)
     assert lib.md2_loss_workspace_bytes(C.byref(bad), C.byref(n)) == -1
-    bad2 = Md2Problem(batch=12, height=192, width=640, num_scales=4, num_src=4, min_depth=0.1, max_depth=100.0)
-    assert lib.md2_loss_workspace_bytes(C.byref(bad2), C.byref(n)) == -2
+    four = Md2Problem(batch=12, height=192, width=640, num_scales=4, num_src=4, min_depth=0.1, max_depth=100.0)
+    assert lib.md2_loss_workspace_bytes(C.byref(four), C.byref(n)) == 0          # MD2_MAX_SRC sources are supported
+    bad2 = Md2Problem(batch=12, height=192, width=640, num_scales=4, num_src=5, min_depth=0.1, max_depth=100.0)
+    assert lib.md2_loss_workspace_bytes(C.byref(bad2), C.byref(n)) == -1
     assert lib.md2_status_string(-3) == b"workspace too small"
     assert lib.md2_version() >= 100
 

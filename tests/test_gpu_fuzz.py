@@ -15,7 +15,7 @@ from oracle import view_synthesis as O
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
-FRAME_SETS = [[0, -1], [0, 1], [0, -1, 1], [0, "s"], [0, -1, 1, "s"], [0, 1, "s"]]
+FRAME_SETS = [[0, -1], [0, 1], [0, -1, 1], [0, "s"], [0, -1, 1, "s"], [0, 1, "s"], [0, -2, -1, 1, 2], [0, -1, 1, 2, "s"]]
 
 
 def _cases(n=14, seed=2024):

@@ -154,3 +154,27 @@ def test_logging_step_materialises_side_outputs_on_demand():
         tv.compute_depth_losses(insv, outsv, lv)
         tv.log("val", insv, outsv, lv)
         assert seen["depth"].shape == (B, 1, H, W) and seen[("mask", 3)].shape == (B, H, W)
+
+
+def test_graphed_loss_replays_match_the_eager_call():
+    """GraphedLoss (public API): the fused call + backward captured in a CUDA graph over static buffers.  With
+    --disable_automasking there is no tie-break noise, so a replay on freshly loaded inputs must reproduce the eager
+    call on the same inputs exactly (per-pixel gradients; the scalar loss up to the order of its fp64 atomics)."""
+    from monodepth2_b200.fused_loss import GraphedLoss, LossPlan, view_synthesis_loss
+    from monodepth2_b200.synthetic import make_batch
+    B, H, W, fids = 2, 64, 96, [0, -1, 1]
+    plan = LossPlan(B, H, W, fids, disable_automasking=True)
+    b0 = make_batch(B, H, W, fids, 4, 71, "structured")
+    b1 = make_batch(B, H, W, fids, 4, 72, "iid")
+    need = lambda ins: {k: v for k, v in ins.items() if k in [("color", f, 0) for f in fids] + [("color", 0, s) for s in range(1, 4)] + [("K", 0), ("inv_K", 0)]}
+    g = GraphedLoss(plan, {k: v.to(DEV) for k, v in need(b0[0]).items()}, {k: v.to(DEV) for k, v in b0[1].items()})
+    for batch in (b1, b0, b1):
+        g.load({k: v.pin_memory() for k, v in need(batch[0]).items()}, {k: v.pin_memory() for k, v in batch[1].items()})
+        loss = float(g.run().item())
+        ins = {k: v.to(DEV) for k, v in batch[0].items()}
+        outs = {k: v.to(DEV).requires_grad_(True) for k, v in batch[1].items()}
+        ref = view_synthesis_loss(plan, ins, outs)
+        ref["loss"].backward()
+        assert abs(loss - float(ref["loss"].detach())) <= 1e-7 * abs(loss)
+        for s in range(4):
+            assert torch.equal(g.grads[("disp", s)], outs[("disp", s)].grad), s
