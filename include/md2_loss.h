@@ -171,6 +171,27 @@ int md2_pose_to_matrix_backward(const float *grad_T, const float *axisangle, con
                                 int invert, float *grad_axisangle, float *grad_translation,
                                 int batch, void *stream);
 
+/* ---- decoder tail feeding the path: outputs[("disp", s)] = sigmoid(Conv3x3(C -> 1)(x)),
+ * networks/depth_decoder.py:60-63 with Conv3x3 = ReflectionPad2d(1) + Conv2d(C, 1, 3), layers.py:119-136.
+ * x (B,C,H,W), weight (1,C,3,3), bias (1) -> disp (B,1,H,W); pad + conv + bias + sigmoid in one pass. ---- */
+int md2_dispconv_sigmoid(const float *x, const float *weight, const float *bias, float *disp,
+                         int batch, int channels, int height, int width, void *stream);
+/* grad_x (B,C,H,W), grad_weight (1,C,3,3) and grad_bias (1) are written (not accumulated); grad_x and
+ * grad_weight may each be NULL (grad_bias is produced with grad_weight). */
+int md2_dispconv_sigmoid_backward(const float *grad_disp, const float *disp, const float *x, const float *weight,
+                                  float *grad_x, float *grad_weight, float *grad_bias,
+                                  int batch, int channels, int height, int width, void *stream);
+
+/* ---- monitoring path: Trainer.compute_depth_losses, trainer.py:498-526, with
+ * compute_depth_errors, layers.py:251-269.  depth = outputs[("depth",0,0)] (B,1,H,W), depth_gt (B,1,Hg,Wg);
+ * metrics[7] = abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3 (device floats, the order of depth_metric_names,
+ * trainer.py:105-106) over the pixels with gt > 0 inside crop [y0,y1) x [x0,x1) (153:371, 44:1197 in the reference),
+ * after median scaling (torch.median = lower median, found exactly by radix select).  No host synchronisation. ---- */
+int md2_depth_metrics_scratch_bytes(int batch, int gt_height, int gt_width, size_t *bytes);
+int md2_depth_metrics(const float *depth, const float *depth_gt, float *metrics, void *scratch, size_t scratch_bytes,
+                      int batch, int height, int width, int gt_height, int gt_width,
+                      int crop_y0, int crop_y1, int crop_x0, int crop_x1, void *stream);
+
 /* autograd glue (trainer.py:208, losses["loss"].backward()): dst[i] = src[i] * (*scale) for n_tensors <=
  * MD2_MAX_SCALE_TENSORS device tensors in one launch; `src`, `dst`, `numel` are HOST arrays, `scale` a device scalar. */
 #define MD2_MAX_SCALE_TENSORS 16

@@ -70,7 +70,8 @@ SYMBOLS = [
     "md2_ssim", "md2_ssim_backward",
     "md2_smooth_loss", "md2_smooth_loss_backward",
     "md2_pose_to_matrix", "md2_pose_to_matrix_backward",
-    "md2_scale_tensors",
+    "md2_depth_metrics_scratch_bytes", "md2_depth_metrics",
+    "md2_scale_tensors", "md2_dispconv_sigmoid", "md2_dispconv_sigmoid_backward",
     "md2_resize_plan_create", "md2_resize_plan_destroy", "md2_resize_scratch_bytes", "md2_resize_lanczos_u8",
 ]
 
@@ -103,6 +104,8 @@ def load_library(path: str = None) -> C.CDLL:
             getattr(lib, name).restype = C.c_int
     lib.md2_scale_tensors.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_longlong),
                                       C.c_void_p, C.c_void_p]
+    lib.md2_depth_metrics_scratch_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+    lib.md2_depth_metrics.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t] + [C.c_int] * 9 + [C.c_void_p]
     lib.md2_resize_plan_destroy.restype = None
     lib.md2_resize_plan_destroy.argtypes = [C.c_void_p]
     lib.md2_resize_plan_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]

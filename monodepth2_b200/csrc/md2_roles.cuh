@@ -534,8 +534,10 @@ __global__ void MD2_ROLE_BOUNDS(C) md2_march_roles(Params P) {
   const int jy0 = seg * P.seg_rows;
   WarpJob J = make_job(P, js, jb, (r2 - js * P.nband) * kOwnCols, jy0, min(jy0 + P.seg_rows, P.H));
   // bands whose 32 lanes all lie inside the image: the target row is staged by TMA (others read reflected columns)
+  // (1-2 sources: measured on one box 0.389 vs 0.419 ms at 640x192, 1.017 vs 1.071 ms at 1024x320; the 3-source
+  // kernels, at their register limit, lose: 0.533 vs 0.499 ms, and keep the per-lane loads)
 #ifndef MD2_ROLE_NO_TMA
-  J.staged = (J.x0 - 2 >= 0) && (J.x0 + 30 <= J.W);
+  if (C::NSRC <= 2) J.staged = (J.x0 - 2 >= 0) && (J.x0 + 30 <= J.W);
 #endif
 
   StashT<RC::RING> st;

@@ -610,8 +610,16 @@ class FusedLossMixin:
                 outputs[k] = v
 
     def compute_depth_losses(self, inputs, outputs, losses):
+        """trainer.py:498-526 through md2_depth_metrics (one fused call); same keys, same value
+        type (numpy scalars, trainer.py:526).  Set ``md2_fused_metrics = False`` to run the reference's own code."""
         self._md2_materialise(inputs, outputs, depth=True)
-        return super().compute_depth_losses(inputs, outputs, losses)
+        if not getattr(self, "md2_fused_metrics", True):
+            return super().compute_depth_losses(inputs, outputs, losses)
+        import numpy as np
+        from . import layers as L
+        vals = L.depth_metrics(outputs[("depth", 0, 0)], inputs["depth_gt"]).cpu()
+        for i, metric in enumerate(getattr(self, "depth_metric_names", L.DEPTH_METRIC_NAMES)):
+            losses[metric] = np.array(vals[i])
 
     def log(self, mode, inputs, outputs, losses):
         self._md2_materialise(inputs, outputs, color=True, masks=True)

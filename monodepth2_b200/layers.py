@@ -23,7 +23,8 @@ from . import _capi
 
 __all__ = ["disp_to_depth", "transformation_from_parameters", "get_translation_matrix",
            "rot_from_axisangle", "BackprojectDepth", "Project3D", "SSIM", "get_smooth_loss",
-           "grid_sample_border", "ConvBlock", "Conv3x3", "upsample", "compute_depth_errors"]
+           "grid_sample_border", "ConvBlock", "Conv3x3", "upsample", "compute_depth_errors",
+           "DispConvSigmoid", "fuse_disp_heads", "depth_metrics", "DEPTH_METRIC_NAMES"]
 
 
 def _lib():
@@ -303,6 +304,93 @@ class _Smooth(torch.autograd.Function):
 def get_smooth_loss(disp, img):
     """Edge-aware smoothness of a disparity image (layers.py:202-215); differentiable w.r.t. disp."""
     return _Smooth.apply(disp, img)
+
+
+# ------------------------------------------------------------------ decoder tail feeding the path (SURVEY.md 8f-4)
+class _DispHead(torch.autograd.Function):
+    """sigmoid(Conv3x3(C -> 1)(x)) in one pass (md2_dispconv_sigmoid): networks/depth_decoder.py:60-63."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x, w, b = _f32c(x, "x"), _f32c(weight, "weight"), _f32c(bias, "bias")
+        B, Cc, H, W = x.shape
+        if tuple(w.shape) != (1, Cc, 3, 3) or b.numel() != 1:
+            raise RuntimeError("DispConvSigmoid: weight %s / bias %s do not fit x %s" % (tuple(w.shape), tuple(b.shape), tuple(x.shape)))
+        disp = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+        _call("md2_dispconv_sigmoid", x.device, _p(x), _p(w), _p(b), _p(disp), C.c_int(B), C.c_int(Cc), C.c_int(H),
+              C.c_int(W), _stream(x))
+        ctx.save_for_backward(x, w, disp)
+        return disp
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, w, disp = ctx.saved_tensors
+        g = _f32c(g, "grad_disp")
+        B, Cc, H, W = x.shape
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        gw = torch.empty_like(w) if need_w else None
+        gb = torch.empty(1, dtype=torch.float32, device=x.device) if need_w else None
+        _call("md2_dispconv_sigmoid_backward", x.device, _p(g), _p(disp), _p(x), _p(w),
+              _p(gx) if gx is not None else None, _p(gw) if gw is not None else None,
+              _p(gb) if gb is not None else None, C.c_int(B), C.c_int(Cc), C.c_int(H), C.c_int(W), _stream(x))
+        return gx, (gw if ctx.needs_input_grad[1] else None), (gb if ctx.needs_input_grad[2] else None)
+
+
+class DispConvSigmoid(nn.Module):
+    """Drop-in for ``sigmoid(Conv3x3(C, 1)(x))`` - the disparity head of DepthDecoder
+    (/root/reference/networks/depth_decoder.py:43-44,60-63).  Same parameter names as ``Conv3x3`` (``conv.weight``,
+    ``conv.bias``), so checkpoints load unchanged; reflection padding only (what the reference uses)."""
+
+    def __init__(self, in_channels, out_channels=1, use_refl=True):
+        super().__init__()
+        if int(out_channels) != 1 or not use_refl:
+            raise RuntimeError("DispConvSigmoid: one output channel, reflection padding")
+        self.conv = nn.Conv2d(int(in_channels), 1, 3)
+
+    def forward(self, x):
+        return _DispHead.apply(x, self.conv.weight, self.conv.bias)
+
+
+def fuse_disp_heads(depth_decoder):
+    """Replace every ``("dispconv", s)`` Conv3x3 of a reference DepthDecoder by a DispConvSigmoid that shares its
+    parameters, and its trailing ``sigmoid`` by the identity: ``decoder.forward`` (depth_decoder.py:48-65) then hands
+    ``outputs[("disp", s)]`` straight from the fused head.  Returns the decoder."""
+    for key, mod in list(depth_decoder.convs.items()):
+        if not (isinstance(key, tuple) and key[0] == "dispconv"):
+            continue
+        head = DispConvSigmoid(mod.conv.in_channels)
+        head.conv = mod.conv                                     # the same Parameter objects
+        depth_decoder.convs[key] = head
+        for i, m in enumerate(depth_decoder.decoder):
+            if m is mod:
+                depth_decoder.decoder[i] = head
+    depth_decoder.sigmoid = nn.Identity()
+    return depth_decoder
+
+
+# ------------------------------------------------------------------ monitoring path (SURVEY.md 8f-5)
+DEPTH_METRIC_NAMES = ["de/abs_rel", "de/sq_rel", "de/rms", "de/log_rms", "da/a1", "da/a2", "da/a3"]   # trainer.py:105-106
+
+
+def depth_metrics(depth_pred, depth_gt, crop=(153, 371, 44, 1197)):
+    """``Trainer.compute_depth_losses`` (/root/reference/trainer.py:498-526) as one fused call: bilinear up-sampling of
+    ``outputs[("depth", 0, 0)]`` to the ground-truth size, clamp, gt > 0 and Garg/Eigen crop mask, median scaling and
+    the seven metrics of ``compute_depth_errors`` (layers.py:251-269).  Returns a (7,) CUDA tensor in the order of
+    ``DEPTH_METRIC_NAMES``; nothing is synchronised with the host."""
+    d = _f32c(depth_pred.detach(), "depth_pred")
+    g = _f32c(depth_gt, "depth_gt")
+    B, _, H, W = d.shape
+    Hg, Wg = g.shape[-2:]
+    lib = _lib()
+    n = C.c_size_t(0)
+    _capi.check(lib, lib.md2_depth_metrics_scratch_bytes(B, Hg, Wg, C.byref(n)), "md2_depth_metrics_scratch_bytes")
+    scratch = torch.empty(n.value, dtype=torch.uint8, device=d.device)
+    out = torch.empty(7, dtype=torch.float32, device=d.device)
+    _call("md2_depth_metrics", d.device, _p(d), _p(g), _p(out), _p(scratch), scratch.numel(), B, H, W, Hg, Wg,
+          int(crop[0]), int(crop[1]), int(crop[2]), int(crop[3]), _stream(d))
+    return out
 
 
 # ------------------------------------------------------------------ off-path symbols kept importable

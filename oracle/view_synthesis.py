@@ -245,3 +245,32 @@ def view_synthesis_loss(inputs: Dict, outputs: Dict, cfg: OracleConfig,
     """generate_images_pred followed by compute_losses (trainer.py:257-258)."""
     generate_images_pred(inputs, outputs, cfg)
     return compute_losses(inputs, outputs, cfg, noise)
+
+
+# ------------------------------------------------------------------ monitoring path (SURVEY.md 8f-5)
+def compute_depth_errors(gt, pred):
+    """layers.py:251-269."""
+    thresh = torch.max((gt / pred), (pred / gt))
+    a1 = (thresh < 1.25).float().mean()
+    a2 = (thresh < 1.25 ** 2).float().mean()
+    a3 = (thresh < 1.25 ** 3).float().mean()
+    rmse = torch.sqrt(((gt - pred) ** 2).mean())
+    rmse_log = torch.sqrt(((torch.log(gt) - torch.log(pred)) ** 2).mean())
+    abs_rel = torch.mean(torch.abs(gt - pred) / gt)
+    sq_rel = torch.mean((gt - pred) ** 2 / gt)
+    return abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3
+
+
+def depth_metrics(depth_pred, depth_gt, crop=(153, 371, 44, 1197)):
+    """Trainer.compute_depth_losses (trainer.py:498-526): (7,) tensor abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3."""
+    hg, wg = depth_gt.shape[-2:]
+    pred = torch.clamp(F.interpolate(depth_pred, [hg, wg], mode="bilinear", align_corners=False), 1e-3, 80).detach()
+    mask = depth_gt > 0
+    crop_mask = torch.zeros_like(mask)
+    crop_mask[:, :, crop[0]:crop[1], crop[2]:crop[3]] = 1
+    mask = mask * crop_mask
+    gt = depth_gt[mask]
+    pred = pred[mask]
+    pred = pred * (torch.median(gt) / torch.median(pred))
+    pred = torch.clamp(pred, min=1e-3, max=80)
+    return torch.stack([torch.as_tensor(v, dtype=torch.float32) for v in compute_depth_errors(gt, pred)])

@@ -175,6 +175,7 @@ def test_reference_run_epoch_drives_the_mixin_through_logging_and_val(ref, monke
         def __init__(self):          # Trainer.__init__ needs KITTI on disk (trainer.py:118-139): build the state by hand
             pass
     t = FusedTrainer()
+    t.md2_fused_metrics = False       # no GPU here: compute_depth_losses runs the reference's own code
     t.opt, t.device = opt, torch.device("cpu")
     t.models = {"encoder": Enc(3), "depth": Depth(), "pose_encoder": Enc(6), "pose": Pose()}
     params = [p for m in t.models.values() for p in m.parameters()]

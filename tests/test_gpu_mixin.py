@@ -112,6 +112,8 @@ def test_logging_step_materialises_side_outputs_on_demand():
                 seen[("mask", s)] = outputs["identity_selection/{}".format(s)]   # trainer.py:570-572
 
     class T(FusedLossMixin, RefLike):
+        md2_fused_metrics = False          # this test is about the side outputs the base-class methods read
+
         def __init__(self, opt):
             self.opt = opt
 
@@ -178,3 +180,31 @@ def test_graphed_loss_replays_match_the_eager_call():
         assert abs(loss - float(ref["loss"].detach())) <= 1e-7 * abs(loss)
         for s in range(4):
             assert torch.equal(g.grads[("disp", s)], outs[("disp", s)].grad), s
+
+
+def test_mixin_compute_depth_losses_runs_the_fused_metrics():
+    """trainer.py:498-526 through md2_depth_metrics: same keys, numpy values, equal to the oracle restatement."""
+    from monodepth2_b200.fused_loss import FusedLossMixin
+    from monodepth2_b200.synthetic import make_batch
+    B, H, W, fids = 2, 48, 80, [0, -1, 1]
+    inputs, outputs, pose, _ = make_batch(B, H, W, fids, 4, 55, "structured")
+
+    class T(FusedLossMixin):
+        depth_metric_names = ["de/abs_rel", "de/sq_rel", "de/rms", "de/log_rms", "da/a1", "da/a2", "da/a3"]
+
+        def __init__(self, opt):
+            self.opt = opt
+    t = T(_opt(B, H, W, fids))
+    ins = {k: v.to(DEV) for k, v in inputs.items()}
+    g = torch.Generator().manual_seed(3)
+    gt = torch.rand(B, 1, 375, 1242, generator=g) * 60
+    gt[torch.rand(gt.shape, generator=g) < 0.8] = 0
+    ins["depth_gt"] = gt.to(DEV)
+    outs = {k: v.to(DEV).requires_grad_(True) for k, v in outputs.items()}
+    t.generate_images_pred(ins, outs)
+    losses = t.compute_losses(ins, outs)
+    t.compute_depth_losses(ins, outs, losses)
+    ref = O.depth_metrics(outs[("depth", 0, 0)].detach().cpu(), gt)
+    for i, k in enumerate(T.depth_metric_names):
+        assert isinstance(losses[k], np.ndarray)
+        assert abs(float(losses[k]) - float(ref[i])) <= 2e-5 * abs(float(ref[i])) + 1e-7, k
