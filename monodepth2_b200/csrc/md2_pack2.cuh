@@ -208,10 +208,15 @@ __device__ __forceinline__ void load_identity_row2(Lane2<C>& L, const WarpJob& J
   }
 }
 
-template <class C, bool WITH_ID = true, int ROW_STEP = 1, bool TG_DIRECT = false, bool ASYNC = false>
-__device__ __forceinline__ void stage_a_issue2(Lane2<C>& L, Flight2& F, const Params& P, const WarpJob& J, int t, F4* tapdst = nullptr) {
+// UNI: the lane-invariant projection rows (qb, p4 over the two sources; 6 float2) are read from shared memory
+// (`uni`, broadcast LDS) instead of living in 12 registers, and the target texel is left to the caller (role_a2_pipe
+// keeps ONE copy for the row being interpolated instead of one per Flight record).
+template <class C, bool WITH_ID = true, int ROW_STEP = 1, bool TG_DIRECT = false, bool ASYNC = false, bool UNI = false>
+__device__ __forceinline__ void stage_a_issue2(Lane2<C>& L, Flight2& F, const Params& P, const WarpJob& J, int t, F4* tapdst = nullptr,
+                                               const P2* uni = nullptr) {
   const int tr = reflect_clamp(t, J.H);
-  if (TG_DIRECT) {
+  if (UNI) {
+  } else if (TG_DIRECT) {
     if (J.staged) F.ctg = make_f4(0.f, 0.f, 0.f, 0.f);      // the row goes into the ring by TMA
     else F.ctg = MD2_LDS4(J.tgt4 + 4 * (tr * J.W + L.xi));
   } else F.ctg = L.ntg;
@@ -232,12 +237,14 @@ __device__ __forceinline__ void stage_a_issue2(Lane2<C>& L, Flight2& F, const Pa
   const float z = MD2_RCP(sd);
   F.cz = z;
   const float yf = (float)tr;
-  const P2 q0 = fma2(L.qb[0], bc(yf), L.qa[0]);
-  const P2 q1 = fma2(L.qb[1], bc(yf), L.qa[1]);
-  const P2 q2 = fma2(L.qb[2], bc(yf), L.qa[2]);
-  const P2 c0 = fma2(bc(z), q0, L.p4[0]);
-  const P2 c1 = fma2(bc(z), q1, L.p4[1]);
-  const P2 c2 = fma2(bc(z), q2, L.p4[2]);
+  const P2 qb0 = UNI ? uni[0] : L.qb[0], qb1 = UNI ? uni[1] : L.qb[1], qb2 = UNI ? uni[2] : L.qb[2];
+  const P2 p40 = UNI ? uni[3] : L.p4[0], p41 = UNI ? uni[4] : L.p4[1], p42 = UNI ? uni[5] : L.p4[2];
+  const P2 q0 = fma2(qb0, bc(yf), L.qa[0]);
+  const P2 q1 = fma2(qb1, bc(yf), L.qa[1]);
+  const P2 q2 = fma2(qb2, bc(yf), L.qa[2]);
+  const P2 c0 = fma2(bc(z), q0, p40);
+  const P2 c1 = fma2(bc(z), q1, p41);
+  const P2 c2 = fma2(bc(z), q2, p42);
   const P2 den = add2(c2, bc(P.eps));
   const P2 r0 = p2(rcp_fast(den.x), rcp_fast(den.y));
   const P2 inv = fma2(r0, fma2(neg2(den), r0, bc(1.0f)), r0);      // Newton step of rcp_nr
@@ -266,11 +273,29 @@ __device__ __forceinline__ void stage_a_issue2(Lane2<C>& L, Flight2& F, const Pa
       cp_async16(tapdst + (f * 4 + 2) * kLanes, t00 + dy1);
       cp_async16(tapdst + (f * 4 + 3) * kLanes, t00 + dy1 + dx1);
     } else {
+#if defined(MD2_TAP_SPLIT) && defined(__CUDA_ARCH__)
+      // 8-byte + 4-byte load per texel instead of one 16-byte load: no register is tied up by the unused 4th component
+      auto ld3 = [](const float* p) {
+        const float2 a = __ldg(reinterpret_cast<const float2*>(p));
+        return make_f4(a.x, a.y, __ldg(p + 2), 0.f);
+      };
+      F.tap[f][0] = ld3(t00);
+      F.tap[f][1] = ld3(t00 + dx1);
+      F.tap[f][2] = ld3(t00 + dy1);
+      F.tap[f][3] = ld3(t00 + dy1 + dx1);
+#else
       F.tap[f][0] = MD2_LD4(t00);
       F.tap[f][1] = MD2_LD4(t00 + dx1);
       F.tap[f][2] = MD2_LD4(t00 + dy1);
       F.tap[f][3] = MD2_LD4(t00 + dy1 + dx1);
+#endif
     }
+#ifdef MD2_TAP_PREFETCH
+    // the next image row gathers (to first order) one source row further down: its upper taps are this row's lower
+    // taps (already in L1), its lower taps are pulled into L1 now - no destination register, no scoreboard - so that
+    // the gather issued one period later does not pay the L2 / HBM latency inside role A, the role every barrier waits for
+    MD2_PREFETCH_L1(t00 + ((y0 + MD2_TAP_PREFETCH < J.H) ? MD2_TAP_PREFETCH * J.W * 4 : dy1));
+#endif
   }
 }
 
@@ -293,6 +318,12 @@ __device__ __forceinline__ void stage_a_finish2(Lane2<C>& L, const Flight2& F, c
 #pragma unroll
   for (int f = 0; f < 2; ++f) {
     const F4 nw = F.tap[f][0], ne = F.tap[f][1], sw = F.tap[f][2], se = F.tap[f][3];
+#if defined(MD2_KEEP_W) && defined(__CUDA_ARCH__)
+    // the unused 4th component of a texel load stays reserved until the load is consumed: ptxas otherwise reuses the
+    // register as scratch while the load is in flight, and the write waits for the load (measured: 1 700 of A's 8 300
+    // stall samples on one such FSEL / MOV)
+    asm volatile("" ::"f"(nw.w), "f"(ne.w), "f"(sw.w), "f"(se.w));
+#endif
     const float wx = f ? F.cwx.y : F.cwx.x, wy = f ? F.cwy.y : F.cwy.x;
     const float gxs = f ? F.cgx.y : F.cgx.x, gys = f ? F.cgy.y : F.cgy.x;
     // channels (r,g) as a pair

@@ -44,6 +44,11 @@ namespace md2 {
 #define MD2_ROLE_ASYNC_TAPS 0
 #endif
 constexpr int kRoleAWarps = MD2_ROLE_A_WARPS;
+// cp.async form of role A: 1 = the disparity taps of row t+2 are put in flight inside the issue phase of row t+1,
+// right after those of row t+1 are consumed (a whole period to land); 0 = after the finish phase (round-2 first form)
+#ifndef MD2_ASYNC_ROW_STEP
+#define MD2_ASYNC_ROW_STEP 1
+#endif
 #ifndef MD2_ROLE_MIN_CTAS3
 #define MD2_ROLE_MIN_CTAS3 3      // three and more sources: 168 registers, no spills (4 CTAs: 128 registers, 0.4 KB of spills)
 #endif
@@ -75,7 +80,8 @@ struct RoleCfg {
   static constexpr bool ASYNC_TAPS = (NA == 1) && (MD2_ROLE_ASYNC_TAPS != 0);
   static constexpr int TAP_F4 = ASYNC_TAPS ? 2 * TAPROW_F4 : 0;
   static constexpr int BAR_F4 = (RING * 8 + 15) / 16;            // one mbarrier per ring slot (TMA-staged target row)
-  static constexpr int SMEM_F4 = STASH_F4 + COEF_F4 + TAP_F4 + BAR_F4;
+  static constexpr int UNI_F4 = 3;                                // lane-invariant projection rows (role_a2_pipe)
+  static constexpr int SMEM_F4 = STASH_F4 + COEF_F4 + TAP_F4 + BAR_F4 + UNI_F4;
 };
 
 template <int NT>
@@ -316,11 +322,11 @@ __device__ __forceinline__ void role_a2_async(const Params& P, const WarpJob& J,
   Lane2<C> L;
   lane_init2(L, P, J, lane);
   Flight2 F[2];
-  stage_a_issue2<C, false, 0, true, true>(L, F[0], P, J, t0, tapbuf);
+  stage_a_issue2<C, false, MD2_ASYNC_ROW_STEP, true, true>(L, F[0], P, J, t0, tapbuf);
   cp_async_commit();
-  prefetch_row2<C, false>(L, J, t0 + 1);
+  if (MD2_ASYNC_ROW_STEP == 0) prefetch_row2<C, false>(L, J, t0 + 1);
   auto half = [&](int t, Flight2& Fc, Flight2& Fn, F4* bufc, F4* bufn) {
-    if (t + 1 <= t1) stage_a_issue2<C, false, 0, true, true>(L, Fn, P, J, t + 1, bufn);
+    if (t + 1 <= t1) stage_a_issue2<C, false, MD2_ASYNC_ROW_STEP, true, true>(L, Fn, P, J, t + 1, bufn);
     cp_async_commit();
     if (t <= t1) {
       stage_target_row<C>(J, st, t, lane);
@@ -330,7 +336,7 @@ __device__ __forceinline__ void role_a2_async(const Params& P, const WarpJob& J,
 #pragma unroll
         for (int q = 0; q < 4; ++q) Fc.tap[f][q] = bufc[(f * 4 + q) * kLanes];
       stage_a_finish2<C, ST, true>(L, Fc, P, J, t, st);
-      prefetch_row2<C, false>(L, J, t + 2);
+      if (MD2_ASYNC_ROW_STEP == 0) prefetch_row2<C, false>(L, J, t + 2);
     }
     role_sync<RC::THREADS>();
   };
@@ -377,6 +383,45 @@ __device__ __forceinline__ void role_a2(const Params& P, const WarpJob& J, int l
       }
     }
     role_sync<RoleCfg<C>::THREADS>();
+  }
+}
+
+// NA == 1, register form of the two-rows-in-flight schedule: the gather of row t+1 is issued BEFORE row t is
+// interpolated, into the other of two Flight records (loop unrolled by two, so the records alternate without moves and
+// the loads of even and odd rows are different static instructions: ptxas gives them different scoreboards, and the
+// interpolation of row t does not wait for the gather of row t+1).  Measured reason (profiles/r02n): with issue and
+// finish of the SAME row back to back, role A spends 39 % of its time waiting for the gather it just issued, and A is
+// the role every barrier waits for (B waits 32 % of its time at the barrier, C 50 %).
+template <class C, class ST>
+__device__ __forceinline__ void role_a2_pipe(const Params& P, const WarpJob& J, int lane, const ST& st, P2* uni,
+                                             int t0, int t1, int nit) {
+  typedef RoleCfg<C> RC;
+  Lane2<C> L;
+  lane_init2(L, P, J, lane);
+  // lane-invariant projection rows -> shared memory (read back as broadcast loads in every issue phase)
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { uni[i] = L.qb[i]; uni[3 + i] = L.p4[i]; }
+  }
+  __syncwarp();
+  Flight2 F[2];
+  stage_a_issue2<C, false, 1, true, false, true>(L, F[0], P, J, t0, nullptr, uni);
+  auto half = [&](int t, Flight2& Fc, Flight2& Fn) {
+    if (t <= t1) {
+      stage_target_row<C>(J, st, t, lane);
+      // border bands (not staged by TMA): the target texel of row t, in flight across the issue phase of row t+1
+      F4 tg = make_f4(0.f, 0.f, 0.f, 0.f);
+      if (!J.staged) tg = MD2_LDS4(J.tgt4 + 4 * (reflect_clamp(t, J.H) * J.W + L.xi));
+      if (t + 1 <= t1) stage_a_issue2<C, false, 1, true, false, true>(L, Fn, P, J, t + 1, nullptr, uni);
+      Fc.ctg = tg;
+      stage_a_finish2<C, ST, true>(L, Fc, P, J, t, st);
+    }
+    role_sync<RC::THREADS>();
+  };
+#pragma unroll 1
+  for (int p = 0; p < nit; p += 2) {
+    half(t0 + p, F[0], F[1]);
+    if (p + 1 < nit) half(t0 + p + 1, F[1], F[0]);
   }
 }
 
@@ -564,7 +609,11 @@ __global__ void MD2_ROLE_BOUNDS(C) md2_march_roles(Params P) {
     }
   }
   if constexpr (PACKED) {
+#ifdef MD2_ROLE_A_PIPE
+    if (role < RC::NA) role_a2_pipe<C>(P, J, lane, st, reinterpret_cast<P2*>(smem + RC::STASH_F4 + RC::COEF_F4 + RC::TAP_F4 + RC::BAR_F4), t0, t1, nit);
+#else
     if (role < RC::NA) role_a2<C>(P, J, lane, role, st, t0, t1, nit);
+#endif
     else if (role == RC::NA) role_b2<C>(P, J, lane, st, cring, t0, t1, nit);
 #ifdef MD2_ROLE_PACKED_C
     else if (C::GRAD) role_c2<C>(P, J, lane, st, cring, t0, t1, nit);
