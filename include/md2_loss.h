@@ -48,6 +48,10 @@ typedef struct md2_problem {
   int want_grad;              /* 0: forward only (Trainer.val under no_grad, trainer.py:330) */
   int rows_per_segment;       /* tuning: rows marched per warp job (0 = default) */
   int no_ssim;                /* opt.no_ssim: L1 only                  options.py:117 */
+  int posecnn;                /* opt.pose_model_type == "posecnn" (options.py:101, trainer.py:366-375): T is built per
+                                 scale from the pose leaves with the translation multiplied by the mean inverse depth
+                                 of that scale; needs axisangle / translation for every source without a fixed T */
+  int predictive_mask;        /* opt.predictive_mask (options.py:114, trainer.py:447-459); needs automask == 0 */
 } md2_problem;
 
 /* Tensors of one evaluation.  Names follow the reference's dict keys. */
@@ -94,6 +98,12 @@ typedef struct md2_tensors {
   const unsigned char *source_u8[MD2_MAX_SRC];
   const unsigned char *color_u8[MD2_MAX_SCALES];
   int u8_hwc;
+  /* ---- --predictive_mask (trainer.py:447-459): outputs["predictive_mask"][("disp", s)], (B,num_src,H>>s,W>>s)
+   *      in (0,1); up-sampled to (H,W) inside the call, multiplied into the reprojection losses before the per-pixel
+   *      minimum, and pushed towards 1 by 0.2 * BCE(mask, 1) added to loss/s.  grad_pmask[s] (same shape) receives
+   *      d loss / d mask when want_grad; NULL = not wanted. ---- */
+  const float *pmask[MD2_MAX_SCALES];
+  float *grad_pmask[MD2_MAX_SCALES];
 } md2_tensors;
 
 int md2_version(void);

@@ -21,6 +21,7 @@ class Md2Problem(C.Structure):
         ("automask", C.c_int), ("avg_reprojection", C.c_int), ("align_corners", C.c_int),
         ("min_depth", C.c_float), ("max_depth", C.c_float), ("disparity_smoothness", C.c_float),
         ("want_grad", C.c_int), ("rows_per_segment", C.c_int), ("no_ssim", C.c_int),
+        ("posecnn", C.c_int), ("predictive_mask", C.c_int),
     ]
 
 
@@ -53,6 +54,8 @@ class Md2Tensors(C.Structure):
         ("source_u8", C.c_void_p * MAX_SRC),
         ("color_u8", C.c_void_p * MAX_SCALES),
         ("u8_hwc", C.c_int),
+        ("pmask", C.c_void_p * MAX_SCALES),
+        ("grad_pmask", C.c_void_p * MAX_SCALES),
     ]
 
 

@@ -193,6 +193,12 @@ constexpr float kSsimC2 = 0.0009f;
 struct Params {
   int B, H, W, S, nsrc, nid;
   int automask, avg, align_corners, want_grad, no_ssim;
+  // --pose_model_type posecnn (trainer.py:366-375): one T per (scale, sample, source), built from the pose leaves
+  // with the translation multiplied by the mean inverse depth of the scale.  npose = S (posecnn) or 1: the number of
+  // projection tables / pose-gradient accumulators per (sample, source).
+  int posecnn, npose;
+  // --predictive_mask (trainer.py:447-459)
+  int pmask_on;
   float a_disp, c_disp;      // scaled_disp = a + c*disp            layers.py:21-23
   float sx, ox, sy, oy;      // ix = u*sx + ox ; iy = v*sy + oy     (grid normalise o unnormalise)
   float wmax, hmax;          // W-1, H-1
@@ -234,6 +240,12 @@ struct Params {
   float* dD[kMaxScales];   // (B,H,W)   d loss / d upsampled disp_s
   float* gn[kMaxScales];   // (B,Hs,Ws) smoothness numerator gradient
   float* smsc;             // (S,B,2): 1/m and (sum gn*disp)/(m^2 N) of the smoothness adjoint, as floats
+  float* mid;              // posecnn: (S,B) mean inverse depth of the up-sampled disparity (trainer.py:371-372)
+  float* gmidc;            // posecnn: (S,B) d loss / d (every pixel of the up-sampled disp_s) through mean_inv_depth
+  const float* pmask[kMaxScales];   // predictive mask, (B,nsrc,Hs,Ws)
+  float* pm[kMaxScales];            // (B,nsrc,H,W) mask up-sampled to full resolution (trainer.py:451-454)
+  float* gpm[kMaxScales];           // (B,nsrc,H,W) d loss / d up-sampled mask (photometric part)
+  float* grad_pmask[kMaxScales];    // out (B,nsrc,Hs,Ws)
   double* acc;     // accumulators, layout below
   // outputs
   float* losses;
@@ -250,14 +262,25 @@ MD2_HD int acc_photo(int s) { return s; }
 // acc_smx / acc_smy below, so that the blocks of md2_smooth do not all hit two addresses per scale)
 MD2_HD int acc_dispsum(const Params& P, int s, int b) { return 3 * kMaxScales + s * P.B + b; }
 MD2_HD int acc_dot(const Params& P, int s, int b) { return 3 * kMaxScales + kMaxScales * P.B + s * P.B + b; }
-MD2_HD int acc_dP(const Params& P, int b, int f, int k) {
-  return 3 * kMaxScales + 2 * kMaxScales * P.B + (b * P.nsrc + f) * 12 + k;
+// ps: pose set (the scale under posecnn, else 0)
+MD2_HD int acc_dP(const Params& P, int ps, int b, int f, int k) {
+  return 3 * kMaxScales + 2 * kMaxScales * P.B + ((ps * P.B + b) * P.nsrc + f) * 12 + k;
 }
 MD2_HD int acc_smx(const Params& P, int s, int b) {
-  return 3 * kMaxScales + 2 * kMaxScales * P.B + P.B * P.nsrc * 12 + 2 * (s * P.B + b);
+  return 3 * kMaxScales + 2 * kMaxScales * P.B + P.npose * P.B * P.nsrc * 12 + 2 * (s * P.B + b);
 }
 MD2_HD int acc_smy(const Params& P, int s, int b) { return acc_smx(P, s, b) + 1; }
-MD2_HD int acc_count(const Params& P) { return 3 * kMaxScales + 4 * kMaxScales * P.B + P.B * P.nsrc * 12; }
+// posecnn: sum of the up-sampled disparity of (scale, sample) over the full-resolution grid
+MD2_HD int acc_updisp(const Params& P, int s, int b) {
+  return 3 * kMaxScales + 4 * kMaxScales * P.B + P.npose * P.B * P.nsrc * 12 + s * P.B + b;
+}
+// predictive mask: sum of -log(mask) over the up-sampled mask of scale s (BCE against ones, trainer.py:458)
+MD2_HD int acc_bce(const Params& P, int s) {
+  return 3 * kMaxScales + 5 * kMaxScales * P.B + P.npose * P.B * P.nsrc * 12 + s;
+}
+MD2_HD int acc_count(const Params& P) {
+  return 3 * kMaxScales + 5 * kMaxScales * P.B + P.npose * P.B * P.nsrc * 12 + kMaxScales;
+}
 
 // ToTensor (torchvision.transforms.functional.to_tensor): uint8 -> float32, then .div(255)
 MD2_HD float u8_unit(unsigned char v) { return MD2_DIV((float)v, 255.0f); }
@@ -280,6 +303,10 @@ MD2_HD float load_px(const float* f32, const unsigned char* u8, int hwc, int b, 
 // is 32-bit index arithmetic (validate() bounds the tensors below 2^31 elements).
 struct WarpJob {
   int s, b;
+  int ps;        // pose set: s under posecnn, else 0
+  const float* proj;   // projection table of (ps, b): nsrc x 12 floats
+  const float* pm;     // predictive mask up-sampled to (H,W), planes [nsrc] of sample b at scale s (or null)
+  float* gpm;          // its gradient planes (or null)
   int x0;        // first owned column
   int y0, y1;    // owned rows [y0, y1)
   int H, W, Hs, Ws, plane;
@@ -309,7 +336,11 @@ MD2_HD WarpJob make_job(const Params& P, int s, int b, int x0, int y0, int y1) {
   J.s = s; J.b = b; J.x0 = x0; J.y0 = y0; J.y1 = y1;
   J.H = P.H; J.W = P.W; J.Hs = P.H >> s; J.Ws = P.W >> s; J.plane = P.H * P.W;
   J.rs = 1.0f / (float)(1 << s);
+  J.ps = P.posecnn ? s : 0;
+  J.proj = P.proj + (size_t)((J.ps * P.B + b) * P.nsrc) * 12;
   const int boff = b * J.plane;
+  J.pm = (P.pmask_on && P.pm[s]) ? P.pm[s] + (size_t)P.nsrc * boff : nullptr;
+  J.gpm = (P.pmask_on && P.want_grad && P.gpm[s]) ? P.gpm[s] + (size_t)P.nsrc * boff : nullptr;
   J.tgt4 = P.tgt4 + 4 * boff;
   for (int f = 0; f < kMaxSrc; ++f) {
     J.src4[f] = f < P.nsrc ? P.src4[f] + 4 * boff : nullptr;
@@ -508,7 +539,7 @@ MD2_HD void lane_init(Lane<C>& L, const Params& P, const WarpJob& J, int lane) {
   const float xf = (float)L.xi;
 #pragma unroll
   for (int f = 0; f < C::NSRC; ++f) {
-    const float* m = P.proj + (J.b * C::NSRC + f) * 12;
+    const float* m = J.proj + f * 12;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       L.qa[f][i] = fmaf(MD2_LD(m + i * 3 + 0), xf, MD2_LD(m + i * 3 + 2));
@@ -584,6 +615,45 @@ MD2_HD void load_identity_row(Lane<C>& L, const WarpJob& J, int t) {
     for (int f = 0; f < C::NSRC; ++f) L.idv[f] = MD2_LDS1(J.idl + f * J.plane + pix);
 #pragma unroll
     for (int f = 0; f < C::NID; ++f) L.nzv[f] = MD2_LDS1(J.noise + f * J.plane + pix);
+  } else if (J.pm) {
+    // --predictive_mask (needs --disable_automasking, trainer.py:90-92): the up-sampled mask of window row t-1
+    const int yw = t - 1;
+    const int pix = (yw < 0 ? 0 : (yw >= J.H ? J.H - 1 : yw)) * J.W + L.xi;
+    MD2_CHK(pix, J.plane);
+#pragma unroll
+    for (int f = 0; f < C::NSRC; ++f) L.nzv[f] = MD2_LDS1(J.pm + f * J.plane + pix);
+  }
+}
+
+// --predictive_mask, stage B (trainer.py:456): reprojection_losses *= mask, before the mean / minimum over sources.
+// rl keeps the unmasked loss (it is d loss / d mask of the winner), rlm receives the masked one.
+template <class C>
+MD2_HD void pmask_apply(const Lane<C>& L, const WarpJob& J, const float* rl, float* rlm) {
+#pragma unroll
+  for (int f = 0; f < C::NSRC; ++f) rlm[f] = (!C::AUTOMASK && J.pm) ? rl[f] * L.nzv[f] : rl[f];
+}
+// d loss / d (up-sampled mask) of the window pixel (photometric part; the BCE part is added by the final pass),
+// and the winner's SSIM-adjoint coefficients scaled by its mask value
+template <class C>
+MD2_HD void pmask_backward(Lane<C>& L, const Params& P, const WarpJob& J, const float* rl, int tag, bool own_win, int yw) {
+  if (C::AUTOMASK || !J.pm) return;
+  if (C::GRAD) {
+#pragma unroll
+    for (int n = 0; n < C::NCS; ++n) {
+      float m = L.nzv[0];
+      if (C::AVG) m = L.nzv[n];
+      else {
+#pragma unroll
+        for (int f = 1; f < C::NSRC; ++f) m = (tag == f) ? L.nzv[f] : m;
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) L.coef[n][k] *= m;
+    }
+    if (own_win && J.gpm) {
+#pragma unroll
+      for (int f = 0; f < C::NSRC; ++f)
+        J.gpm[f * J.plane + yw * J.W + L.xi] = (C::AVG ? (tag >= 0) : (tag == f)) ? rl[f] * P.gscale : 0.0f;
+    }
   }
 }
 
@@ -807,16 +877,18 @@ MD2_HD void stage_b_divergent(Lane<C>& L, const Params& P, const WarpJob& J, int
         }
       }
     }
+    float rlm[C::NSRC];
+    pmask_apply<C>(L, J, rl, rlm);
     if (C::AVG) {
       float acc = 0.f;
 #pragma unroll
-      for (int f = 0; f < C::NSRC; ++f) acc += rl[f];
+      for (int f = 0; f < C::NSRC; ++f) acc += rlm[f];
       const float cand = acc * (1.0f / (float)C::NSRC);
       if (cand < best) { best = cand; tag = 0; }
     } else {
 #pragma unroll
       for (int f = 0; f < C::NSRC; ++f)
-        if (rl[f] < best) { best = rl[f]; tag = f; }
+        if (rlm[f] < best) { best = rlm[f]; tag = f; }
     }
     if (own_win) {
       L.loss += best;
@@ -857,6 +929,7 @@ MD2_HD void stage_b_divergent(Lane<C>& L, const Params& P, const WarpJob& J, int
         }
       }
     }
+    pmask_backward<C>(L, P, J, rl, tag, own_win, yw);
   }
   L.tag = tag;
   MD2_DBG(if (own_win) D.tag[(((long)J.s * D.B + J.b) * D.H + yw) * D.W + L.x] = (signed char)tag;);
@@ -941,18 +1014,20 @@ MD2_HD void stage_b_straight(Lane<C>& L, const Params& P, const WarpJob& J, int 
         }
       }
     }
+    float rlm[C::NSRC];
+    pmask_apply<C>(L, J, rl, rlm);
     if (C::AVG) {
       float acc = 0.f;
 #pragma unroll
-      for (int f = 0; f < C::NSRC; ++f) acc += rl[f];
+      for (int f = 0; f < C::NSRC; ++f) acc += rlm[f];
       const float cand = acc * (1.0f / (float)C::NSRC);
       tag = (cand < best) ? 0 : tag;
       best = (cand < best) ? cand : best;
     } else {
 #pragma unroll
       for (int f = 0; f < C::NSRC; ++f) {
-        tag = (rl[f] < best) ? f : tag;
-        best = (rl[f] < best) ? rl[f] : best;
+        tag = (rlm[f] < best) ? f : tag;
+        best = (rlm[f] < best) ? rlm[f] : best;
       }
     }
     tag = win_ok ? tag : -1;
@@ -999,6 +1074,7 @@ MD2_HD void stage_b_straight(Lane<C>& L, const Params& P, const WarpJob& J, int 
 #pragma unroll
         for (int k = 0; k < 9; ++k) L.coef[n][k] = 0.f;
     }
+    pmask_backward<C>(L, P, J, rl, tag, own_win, yw);
   }
   L.tag = tag;
   MD2_DBG(if (own_win) D.tag[(((long)J.s * D.B + J.b) * D.H + yw) * D.W + L.x] = (signed char)tag;);
@@ -1087,6 +1163,8 @@ MD2_HD void stage_c_divergent(Lane<C>& L, const Params& P, const WarpJob& J, int
       const float xs[3] = {sp.x, sp.y, sp.z};
       const float dxs[3] = {sdx.x, sdx.y, sdx.z}, dys[3] = {sdy.x, sdy.y, sdy.z};
       const bool won = C::AVG ? (L.tag1 >= 0) : (L.tag1 == f);
+      // --predictive_mask: the L1 term of this pixel carries its mask value (the SSIM coefficients already do)
+      const float mk = (!C::AUTOMASK && J.pm && won) ? MD2_LD(J.pm + f * J.plane + yp * J.W + L.xi) : 1.0f;
       float d0 = 0.f, d1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -1097,7 +1175,7 @@ MD2_HD void stage_c_divergent(Lane<C>& L, const Params& P, const WarpJob& J, int
         // d loss / d pred_c = 0.85/3 * SSIM part + 0.15/3 * sign(x - y) [if this source won here]
         float g = C::NOSSIM ? 0.0f : (0.85f / 3.0f) * fmaf(xj, Bq, fmaf(tg[c], G, A));
         if (won) {
-          const float kl1 = C::NOSSIM ? (1.0f / 3.0f) : (0.15f / 3.0f);
+          const float kl1 = (C::NOSSIM ? (1.0f / 3.0f) : (0.15f / 3.0f)) * mk;
           const float df = xj - tg[c];
           g += (df != 0.f) ? copysignf(kl1, df) : 0.0f;
           MD2_DBG(D.l1sgn[(((((long)J.s * D.B + J.b) * D.nsrc + f) * 3 + c) * D.H + yp) * D.W + L.x] =
@@ -1200,6 +1278,7 @@ MD2_HD void stage_c_straight(Lane<C>& L, const Params& P, const WarpJob& J, int 
       const float xs[3] = {sp.x, sp.y, sp.z};
       const float dxs[3] = {sdx.x, sdx.y, sdx.z}, dys[3] = {sdy.x, sdy.y, sdy.z};
       const bool won = C::AVG ? (L.tag1 >= 0) : (L.tag1 == f);
+      const float mk = (!C::AUTOMASK && J.pm && won && own) ? MD2_LD(J.pm + f * J.plane + yp * J.W + L.xi) : 1.0f;
       float d0 = 0.f, d1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -1210,7 +1289,7 @@ MD2_HD void stage_c_straight(Lane<C>& L, const Params& P, const WarpJob& J, int 
         // d loss / d pred_c = 0.85/3 * SSIM part + 0.15/3 * sign(x - y) [if this source won here]
         float g = C::NOSSIM ? 0.0f : (0.85f / 3.0f) * fmaf(xj, Bq, fmaf(tg[c], G, A));
         {
-          const float kl1 = C::NOSSIM ? (1.0f / 3.0f) : (0.15f / 3.0f);
+          const float kl1 = (C::NOSSIM ? (1.0f / 3.0f) : (0.15f / 3.0f)) * mk;
           const float df = xj - tg[c];
           g += (won && df != 0.f) ? copysignf(kl1, df) : 0.0f;
           MD2_DBG(if (own) D.l1sgn[(((((long)J.s * D.B + J.b) * D.nsrc + f) * 3 + c) * D.H + yp) * D.W + L.x] =
@@ -1500,22 +1579,60 @@ MD2_HD void pose_to_matrix_backward(const float* g, const float* v, const float*
 
 // ------------------------------------------------------------------ small per-element pieces
 // proj table: M = (K T)[:3,:3] * invK[:3,:3], p4 = (K T)[:3,3], in double then rounded once.
-MD2_HD void setup_projection(const Params& P, int b, int f) {
+// value at fine pixel (y, x) of plane `d` (Hs x Ws, level s) up-sampled bilinearly to (Hs << s, Ws << s):
+// F.interpolate(..., mode="bilinear", align_corners=False) (trainer.py:350-351, 451-454), torch upsample_bilinear2d
+MD2_HD float upsample_at(const float* d, int s, int Hs, int Ws, int y, int x) {
+  if (s == 0) return MD2_LD(d + y * Ws + x);
+  const float rs = 1.0f / (float)(1 << s);
+  float sy = fmaf(rs, (float)y + 0.5f, -0.5f);
+  sy = sy < 0.0f ? 0.0f : sy;
+  float sx = fmaf(rs, (float)x + 0.5f, -0.5f);
+  sx = sx < 0.0f ? 0.0f : sx;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + ((y0 < Hs - 1) ? 1 : 0), x1 = x0 + ((x0 < Ws - 1) ? 1 : 0);
+  const float ly1 = sy - (float)y0, ly0 = 1.0f - ly1, lx1 = sx - (float)x0, lx0 = 1.0f - lx1;
+  const float top = lx0 * MD2_LD(d + y0 * Ws + x0) + lx1 * MD2_LD(d + y0 * Ws + x1);
+  const float bot = lx0 * MD2_LD(d + y1 * Ws + x0) + lx1 * MD2_LD(d + y1 * Ws + x1);
+  return ly0 * top + ly1 * bot;
+}
+
+// posecnn (trainer.py:366-375): mean_inv_depth = (1 / depth).mean(3).mean(2) = a + c * mean(up-sampled disp_s);
+// the sums come from acc_updisp (md2_updisp_sum)
+MD2_HD void posecnn_mid(const Params& P, int s, int b) {
+  const double m = P.acc[acc_updisp(P, s, b)] / ((double)P.H * P.W);
+  P.mid[s * P.B + b] = (float)((double)P.a_disp + (double)P.c_disp * m);
+}
+
+// ps: pose set (scale under posecnn, else 0)
+MD2_HD void setup_projection(const Params& P, int ps, int b, int f) {
   const float* K = P.K + (size_t)b * 16;
-  if (P.aa[f]) {     // T from the pose leaves, written where Tm[f] points (P.Tws[f])
-    pose_to_matrix(P.aa[f] + (size_t)b * P.pose_stride[f], P.tr[f] + (size_t)b * P.pose_stride[f], P.pose_invert[f],
-                   P.Tws[f] + (size_t)b * 16);
+  float Tl[16];
+  const float* T;
+  if (P.aa[f]) {     // T from the pose leaves
+    const float* aa = P.aa[f] + (size_t)b * P.pose_stride[f];
+    const float* tr = P.tr[f] + (size_t)b * P.pose_stride[f];
+    // the unscaled T is what predict_poses stores as outputs[("cam_T_cam", 0, f)] (trainer.py:294-295)
+    if (ps == 0) pose_to_matrix(aa, tr, P.pose_invert[f], P.Tws[f] + (size_t)b * 16);
+    if (P.posecnn) {
+      const float m = P.mid[ps * P.B + b];
+      const float trs[3] = {MD2_LD(tr) * m, MD2_LD(tr + 1) * m, MD2_LD(tr + 2) * m};     // trainer.py:374-375
+      pose_to_matrix(aa, trs, P.pose_invert[f], Tl);
+      T = Tl;
+    } else {
+      T = P.Tws[f] + (size_t)b * 16;
+    }
+  } else {
+    T = P.Tm[f] + (size_t)b * 16;
   }
-  const float* T = (P.aa[f] ? P.Tws[f] : P.Tm[f]) + (size_t)b * 16;
   const float* iK = P.invK + (size_t)b * 16;
   double Pm[3][4];
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 4; ++j) {
       double a = 0.0;
-      for (int k = 0; k < 4; ++k) a += (double)MD2_LD(K + i * 4 + k) * (double)MD2_LD(T + k * 4 + j);
+      for (int k = 0; k < 4; ++k) a += (double)MD2_LD(K + i * 4 + k) * (double)T[k * 4 + j];   // (T may be the local Tl)
       Pm[i][j] = a;
     }
-  float* o = P.proj + (size_t)(b * P.nsrc + f) * 12;
+  float* o = P.proj + (size_t)((ps * P.B + b) * P.nsrc + f) * 12;
   for (int i = 0; i < 3; ++i) {
     for (int j = 0; j < 3; ++j) {
       double a = 0.0;
@@ -1600,6 +1717,7 @@ MD2_HD float up_weight(int i, int X, int n) {
 template <int K>
 MD2_HD float upsample_adjoint_part(const Params& P, int s, int b, int Y, int X, int j) {
   const int Hs = P.H >> s, Ws = P.W >> s;
+  const float cst = P.posecnn ? MD2_LD(P.gmidc + s * P.B + b) : 0.0f;    // see final_pose_posecnn
   const float* dD = P.dD[s] + (size_t)b * P.H * P.W;
   const int xlo = K * X - K / 2, ylo = K * Y - K / 2;
   const bool interior_x = (X > 0) && (X < Ws - 1);
@@ -1617,14 +1735,14 @@ MD2_HD float upsample_adjoint_part(const Params& P, int s, int b, int Y, int X, 
 #pragma unroll
       for (int i = 0; i < 2 * K; ++i) {
         const float w = (i < K) ? ((float)i + 0.5f) * (1.0f / (float)K) : ((float)(2 * K - i) - 0.5f) * (1.0f / (float)K);
-        row = fmaf(w, MD2_LD(rowp + xlo + i), row);
+        row = fmaf(w, MD2_LD(rowp + xlo + i) + cst, row);
       }
     } else {
 #pragma unroll
       for (int i = 0; i < 2 * K; ++i) {
         const int x = xlo + i;
         const int xc = x < 0 ? 0 : (x >= P.W ? P.W - 1 : x);
-        row = fmaf(up_weight<K>(i, X, Ws), MD2_LD(rowp + xc), row);
+        row = fmaf(up_weight<K>(i, X, Ws), MD2_LD(rowp + xc) + cst, row);
       }
     }
     acc = fmaf(wy, row, acc);
@@ -1641,13 +1759,16 @@ MD2_HD void final_scalars(const Params& P) {
     double sx = 0.0, sy = 0.0;
     for (int b = 0; b < P.B; ++b) { sx += P.acc[acc_smx(P, s, b)]; sy += P.acc[acc_smy(P, s, b)]; }
     const double sm = sx / ((double)P.B * Hs * (Ws - 1)) + sy / ((double)P.B * (Hs - 1) * Ws);
-    const double ls = photo + (double)P.smooth_w[s] * sm;
+    double ls = photo + (double)P.smooth_w[s] * sm;
+    if (P.pmask_on)       // trainer.py:458-459: loss += 0.2 * BCELoss(mask, ones)
+      ls += 0.2 * P.acc[acc_bce(P, s)] / ((double)P.B * P.nsrc * P.H * P.W);
     P.losses[1 + s] = (float)ls;
     total += ls;
   }
   P.losses[0] = (float)(total / P.S);
 }
 MD2_HD void final_grad_T(const Params& P, int b, int f) {
+  if (P.posecnn) return;            // see final_pose_posecnn
   float* g = P.grad_T[f];
   const bool leaves = P.aa[f] && P.grad_aa[f] && P.grad_tr[f];
   if (!g && !leaves) return;
@@ -1657,7 +1778,7 @@ MD2_HD void final_grad_T(const Params& P, int b, int f) {
     for (int j = 0; j < 4; ++j) {
       double a = 0.0;
       if (P.pose_grad[f])
-        for (int i = 0; i < 3; ++i) a += (double)MD2_LD(K + i * 4 + k) * P.acc[acc_dP(P, b, f, i * 4 + j)];
+        for (int i = 0; i < 3; ++i) a += (double)MD2_LD(K + i * 4 + k) * P.acc[acc_dP(P, 0, b, f, i * 4 + j)];
       gT[k * 4 + j] = (float)(a * (double)P.gscale);
     }
   if (g)
@@ -1665,6 +1786,102 @@ MD2_HD void final_grad_T(const Params& P, int b, int f) {
   if (leaves)      // adjoint of transformation_from_parameters: the pose gradient leaves the path here
     pose_to_matrix_backward(gT, P.aa[f] + (size_t)b * P.pose_stride[f], P.tr[f] + (size_t)b * P.pose_stride[f],
                             P.pose_invert[f], P.grad_aa[f] + (size_t)b * 3, P.grad_tr[f] + (size_t)b * 3);
+}
+
+// posecnn epilogue of sample b: the pose gradient of every scale flows through transformation_from_parameters
+// (layers.py:28-45) to the leaves - axisangle directly, translation through the factor mean_inv_depth (trainer.py:374-375)
+// - and through that factor to every pixel of the up-sampled disparity of the scale (gmidc, added by the final pass).
+MD2_HD void final_pose_posecnn(const Params& P, int b) {
+  const float* K = P.K + (size_t)b * 16;
+  float gaa[kMaxSrc][3], gtr[kMaxSrc][3];
+  for (int f = 0; f < P.nsrc; ++f)
+    for (int i = 0; i < 3; ++i) { gaa[f][i] = 0.f; gtr[f][i] = 0.f; }
+  for (int ps = 0; ps < P.S; ++ps) {
+    const float m = P.mid[ps * P.B + b];
+    float gm = 0.f;
+    for (int f = 0; f < P.nsrc; ++f) {
+      if (!P.aa[f] || !P.pose_grad[f]) continue;
+      float gT[16];
+      for (int k = 0; k < 4; ++k)
+        for (int j = 0; j < 4; ++j) {
+          double a = 0.0;
+          for (int i = 0; i < 3; ++i) a += (double)MD2_LD(K + i * 4 + k) * P.acc[acc_dP(P, ps, b, f, i * 4 + j)];
+          gT[k * 4 + j] = (float)(a * (double)P.gscale);
+        }
+      const float* aa = P.aa[f] + (size_t)b * P.pose_stride[f];
+      const float* tr = P.tr[f] + (size_t)b * P.pose_stride[f];
+      const float trs[3] = {MD2_LD(tr) * m, MD2_LD(tr + 1) * m, MD2_LD(tr + 2) * m};
+      float ga[3], gt[3];
+      pose_to_matrix_backward(gT, aa, trs, P.pose_invert[f], ga, gt);
+      for (int i = 0; i < 3; ++i) {
+        gaa[f][i] += ga[i];
+        gtr[f][i] = fmaf(gt[i], m, gtr[f][i]);
+        gm = fmaf(gt[i], MD2_LD(tr + i), gm);
+      }
+    }
+    // d mean_inv_depth / d (up-sampled disp)(p) = c / (H W)
+    P.gmidc[ps * P.B + b] = (float)((double)gm * (double)P.c_disp / ((double)P.H * P.W));
+  }
+  for (int f = 0; f < P.nsrc; ++f) {
+    if (!P.aa[f]) continue;
+    if (P.grad_aa[f]) for (int i = 0; i < 3; ++i) P.grad_aa[f][(size_t)b * 3 + i] = gaa[f][i];
+    if (P.grad_tr[f]) for (int i = 0; i < 3; ++i) P.grad_tr[f][(size_t)b * 3 + i] = gtr[f][i];
+  }
+}
+
+// --predictive_mask: pixel (y, x) of the mask of (scale s, sample b, source f) up-sampled to full resolution
+// (trainer.py:451-454); stores it in the plane the marching pass reads and returns its BCE term against 1
+// (nn.BCELoss clamps log at -100, trainer.py:458)
+MD2_HD float pmask_up_pixel(const Params& P, int s, int b, int f, int y, int x) {
+  const int Hs = P.H >> s, Ws = P.W >> s;
+  const float m = upsample_at(P.pmask[s] + (size_t)(b * P.nsrc + f) * Hs * Ws, s, Hs, Ws, y, x);
+  P.pm[s][((size_t)(b * P.nsrc + f) * P.H + y) * P.W + x] = m;
+  const float lg = logf(m);
+  return -(lg < -100.0f ? -100.0f : lg);
+}
+// d loss / d (up-sampled mask) at full-resolution index i of the (b, f) plane: photometric part written by the
+// marching pass + the BCE part (torch binary_cross_entropy_backward with target 1: (x - 1) / max((1 - x) x, 1e-12)),
+// 0.2 / (B nsrc H W) per scale and 1 / S for the total
+MD2_HD float pmask_full_grad(const Params& P, int s, size_t i) {
+  const float m = MD2_LD(P.pm[s] + i);
+  const float den = (1.0f - m) * m;
+  const float bce = (m - 1.0f) / (den > 1e-12f ? den : 1e-12f);
+  const float k = (float)(0.2 / ((double)P.B * P.nsrc * P.H * P.W * P.S));
+  return MD2_LD(P.gpm[s] + i) + k * bce;
+}
+// adjoint of the up-sampling for the mask: coarse pixel (Y, X) of plane (b, f) at scale s, gather form
+template <int K>
+MD2_HD float pmask_adjoint(const Params& P, int s, int b, int f, int Y, int X) {
+  const int Hs = P.H >> s, Ws = P.W >> s;
+  const size_t base = (size_t)(b * P.nsrc + f) * P.H * P.W;
+  if (K == 1) return pmask_full_grad(P, s, base + (size_t)Y * P.W + X);
+  const int xlo = K * X - K / 2, ylo = K * Y - K / 2;
+  float acc = 0.f;
+  for (int iy = 0; iy < 2 * K; ++iy) {
+    const int y = ylo + iy;
+    const float wy = up_weight<K>(iy, Y, Hs);
+    if (y < 0 || y >= P.H || wy == 0.0f) continue;
+    float row = 0.f;
+    for (int i = 0; i < 2 * K; ++i) {
+      const int x = xlo + i;
+      const float wx = up_weight<K>(i, X, Ws);
+      if (x < 0 || x >= P.W || wx == 0.0f) continue;
+      row = fmaf(wx, pmask_full_grad(P, s, base + (size_t)y * P.W + x), row);
+    }
+    acc = fmaf(wy, row, acc);
+  }
+  return acc;
+}
+MD2_HD void pmask_grad_pixel(const Params& P, int s, int b, int f, int Y, int X) {
+  const int Hs = P.H >> s, Ws = P.W >> s;
+  float g;
+  switch (s) {
+    case 0: g = pmask_adjoint<1>(P, 0, b, f, Y, X); break;
+    case 1: g = pmask_adjoint<2>(P, 1, b, f, Y, X); break;
+    case 2: g = pmask_adjoint<4>(P, 2, b, f, Y, X); break;
+    default: g = pmask_adjoint<8>(P, 3, b, f, Y, X); break;
+  }
+  P.grad_pmask[s][((size_t)(b * P.nsrc + f) * Hs + Y) * Ws + X] = g;
 }
 
 }  // namespace md2

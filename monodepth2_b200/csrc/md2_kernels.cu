@@ -48,7 +48,75 @@ __global__ void md2_prologue(Params P) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nacc = acc_count(P);
   for (int i = tid; i < nacc; i += gridDim.x * blockDim.x) P.acc[i] = 0.0;
-  for (int i = tid; i < P.B * P.nsrc; i += gridDim.x * blockDim.x) setup_projection(P, i / P.nsrc, i % P.nsrc);
+  // (posecnn: the projections depend on the mean inverse depth of every scale and are built by md2_posecnn_setup)
+  if (!P.posecnn)
+    for (int i = tid; i < P.B * P.nsrc; i += gridDim.x * blockDim.x) setup_projection(P, 0, i / P.nsrc, i % P.nsrc);
+}
+
+// ------------------------------------------------------------------ posecnn (trainer.py:366-375)
+// sum of the up-sampled disparity of every (scale, sample) over the full-resolution grid: one thread per fine pixel
+__global__ void __launch_bounds__(256) md2_updisp_sum(Params P) {
+  const int s = blockIdx.z, b = blockIdx.y;
+  const int Hs = P.H >> s, Ws = P.W >> s, n = P.H * P.W;
+  const float* d = P.disp[s] + (size_t)b * Hs * Ws;
+  float a = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    a += upsample_at(d, s, Hs, Ws, i / P.W, i % P.W);
+  a = warp_sum(a);
+  __shared__ float part[8];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) part[w] = a;
+  __syncthreads();
+  if (w == 0) {
+    a = (l < 8) ? part[l] : 0.f;
+    a = warp_sum(a);
+    if (l == 0) atomicAdd(&P.acc[acc_updisp(P, s, b)], (double)a);
+  }
+}
+// mean inverse depth, then T and the projection table of every (scale, sample, source)
+__global__ void md2_posecnn_setup(Params P) {
+  const int b = blockIdx.x, s = threadIdx.x;
+  if (s < P.S) posecnn_mid(P, s, b);
+  __syncthreads();
+  for (int i = threadIdx.x; i < P.S * P.nsrc; i += blockDim.x) setup_projection(P, i / P.nsrc, b, i % P.nsrc);
+}
+// pose epilogue of every sample (gradients of the leaves, and the constant each scale adds to d loss / d up-sampled
+// disparity), then that constant for scale 0, whose gradient the marching pass has already finished
+__global__ void md2_posecnn_final(Params P) {
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) final_pose_posecnn(P, b);
+  __syncthreads();
+  const float cst = P.gmidc[b];
+  float* g = P.grad_disp[0] + (size_t)b * P.H * P.W;
+  for (int i = threadIdx.x; i < P.H * P.W; i += blockDim.x) g[i] += cst;
+}
+
+// ------------------------------------------------------------------ --predictive_mask (trainer.py:447-459)
+// masks up-sampled to full resolution (read by the marching pass) + the BCE sums
+__global__ void __launch_bounds__(256) md2_pmask_up(Params P) {
+  const int s = blockIdx.z, bf = blockIdx.y;
+  const int n = P.H * P.W;
+  float a = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    a += pmask_up_pixel(P, s, bf / P.nsrc, bf % P.nsrc, i / P.W, i % P.W);
+  a = warp_sum(a);
+  __shared__ float part[8];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) part[w] = a;
+  __syncthreads();
+  if (w == 0) {
+    a = (l < 8) ? part[l] : 0.f;
+    a = warp_sum(a);
+    if (l == 0) atomicAdd(&P.acc[acc_bce(P, s)], (double)a);
+  }
+}
+// d loss / d mask_s: adjoint of the up-sampling over (photometric part + BCE part), one thread per coarse pixel
+__global__ void __launch_bounds__(256) md2_pmask_grad(Params P) {
+  const int s = blockIdx.z, bf = blockIdx.y;
+  if (!P.grad_pmask[s]) return;
+  const int Hs = P.H >> s, Ws = P.W >> s;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Hs * Ws) pmask_grad_pixel(P, s, bf / P.nsrc, bf % P.nsrc, i / Ws, i % Ws);
 }
 
 // re-layout of target and sources to RGBx texels (one 16-byte load per bilinear tap later on)
@@ -544,7 +612,7 @@ __global__ void MD2_MARCH_BOUNDS md2_march(Params P) {
 #pragma unroll
       for (int k = 0; k < 12; ++k) {
         const float v = warp_sum(dP[k]);
-        if (lane == 0) atomicAdd(&P.acc[acc_dP(P, J.b, f, k)], (double)v);
+        if (lane == 0) atomicAdd(&P.acc[acc_dP(P, J.ps, J.b, f, k)], (double)v);
       }
     }
   }
@@ -623,7 +691,7 @@ __global__ void MD2_MARCH_BOUNDS md2_march2(Params P) {
 #pragma unroll
       for (int k = 0; k < 12; ++k) {
         const float v = warp_sum(dP[k]);
-        if (lane == 0) atomicAdd(&P.acc[acc_dP(P, J.b, f, k)], (double)v);
+        if (lane == 0) atomicAdd(&P.acc[acc_dP(P, J.ps, J.b, f, k)], (double)v);
       }
     }
   }
@@ -651,6 +719,9 @@ __device__ __forceinline__ void final_tile(const Params& P, int s, int b, int tx
   const int Hs = P.H >> s, Ws = P.W >> s;
   const int X0 = tx * TXC, Y0 = ty * TYC;
   const float* dD = P.dD[s] + (size_t)b * P.H * P.W;
+  // posecnn: d loss / d (every pixel of the up-sampled disparity) through mean_inv_depth (fine indices outside the
+  // image have weight 0, so the constant may be added to every value read)
+  const float cst = P.posecnn ? __ldg(P.gmidc + s * P.B + b) : 0.0f;
   {
     const int x = K * X0 - K / 2 + (int)threadIdx.x;
     const int xc = x < 0 ? 0 : (x >= P.W ? P.W - 1 : x);
@@ -663,7 +734,7 @@ __device__ __forceinline__ void final_tile(const Params& P, int s, int b, int tx
     for (int r = 0; r < NR; ++r) {
       const int y = ylo + r;
       const int yc = y < 0 ? 0 : (y >= P.H ? P.H - 1 : y);
-      v[r] = __ldg(dD + yc * P.W + xc);
+      v[r] = __ldg(dD + yc * P.W + xc) + cst;
     }
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
@@ -943,6 +1014,18 @@ cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
   if ((e = get_side(&side)) != cudaSuccess) return e;
   md2_prologue<<<4, 256, 0, stream>>>(P);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (P.posecnn) {
+    dim3 grid(16, P.B, P.S);
+    md2_updisp_sum<<<grid, 256, 0, stream>>>(P);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    md2_posecnn_setup<<<P.B, 32, 0, stream>>>(P);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  if (P.pmask_on) {
+    dim3 grid(16, P.B * P.nsrc, P.S);
+    md2_pmask_up<<<grid, 256, 0, stream>>>(P);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
   // ---- fork: disparity means + smoothness on the side stream
   if ((e = cudaEventRecord(side->fork, stream)) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return e;
@@ -988,6 +1071,15 @@ cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
   }
   if (e != cudaSuccess) return e;
   if (g_prof_on) cudaEventRecord(g_prof_ev[1], stream);
+  if (P.posecnn && P.want_grad) {
+    md2_posecnn_final<<<P.B, 256, 0, stream>>>(P);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  if (P.pmask_on && P.want_grad) {
+    dim3 grid((P.H * P.W + 255) / 256, P.B * P.nsrc, P.S);
+    md2_pmask_grad<<<grid, 256, 0, stream>>>(P);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
   // ---- scales >= 1: up-sampling adjoint + smoothness adjoint; losses; grad_T
   {
     int blocks = 0;

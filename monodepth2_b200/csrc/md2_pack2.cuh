@@ -153,7 +153,7 @@ __device__ __forceinline__ void lane_init2(Lane2<C>& L, const Params& P, const W
   L.colok = (L.x >= 0) && (L.x < P.W);
   L.xi = reflect_clamp(L.x, P.W);
   const float xf = (float)L.xi;
-  const float* m0 = P.proj + (J.b * 2 + 0) * 12;
+  const float* m0 = J.proj;
   const float* m1 = m0 + 12;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -205,6 +205,11 @@ __device__ __forceinline__ void load_identity_row2(Lane2<C>& L, const WarpJob& J
     L.idv[1] = MD2_LDS1(J.idl + J.plane + pix);
     L.nzv[0] = MD2_LDS1(J.noise + pix);
     L.nzv[1] = MD2_LDS1(J.noise + J.plane + pix);
+  } else if (J.pm) {       // --predictive_mask: see load_identity_row
+    const int yw = t - 1;
+    const int pix = (yw < 0 ? 0 : (yw >= J.H ? J.H - 1 : yw)) * J.W + L.xi;
+    L.nzv[0] = MD2_LDS1(J.pm + pix);
+    L.nzv[1] = MD2_LDS1(J.pm + J.plane + pix);
   }
 }
 
@@ -419,12 +424,19 @@ __device__ __forceinline__ void stage_b2(Lane2<C>& L, const Params& P, const War
         if (cand < best) best = cand;
       }
     }
+    const bool pm = !C::AUTOMASK && J.pm;             // --predictive_mask (see pmask_apply in md2_core.cuh)
 #pragma unroll
-    for (int f = 0; f < 2; ++f)
-      if (rl[f] < best) { best = rl[f]; tag = f; }
+    for (int f = 0; f < 2; ++f) {
+      const float cand = pm ? rl[f] * L.nzv[f] : rl[f];
+      if (cand < best) { best = cand; tag = f; }
+    }
     if (own_win) {
       L.loss += best;
       if (C::AUTOMASK && J.idsel) J.idsel[yw * J.W + L.xi] = (tag >= 0) ? 1.0f : 0.0f;
+      if (pm && C::GRAD && J.gpm) {
+#pragma unroll
+        for (int f = 0; f < 2; ++f) J.gpm[f * J.plane + yw * J.W + L.xi] = (tag == f) ? rl[f] * P.gscale : 0.0f;
+      }
     }
     if (C::GRAD && !C::NOSSIM && tag >= 0) {
       // the winner's window sums: (r,g) pair from slot `tag`, b from that half of slot 2
@@ -435,6 +447,11 @@ __device__ __forceinline__ void stage_b2(Lane2<C>& L, const Params& P, const War
       for (int k = 0; k < 3; ++k) { Wrg[k] = sel2(w1, V[1][k], V[0][k]); Wb[k] = w1 ? V[2][k].y : V[2][k].x; }
       ssim_window2(Wrg[0], Wrg[1], Wrg[2], VYrg[0], VYrg[1], L.cf);
       ssim_window(Wb[0], Wb[1], Wb[2], VYb[0], VYb[1], L.cfb);
+      if (pm) {
+        const float m = w1 ? L.nzv[1] : L.nzv[0];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { L.cf[k] = mul2(L.cf[k], bc(m)); L.cfb[k] *= m; }
+      }
     }
   }
   L.tag = tag;
@@ -505,7 +522,8 @@ __device__ __forceinline__ void stage_c2(Lane2<C>& L, const Params& P, const War
       float gb = C::NOSSIM ? 0.0f
                            : (0.85f / 3.0f) * fmaf(sp.z, f ? Bb.y : Bb.x, fmaf(tgb, f ? Gb.y : Gb.x, f ? Ab.y : Ab.x));
       if (won) {
-        const float kl1 = C::NOSSIM ? (1.0f / 3.0f) : (0.15f / 3.0f);
+        const float mk = (!C::AUTOMASK && J.pm) ? MD2_LD(J.pm + f * J.plane + yp * J.W + L.xi) : 1.0f;
+        const float kl1 = (C::NOSSIM ? (1.0f / 3.0f) : (0.15f / 3.0f)) * mk;
         const float dr = sp.x - tgrg.x, dg = sp.y - tgrg.y, db = sp.z - tgb;
         grg.x += (dr != 0.f) ? copysignf(kl1, dr) : 0.0f;
         grg.y += (dg != 0.f) ? copysignf(kl1, dg) : 0.0f;

@@ -20,6 +20,8 @@ struct Layout {
   size_t tgt4_off, src4_off[kMaxSrc];
   size_t dD_off[kMaxScales], gn_off[kMaxScales];
   size_t Tws_off[kMaxSrc];
+  size_t mid_off, gmidc_off;                       // posecnn
+  size_t pm_off[kMaxScales], gpm_off[kMaxScales];  // predictive mask
   size_t total;
 };
 
@@ -34,6 +36,8 @@ inline int validate(const md2_problem* p) {
     return MD2_ERR_INVALID_ARGUMENT;
   if (!(p->min_depth > 0.f) || !(p->max_depth > p->min_depth)) return MD2_ERR_INVALID_ARGUMENT;
   if ((long long)p->batch * 3 * p->height * p->width * MD2_MAX_SRC >= (1LL << 31)) return MD2_ERR_UNSUPPORTED;
+  // trainer.py:90-92: "When using predictive_mask, please disable automasking with --disable_automasking"
+  if (p->predictive_mask && p->automask) return MD2_ERR_INVALID_ARGUMENT;
   return MD2_OK;
 }
 
@@ -42,10 +46,13 @@ inline Layout make_layout(const md2_problem* p) {
   memset(&L, 0, sizeof(L));
   const size_t B = p->batch, H = p->height, W = p->width;
   size_t off = 0;
-  const size_t nacc = 3 * kMaxScales + 4 * kMaxScales * B + B * p->num_src * 12;   // = acc_count()
+  const size_t npose = p->posecnn ? p->num_scales : 1;
+  const size_t nacc = 3 * kMaxScales + 5 * kMaxScales * B + npose * B * p->num_src * 12 + kMaxScales;   // = acc_count()
   L.acc_off = off; L.acc_bytes = nacc * sizeof(double);
   off = align_up(off + L.acc_bytes, 256);
-  L.proj_off = off; off = align_up(off + B * p->num_src * 12 * sizeof(float), 256);
+  L.proj_off = off; off = align_up(off + npose * B * p->num_src * 12 * sizeof(float), 256);
+  L.mid_off = off; off = align_up(off + kMaxScales * B * sizeof(float), 256);
+  L.gmidc_off = off; off = align_up(off + kMaxScales * B * sizeof(float), 256);
   L.smsc_off = off; off = align_up(off + kMaxScales * B * 2 * sizeof(float), 256);
   for (int f = 0; f < p->num_src; ++f) { L.Tws_off[f] = off; off = align_up(off + B * 16 * sizeof(float), 256); }
   L.idloss_off = off; off = align_up(off + B * p->num_src * H * W * sizeof(float), 256);
@@ -56,6 +63,10 @@ inline Layout make_layout(const md2_problem* p) {
   for (int s = 0; s < p->num_scales; ++s) {
     L.dD_off[s] = off; off = align_up(off + B * H * W * sizeof(float), 256);
     L.gn_off[s] = off; off = align_up(off + B * (H >> s) * (W >> s) * sizeof(float), 256);
+    if (p->predictive_mask) {
+      L.pm_off[s] = off; off = align_up(off + B * p->num_src * H * W * sizeof(float), 256);
+      L.gpm_off[s] = off; off = align_up(off + B * p->num_src * H * W * sizeof(float), 256);
+    }
   }
   L.total = off;
   return L;
@@ -96,6 +107,9 @@ inline int fill_params(const md2_problem* p, const md2_tensors* t, void* workspa
   P->align_corners = p->align_corners ? 1 : 0;
   P->want_grad = p->want_grad ? 1 : 0;
   P->no_ssim = p->no_ssim ? 1 : 0;
+  P->posecnn = p->posecnn ? 1 : 0;
+  P->npose = P->posecnn ? p->num_scales : 1;
+  P->pmask_on = p->predictive_mask ? 1 : 0;
   // layers.py:21-23: min_disp = 1/max_depth, max_disp = 1/min_depth (python doubles -> fp32 scalars)
   const double lo = 1.0 / (double)p->max_depth, hi = 1.0 / (double)p->min_depth;
   P->a_disp = (float)lo;
@@ -152,10 +166,15 @@ inline int fill_params(const md2_problem* p, const md2_tensors* t, void* workspa
     } else {
       if (!t->T[f]) return MD2_ERR_INVALID_ARGUMENT;
       P->Tm[f] = t->T[f];
+      // posecnn: a source given as a fixed matrix keeps that matrix at every scale and gets no pose gradient
+      if (p->posecnn && t->pose_requires_grad[f] && p->want_grad) return MD2_ERR_INVALID_ARGUMENT;
     }
     P->src[f] = u8 ? nullptr : t->source[f];
     P->src8[f] = u8 ? t->source_u8[f] : nullptr;
     P->pose_grad[f] = (t->pose_requires_grad[f] && p->want_grad) ? 1 : 0;
+    // posecnn: the disparity gradient depends on the pose adjoint (through mean_inv_depth) whether or not the leaves
+    // themselves want one
+    if (p->posecnn && p->want_grad && t->axisangle[f]) P->pose_grad[f] = 1;
     P->grad_T[f] = p->want_grad ? t->grad_T[f] : nullptr;
   }
   for (int s = 0; s < p->num_scales; ++s) {
@@ -170,12 +189,21 @@ inline int fill_params(const md2_problem* p, const md2_tensors* t, void* workspa
     for (int f = 0; f < p->num_src; ++f) P->warped[f][s] = t->warped[f][s];
     P->dD[s] = t->grad_depth_dbg[s] ? t->grad_depth_dbg[s] : (float*)(ws + L.dD_off[s]);
     P->gn[s] = (float*)(ws + L.gn_off[s]);
+    if (p->predictive_mask) {
+      if (!t->pmask[s]) return MD2_ERR_INVALID_ARGUMENT;
+      P->pmask[s] = t->pmask[s];
+      P->pm[s] = (float*)(ws + L.pm_off[s]);
+      P->gpm[s] = (float*)(ws + L.gpm_off[s]);
+      P->grad_pmask[s] = p->want_grad ? t->grad_pmask[s] : nullptr;
+    }
   }
   P->losses = t->losses;
   P->acc = (double*)(ws + L.acc_off);
   P->proj = (float*)(ws + L.proj_off);
   P->idloss = (float*)(ws + L.idloss_off);
   P->smsc = (float*)(ws + L.smsc_off);
+  P->mid = (float*)(ws + L.mid_off);
+  P->gmidc = (float*)(ws + L.gmidc_off);
   P->tgt4 = (float*)(ws + L.tgt4_off);
   for (int f = 0; f < p->num_src; ++f) P->src4[f] = (float*)(ws + L.src4_off[f]);
   return MD2_OK;

@@ -50,7 +50,7 @@ constexpr int kRoleAWarps = MD2_ROLE_A_WARPS;
 #define MD2_ASYNC_ROW_STEP 1
 #endif
 #ifndef MD2_ROLE_MIN_CTAS3
-#define MD2_ROLE_MIN_CTAS3 3      // three and more sources: 168 registers, no spills (4 CTAs: 128 registers, 0.4 KB of spills)
+#define MD2_ROLE_MIN_CTAS3 4      // three sources, or --avg_reprojection, with gradients: 168 registers (__maxnreg__), no spills, 4 CTAs per SM; three sources AND --avg_reprojection: 3 CTAs (224 registers)
 #endif
 
 // the role kernel keeps the backward box sums of every source count in registers (role C has room)
@@ -66,8 +66,9 @@ struct RoleCfg {
   static constexpr int THREADS = 32 * NROLES;
   static constexpr int RING = C::GRAD ? 5 : 2;                   // rows in flight: A writes t, B reads t-1, C reads t-4
   // register budget per instantiation (no spills anywhere): 4 sources 255, 3 sources or --avg_reprojection with
-  // gradients 168, everything else 128
-  static constexpr int MIN_CTAS = (C::NSRC >= 4) ? 2 : ((C::NSRC >= 3 || C::AVG) && C::GRAD) ? MD2_ROLE_MIN_CTAS3 : MD2_ROLE_MIN_CTAS;
+  // gradients 168 (4 CTAs per SM: the 3-source kernel at 176 registers dropped to 3 CTAs and 0.81 ms instead of
+  // 0.53 ms at 640x192 x 12), both together 224, everything else 136
+  static constexpr int MIN_CTAS = (C::NSRC >= 4) ? 2 : (C::NSRC >= 3 && C::AVG && C::GRAD) ? 3 : ((C::NSRC >= 3 || C::AVG) && C::GRAD) ? MD2_ROLE_MIN_CTAS3 : MD2_ROLE_MIN_CTAS;
   // registers per thread such that MIN_CTAS CTAs fit an SM (64 K registers, allocation unit 8 per thread); given as
   // __maxnreg__ rather than as the min-blocks argument of __launch_bounds__, under which ptxas picks 168 registers
   // plus a few bytes of spills for the 3-source kernels although 224 would fit
@@ -288,7 +289,7 @@ __device__ __forceinline__ void c_reduce(const Lane<C>& L, const Params& P, cons
 #pragma unroll
     for (int k = 0; k < 12; ++k) {
       const float v = warp_sum(dP[k]);
-      if (lane == 0) atomicAdd(&P.acc[acc_dP(P, J.b, f, k)], (double)v);
+      if (lane == 0) atomicAdd(&P.acc[acc_dP(P, J.ps, J.b, f, k)], (double)v);
     }
   }
 }
@@ -531,7 +532,7 @@ __device__ __forceinline__ void c_reduce2(const Lane2<C>& L, const Params& P, co
 #pragma unroll
     for (int k = 0; k < 12; ++k) {
       const float v = warp_sum(dP[k]);
-      if (lane == 0) atomicAdd(&P.acc[acc_dP(P, J.b, f, k)], (double)v);
+      if (lane == 0) atomicAdd(&P.acc[acc_dP(P, J.ps, J.b, f, k)], (double)v);
     }
   }
 }

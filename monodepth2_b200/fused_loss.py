@@ -61,16 +61,13 @@ class LossPlan:
         self.rows_per_segment = int(rows_per_segment)
         self.no_ssim = bool(no_ssim)
         self.v1_multiscale = bool(v1_multiscale)
+        # --pose_model_type posecnn (trainer.py:366-375) and --predictive_mask (trainer.py:447-459) are variants of
+        # the fused kernels themselves (md2_problem.posecnn / .predictive_mask)
         self.posecnn = bool(posecnn)
-        if self.posecnn and self.v1_multiscale:
-            raise RuntimeError("posecnn together with --v1_multiscale is not supported by the fused loss")
-        # --predictive_mask (trainer.py:447-459) needs --disable_automasking (trainer.py:90-92)
+        # --predictive_mask needs --disable_automasking (trainer.py:90-92)
         self.predictive_mask = bool(predictive_mask)
         if self.predictive_mask and self.automask:
             raise RuntimeError("When using predictive_mask, please disable automasking with --disable_automasking")
-        if self.predictive_mask and (self.v1_multiscale or self.posecnn):
-            raise RuntimeError("--predictive_mask together with --v1_multiscale / posecnn is not supported")
-        self._layer_modules = None
         self.n_src = len(self.src_ids)
         self.n_id = 0 if not self.automask else (1 if self.avg_reprojection else self.n_src)
         self.lib = _capi.load_library()
@@ -82,17 +79,9 @@ class LossPlan:
             self._scale_plans = [
                 LossPlan(self.batch_size, self.height >> s, self.width >> s, self.frame_ids, [0], self.min_depth,
                          self.max_depth, self.disparity_smoothness / (2 ** s), self.avg_reprojection,
-                         not self.automask, self.align_corners, self.rows_per_segment, self.no_ssim, False)
+                         not self.automask, self.align_corners, self.rows_per_segment, self.no_ssim, False,
+                         self.posecnn, self.predictive_mask)
                 for s in self.scales]
-        # --pose_model_type posecnn (trainer.py:366-375): T depends on the mean inverse depth of each
-        # scale, so every scale is a single-scale photometric call at full resolution on the up-sampled
-        # disparity with its own T; the smoothness term is evaluated by the per-layer op
-        self._photo_plan = None
-        if self.posecnn:
-            self._photo_plan = LossPlan(self.batch_size, self.height, self.width, self.frame_ids, [0],
-                                        self.min_depth, self.max_depth, 0.0, self.avg_reprojection,
-                                        not self.automask, self.align_corners, self.rows_per_segment,
-                                        self.no_ssim, False)
 
     @classmethod
     def from_opt(cls, opt, **kw) -> "LossPlan":
@@ -110,7 +99,8 @@ class LossPlan:
                           avg_reprojection=int(self.avg_reprojection), align_corners=int(self.align_corners),
                           min_depth=self.min_depth, max_depth=self.max_depth,
                           disparity_smoothness=self.disparity_smoothness, want_grad=int(want_grad),
-                          rows_per_segment=self.rows_per_segment, no_ssim=int(self.no_ssim))
+                          rows_per_segment=self.rows_per_segment, no_ssim=int(self.no_ssim),
+                          posecnn=int(self.posecnn), predictive_mask=int(self.predictive_mask))
 
     def workspace(self, device: torch.device) -> torch.Tensor:
         key = (device.type, device.index)
@@ -128,8 +118,9 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
     """forward(plan, side, target, sources, K, inv_K, colors, noise, pose_grad, pose_invert, *leaves)
 
     leaves = S disparities, then per source the matrix T (B,4,4) *or* the axisangle leaf, then per source
-    the translation leaf (None for a source given as a matrix).  ``pose_invert[i]`` is None for a matrix
-    source, else the ``invert`` flag of transformation_from_parameters (frame_id < 0)."""
+    the translation leaf (None for a source given as a matrix), then (--predictive_mask) S masks.
+    ``pose_invert[i]`` is None for a matrix source, else the ``invert`` flag of
+    transformation_from_parameters (frame_id < 0)."""
 
     N_FIXED = 10
 
@@ -138,6 +129,7 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
                 pose_invert, *leaves):
         S, F = len(plan.scales), plan.n_src
         disps, firsts, seconds = leaves[:S], leaves[S:S + F], leaves[S + F:S + 2 * F]
+        masks = leaves[S + 2 * F:S + 2 * F + S] if plan.predictive_mask else ()
         B, H, W = plan.batch_size, plan.height, plan.width
         dev = target.device
         want_grad = any(ctx.needs_input_grad[_ViewSynthesisLossFn.N_FIXED:])
@@ -197,6 +189,7 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
         t.K = ptr(_check_f32_cuda(K, "K", (B, 4, 4)))
         t.inv_K = ptr(_check_f32_cuda(inv_K, "inv_K", (B, 4, 4)))
         grad_disp = []
+        grad_mask = [None] * S
         for s in range(S):
             hs, ws = H >> s, W >> s
             t.disp[s] = ptr(_check_f32_cuda(disps[s], "disp[%d]" % s, (B, 1, hs, ws)))
@@ -210,6 +203,12 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
                 g = torch.empty((B, 1, hs, ws), dtype=torch.float32, device=dev)
                 grad_disp.append(g)
                 t.grad_disp[s] = ptr(g)
+            if plan.predictive_mask:
+                t.pmask[s] = ptr(_check_f32_cuda(masks[s], "predictive_mask[%d]" % s, (B, F, hs, ws)))
+                if want_grad and ctx.needs_input_grad[_ViewSynthesisLossFn.N_FIXED + S + 2 * F + s]:
+                    g = torch.empty((B, F, hs, ws), dtype=torch.float32, device=dev)
+                    grad_mask[s] = g
+                    t.grad_pmask[s] = ptr(g)
         if side is not None:
             for s in side.get("depth_scales", []):
                 d = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
@@ -246,9 +245,12 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
         ctx.first_shapes = [tuple(x.shape) for x in firsts]
         ctx.second_shapes = [tuple(x.shape) if x is not None else None for x in seconds]
         ctx.have = [(grad_first[i] is not None, grad_second[i] is not None) for i in range(F)]
+        ctx.have_mask = [g is not None for g in grad_mask]
+        ctx.n_leaves = len(leaves)
         if want_grad:
             ctx.save_for_backward(*grad_disp, *[g for g in grad_first if g is not None],
-                                  *[g for g in grad_second if g is not None])
+                                  *[g for g in grad_second if g is not None],
+                                  *[g for g in grad_mask if g is not None])
         total = losses[0]
         per_scale = losses[1:1 + S]
         ctx.mark_non_differentiable(per_scale)
@@ -265,8 +267,10 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
         for s in range(S):
             if ctx.needs_input_grad[n0 + s]:
                 want.append((n0 + s, saved[s], saved[s].shape))
-        firsts = iter(saved[S:S + sum(1 for h in ctx.have if h[0])])
-        seconds = iter(saved[S + sum(1 for h in ctx.have if h[0]):])
+        n1, n2 = sum(1 for h in ctx.have if h[0]), sum(1 for h in ctx.have if h[1])
+        firsts = iter(saved[S:S + n1])
+        seconds = iter(saved[S + n1:S + n1 + n2])
+        gmasks = iter(saved[S + n1 + n2:])
         for i in range(F):
             a = next(firsts) if ctx.have[i][0] else None
             b = next(seconds) if ctx.have[i][1] else None
@@ -274,7 +278,11 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
                 want.append((n0 + S + i, a, ctx.first_shapes[i]))
             if ctx.needs_input_grad[n0 + S + F + i] and ctx.pose_grad[i] and b is not None:
                 want.append((n0 + S + F + i, b, ctx.second_shapes[i]))
-        out = [None] * (n0 + S + 2 * F)
+        for s, have in enumerate(ctx.have_mask):
+            if have:
+                gm = next(gmasks)
+                want.append((n0 + S + 2 * F + s, gm, gm.shape))
+        out = [None] * (n0 + ctx.n_leaves)
         if want:
             n = len(want)
             res = [torch.empty_like(w[1]) for w in want]
@@ -302,12 +310,8 @@ def view_synthesis_loss(plan: LossPlan, inputs: Dict, outputs: Dict,
     ``side`` selects optional outputs: {"depth_scales": [...], "color_scales": [...], "mask_scales": [...]};
     the produced tensors are stored both in ``side`` and in ``outputs`` under the reference's keys.
     """
-    if plan.predictive_mask:
-        return _view_synthesis_loss_predictive_mask(plan, inputs, outputs, side)
     if plan.v1_multiscale:
         return _view_synthesis_loss_v1_multiscale(plan, inputs, outputs, noise, side)
-    if plan.posecnn:
-        return _view_synthesis_loss_posecnn(plan, inputs, outputs, noise, side)
     S = len(plan.scales)
     target = inputs[("color", 0, 0)]
     dev = target.device
@@ -319,7 +323,7 @@ def view_synthesis_loss(plan: LossPlan, inputs: Dict, outputs: Dict,
         if f == "s":
             firsts.append(inputs["stereo_T"]); seconds.append(None)
             pose_grad.append(False); pose_invert.append(None)
-        elif ("cam_T_cam", 0, f) in outputs:
+        elif ("cam_T_cam", 0, f) in outputs and not plan.posecnn:
             T = outputs[("cam_T_cam", 0, f)]
             firsts.append(T); seconds.append(None)
             pose_grad.append(bool(T.requires_grad) and torch.is_grad_enabled()); pose_invert.append(None)
@@ -336,12 +340,14 @@ def view_synthesis_loss(plan: LossPlan, inputs: Dict, outputs: Dict,
         noise = [torch.randn(shape, device=dev) for _ in plan.scales]
     if side is None and any(pi is not None for pi in pose_invert):
         side = {}
+    # --predictive_mask: outputs["predictive_mask"][("disp", s)] (trainer.py:449), (B, n_src, H>>s, W>>s)
+    masks = [outputs["predictive_mask"][("disp", s)] for s in plan.scales] if plan.predictive_mask else []
     total, per_scale = _ViewSynthesisLossFn.apply(plan, side, target, sources, inputs[("K", 0)],
                                                   inputs[("inv_K", 0)], colors, noise, pose_grad, pose_invert,
-                                                  *disps, *firsts, *seconds)
+                                                  *disps, *firsts, *seconds, *masks)
     if side is not None:
         for i, T in enumerate(side.pop("_cam_T_cam", [])):
-            if T is not None:
+            if T is not None and ("cam_T_cam", 0, plan.src_ids[i]) not in outputs:
                 outputs[("cam_T_cam", 0, plan.src_ids[i])] = T
     losses = {"loss": total}
     for i, s in enumerate(plan.scales):
@@ -370,6 +376,8 @@ def _view_synthesis_loss_v1_multiscale(plan: LossPlan, inputs: Dict, outputs: Di
                 for key in (("cam_T_cam", 0, f), ("axisangle", 0, f), ("translation", 0, f)):
                     if key in outputs:
                         outs[key] = outputs[key]
+        if plan.predictive_mask:      # not up-sampled under --v1_multiscale (trainer.py:450)
+            outs["predictive_mask"] = {("disp", 0): outputs["predictive_mask"][("disp", s)]}
         sub_side = None
         if side is not None:
             sub_side = {k: ([0] if s in side.get(k, []) else []) for k in
@@ -389,104 +397,6 @@ def _view_synthesis_loss_v1_multiscale(plan: LossPlan, inputs: Dict, outputs: Di
                 elif isinstance(k, str) and k.startswith("identity_selection/"):
                     side["identity_selection/{}".format(s)] = v
                     outputs["identity_selection/{}".format(s)] = v
-    losses["loss"] = total / len(plan.scales)
-    return losses
-
-
-def _view_synthesis_loss_posecnn(plan: LossPlan, inputs: Dict, outputs: Dict, noise, side):
-    """--pose_model_type posecnn (trainer.py:366-375): the translation is rescaled by the mean inverse
-    depth of the scale before T is built, so T differs per scale and depends on the disparity."""
-    import torch.nn.functional as F
-    from . import layers as L
-    losses: Dict[str, torch.Tensor] = {}
-    total = 0
-    H, W = plan.height, plan.width
-    lo, hi = 1.0 / plan.max_depth, 1.0 / plan.min_depth
-    for i, s in enumerate(plan.scales):
-        disp = outputs[("disp", s)]
-        up = F.interpolate(disp, [H, W], mode="bilinear", align_corners=False) if s > 0 else disp
-        # inv_depth = 1/depth = scaled disparity (layers.py:21-24); mean over H then W (trainer.py:371-372)
-        mean_inv_depth = (lo + (hi - lo) * up).mean(3, True).mean(2, True)
-        outs = {("disp", 0): up}
-        for f in plan.src_ids:
-            if f == "s":
-                continue
-            aa = outputs[("axisangle", 0, f)][:, 0]
-            tr = outputs[("translation", 0, f)][:, 0] * mean_inv_depth[:, 0]
-            outs[("cam_T_cam", 0, f)] = L.transformation_from_parameters(aa, tr, f < 0)
-        ins = {k: v for k, v in inputs.items() if not (isinstance(k, tuple) and k[0] == "color" and k[2] != 0)}
-        sub_side = None
-        if side is not None:
-            sub_side = {k: ([0] if s in side.get(k, []) else []) for k in
-                        ("depth_scales", "color_scales", "mask_scales", "grad_updisp_scales")}
-        ls = view_synthesis_loss(plan._photo_plan, ins, outs, [noise[i]] if noise is not None else None, sub_side)
-        mean_disp = disp.mean(2, True).mean(3, True)
-        smooth = L.get_smooth_loss(disp / (mean_disp + 1e-7), inputs[("color", 0, s)])
-        loss = ls["loss"] + plan.disparity_smoothness * smooth / (2 ** s)
-        losses["loss/{}".format(s)] = loss
-        total = total + loss
-        if sub_side is not None:
-            for k, v in sub_side.items():
-                if isinstance(k, tuple):
-                    key = (k[0], k[1], s) if len(k) == 3 else (k[0], s)
-                    if k[0] == "grad_updisp":
-                        v = v / len(plan.scales)
-                    side[key] = v
-                    if k[0] in ("depth", "color"):
-                        outputs[key] = v
-                elif isinstance(k, str) and k.startswith("identity_selection/"):
-                    side["identity_selection/{}".format(s)] = v
-                    outputs["identity_selection/{}".format(s)] = v
-    losses["loss"] = total / len(plan.scales)
-    return losses
-
-
-def _view_synthesis_loss_predictive_mask(plan: LossPlan, inputs: Dict, outputs: Dict, side):
-    """--predictive_mask (trainer.py:447-459): the per-source mask of the mask decoder weights the
-    reprojection losses *before* the per-pixel minimum and is pushed towards 1 by 0.2 * BCE(mask, 1).
-    This ablation is not fused: it is composed from the per-layer sm_100a ops of ``layers.py``
-    (md2_disp_to_depth, md2_backproject_depth, md2_project3d, md2_grid_sample_border, md2_ssim,
-    md2_smooth_loss); the mask weighting, minimum, means and BCE are torch element-wise glue."""
-    import torch.nn.functional as F
-    from . import layers as L
-    B, H, W = plan.batch_size, plan.height, plan.width
-    if plan._layer_modules is None:
-        dev = inputs[("color", 0, 0)].device
-        plan._layer_modules = (L.BackprojectDepth(B, H, W).to(dev), L.Project3D(B, H, W).to(dev), L.SSIM().to(dev))
-    backproject, project, ssim = plan._layer_modules
-    target = inputs[("color", 0, 0)]
-    K, inv_K = inputs[("K", 0)], inputs[("inv_K", 0)]
-    losses: Dict[str, torch.Tensor] = {}
-    total = 0
-    for s in plan.scales:
-        disp = outputs[("disp", s)]
-        up = F.interpolate(disp, [H, W], mode="bilinear", align_corners=False) if s > 0 else disp
-        _, depth = L.disp_to_depth(up, plan.min_depth, plan.max_depth)
-        if side is not None and s in side.get("depth_scales", []):
-            side[("depth", 0, s)] = outputs[("depth", 0, s)] = depth.detach()
-        points = backproject(depth, inv_K)
-        rls = []
-        for f in plan.src_ids:
-            T = inputs["stereo_T"] if f == "s" else outputs[("cam_T_cam", 0, f)]
-            pred = L.grid_sample_border(inputs[("color", f, 0)], project(points, K, T), plan.align_corners)
-            if side is not None and s in side.get("color_scales", []):
-                side[("color", f, s)] = outputs[("color", f, s)] = pred.detach()
-            l1 = (target - pred).abs().mean(1, True)
-            rls.append(l1 if plan.no_ssim else 0.85 * ssim(pred, target).mean(1, True) + 0.15 * l1)
-        reproj = torch.cat(rls, 1)
-        mask = outputs["predictive_mask"][("disp", s)]
-        mask = F.interpolate(mask, [H, W], mode="bilinear", align_corners=False)
-        reproj = reproj * mask
-        loss = 0.2 * F.binary_cross_entropy(mask, torch.ones_like(mask))
-        if plan.avg_reprojection:
-            reproj = reproj.mean(1, True)
-        to_optimise = reproj if reproj.shape[1] == 1 else torch.min(reproj, dim=1)[0]
-        loss = loss + to_optimise.mean()
-        mean_disp = disp.mean(2, True).mean(3, True)
-        smooth = L.get_smooth_loss(disp / (mean_disp + 1e-7), inputs[("color", 0, s)])
-        loss = loss + plan.disparity_smoothness * smooth / (2 ** s)
-        losses["loss/{}".format(s)] = loss
-        total = total + loss
     losses["loss"] = total / len(plan.scales)
     return losses
 
@@ -575,7 +485,7 @@ class FusedLossMixin:
         plan = self._md2_plan
         side = dict(self.md2_side) if self.md2_side else None
         noise = None
-        if plan.n_id > 0 and not (plan.predictive_mask or plan.v1_multiscale or plan.posecnn):
+        if plan.n_id > 0 and not plan.v1_multiscale:
             # drawn here exactly as view_synthesis_loss would (one torch.randn per scale, in scale order,
             # trainer.py:468-469) and kept so that a later on-demand side-output call sees the same masks
             shape = (plan.batch_size, plan.n_id, plan.height, plan.width)

@@ -98,7 +98,7 @@ static void emu_march(const Params& P) {
                 lane_dP(L[l], P, J, f, dP);
                 for (int k = 0; k < 12; ++k) sum[k] += dP[k];
               }
-              for (int k = 0; k < 12; ++k) P.acc[acc_dP(P, b, f, k)] += (double)sum[k];
+              for (int k = 0; k < 12; ++k) P.acc[acc_dP(P, J.ps, b, f, k)] += (double)sum[k];
             }
         }
 }
@@ -143,8 +143,24 @@ extern "C" int md2_emu_view_synthesis_loss(const md2_problem* p, const md2_tenso
   if (st != MD2_OK) return st;
   // 1. prologue
   for (int i = 0; i < acc_count(P); ++i) P.acc[i] = 0.0;
-  for (int b = 0; b < P.B; ++b)
-    for (int f = 0; f < P.nsrc; ++f) setup_projection(P, b, f);
+  if (P.posecnn) {
+    for (int s = 0; s < P.S; ++s)
+      for (int b = 0; b < P.B; ++b) {
+        const int Hs = P.H >> s, Ws = P.W >> s;
+        double a = 0.0;
+        for (int i = 0; i < P.H * P.W; ++i) a += upsample_at(P.disp[s] + (size_t)b * Hs * Ws, s, Hs, Ws, i / P.W, i % P.W);
+        P.acc[acc_updisp(P, s, b)] = a;
+        posecnn_mid(P, s, b);
+      }
+  }
+  for (int ps = 0; ps < P.npose; ++ps)
+    for (int b = 0; b < P.B; ++b)
+      for (int f = 0; f < P.nsrc; ++f) setup_projection(P, ps, b, f);
+  if (P.pmask_on)
+    for (int s = 0; s < P.S; ++s)
+      for (int b = 0; b < P.B; ++b)
+        for (int f = 0; f < P.nsrc; ++f)
+          for (int i = 0; i < P.H * P.W; ++i) P.acc[acc_bce(P, s)] += (double)pmask_up_pixel(P, s, b, f, i / P.W, i % P.W);
   if (!P.automask)   // with automasking the identity pass writes the RGBx texels itself
     for (int img = 0; img <= P.nsrc; ++img)
       for (int b = 0; b < P.B; ++b)
@@ -184,6 +200,19 @@ extern "C" int md2_emu_view_synthesis_loss(const md2_problem* p, const md2_tenso
   else emu_march_n<4>(P);
   // 6. final
   final_scalars(P);
+  if (P.want_grad && P.posecnn)
+    for (int b = 0; b < P.B; ++b) {
+      final_pose_posecnn(P, b);
+      for (int i = 0; i < P.H * P.W; ++i) P.grad_disp[0][(size_t)b * P.H * P.W + i] += P.gmidc[b];
+    }
+  if (P.want_grad && P.pmask_on)
+    for (int s = 0; s < P.S; ++s) {
+      if (!P.grad_pmask[s]) continue;
+      const int Hs = P.H >> s, Ws = P.W >> s;
+      for (int b = 0; b < P.B; ++b)
+        for (int f = 0; f < P.nsrc; ++f)
+          for (int i = 0; i < Hs * Ws; ++i) pmask_grad_pixel(P, s, b, f, i / Ws, i % Ws);
+    }
   if (P.want_grad) {
     for (int b = 0; b < P.B; ++b)
       for (int f = 0; f < P.nsrc; ++f) final_grad_T(P, b, f);

@@ -61,7 +61,8 @@ def run_emu(g, want_grad=True, rows_per_segment=0, align_corners=False, side_out
                    automask=int(not g.disable_automasking), avg_reprojection=int(g.avg_reprojection),
                    align_corners=int(align_corners), min_depth=0.1, max_depth=100.0,
                    disparity_smoothness=1e-3, want_grad=int(want_grad), rows_per_segment=rows_per_segment,
-                   no_ssim=int(g.no_ssim))
+                   no_ssim=int(g.no_ssim), posecnn=int(g.posecnn), predictive_mask=int(g.predictive_mask))
+    pose_leaves = pose_leaves or g.posecnn      # posecnn rebuilds T per scale from the leaves (trainer.py:366-375)
     keep = []
 
     def arr(a):
@@ -107,9 +108,10 @@ def run_emu(g, want_grad=True, rows_per_segment=0, align_corners=False, side_out
         else:
             t.T[i] = _ptr(arr(z["cam_T_cam__%s" % f]))
             t.pose_requires_grad[i] = 1
-        gT = np.zeros((B, 4, 4), np.float32)
-        out["grad_T"][f] = gT
-        t.grad_T[i] = _ptr(gT)
+        if not g.posecnn:
+            gT = np.zeros((B, 4, 4), np.float32)
+            out["grad_T"][f] = gT
+            t.grad_T[i] = _ptr(gT)
     t.K = _ptr(arr(z["in__K__0"]))
     t.inv_K = _ptr(arr(z["in__inv_K__0"]))
     out["grad_disp"], out["grad_updisp"], out["idsel"], out["depth"] = [], [], [], []
@@ -121,6 +123,11 @@ def run_emu(g, want_grad=True, rows_per_segment=0, align_corners=False, side_out
         gd = np.zeros((B, 1, H >> s, W >> s), np.float32)
         out["grad_disp"].append(gd)
         t.grad_disp[s] = _ptr(gd)
+        if g.predictive_mask:
+            t.pmask[s] = _ptr(arr(z["mask__%d" % s]))
+            gm = np.zeros((B, len(srcs), H >> s, W >> s), np.float32)
+            out.setdefault("grad_mask", []).append(gm)
+            t.grad_pmask[s] = _ptr(gm)
         if side_outputs:
             gu = np.zeros((B, 1, H, W), np.float32)
             out["grad_updisp"].append(gu)

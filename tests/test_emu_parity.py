@@ -8,7 +8,7 @@ from helpers import Golden, golden_cases, rel_l2
 
 
 @pytest.mark.parametrize("rows", [16, 5])
-@pytest.mark.parametrize("name", [c for c in golden_cases() if c not in ("v1_multiscale", "posecnn", "predictive_mask")])  # composition is host-side
+@pytest.mark.parametrize("name", [c for c in golden_cases() if c != "v1_multiscale"])  # (one call per level: host-side)
 def test_emulated_kernels_match_reference_golden(name, rows):
     from emu_driver import run_emu
     g = Golden(name)
@@ -21,8 +21,16 @@ def test_emulated_kernels_match_reference_golden(name, rows):
     np.testing.assert_allclose(o["depth"][0], z["depth__0"], rtol=2e-6)
     for f in g.frame_ids[1:]:
         np.testing.assert_allclose(o["warped"][(f, 0)], z["color__%s__0" % f], atol=5e-5)
-        if f != "s":
+        if f == "s":
+            continue
+        if g.posecnn:     # kernel variant (md2_problem.posecnn): T per scale from the leaves, gradient on the leaves
+            assert rel_l2(o["grad_axisangle"][f].reshape(-1), z["grad_axisangle__%s" % f].reshape(-1)) < 8e-2
+            assert rel_l2(o["grad_translation"][f].reshape(-1), z["grad_translation__%s" % f].reshape(-1)) < 8e-2
+        else:
             assert rel_l2(o["grad_T"][f], z["grad_cam_T_cam__%s" % f]) < 8e-2
+    if g.predictive_mask:   # kernel variant (md2_problem.predictive_mask)
+        for s in range(4):
+            assert rel_l2(o["grad_mask"][s], z["grad_mask__%d" % s]) < 1e-3, s
     if g.n_id > 0:
         for s in range(4):
             assert (o["idsel"][s].astype(np.uint8) != z["idsel__%d" % s]).mean() <= 5e-4

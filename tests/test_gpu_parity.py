@@ -37,9 +37,9 @@ def test_cuda_matches_reference_golden(name, rows):
             assert (m != z["idsel__%d" % s]).mean() <= 5e-4     # tiny fixtures: 1 flip of 7680 px = 1.3e-4
     # per-pixel (pre-aggregation) gradient, protocol P2
     a, c = 0.01, 9.99
-    # (under posecnn the disparity also acts through the per-scale T, outside the kernel's per-pixel map)
-    # (--predictive_mask is composed from the per-layer ops and has no per-pixel debug map)
-    for s in range(4) if not (g.posecnn or g.predictive_mask) else []:
+    # (under posecnn the disparity also acts through the per-scale T: that part is a per-(scale, sample) constant added
+    # by the final pass, outside the per-pixel map exported here)
+    for s in range(4) if not g.posecnn else []:
         gd = r["side"][("grad_updisp", s)].cpu().numpy()
         d_s = g.t("disp__%d" % s)
         if not g.v1_multiscale:
