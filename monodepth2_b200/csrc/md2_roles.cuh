@@ -435,9 +435,19 @@ __device__ __forceinline__ void b_step2(Lane2<C>& L, const Params& P, const Warp
   const F4* p0 = &st.at(slot, 0, C::STASH4);
   const F4* p1 = &st.at(slot, 1, C::STASH4);
   const F4* p2_ = &st.at(slot, 4, C::STASH4);
+#ifdef MD2_ROLE_SHFL_XCHG
+  // neighbours by warp shuffle instead of a second and third LDS.128 of the same ring row: 24 shared-memory
+  // wavefronts fewer per row (the LSU pipe is the busiest unit of this kernel, profiles/r02n_march_keys.txt)
+  const F4 tc = p0[0], ac = p1[0], bc_ = p2_[0];
+  auto up3 = [](const F4& v) { return make_f4(__shfl_up_sync(kFull, v.x, 1), __shfl_up_sync(kFull, v.y, 1), __shfl_up_sync(kFull, v.z, 1), 0.f); };
+  auto dn3 = [](const F4& v) { return make_f4(__shfl_down_sync(kFull, v.x, 1), __shfl_down_sync(kFull, v.y, 1), __shfl_down_sync(kFull, v.z, 1), 0.f); };
+  const F4 tl = up3(tc), tr = dn3(tc), al = up3(ac), ar = dn3(ac), bl = up3(bc_), br = dn3(bc_);
+  (void)ol; (void)orr;
+#else
   const F4 tc = p0[0], tl = p0[ol], tr = p0[orr];
   const F4 ac = p1[0], al = p1[ol], ar = p1[orr];          // source 0: pred (r,g,b), u
   const F4 bc_ = p2_[0], bl = p2_[ol], br = p2_[orr];      // source 1
+#endif
   L.tgrg = p2(tc.x, tc.y); L.tgb = tc.z;
   lf.tgrg = p2(tl.x, tl.y); lf.tgb = tl.z;
   rt.tgrg = p2(tr.x, tr.y); rt.tgb = tr.z;
@@ -500,8 +510,19 @@ __device__ __forceinline__ void c_step_from_packed(Lane<C>& L, const Params& P, 
   };
   Xchg2<C> lf, rt;
   unpack(q[0], q[32], q[64], L.coef[0], L.tag);
+#ifdef MD2_ROLE_SHFL_XCHG
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    lf.coef[0][k] = __shfl_up_sync(kFull, L.coef[0][k], 1);
+    rt.coef[0][k] = __shfl_down_sync(kFull, L.coef[0][k], 1);
+  }
+  lf.tag = __shfl_up_sync(kFull, L.tag, 1);
+  rt.tag = __shfl_down_sync(kFull, L.tag, 1);
+  (void)ol; (void)orr;
+#else
   unpack(q[ol], q[32 + ol], q[64 + ol], lf.coef[0], lf.tag);
   unpack(q[orr], q[32 + orr], q[64 + orr], rt.coef[0], rt.tag);
+#endif
   wait_target_row<C>(J, st, t - 2);
   stage_c(L, P, J, t, lane, lf, rt, st);
 }
