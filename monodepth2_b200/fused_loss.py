@@ -409,6 +409,8 @@ class GraphedLoss:
         g = GraphedLoss(plan, inputs, outputs)     # device tensors shaped like every later step's; captures
         g.load(inputs, outputs)                    # copies a step's tensors (pinned host or device) into the buffers
         loss = g.run()                             # replays; g.loss / g.grads[key] are the static results
+        flat, ins, outs = g.staging()              # or: fill a pinned staging buffer (views per tensor) ...
+        g.load_staged(flat)                        # ... and bring the whole step in with ONE host-to-device copy
 
     ``inputs`` holds the tensors the path reads (``("color", f, 0)`` float or uint8, ``("color", 0, s)``, ``("K", 0)``,
     ``("inv_K", 0)``, ``"stereo_T"``), ``outputs`` the leaves (``("disp", s)`` and ``("cam_T_cam", 0, f)`` or the pose
@@ -421,9 +423,27 @@ class GraphedLoss:
         if dev.type != "cuda":
             raise RuntimeError("GraphedLoss needs CUDA tensors (there is no CPU path)")
         self.plan = plan
-        self.inputs = {k: torch.empty_like(v, device=dev).copy_(v) for k, v in inputs.items() if torch.is_tensor(v)}
-        self.leaves = {k: torch.empty_like(v, device=dev).copy_(v).requires_grad_(True)
-                       for k, v in outputs.items() if torch.is_tensor(v)}
+        # every static buffer is a view of ONE flat device allocation, so that a whole step's tensors can be brought
+        # in by a single host-to-device copy from a pinned staging buffer of the same layout (staging / load_staged)
+        self._layout = []          # (is_leaf, key, shape, dtype, offset, nbytes)
+        off = 0
+        for is_leaf, d in ((False, inputs), (True, outputs)):
+            for k, v in d.items():
+                if not torch.is_tensor(v):
+                    continue
+                n = v.numel() * v.element_size()
+                self._layout.append((is_leaf, k, tuple(v.shape), v.dtype, off, n))
+                off = (off + n + 255) // 256 * 256
+        self._nbytes = off
+        self._flat = torch.empty(off, dtype=torch.uint8, device=dev)
+        self.inputs, self.leaves = self._views(self._flat)
+        with torch.no_grad():
+            for k, dst in self.inputs.items():
+                dst.copy_(inputs[k])
+            for k, dst in self.leaves.items():
+                dst.copy_(outputs[k])
+        for v in self.leaves.values():
+            v.requires_grad_(True)
         cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(cur)
@@ -446,6 +466,24 @@ class GraphedLoss:
         losses = view_synthesis_loss(self.plan, self.inputs, dict(self.leaves))
         losses["loss"].backward()
         return losses
+
+    def _views(self, flat: torch.Tensor):
+        ins, leaves = {}, {}
+        for is_leaf, k, shape, dtype, off, n in self._layout:
+            (leaves if is_leaf else ins)[k] = flat[off:off + n].view(dtype).view(shape)
+        return ins, leaves
+
+    def staging(self):
+        """A pinned host buffer laid out like the static device buffers, and its views ``(flat, inputs, outputs)``:
+        what a dataloader's collate step fills.  ``load_staged(flat)`` then moves the whole step with one copy."""
+        flat = torch.empty(self._nbytes, dtype=torch.uint8).pin_memory()
+        ins, leaves = self._views(flat)
+        return flat, ins, leaves
+
+    def load_staged(self, flat: torch.Tensor) -> None:
+        """One host-to-device copy of a staging buffer (see ``staging``) into the static buffers."""
+        with torch.no_grad():
+            self._flat.copy_(flat, non_blocking=True)
 
     def load(self, inputs: Dict, outputs: Dict) -> None:
         with torch.no_grad():

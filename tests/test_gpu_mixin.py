@@ -170,8 +170,16 @@ def test_graphed_loss_replays_match_the_eager_call():
     b1 = make_batch(B, H, W, fids, 4, 72, "iid")
     need = lambda ins: {k: v for k, v in ins.items() if k in [("color", f, 0) for f in fids] + [("color", 0, s) for s in range(1, 4)] + [("K", 0), ("inv_K", 0)]}
     g = GraphedLoss(plan, {k: v.to(DEV) for k, v in need(b0[0]).items()}, {k: v.to(DEV) for k, v in b0[1].items()})
-    for batch in (b1, b0, b1):
-        g.load({k: v.pin_memory() for k, v in need(batch[0]).items()}, {k: v.pin_memory() for k, v in batch[1].items()})
+    flat, s_in, s_out = g.staging()          # pinned staging buffer laid out like the static device buffers
+    for n, batch in enumerate((b1, b0, b1, b0)):
+        if n < 2:     # per-tensor copies
+            g.load({k: v.pin_memory() for k, v in need(batch[0]).items()}, {k: v.pin_memory() for k, v in batch[1].items()})
+        else:         # one copy of the whole step
+            for k, v in need(batch[0]).items():
+                s_in[k].copy_(v)
+            for k, v in batch[1].items():
+                s_out[k].copy_(v)
+            g.load_staged(flat)
         loss = float(g.run().item())
         ins = {k: v.to(DEV) for k, v in batch[0].items()}
         outs = {k: v.to(DEV).requires_grad_(True) for k, v in batch[1].items()}
