@@ -474,20 +474,27 @@ def run_own(args, wl):
             ev_loaded[j].record(copy_stream)
 
     def e2e_run(n):
+        """Every step: H2D copy of its inputs (copy stream), graph replay, D2H read of its loss.  The read of step i is
+        put in flight with the step (pinned slot + event, GraphedLoss.run_async) and collected after step i+1 has been
+        enqueued, so the host never drains the GPU between steps; every step's loss reaches the host inside the region."""
         stage(0)
         last = 0.0
         for i in range(n):
             j = i % 2
             stage(i + 1)
             main_stream.wait_event(ev_loaded[j])
-            loss = graphed[j].run()
+            graphed[j].run_async()
             ev_done[j].record(main_stream)
-            last = float(loss.item())                     # D2H read of the step's result
+            if i >= 1:
+                last = graphed[1 - j].read()              # D2H read of step i-1's result
+        last = graphed[(n - 1) % 2].read()
         return last
 
-    e2e_run(3)
+    # (freshly pinned host buffers copy at a fraction of the PCIe rate for their first few dozen transfers - measured
+    # 0.73 ms falling to 0.41 ms per 22.5 MB, scripts/e2e_probe.py - so the warm-up is longer than for the kernels)
+    e2e_run(40)
     barrier()
-    n_e2e = max(5, min(args.steps, 30))
+    n_e2e = max(5, min(args.steps, 50))
     t0 = time.perf_counter()
     e2e_run(n_e2e)
     barrier()
@@ -496,7 +503,7 @@ def run_own(args, wl):
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = {"value": world * BATCH * n_e2e / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": 4, "steps": n_e2e, "pipeline": "GraphedLoss (public API): one H2D copy per step from a pinned staging buffer (GraphedLoss.staging / load_staged) into the static buffers, step i+1's copy overlapping the graph replay of step i",
+           "d2h_bytes_per_step": 4, "steps": n_e2e, "pipeline": "GraphedLoss (public API): one H2D copy per step from a pinned staging buffer (GraphedLoss.staging / load_staged) into the static buffers, step i+1's copy overlapping the graph replay of step i; the loss of step i is copied to a pinned host slot with the step and read by the host after step i+1 has been enqueued (GraphedLoss.run_async / read)",
            "entry": "uint8 frames (B,H,W,3) + uint8 target pyramid, converted in-kernel (x/255 = ToTensor); fp32 "
                     "disparities, cam_T_cam, K, inv_K"}
 

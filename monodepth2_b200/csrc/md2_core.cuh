@@ -242,6 +242,10 @@ struct Params {
   float* smsc;             // (S,B,2): 1/m and (sum gn*disp)/(m^2 N) of the smoothness adjoint, as floats
   float* mid;              // posecnn: (S,B) mean inverse depth of the up-sampled disparity (trainer.py:371-372)
   float* gmidc;            // posecnn: (S,B) d loss / d (every pixel of the up-sampled disp_s) through mean_inv_depth
+  // uint8 entry: the frames (and the target pyramid) converted once to planar float, so that every later pass runs
+  // its float form (the TMA-staged identity pass reads planar float through tensor maps)
+  float* cvt_img[1 + kMaxSrc];      // (B,3,H,W): target, sources
+  float* cvt_col[kMaxScales];       // (B,3,Hs,Ws), s >= 1
   const float* pmask[kMaxScales];   // predictive mask, (B,nsrc,Hs,Ws)
   float* pm[kMaxScales];            // (B,nsrc,H,W) mask up-sampled to full resolution (trainer.py:451-454)
   float* gpm[kMaxScales];           // (B,nsrc,H,W) d loss / d up-sampled mask (photometric part)
@@ -283,7 +287,18 @@ MD2_HD int acc_count(const Params& P) {
 }
 
 // ToTensor (torchvision.transforms.functional.to_tensor): uint8 -> float32, then .div(255)
-MD2_HD float u8_unit(unsigned char v) { return MD2_DIV((float)v, 255.0f); }
+// Device: q = v * rn(1/255) followed by one Newton correction, rem = fma(-q, 255, v), q' = fma(rem, rn(1/255), q), is
+// the correctly rounded quotient for every one of the 256 byte values (checked exhaustively against the IEEE division,
+// tests/test_u8_entry.py) - three instructions instead of the division's slow path, nine times per pixel and row.
+MD2_HD float u8_unit(unsigned char v) {
+#if defined(__CUDA_ARCH__)
+  const float x = (float)v, r = 0.003921568859368563f;      // rn(1 / 255)
+  const float q = x * r;
+  return fmaf(fmaf(-q, 255.0f, x), r, q);
+#else
+  return MD2_DIV((float)v, 255.0f);
+#endif
+}
 // channel c of pixel `pix` (= y * w + x) of sample b of a 3-channel image given as float planar NCHW (`f32`)
 // or, when `u8` is set, as uint8 (planar or interleaved); `plane` = h * w of that image
 MD2_HD float load_px(const float* f32, const unsigned char* u8, int hwc, int b, int c, int plane, int pix) {

@@ -1038,7 +1038,45 @@ static cudaError_t get_side(SideStream** out) {
   return cudaSuccess;
 }
 
+// uint8 entry (md2_tensors::target_u8 ...): every frame and pyramid level converted once to planar float (x / 255,
+// bit-identical to torchvision's ToTensor) - one thread per pixel, three coalesced byte reads, three coalesced stores
+__global__ void __launch_bounds__(256) md2_u8_to_f32(Params P) {
+  const int img = blockIdx.z, b = blockIdx.y;
+  const int nfull = 1 + P.nsrc;
+  const int s = img < nfull ? 0 : img - nfull + 1;
+  const int plane = (P.H >> s) * (P.W >> s);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= plane) return;
+  const unsigned char* in = img == 0 ? P.tgt8 : (img < nfull ? P.src8[img - 1] : P.color8[s]);
+  float* out = img < nfull ? P.cvt_img[img] : P.cvt_col[s];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const size_t o = P.u8_hwc ? ((size_t)b * plane + p) * 3 + c : ((size_t)b * 3 + c) * plane + p;
+    out[((size_t)b * 3 + c) * plane + p] = u8_unit(__ldg(in + o));
+  }
+}
+
+static cudaError_t launch_float_entry(const Params& P, cudaStream_t stream);
+
 cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
+#ifndef MD2_DBG_DEVICE
+  static const bool cvt_on = !(getenv("MD2_U8_CONVERT") && atoi(getenv("MD2_U8_CONVERT")) == 0);
+  if (P.tgt8 && cvt_on) {
+    dim3 grid((P.H * P.W + 255) / 256, P.B, 1 + P.nsrc + (P.S - 1));
+    md2_u8_to_f32<<<grid, 256, 0, stream>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    Params Q = P;
+    Q.tgt = P.cvt_img[0]; Q.tgt8 = nullptr;
+    for (int f = 0; f < P.nsrc; ++f) { Q.src[f] = P.cvt_img[1 + f]; Q.src8[f] = nullptr; }
+    for (int s2 = 0; s2 < P.S; ++s2) { Q.color[s2] = s2 == 0 ? P.cvt_img[0] : P.cvt_col[s2]; Q.color8[s2] = nullptr; }
+    return launch_float_entry(Q, stream);
+  }
+#endif
+  return launch_float_entry(P, stream);
+}
+
+static cudaError_t launch_float_entry(const Params& P, cudaStream_t stream) {
   cudaError_t e;
   SideStream* side = nullptr;
   if ((e = get_side(&side)) != cudaSuccess) return e;

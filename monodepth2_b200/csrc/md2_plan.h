@@ -22,6 +22,7 @@ struct Layout {
   size_t Tws_off[kMaxSrc];
   size_t mid_off, gmidc_off;                       // posecnn
   size_t pm_off[kMaxScales], gpm_off[kMaxScales];  // predictive mask
+  size_t cvt_img_off[1 + kMaxSrc], cvt_col_off[kMaxScales];   // uint8 entry: frames / pyramid as planar float
   size_t total;
 };
 
@@ -68,6 +69,9 @@ inline Layout make_layout(const md2_problem* p) {
       L.gpm_off[s] = off; off = align_up(off + B * p->num_src * H * W * sizeof(float), 256);
     }
   }
+  // (reserved whether or not the caller uses the uint8 entry: the workspace size is a function of md2_problem alone)
+  for (int i = 0; i <= p->num_src; ++i) { L.cvt_img_off[i] = off; off = align_up(off + B * 3 * H * W * sizeof(float), 256); }
+  for (int s = 1; s < p->num_scales; ++s) { L.cvt_col_off[s] = off; off = align_up(off + B * 3 * (H >> s) * (W >> s) * sizeof(float), 256); }
   L.total = off;
   return L;
 }
@@ -202,6 +206,8 @@ inline int fill_params(const md2_problem* p, const md2_tensors* t, void* workspa
   P->proj = (float*)(ws + L.proj_off);
   P->idloss = (float*)(ws + L.idloss_off);
   P->smsc = (float*)(ws + L.smsc_off);
+  for (int i = 0; i <= p->num_src; ++i) P->cvt_img[i] = (float*)(ws + L.cvt_img_off[i]);
+  for (int s = 1; s < p->num_scales; ++s) P->cvt_col[s] = (float*)(ws + L.cvt_col_off[s]);
   P->mid = (float*)(ws + L.mid_off);
   P->gmidc = (float*)(ws + L.gmidc_off);
   P->tgt4 = (float*)(ws + L.tgt4_off);

@@ -459,6 +459,7 @@ class GraphedLoss:
             self.losses = self._step()
         self.loss = self.losses["loss"].detach()
         self.grads = {k: v.grad for k, v in self.leaves.items()}
+        self._loss_host, self._loss_ev = None, None
 
     def _step(self):
         for v in self.leaves.values():
@@ -495,6 +496,22 @@ class GraphedLoss:
     def run(self) -> torch.Tensor:
         self.graph.replay()
         return self.loss
+
+    def run_async(self) -> None:
+        """Replay and put the device-to-host read of the loss in flight (pinned host slot + event) without blocking
+        the host: ``read()`` returns the value later, e.g. after the next step has been enqueued - how a training
+        loop reads its loss for logging without draining the GPU every step."""
+        if self._loss_host is None:
+            self._loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+            self._loss_ev = torch.cuda.Event()
+        self.graph.replay()
+        self._loss_host.copy_(self.loss, non_blocking=True)
+        self._loss_ev.record()
+
+    def read(self) -> float:
+        """The loss of the last ``run_async()`` (waits for that step only)."""
+        self._loss_ev.synchronize()
+        return float(self._loss_host)
 
 
 class FusedLossMixin:

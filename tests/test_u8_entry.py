@@ -68,3 +68,18 @@ def test_cuda_u8_entry_is_bit_identical_to_float_entry(case, layout):
     # the scalar sums are accumulated with fp64 atomics (order varies run to run): per-pixel gradients are exact
     for s in range(4):
         assert torch.equal(o0[("disp", s)].grad, o1[("disp", s)].grad), s
+
+
+def test_device_form_of_the_byte_to_unit_conversion_is_the_exact_quotient():
+    """md2_core.cuh u8_unit, device branch: q = v * rn(1/255); q' = fma(fma(-q, 255, v), rn(1/255), q) must equal the
+    correctly rounded v / 255 (torchvision's ToTensor) for all 256 byte values.  Emulated here in float64, in which
+    every product of two fp32 values and the fused operands are exact before the single rounding of each fma."""
+    v = np.arange(256, dtype=np.float32)
+    exact = (v / np.float32(255.0)).astype(np.float32)
+    r = np.float32(0.003921568859368563)
+    assert r == np.float32(1.0) / np.float32(255.0)
+    q = (v * r).astype(np.float32)
+    rem = (v.astype(np.float64) - q.astype(np.float64) * 255.0).astype(np.float32)          # fma(-q, 255, v)
+    q2 = (q.astype(np.float64) + rem.astype(np.float64) * np.float64(r)).astype(np.float32)  # fma(rem, r, q)
+    assert (q != exact).sum() > 0          # the plain product is NOT exact: the correction is needed
+    assert np.array_equal(q2, exact)
