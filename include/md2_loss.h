@@ -104,6 +104,11 @@ typedef struct md2_tensors {
    *      d loss / d mask when want_grad; NULL = not wanted. ---- */
   const float *pmask[MD2_MAX_SCALES];
   float *grad_pmask[MD2_MAX_SCALES];
+  /* ---- optional: a cudaEvent_t recorded (on any stream) after the last write of noise[]; the call waits for it
+   *      right before the first kernel that reads the noise, not at its start, so the torch.randn draws of
+   *      trainer.py:468-469 can run on another stream beside the identity pass.  NULL = noise[] is ready in
+   *      stream order. ---- */
+  void *noise_ready_event;
 } md2_tensors;
 
 int md2_version(void);

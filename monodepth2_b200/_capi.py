@@ -56,6 +56,7 @@ class Md2Tensors(C.Structure):
         ("u8_hwc", C.c_int),
         ("pmask", C.c_void_p * MAX_SCALES),
         ("grad_pmask", C.c_void_p * MAX_SCALES),
+        ("noise_ready_event", C.c_void_p),
     ]
 
 

@@ -232,6 +232,7 @@ struct Params {
   const float* disp[kMaxScales];
   const float* color[kMaxScales];
   const float* noise[kMaxScales];
+  void* noise_event;               // host side only: cudaEvent_t the marching kernel's launch waits for (md2_tensors.noise_ready_event)
   // workspace
   float* tgt4;             // (B,H,W,4) target re-laid out as RGBx texels
   float* src4[kMaxSrc];    // (B,H,W,4) sources as RGBx texels: one 16-byte load per bilinear tap
@@ -1282,7 +1283,8 @@ MD2_HD void stage_c_straight(Lane<C>& L, const Params& P, const WarpJob& J, int 
     const int slot = st.slot(yp);
     const F4 s0 = st.at(slot, 0, C::STASH4);
     const float tg[3] = {s0.x, s0.y, s0.z};
-    const float z = st.at(slot, 3, C::STASH4).w;
+    // (select: rows t0 - 2, t0 - 1 of the ring are never written, and 0 * stale non-finite z would poison the pose sums)
+    const float z = own ? st.at(slot, 3, C::STASH4).w : 0.0f;
     const float yf = (float)yp;
     float dzsum = 0.f;
 #pragma unroll

@@ -1129,6 +1129,8 @@ static cudaError_t launch_float_entry(const Params& P, cudaStream_t stream) {
   }
   // ---- join: the marching kernel finishes grad_disp_0 and needs the smoothness sums
   if ((e = cudaStreamWaitEvent(stream, side->join, 0)) != cudaSuccess) return e;
+  // the tie-break noise may have been drawn on another stream (md2_tensors.noise_ready_event): first read is here
+  if (P.noise_event && (e = cudaStreamWaitEvent(stream, (cudaEvent_t)P.noise_event, 0)) != cudaSuccess) return e;
   if (g_prof_on) cudaEventRecord(g_prof_ev[0], stream);
   switch (P.nsrc) {
     case 1: e = launch_march_ns<1>(P, stream); break;

@@ -216,30 +216,38 @@ __device__ __forceinline__ void load_identity_row2(Lane2<C>& L, const WarpJob& J
 // UNI: the lane-invariant projection rows (qb, p4 over the two sources; 6 float2) are read from shared memory
 // (`uni`, broadcast LDS) instead of living in 12 registers, and the target texel is left to the caller (role_a2_pipe
 // keeps ONE copy for the row being interpolated instead of one per Flight record).
-template <class C, bool WITH_ID = true, int ROW_STEP = 1, bool TG_DIRECT = false, bool ASYNC = false, bool UNI = false>
+// ZEXT: the depth of the row comes from shared memory (`zsrc`, written by role C one period earlier, see c_publish_z
+// in md2_roles.cuh): no disparity loads, up-sampling or reciprocal in this warp.
+template <class C, bool WITH_ID = true, int ROW_STEP = 1, bool TG_DIRECT = false, bool ASYNC = false, bool UNI = false, bool ZEXT = false>
 __device__ __forceinline__ void stage_a_issue2(Lane2<C>& L, Flight2& F, const Params& P, const WarpJob& J, int t, F4* tapdst = nullptr,
-                                               const P2* uni = nullptr) {
+                                               const P2* uni = nullptr, const float* zsrc = nullptr) {
   const int tr = reflect_clamp(t, J.H);
   if (UNI) {
   } else if (TG_DIRECT) {
     if (J.staged) F.ctg = make_f4(0.f, 0.f, 0.f, 0.f);      // the row goes into the ring by TMA
     else F.ctg = MD2_LDS4(J.tgt4 + 4 * (tr * J.W + L.xi));
   } else F.ctg = L.ntg;
-  float D;
-  if (J.s == 0) {
-    D = L.nd[0];
+  float z;
+  if (ZEXT) {
+    z = *zsrc;
+    if (WITH_ID) load_identity_row2(L, J, t);
   } else {
-    float syr = fmaf(J.rs, (float)tr + 0.5f, -0.5f);
-    syr = syr < 0.0f ? 0.0f : syr;
-    const float l1 = syr - (float)(int)syr, l0 = 1.0f - l1;
-    const float top = L.ul0 * L.nd[0] + L.ul1 * L.nd[1];
-    const float bot = L.ul0 * L.nd[2] + L.ul1 * L.nd[3];
-    D = l0 * top + l1 * bot;
+    float D;
+    if (J.s == 0) {
+      D = L.nd[0];
+    } else {
+      float syr = fmaf(J.rs, (float)tr + 0.5f, -0.5f);
+      syr = syr < 0.0f ? 0.0f : syr;
+      const float l1 = syr - (float)(int)syr, l0 = 1.0f - l1;
+      const float top = L.ul0 * L.nd[0] + L.ul1 * L.nd[1];
+      const float bot = L.ul0 * L.nd[2] + L.ul1 * L.nd[3];
+      D = l0 * top + l1 * bot;
+    }
+    if (ROW_STEP > 0) prefetch_row2<C, !TG_DIRECT>(L, J, t + ROW_STEP);
+    if (WITH_ID) load_identity_row2(L, J, t);
+    const float sd = MD2_FADD(P.a_disp, MD2_FMUL(P.c_disp, D));
+    z = MD2_RCP(sd);
   }
-  if (ROW_STEP > 0) prefetch_row2<C, !TG_DIRECT>(L, J, t + ROW_STEP);
-  if (WITH_ID) load_identity_row2(L, J, t);
-  const float sd = MD2_FADD(P.a_disp, MD2_FMUL(P.c_disp, D));
-  const float z = MD2_RCP(sd);
   F.cz = z;
   const float yf = (float)tr;
   const P2 qb0 = UNI ? uni[0] : L.qb[0], qb1 = UNI ? uni[1] : L.qb[1], qb2 = UNI ? uni[2] : L.qb[2];

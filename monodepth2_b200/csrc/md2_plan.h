@@ -130,6 +130,7 @@ inline int fill_params(const md2_problem* p, const md2_tensors* t, void* workspa
   P->eps = 1e-7f;
   P->gscale = (float)(1.0 / ((double)p->num_scales * p->batch * H * W) / (P->avg ? (double)p->num_src : 1.0));
   for (int s = 0; s < p->num_scales; ++s) P->smooth_w[s] = (float)((double)p->disparity_smoothness / (double)(1 << s));
+  P->noise_event = t->noise_ready_event;
   P->seg_rows = default_seg_rows(p);
   P->nseg = (p->height + P->seg_rows - 1) / P->seg_rows;
   P->nband = (p->width + kOwnCols - 1) / kOwnCols;

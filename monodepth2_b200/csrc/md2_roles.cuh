@@ -44,6 +44,25 @@ namespace md2 {
 #define MD2_ROLE_ASYNC_TAPS 0
 #endif
 constexpr int kRoleAWarps = MD2_ROLE_A_WARPS;
+// who issues the TMA bulk copy of the target row (kernels with gradients): 1 = role C, right after its last read of
+// the ring slot the row goes to, one period before role A fills the rest of that slot (role A is the role every
+// barrier waits for, role C has ~50 % slack: profiles/r02f_march_roles.txt); 0 = role A, in the period of the row
+#ifndef MD2_ROLE_TMA_IN_C
+#define MD2_ROLE_TMA_IN_C 1
+#endif
+// who turns the disparity of a row into depth (packed two-source kernels with gradients): 1 = role C, one period ahead
+// of role A, handing the row of depths over in shared memory (two 32-float rows); role A then runs no disparity
+// loads, no up-sampling and no reciprocal.  Same instruction sequence on the same values: results are bit-identical.
+// Measured (gpurun_out/t_times.log): role A 328 -> 213 instructions per row and no longer the role the barrier waits
+// for, but role C (403 -> 470) now is, and ptxas puts its next-row disparity loads in front of the consumer of the
+// previous ones, whose register the address computation reuses: 0.475 ms against 0.366 ms.  Off.
+#ifndef MD2_ROLE_Z_IN_C
+#define MD2_ROLE_Z_IN_C 0
+#endif
+#if defined(MD2_ROLE_PACKED_C) || defined(MD2_ROLE_A_PIPE) || (MD2_ROLE_ASYNC_TAPS != 0)     // (experimental role forms keep their own depth path)
+#undef MD2_ROLE_Z_IN_C
+#define MD2_ROLE_Z_IN_C 0
+#endif
 // cp.async form of role A: 1 = the disparity taps of row t+2 are put in flight inside the issue phase of row t+1,
 // right after those of row t+1 are consumed (a whole period to land); 0 = after the finish phase (round-2 first form)
 #ifndef MD2_ASYNC_ROW_STEP
@@ -82,7 +101,8 @@ struct RoleCfg {
   static constexpr int TAP_F4 = ASYNC_TAPS ? 2 * TAPROW_F4 : 0;
   static constexpr int BAR_F4 = (RING * 8 + 15) / 16;            // one mbarrier per ring slot (TMA-staged target row)
   static constexpr int UNI_F4 = 3;                                // lane-invariant projection rows (role_a2_pipe)
-  static constexpr int SMEM_F4 = STASH_F4 + COEF_F4 + TAP_F4 + BAR_F4 + UNI_F4;
+  static constexpr int ZR_F4 = 16;                                // two rows of 32 depths (role C -> role A)
+  static constexpr int SMEM_F4 = STASH_F4 + COEF_F4 + TAP_F4 + BAR_F4 + UNI_F4 + ZR_F4;
 };
 
 template <int NT>
@@ -101,6 +121,38 @@ __device__ __forceinline__ void stage_target_row(const WarpJob& J, const ST& st,
     const int slot = st.slot(t);
     mbar_expect_tx(st.tbar + slot, 32 * 16);
     tma_bulk_g2s(&st.at(slot, 0, C::STASH4), J.tgt4 + 4 * (tr * J.W + J.x0 - 2), 32 * 16, st.tbar + slot);
+  }
+}
+template <class C, bool PACKED>
+__host__ __device__ constexpr bool z_in_c() { return PACKED && C::GRAD && (MD2_ROLE_A_WARPS == 1) && (MD2_ROLE_Z_IN_C != 0); }
+// role C: depth of row t (the arithmetic of stage_a_issue, same order) -> shared memory; puts the disparity taps of
+// row t + 1 in flight after those of row t are consumed
+template <class C>
+__device__ __forceinline__ void c_publish_z(Lane<C>& L, const Params& P, const WarpJob& J, int t, float* zdst) {
+  const int tr = reflect_clamp(t, J.H);
+  float D;
+  if (J.s == 0) {
+    D = L.nd[0];
+  } else {
+    float syr = fmaf(J.rs, (float)tr + 0.5f, -0.5f);
+    syr = syr < 0.0f ? 0.0f : syr;
+    const float l1 = syr - (float)(int)syr, l0 = 1.0f - l1;
+    const float top = L.ul0 * L.nd[0] + L.ul1 * L.nd[1];
+    const float bot = L.ul0 * L.nd[2] + L.ul1 * L.nd[3];
+    D = l0 * top + l1 * bot;
+  }
+  prefetch_row<C, false>(L, J, t + 1);
+  const float sd = MD2_FADD(P.a_disp, MD2_FMUL(P.c_disp, D));
+  *zdst = MD2_RCP(sd);
+}
+template <class C>
+__host__ __device__ constexpr bool tma_in_c() { return C::GRAD && (MD2_ROLE_TMA_IN_C != 0); }
+// role C, period i (after its reads of slot(t0 + i - 4) == slot(t0 + i + 1)): stage the target row role A publishes next
+template <class C, class ST>
+__device__ __forceinline__ void stage_next_target_row(const WarpJob& J, const ST& st, int t, int t1, int lane) {
+  if (tma_in_c<C>() && J.staged && t <= t1) {
+    __syncwarp();
+    stage_target_row<C>(J, st, t, lane);
   }
 }
 template <class C, class ST>
@@ -128,7 +180,7 @@ __device__ __forceinline__ void role_a_async(const Params& P, const WarpJob& J, 
     if (t + 1 <= t1) stage_a_issue<C, false, 0, true, true>(L, Fn, P, J, t + 1, bufn);
     cp_async_commit();
     if (t <= t1) {
-      stage_target_row<C>(J, st, t, lane);
+      if (!tma_in_c<C>()) stage_target_row<C>(J, st, t, lane);
       cp_async_wait<1>();
 #pragma unroll
       for (int f = 0; f < C::NSRC; ++f)
@@ -167,7 +219,7 @@ __device__ __forceinline__ void role_a(const Params& P, const WarpJob& J, int la
     const int t = t0 + p;
     if (NA == 1) {
       if (t <= t1) {
-        stage_target_row<C>(J, st, t, lane);
+        if (!tma_in_c<C>()) stage_target_row<C>(J, st, t, lane);
         stage_a_issue<C, false, 1, true>(L, P, J, t);
         stage_a_finish<C, ST, true>(L, P, J, t, st);
       }
@@ -176,7 +228,7 @@ __device__ __forceinline__ void role_a(const Params& P, const WarpJob& J, int la
       ph = ph < 0 ? ph + NA : ph;
       if (ph == 0) {
         if (t <= t1) {
-          stage_target_row<C>(J, st, t, lane);
+          if (!tma_in_c<C>()) stage_target_row<C>(J, st, t, lane);
           stage_a_finish<C, ST, true>(L, P, J, t, st);
           if (t >= t0 + NA - 1) prefetch_row<C, false>(L, J, t + NA);    // (the prologue did it for the first rows)
         }
@@ -302,10 +354,12 @@ __device__ __forceinline__ void role_c(const Params& P, const WarpJob& J, int la
   Lane<C> L;
   lane_init(L, P, J, lane);
   const int ol = (lane > 0) ? -1 : 0, orr = (lane < 31) ? 1 : 0;
+stage_next_target_row<C>(J, st, t0, t1, lane);
 #pragma unroll 1
   for (int i = 0; i < nit; ++i) {
     const int t = t0 + i - 2;
     if (i >= 2) c_step(L, P, J, lane, st, cring + (t & 1) * RC::NCF4 * 32, t, ol, orr);
+    stage_next_target_row<C>(J, st, t0 + i + 1, t1, lane);
     role_sync<RC::THREADS>();
   }
   c_reduce(L, P, J, lane);
@@ -330,7 +384,7 @@ __device__ __forceinline__ void role_a2_async(const Params& P, const WarpJob& J,
     if (t + 1 <= t1) stage_a_issue2<C, false, MD2_ASYNC_ROW_STEP, true, true>(L, Fn, P, J, t + 1, bufn);
     cp_async_commit();
     if (t <= t1) {
-      stage_target_row<C>(J, st, t, lane);
+      if (!tma_in_c<C>()) stage_target_row<C>(J, st, t, lane);
       cp_async_wait<1>();
 #pragma unroll
       for (int f = 0; f < 2; ++f)
@@ -350,10 +404,12 @@ __device__ __forceinline__ void role_a2_async(const Params& P, const WarpJob& J,
 }
 
 template <class C, class ST>
-__device__ __forceinline__ void role_a2(const Params& P, const WarpJob& J, int lane, int k, const ST& st, int t0, int t1, int nit) {
+__device__ __forceinline__ void role_a2(const Params& P, const WarpJob& J, int lane, int k, const ST& st, const float* zring,
+                                        int t0, int t1, int nit) {
   constexpr int NA = RoleCfg<C>::NA;
   Lane2<C> L;
   lane_init2(L, P, J, lane);
+  if (z_in_c<C, true>()) role_sync<RoleCfg<C>::THREADS>();      // role C has published the depths of row t0
   if (NA > 1) {
     prefetch_row2<C, false>(L, J, t0 + k);
     if (k < NA - 1) {
@@ -366,8 +422,9 @@ __device__ __forceinline__ void role_a2(const Params& P, const WarpJob& J, int l
     const int t = t0 + p;
     if (NA == 1) {
       if (t <= t1) {
-        stage_target_row<C>(J, st, t, lane);
-        stage_a_issue2<C, false, 1, true>(L, P, J, t);
+        if (!tma_in_c<C>()) stage_target_row<C>(J, st, t, lane);
+        if (z_in_c<C, true>()) stage_a_issue2<C, false, 0, true, false, false, true>(L, L.fl, P, J, t, nullptr, nullptr, zring + (p & 1) * 32);
+        else stage_a_issue2<C, false, 1, true>(L, P, J, t);
         stage_a_finish2<C, ST, true>(L, P, J, t, st);
       }
     } else {
@@ -375,7 +432,7 @@ __device__ __forceinline__ void role_a2(const Params& P, const WarpJob& J, int l
       ph = ph < 0 ? ph + NA : ph;
       if (ph == 0) {
         if (t <= t1) {
-          stage_target_row<C>(J, st, t, lane);
+          if (!tma_in_c<C>()) stage_target_row<C>(J, st, t, lane);
           stage_a_finish2<C, ST, true>(L, P, J, t, st);
           if (t >= t0 + NA - 1) prefetch_row2<C, false>(L, J, t + NA);
         }
@@ -409,7 +466,7 @@ __device__ __forceinline__ void role_a2_pipe(const Params& P, const WarpJob& J, 
   stage_a_issue2<C, false, 1, true, false, true>(L, F[0], P, J, t0, nullptr, uni);
   auto half = [&](int t, Flight2& Fc, Flight2& Fn) {
     if (t <= t1) {
-      stage_target_row<C>(J, st, t, lane);
+      if (!tma_in_c<C>()) stage_target_row<C>(J, st, t, lane);
       // border bands (not staged by TMA): the target texel of row t, in flight across the issue phase of row t+1
       F4 tg = make_f4(0.f, 0.f, 0.f, 0.f);
       if (!J.staged) tg = MD2_LDS4(J.tgt4 + 4 * (reflect_clamp(t, J.H) * J.W + L.xi));
@@ -471,6 +528,7 @@ __device__ __forceinline__ void role_b2(const Params& P, const WarpJob& J, int l
   lane_init2(L, P, J, lane);
   const int ol = (lane > 0) ? -1 : 0, orr = (lane < 31) ? 1 : 0;
   load_identity_row2(L, J, t0);
+  if (z_in_c<C, true>()) role_sync<RC::THREADS>();
 #pragma unroll 1
   for (int i = 0; i < nit; ++i) {
     const int t = t0 + i - 1;
@@ -529,15 +587,22 @@ __device__ __forceinline__ void c_step_from_packed(Lane<C>& L, const Params& P, 
 
 template <class C, class ST>
 __device__ __forceinline__ void role_c_from_packed(const Params& P, const WarpJob& J, int lane, const ST& st, const F4* cring,
-                                                   int t0, int t1, int nit) {
+                                                   float* zring, int t0, int t1, int nit) {
   typedef RoleCfg<C> RC;
   Lane<C> L;
   lane_init(L, P, J, lane);
   const int ol = (lane > 0) ? -1 : 0, orr = (lane < 31) ? 1 : 0;
+stage_next_target_row<C>(J, st, t0, t1, lane);
+  if (z_in_c<C, true>()) {
+    c_publish_z(L, P, J, t0, zring);          // (lane_init put the disparity taps of row t0 in flight)
+    role_sync<RC::THREADS>();
+  }
 #pragma unroll 1
   for (int i = 0; i < nit; ++i) {
     const int t = t0 + i - 2;
     if (i >= 2) c_step_from_packed(L, P, J, lane, st, cring + (t & 1) * RC::NCF4 * 32, t, ol, orr);
+    stage_next_target_row<C>(J, st, t0 + i + 1, t1, lane);
+    if (z_in_c<C, true>() && t0 + i + 1 <= t1) c_publish_z(L, P, J, t0 + i + 1, zring + ((i + 1) & 1) * 32);
     role_sync<RC::THREADS>();
   }
   c_reduce(L, P, J, lane);
@@ -565,10 +630,12 @@ __device__ __forceinline__ void role_c2(const Params& P, const WarpJob& J, int l
   Lane2<C> L;
   lane_init2(L, P, J, lane);
   const int ol = (lane > 0) ? -1 : 0, orr = (lane < 31) ? 1 : 0;
+stage_next_target_row<C>(J, st, t0, t1, lane);
 #pragma unroll 1
   for (int i = 0; i < nit; ++i) {
     const int t = t0 + i - 2;
     if (i >= 2) c_step2(L, P, J, lane, st, cring + (t & 1) * RC::NCF4 * 32, t, ol, orr);
+    stage_next_target_row<C>(J, st, t0 + i + 1, t1, lane);
     role_sync<RC::THREADS>();
   }
   c_reduce2(L, P, J, lane);
@@ -614,6 +681,7 @@ __global__ void MD2_ROLE_BOUNDS(C) md2_march_roles(Params P) {
   st.tbar = reinterpret_cast<unsigned long long*>(smem + RC::STASH_F4 + RC::COEF_F4 + RC::TAP_F4);
   F4* cring = smem + RC::STASH_F4 + lane;
   F4* tapbuf = smem + RC::STASH_F4 + RC::COEF_F4 + lane;
+  float* zring = reinterpret_cast<float*>(smem + RC::STASH_F4 + RC::COEF_F4 + RC::TAP_F4 + RC::BAR_F4 + RC::UNI_F4) + lane;
   const int t0 = J.y0 - 2, t1 = J.y1 + 1;
   st.t0 = t0;
   const int nit = (t1 - t0 + 1) + (C::GRAD ? 2 : 1);
@@ -634,13 +702,13 @@ __global__ void MD2_ROLE_BOUNDS(C) md2_march_roles(Params P) {
 #ifdef MD2_ROLE_A_PIPE
     if (role < RC::NA) role_a2_pipe<C>(P, J, lane, st, reinterpret_cast<P2*>(smem + RC::STASH_F4 + RC::COEF_F4 + RC::TAP_F4 + RC::BAR_F4), t0, t1, nit);
 #else
-    if (role < RC::NA) role_a2<C>(P, J, lane, role, st, t0, t1, nit);
+    if (role < RC::NA) role_a2<C>(P, J, lane, role, st, zring, t0, t1, nit);
 #endif
     else if (role == RC::NA) role_b2<C>(P, J, lane, st, cring, t0, t1, nit);
 #ifdef MD2_ROLE_PACKED_C
     else if (C::GRAD) role_c2<C>(P, J, lane, st, cring, t0, t1, nit);
 #else
-    else if (C::GRAD) role_c_from_packed<C>(P, J, lane, st, cring, t0, t1, nit);
+    else if (C::GRAD) role_c_from_packed<C>(P, J, lane, st, cring, zring, t0, t1, nit);
 #endif
   } else {
     if (role < RC::NA) role_a<C>(P, J, lane, role, st, t0, t1, nit);

@@ -11,6 +11,7 @@ device memory, streams and autograd plumbing only; there is no PyTorch or CPU fa
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -199,6 +200,10 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
                 t.color[s] = ptr(_check_f32_cuda(colors[s], "color[%d]" % s, (B, 3, hs, ws)))
             if plan.n_id > 0:
                 t.noise[s] = ptr(_check_f32_cuda(noise[s], "noise[%d]" % s, (B, plan.n_id, H, W)))
+                ready = getattr(noise, "ready", None)
+                if ready is not None:
+                    keep.append(ready)
+                    t.noise_ready_event = ready.cuda_event
             if want_grad:
                 g = torch.empty((B, 1, hs, ws), dtype=torch.float32, device=dev)
                 grad_disp.append(g)
@@ -299,6 +304,39 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
         return tuple(out)
 
 
+class _Noise(list):
+    """The tie-break draws of one call; ``ready`` is the torch.cuda.Event recorded after the last draw when they were
+    made on the plan's side stream (handed to the library as md2_tensors.noise_ready_event)."""
+    ready = None
+
+
+_NOISE_STREAMS: Dict = {}
+
+
+def _draw_noise(plan: LossPlan, dev) -> "_Noise":
+    """trainer.py:468-469: one ``torch.randn`` per scale, in scale order, from the default CUDA generator - so the
+    generator advances exactly as in the reference and the values are the ones a plain call would draw.  The four
+    draws (~50 us at 640x192 x 12) do not depend on anything the call computes before the marching kernel, so they
+    run on a side stream beside the prologue / identity pass; the library waits for ``ready`` right before the
+    first kernel that reads them.  MD2_NOISE_STREAM=0: draw on the current stream."""
+    shape = (plan.batch_size, plan.n_id, plan.height, plan.width)
+    if os.environ.get("MD2_NOISE_STREAM", "1") == "0":
+        return _Noise(torch.randn(shape, device=dev) for _ in plan.scales)
+    main = torch.cuda.current_stream(dev)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device())
+    side_stream = _NOISE_STREAMS.get(key)
+    if side_stream is None:
+        side_stream = _NOISE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    # fork: everything already queued on the caller's stream - including the previous call's marching kernel, the
+    # last reader of the previous draws, whose memory the allocator may hand out again - comes first
+    side_stream.wait_stream(main)
+    with torch.cuda.stream(side_stream):
+        noise = _Noise(torch.randn(shape, device=dev) for _ in plan.scales)
+        noise.ready = torch.cuda.Event()
+        noise.ready.record(side_stream)
+    return noise
+
+
 def view_synthesis_loss(plan: LossPlan, inputs: Dict, outputs: Dict,
                         noise: Optional[List[torch.Tensor]] = None,
                         side: Optional[dict] = None) -> Dict[str, torch.Tensor]:
@@ -336,8 +374,7 @@ def view_synthesis_loss(plan: LossPlan, inputs: Dict, outputs: Dict,
             pose_grad.append(bool(aa.requires_grad or tr.requires_grad) and torch.is_grad_enabled())
             pose_invert.append(f < 0)
     if plan.n_id > 0 and noise is None:
-        shape = (plan.batch_size, plan.n_id, plan.height, plan.width)
-        noise = [torch.randn(shape, device=dev) for _ in plan.scales]
+        noise = _draw_noise(plan, dev)
     if side is None and any(pi is not None for pi in pose_invert):
         side = {}
     # --predictive_mask: outputs["predictive_mask"][("disp", s)] (trainer.py:449), (B, n_src, H>>s, W>>s)
