@@ -239,6 +239,7 @@ struct Params {
   float* proj;     // (B,nsrc,12): M=P3*invK3 (row-major 3x3) then p4
   float* idloss;   // (B,nsrc,H,W)
   float* dD[kMaxScales];   // (B,H,W)   d loss / d upsampled disp_s
+  float* zup[kMaxScales];  // (B,H,W)   depth of the up-sampled disp_s (md2_depth_up; read by role A of the role kernels)
   float* gn[kMaxScales];   // (B,Hs,Ws) smoothness numerator gradient
   float* smsc;             // (S,B,2): 1/m and (sum gn*disp)/(m^2 N) of the smoothness adjoint, as floats
   float* mid;              // posecnn: (S,B) mean inverse depth of the up-sampled disparity (trainer.py:371-372)
@@ -330,6 +331,7 @@ struct WarpJob {
   const float* tgt4;
   const float* src4[kMaxSrc];
   const float* disp;
+  const float* zup;    // depth plane of (s, b) at full resolution (Cfg::ZUP)
   const float* idl;
   const float* noise;
   float* dD;
@@ -363,6 +365,8 @@ MD2_HD WarpJob make_job(const Params& P, int s, int b, int x0, int y0, int y1) {
     J.warped[f] = (f < P.nsrc && P.warped[f][s]) ? P.warped[f][s] + 3 * boff : nullptr;
   }
   J.disp = P.disp[s] + b * J.Hs * J.Ws;
+  // (scale 0 needs no up-sampling: the plane is the disparity itself, turned into depth by the reader)
+  J.zup = s == 0 ? J.disp : (P.zup[s] ? P.zup[s] + boff : nullptr);
   J.idl = P.idloss + P.nsrc * boff;
   J.noise = P.noise[s] ? P.noise[s] + P.nid * boff : nullptr;
   J.dD = P.dD[s] + boff;
@@ -390,6 +394,11 @@ struct Cfg {
   static constexpr int NCS = AVG_ ? NSRC_ : 1;                   // coefficient sets shipped per window
   static constexpr int NID = AUTOMASK_ ? (AVG_ ? 1 : NSRC_) : 0; // identity candidates
   static constexpr int STASH4 = 1 + 3 * NSRC_;                   // 16-byte fields per ring row
+  // ZUP: the depth of every full-resolution pixel of every scale comes from a plane written by md2_depth_up before the
+  // marching kernel (one coalesced load per lane and row) instead of being rebuilt per row from four disparity taps,
+  // the up-sampling weights and a reciprocal.  The role-specialised kernels set it (RoleOf): their role A is the role
+  // every barrier waits for, and this takes ~45 instructions per row and the head of its dependent chain out of it.
+  static constexpr bool ZUP = false;
   // Backward rolling state (two rows of 9*NSRC box sums): registers for up to two sources, a
   // thread-private shared-memory ring beyond that (3 sources would spill ~0.5 KB per thread).
 #ifdef MD2_BSMEM_ALL
@@ -526,13 +535,26 @@ struct StashT {
 };
 typedef StashT<kRing> Stash;
 
+// one bilinear blend of the disparity up-sampling, w0 a + w1 b, with the contraction spelled out: the same bits in
+// every kernel that up-samples (marching kernels, md2_depth_up) and in the host emulator, whatever the compiler would
+// have fused on its own
+MD2_HD float up_blend(float w0, float a, float w1, float b) { return fmaf(w1, b, MD2_FMUL(w0, a)); }
+
+// layers.py:16-25: depth = 1 / (min_disp + (max_disp - min_disp) * disp)
+MD2_HD float depth_of_disp(const Params& P, float D) {
+  const float sd = MD2_FADD(P.a_disp, MD2_FMUL(P.c_disp, D));
+  return MD2_RCP(sd);
+}
+
 // issue the loads of row `t`'s target texel and disparity taps (consumed one step later)
 template <class C, bool WITH_TG = true>
 MD2_HD void prefetch_row(Lane<C>& L, const WarpJob& J, int t) {
   const int tr = reflect_clamp(t, J.H);
   MD2_CHK(tr * J.W + L.xi, J.plane);
   if (WITH_TG) L.ntg = MD2_LDS4(J.tgt4 + 4 * (tr * J.W + L.xi));
-  if (J.s == 0) {
+  if (C::ZUP) {
+    L.nd[0] = MD2_LD(J.zup + tr * J.W + L.xi);
+  } else if (J.s == 0) {
     L.nd[0] = MD2_LD(J.disp + tr * J.W + L.xi);
   } else {
     float syr = fmaf(J.rs, (float)tr + 0.5f, -0.5f);
@@ -687,21 +709,22 @@ MD2_HD void stage_a_issue(Lane<C>& L, Flight<C>& F, const Params& P, const WarpJ
     if (J.staged) F.ctg = make_f4(0.f, 0.f, 0.f, 0.f);      // the row goes into the ring by TMA
     else F.ctg = MD2_LDS4(J.tgt4 + 4 * (tr * J.W + L.xi));
   } else F.ctg = L.ntg;
-  float D;
-  if (J.s == 0) {
+  float D = 0.f, zpre = 0.f;
+  if (C::ZUP) {
+    zpre = L.nd[0];
+  } else if (J.s == 0) {
     D = L.nd[0];
   } else {
     float syr = fmaf(J.rs, (float)tr + 0.5f, -0.5f);
     syr = syr < 0.0f ? 0.0f : syr;
     const float l1 = syr - (float)(int)syr, l0 = 1.0f - l1;
-    const float top = L.ul0 * L.nd[0] + L.ul1 * L.nd[1];
-    const float bot = L.ul0 * L.nd[2] + L.ul1 * L.nd[3];
-    D = l0 * top + l1 * bot;
+    const float top = up_blend(L.ul0, L.nd[0], L.ul1, L.nd[1]);
+    const float bot = up_blend(L.ul0, L.nd[2], L.ul1, L.nd[3]);
+    D = up_blend(l0, top, l1, bot);
   }
   if (ROW_STEP > 0) prefetch_row<C, !TG_DIRECT>(L, J, t + ROW_STEP);     // ROW_STEP 0: the caller prefetches
   if (WITH_ID) load_identity_row(L, J, t);
-  const float sd = MD2_FADD(P.a_disp, MD2_FMUL(P.c_disp, D));
-  const float z = MD2_RCP(sd);
+  const float z = C::ZUP ? (J.s == 0 ? depth_of_disp(P, zpre) : zpre) : depth_of_disp(P, D);
   F.cz = z;
   const float yf = (float)tr;
 #pragma unroll

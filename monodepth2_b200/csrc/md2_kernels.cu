@@ -150,6 +150,54 @@ __global__ void md2_disp_mean(Params P) {
   }
 }
 
+// ------------------------------------------------------------------ 2b. depth planes of the up-sampled disparities
+// zup[s](b, y, x) = disp_to_depth(bilinear_up(disp_s)(y, x))    (trainer.py:349-353, layers.py:16-25): what role A of the
+// role-specialised marching kernel used to rebuild per row and lane from four disparity taps.  The expressions are the
+// ones of prefetch_row / lane_init / stage_a_issue (md2_core.cuh), term by term, so the values are the same.
+__global__ void __launch_bounds__(256) md2_depth_up(Params P) {
+  // block = 32 x 8 threads, a thread = 4 consecutive columns of one row; blockIdx.z = b * (S - 1) + s - 1, s >= 1
+  // (scale 0 is not up-sampled: its readers take the disparity plane and apply disp_to_depth themselves)
+  const int s = 1 + blockIdx.z % (P.S - 1), b = blockIdx.z / (P.S - 1);
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+  if (y >= P.H || x4 >= P.W) return;
+  const int Hs = P.H >> s, Ws = P.W >> s;
+  const float* d = P.disp[s] + (size_t)b * Hs * Ws;
+  float* out = P.zup[s] + (size_t)b * P.H * P.W + y * P.W + x4;
+  float z[4];
+  {
+    const float rs = 1.0f / (float)(1 << s);
+    float syr = fmaf(rs, (float)y + 0.5f, -0.5f);
+    syr = syr < 0.0f ? 0.0f : syr;
+    const int y0 = (int)syr;
+    const int y1 = y0 + ((y0 < Hs - 1) ? 1 : 0);
+    const float l1 = syr - (float)(int)syr, l0 = 1.0f - l1;
+    const float* r0 = d + y0 * Ws;
+    const float* r1 = d + y1 * Ws;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int x = min(x4 + i, P.W - 1);
+      float sxr = fmaf(rs, (float)x + 0.5f, -0.5f);
+      sxr = sxr < 0.0f ? 0.0f : sxr;
+      const int ux0 = (int)sxr;
+      const int ux1 = ux0 + ((ux0 < Ws - 1) ? 1 : 0);
+      const float ul1 = sxr - (float)ux0;
+      const float ul0 = 1.0f - ul1;
+      const float nd0 = __ldg(r0 + ux0), nd1 = __ldg(r0 + ux1), nd2 = __ldg(r1 + ux0), nd3 = __ldg(r1 + ux1);
+      const float top = up_blend(ul0, nd0, ul1, nd1);
+      const float bot = up_blend(ul0, nd2, ul1, nd3);
+      z[i] = depth_of_disp(P, up_blend(l0, top, l1, bot));
+    }
+  }
+  if ((P.W & 3) == 0) {
+    *reinterpret_cast<float4*>(out) = make_float4(z[0], z[1], z[2], z[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (x4 + i < P.W) out[i] = z[i];
+  }
+}
+
 // ------------------------------------------------------------------ 3. identity losses
 template <int NSRC, bool NOSSIM>
 __global__ void __launch_bounds__(kThreads) md2_identity(Params P) {
@@ -1008,6 +1056,8 @@ cudaError_t profile_march_ms(float* ms) {
 struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  cudaStream_t stream2 = nullptr;      // depth planes (md2_depth_up), beside the identity pass and the smoothness kernels
+  cudaEvent_t join2 = nullptr;
 };
 static SideStream g_side[64];
 static std::mutex g_side_mu;
@@ -1024,10 +1074,14 @@ static cudaError_t get_side(SideStream** out) {
   if (!s.stream) {
     SideStream n;
     if ((e = cudaStreamCreateWithFlags(&n.stream, cudaStreamNonBlocking)) == cudaSuccess &&
-        (e = cudaEventCreateWithFlags(&n.fork, cudaEventDisableTiming)) == cudaSuccess)
+        (e = cudaStreamCreateWithFlags(&n.stream2, cudaStreamNonBlocking)) == cudaSuccess &&
+        (e = cudaEventCreateWithFlags(&n.fork, cudaEventDisableTiming)) == cudaSuccess &&
+        (e = cudaEventCreateWithFlags(&n.join2, cudaEventDisableTiming)) == cudaSuccess)
       e = cudaEventCreateWithFlags(&n.join, cudaEventDisableTiming);
     if (e != cudaSuccess) {
       if (n.join) cudaEventDestroy(n.join);
+      if (n.join2) cudaEventDestroy(n.join2);
+      if (n.stream2) cudaStreamDestroy(n.stream2);
       if (n.fork) cudaEventDestroy(n.fork);
       if (n.stream) cudaStreamDestroy(n.stream);
       return e;
@@ -1110,7 +1164,17 @@ static cudaError_t launch_float_entry(const Params& P, cudaStream_t stream) {
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   if ((e = cudaEventRecord(side->join, side->stream)) != cudaSuccess) return e;
-  // ---- main stream: (identity + re-layout) or re-layout alone, then the marching kernel
+  // ---- main stream: depth planes (role kernels), (identity + re-layout) or re-layout alone, then the marching kernel
+  // (measured at 640x192 x 12: on the caller's stream in front of the identity pass the 12 us of md2_depth_up are
+  // fully exposed; on the smoothness side stream they are too, that stream being as long as the identity pass)
+  const bool zup = (march_mode() != 0 || P.nsrc > 3) && P.S > 1;
+  if (zup) {
+    if ((e = cudaStreamWaitEvent(side->stream2, side->fork, 0)) != cudaSuccess) return e;
+    dim3 grid((P.W + 127) / 128, (P.H + 7) / 8, P.B * (P.S - 1)), block(32, 8);
+    md2_depth_up<<<grid, block, 0, side->stream2>>>(P);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(side->join2, side->stream2)) != cudaSuccess) return e;
+  }
   if (P.automask) {
     const int jobs = P.B * P.nseg_id * P.nband_id;
     const int grid = (jobs + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -1129,6 +1193,7 @@ static cudaError_t launch_float_entry(const Params& P, cudaStream_t stream) {
   }
   // ---- join: the marching kernel finishes grad_disp_0 and needs the smoothness sums
   if ((e = cudaStreamWaitEvent(stream, side->join, 0)) != cudaSuccess) return e;
+  if (zup && (e = cudaStreamWaitEvent(stream, side->join2, 0)) != cudaSuccess) return e;
   // the tie-break noise may have been drawn on another stream (md2_tensors.noise_ready_event): first read is here
   if (P.noise_event && (e = cudaStreamWaitEvent(stream, (cudaEvent_t)P.noise_event, 0)) != cudaSuccess) return e;
   if (g_prof_on) cudaEventRecord(g_prof_ev[0], stream);

