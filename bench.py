@@ -559,7 +559,7 @@ def run_own(args, wl):
             "value_cabi_predrawn_noise": world * BATCH * args.steps / (ms_cabi * 1e-3),
             "ms_per_step_cabi_predrawn_noise": ms_cabi / args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "torch_cuda_baseline": tcb, "e2e": e2e,
-            "gpu_launches": 8 * args.steps,      # prologue, disp_mean, smooth, smooth_scalars, identity, march_roles, final, scale_tensors
+            "gpu_launches": 9 * args.steps,      # prologue, disp_mean, smooth, smooth_scalars, depth_up, identity, march_roles, final, scale_tensors
             "clocks": clocks,
             "train": train,
         }
