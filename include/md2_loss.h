@@ -227,6 +227,23 @@ int md2_resize_scratch_bytes(const md2_resize_plan *plan, int batch, size_t *byt
 int md2_resize_lanczos_u8(const md2_resize_plan *plan, const unsigned char *in, unsigned char *out,
                           void *scratch, size_t scratch_bytes, int batch, int hwc, void *stream);
 
+/* ---- colour augmentation on the GPU: replaces `self.to_tensor(color_aug(f))` of
+ * MonoDataset.preprocess with color_aug = transforms.ColorJitter.get_params(brightness, contrast, saturation, hue)
+ * (datasets/mono_dataset.py:60-70,107-109,169-176): torchvision's adjust_brightness / contrast / saturation / hue
+ * on uint8 RGB images, i.e. Pillow's Image.blend against black / the mean gray level / the "L" image and the
+ * RGB -> HSV -> RGB round trip with the hue byte shifted - byte-exact with Pillow.  One parameter set per image
+ * (`params`: DEVICE array of n_images entries; the reference draws one set per dataset item and applies it to every
+ * frame and scale of the item).  order[k]: 0 brightness, 1 contrast, 2 saturation, 3 hue, -1 skip, applied for
+ * k = 0..3 (ColorJitter.get_params' fn_idx); hue_shift = uint8(int32(hue_factor * 255)).
+ * in / out: (n,H,W,3) when hwc != 0, else (n,3,H,W); scratch: n_images * 8 bytes. ---- */
+typedef struct md2_color_jitter {
+  int order[4];
+  float brightness, contrast, saturation;
+  int hue_shift;
+} md2_color_jitter;
+int md2_color_jitter_u8(const unsigned char *in, unsigned char *out, const md2_color_jitter *params, void *scratch,
+                        size_t scratch_bytes, int n_images, int height, int width, int hwc, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,7 @@ SYMBOLS = [
     "md2_depth_metrics_scratch_bytes", "md2_depth_metrics",
     "md2_scale_tensors", "md2_dispconv_sigmoid", "md2_dispconv_sigmoid_backward",
     "md2_resize_plan_create", "md2_resize_plan_destroy", "md2_resize_scratch_bytes", "md2_resize_lanczos_u8",
+    "md2_color_jitter_u8",
 ]
 
 _lib = None
@@ -114,6 +115,8 @@ def load_library(path: str = None) -> C.CDLL:
     lib.md2_resize_plan_destroy.argtypes = [C.c_void_p]
     lib.md2_resize_plan_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     lib.md2_resize_scratch_bytes.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]
+    lib.md2_color_jitter_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_void_p]
     lib.md2_resize_lanczos_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
                                           C.c_int, C.c_void_p]
     if path is None:

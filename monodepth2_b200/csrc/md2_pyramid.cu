@@ -111,6 +111,118 @@ __global__ void md2_resample_u8(const unsigned char* __restrict__ in, unsigned c
   dst[2 * ocs] = clip8(s2);
 }
 
+// ------------------------------------------------------------------ colour augmentation
+// torchvision ColorJitter on PIL images as MonoDataset applies it (/root/reference/datasets/mono_dataset.py:60-70,
+// 136,169-176): adjust_brightness / contrast / saturation = Pillow's Image.blend(degenerate, image, factor)
+// (libImaging/Blend.c: in1 + alpha * (in2 - in1) in C float, truncated), the "L" conversion of Convert.c, and
+// adjust_hue = RGB -> HSV -> h += shift (mod 256) -> RGB with Convert.c's float / double mix.  Every operation is
+// written with explicit _rn intrinsics (no contraction) so that the bytes equal Pillow's; oracle/color_jitter.py is the
+// restatement the tests hold this to (itself pinned against the installed Pillow, the HSV pair on all 2^24 colours).
+struct Rgb8 { int r, g, b; };
+
+__device__ __forceinline__ int cj_to_l(const Rgb8& c) { return (c.r * 19595 + c.g * 38470 + c.b * 7471 + 0x8000) >> 16; }
+
+__device__ __forceinline__ int cj_blend1(int in1, int in2, float a, bool interp) {
+  const float t = __fadd_rn((float)in1, __fmul_rn(a, (float)(in2 - in1)));
+  if (interp) return (int)t;
+  return t <= 0.0f ? 0 : (t >= 255.0f ? 255 : (int)t);
+}
+__device__ __forceinline__ Rgb8 cj_blend(const Rgb8& d, const Rgb8& c, float a) {
+  const bool interp = a >= 0.0f && a <= 1.0f;
+  Rgb8 o;
+  o.r = cj_blend1(d.r, c.r, a, interp); o.g = cj_blend1(d.g, c.g, a, interp); o.b = cj_blend1(d.b, c.b, a, interp);
+  return o;
+}
+
+__device__ __forceinline__ Rgb8 cj_hue(const Rgb8& c, int shift) {
+  // rgb2hsv_row
+  const int maxc = max(c.r, max(c.g, c.b)), minc = min(c.r, min(c.g, c.b));
+  int uh = 0, us = 0;
+  const int uv = maxc;
+  if (minc != maxc) {
+    const float cr = (float)(maxc - minc);
+    const float sf = __fdiv_rn(cr, (float)maxc);
+    const float rc = __fdiv_rn((float)(maxc - c.r), cr), gc = __fdiv_rn((float)(maxc - c.g), cr), bc = __fdiv_rn((float)(maxc - c.b), cr);
+    float h;
+    if (c.r == maxc) h = __fsub_rn(bc, gc);
+    else if (c.g == maxc) h = __double2float_rn(__dsub_rn(__dadd_rn(2.0, (double)rc), (double)bc));
+    else h = __double2float_rn(__dsub_rn(__dadd_rn(4.0, (double)gc), (double)rc));
+    h = __double2float_rn(fmod(__dadd_rn(__ddiv_rn((double)h, 6.0), 1.0), 1.0));
+    uh = min(max((int)__dmul_rn((double)h, 255.0), 0), 255);
+    us = min(max((int)__dmul_rn((double)sf, 255.0), 0), 255);
+  }
+  uh = (uh + shift) & 255;
+  // hsv2rgb
+  Rgb8 o;
+  if (us == 0) { o.r = o.g = o.b = uv; return o; }
+  const double hf = __ddiv_rn(__dmul_rn((double)(float)uh, 6.0), 255.0);
+  const int i = (int)floor(hf);
+  const double f = (double)__double2float_rn(__dsub_rn(hf, (double)(float)i));
+  const double fs = (double)__double2float_rn(__ddiv_rn((double)(float)us, 255.0));
+  const double vf = (double)(float)uv;
+  const int p = min(max((int)round(__dmul_rn(vf, __dsub_rn(1.0, fs))), 0), 255);
+  const int q = min(max((int)round(__dmul_rn(vf, __dsub_rn(1.0, __dmul_rn(fs, f)))), 0), 255);
+  const int t = min(max((int)round(__dmul_rn(vf, __dsub_rn(1.0, __dmul_rn(fs, __dsub_rn(1.0, f))))), 0), 255);
+  switch (i % 6) {
+    case 0: o.r = uv; o.g = t; o.b = p; break;
+    case 1: o.r = q; o.g = uv; o.b = p; break;
+    case 2: o.r = p; o.g = uv; o.b = t; break;
+    case 3: o.r = p; o.g = q; o.b = uv; break;
+    case 4: o.r = t; o.g = p; o.b = uv; break;
+    default: o.r = uv; o.g = p; o.b = q; break;
+  }
+  return o;
+}
+
+// applies operations [from, to) of the image's order; `mean` is the contrast gray level (used when op 1 is in range)
+__device__ __forceinline__ Rgb8 cj_apply(Rgb8 c, const md2_color_jitter& J, int from, int to, int mean) {
+  for (int k = from; k < to; ++k) {
+    const int op = J.order[k];
+    if (op == 0) { const Rgb8 z = {0, 0, 0}; c = cj_blend(z, c, J.brightness); }
+    else if (op == 1) { const Rgb8 m = {mean, mean, mean}; c = cj_blend(m, c, J.contrast); }
+    else if (op == 2) { const int l = cj_to_l(c); const Rgb8 g = {l, l, l}; c = cj_blend(g, c, J.saturation); }
+    else if (op == 3) c = cj_hue(c, J.hue_shift);
+  }
+  return c;
+}
+__device__ __forceinline__ int cj_contrast_pos(const md2_color_jitter& J) {
+  for (int k = 0; k < 4; ++k) if (J.order[k] == 1) return k;
+  return -1;
+}
+__device__ __forceinline__ Rgb8 cj_load(const unsigned char* in, long long n, int p, int plane, int hwc) {
+  Rgb8 c;
+  if (hwc) { const unsigned char* q = in + (n * plane + p) * 3; c.r = __ldg(q); c.g = __ldg(q + 1); c.b = __ldg(q + 2); }
+  else { const unsigned char* q = in + n * 3 * plane + p; c.r = __ldg(q); c.g = __ldg(q + plane); c.b = __ldg(q + 2 * (long long)plane); }
+  return c;
+}
+
+// pass 1 (only for images whose order contains contrast): sum of the "L" image after the operations in front of it
+__global__ void __launch_bounds__(256) md2_cj_lsum(const unsigned char* in, const md2_color_jitter* params, unsigned long long* sums,
+                                                    int plane, int hwc) {
+  const int n = blockIdx.y;
+  const md2_color_jitter J = params[n];
+  const int cp = cj_contrast_pos(J);
+  if (cp < 0) return;
+  unsigned int acc = 0;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < plane; p += gridDim.x * blockDim.x)
+    acc += (unsigned)cj_to_l(cj_apply(cj_load(in, n, p, plane, hwc), J, 0, cp, 0));
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(sums + n, (unsigned long long)acc);
+}
+
+// pass 2: the whole chain; mean = int(sum / count + 0.5) in double, as ImageStat.Stat(...).mean does in Python
+__global__ void __launch_bounds__(256) md2_cj_apply(const unsigned char* in, unsigned char* out, const md2_color_jitter* params,
+                                                     const unsigned long long* sums, int plane, int hwc) {
+  const int n = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= plane) return;
+  const md2_color_jitter J = params[n];
+  const int mean = (int)(__dadd_rn(__ddiv_rn((double)sums[n], (double)plane), 0.5));
+  const Rgb8 c = cj_apply(cj_load(in, n, p, plane, hwc), J, 0, 4, mean);
+  if (hwc) { unsigned char* q = out + ((long long)n * plane + p) * 3; q[0] = (unsigned char)c.r; q[1] = (unsigned char)c.g; q[2] = (unsigned char)c.b; }
+  else { unsigned char* q = out + (long long)n * 3 * plane + p; q[0] = (unsigned char)c.r; q[plane] = (unsigned char)c.g; q[2 * (long long)plane] = (unsigned char)c.b; }
+}
+
 }  // namespace
 
 struct md2_resize_plan {
@@ -181,6 +293,21 @@ int md2_resize_lanczos_u8(const md2_resize_plan* p, const unsigned char* in, uns
     if (cudaMemcpyAsync(out, in, (size_t)batch * 3 * p->in_h * p->in_w, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
       return MD2_ERR_CUDA;
   }
+  return cudaGetLastError() == cudaSuccess ? MD2_OK : MD2_ERR_CUDA;
+}
+
+int md2_color_jitter_u8(const unsigned char* in, unsigned char* out, const md2_color_jitter* params, void* scratch,
+                        size_t scratch_bytes, int n_images, int height, int width, int hwc, void* stream) {
+  if (!in || !out || !params || n_images < 1 || height < 1 || width < 1) return MD2_ERR_INVALID_ARGUMENT;
+  if (n_images > 65535) return MD2_ERR_UNSUPPORTED;
+  if (!scratch || scratch_bytes < (size_t)n_images * sizeof(unsigned long long)) return MD2_ERR_WORKSPACE_TOO_SMALL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int plane = height * width;
+  unsigned long long* sums = (unsigned long long*)scratch;
+  if (cudaMemsetAsync(sums, 0, (size_t)n_images * sizeof(unsigned long long), s) != cudaSuccess) return MD2_ERR_CUDA;
+  const int bx = (plane + 255) / 256;
+  md2_cj_lsum<<<dim3(bx < 64 ? bx : 64, n_images), 256, 0, s>>>(in, params, sums, plane, hwc);
+  md2_cj_apply<<<dim3(bx, n_images), 256, 0, s>>>(in, out, params, sums, plane, hwc);
   return cudaGetLastError() == cudaSuccess ? MD2_OK : MD2_ERR_CUDA;
 }
 

@@ -1,3 +1,3 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -5 | tee gpurun_out/u_pytest.log
+timeout 600 python -m pytest tests/test_color_jitter.py -q -m gpu 2>&1 | tail -12 | tee gpurun_out/u_pytest_cj.log
