@@ -399,6 +399,9 @@ struct Cfg {
   // the up-sampling weights and a reciprocal.  The role-specialised kernels set it (RoleOf): their role A is the role
   // every barrier waits for, and this takes ~45 instructions per row and the head of its dependent chain out of it.
   static constexpr bool ZUP = false;
+  // PAIRED (packed two-source role kernel, md2_roles.cuh PairedOf): ring fields 1 and 4 hold (r0, g0, r1, g1) and
+  // (b0, b1, u0, u1) - the aligned register pairs role B's f32x2 arithmetic reads - instead of (r, g, b, u) per source
+  static constexpr bool PAIRED = false;
   // Backward rolling state (two rows of 9*NSRC box sums): registers for up to two sources, a
   // thread-private shared-memory ring beyond that (3 sources would spill ~0.5 KB per thread).
 #ifdef MD2_BSMEM_ALL
@@ -1196,7 +1199,11 @@ MD2_HD void stage_c_divergent(Lane<C>& L, const Params& P, const WarpJob& J, int
     float dzsum = 0.f;
 #pragma unroll
     for (int f = 0; f < C::NSRC; ++f) {
-      const F4 sp = st.at(slot, 1 + 3 * f, C::STASH4);
+      F4 sp = st.at(slot, 1 + 3 * f, C::STASH4);
+      if (C::PAIRED) {
+        const F4 a = st.at(slot, 1, C::STASH4), b4 = st.at(slot, 4, C::STASH4);
+        sp = f == 0 ? make_f4(a.x, a.y, b4.x, b4.z) : make_f4(a.z, a.w, b4.y, b4.w);
+      }
       const F4 sdx = st.at(slot, 2 + 3 * f, C::STASH4);
       const F4 sdy = st.at(slot, 3 + 3 * f, C::STASH4);
       const float xs[3] = {sp.x, sp.y, sp.z};

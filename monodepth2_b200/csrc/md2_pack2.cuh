@@ -363,13 +363,17 @@ __device__ __forceinline__ void stage_a_finish2(Lane2<C>& L, const Flight2& F, c
     }
     L.pr[f] = pr2;
     prb[f] = pb;
-    if (PUBLISH) st.at(slot, 1 + 3 * f, C::STASH4) = make_f4(pr2.x, pr2.y, pb, f ? F.cu.y : F.cu.x);
+    if (PUBLISH && !C::PAIRED) st.at(slot, 1 + 3 * f, C::STASH4) = make_f4(pr2.x, pr2.y, pb, f ? F.cu.y : F.cu.x);
     if (C::GRAD) {
       st.at(slot, 2 + 3 * f, C::STASH4) = make_f4(dxp2.x, dxp2.y, dxb, f ? F.cv.y : F.cv.x);
       st.at(slot, 3 + 3 * f, C::STASH4) = make_f4(dyp2.x, dyp2.y, dyb, f == 0 ? z : 0.f);
     }
   }
   L.pr[2] = p2(prb[0], prb[1]);
+  if (PUBLISH && C::PAIRED) {
+    st.at(slot, 1, C::STASH4) = make_f4(L.pr[0].x, L.pr[0].y, L.pr[1].x, L.pr[1].y);
+    st.at(slot, 4, C::STASH4) = make_f4(prb[0], prb[1], F.cu.x, F.cu.y);
+  }
 }
 
 template <class C, class ST, bool PUBLISH = C::GRAD>

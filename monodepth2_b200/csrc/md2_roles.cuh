@@ -73,13 +73,38 @@ constexpr int kRoleAWarps = MD2_ROLE_A_WARPS;
 #endif
 
 // the role kernel keeps the backward box sums of every source count in registers (role C has room)
-template <class C0>
 #ifndef MD2_ROLE_ZUP
 #define MD2_ROLE_ZUP 1
 #endif
+template <class C0>
 struct RoleOf : C0 {
   static constexpr bool BSMEM = false;
   static constexpr bool ZUP = (MD2_ROLE_ZUP != 0);      // depth planes from md2_depth_up (see Cfg::ZUP)
+};
+// loops of the packed roles without a branch around the row body (the first / last periods, in which a role only
+// crosses the barrier, are peeled): with the branch ptxas may park the wait for the loads a role keeps in flight across
+// the barrier on that branch, at the top of the loop, instead of at their first use (measured: 29 % of role B's time)
+#ifndef MD2_ROLE_PEEL
+#define MD2_ROLE_PEEL 1
+#endif
+// (one instantiation - 3 sources, --disable_automasking, SSIM, gradients - spills 12 bytes at its 168-register cap in
+// the peeled form and keeps the branchy loops)
+template <class C>
+__host__ __device__ constexpr bool role_peel() {
+  return (MD2_ROLE_PEEL != 0) && !(C::NSRC == 3 && !C::AUTOMASK && C::GRAD && !C::AVG && !C::NOSSIM);
+}
+// the packed two-source role kernel runs its roles over PairedOf<C>: ring layout in the register pairs role B reads
+// (see Cfg::PAIRED; the experimental packed role C and the free-running kernel keep the per-source layout)
+#ifndef MD2_ROLE_PAIRED
+#define MD2_ROLE_PAIRED 1
+#endif
+#if defined(MD2_ROLE_PACKED_C) || defined(MD2_WITH_FLOW)
+#undef MD2_ROLE_PAIRED
+#define MD2_ROLE_PAIRED 0
+#endif
+template <class C0>
+struct PairedOf : C0 {
+  static constexpr bool PAIRED = (MD2_ROLE_PAIRED != 0);
 };
 
 template <class C>
@@ -218,6 +243,18 @@ __device__ __forceinline__ void role_a(const Params& P, const WarpJob& J, int la
       prefetch_row<C, false>(L, J, t0 + k + NA);
     }
   }
+  if (NA == 1 && role_peel<C>()) {
+#pragma unroll 1
+    for (int t = t0; t <= t1; ++t) {
+      if (!tma_in_c<C>()) stage_target_row<C>(J, st, t, lane);
+      stage_a_issue<C, false, 1, true>(L, P, J, t);
+      stage_a_finish<C, ST, true>(L, P, J, t, st);
+      role_sync<RoleCfg<C>::THREADS>();
+    }
+#pragma unroll 1
+    for (int p = t1 - t0 + 1; p < nit; ++p) role_sync<RoleCfg<C>::THREADS>();
+    return;
+  }
 #pragma unroll 1
   for (int p = 0; p < nit; ++p) {
     const int t = t0 + p;
@@ -296,11 +333,22 @@ __device__ __forceinline__ void role_b(const Params& P, const WarpJob& J, int la
   // neighbour offsets in the ring (the edge lanes read themselves: their windows are never used)
   const int ol = (lane > 0) ? -1 : 0, orr = (lane < 31) ? 1 : 0;
   load_identity_row(L, J, t0);
-#pragma unroll 1
-  for (int i = 0; i < nit; ++i) {
-    const int t = t0 + i - 1;
-    if (i >= 1 && t <= t1) b_step(L, P, J, lane, st, cring + (t & 1) * RC::NCF4 * 32, t, ol, orr);
+  if (role_peel<C>()) {
     role_sync<RC::THREADS>();
+#pragma unroll 1
+    for (int t = t0; t <= t1; ++t) {
+      b_step(L, P, J, lane, st, cring + (t & 1) * RC::NCF4 * 32, t, ol, orr);
+      role_sync<RC::THREADS>();
+    }
+#pragma unroll 1
+    for (int i = t1 - t0 + 2; i < nit; ++i) role_sync<RC::THREADS>();
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < nit; ++i) {
+      const int t = t0 + i - 1;
+      if (i >= 1 && t <= t1) b_step(L, P, J, lane, st, cring + (t & 1) * RC::NCF4 * 32, t, ol, orr);
+      role_sync<RC::THREADS>();
+    }
   }
   const float ls = warp_sum(L.loss);
   if (lane == 0) atomicAdd(&P.acc[acc_photo(J.s)], (double)ls);
@@ -359,6 +407,20 @@ __device__ __forceinline__ void role_c(const Params& P, const WarpJob& J, int la
   lane_init(L, P, J, lane);
   const int ol = (lane > 0) ? -1 : 0, orr = (lane < 31) ? 1 : 0;
 stage_next_target_row<C>(J, st, t0, t1, lane);
+  if (role_peel<C>()) {
+    stage_next_target_row<C>(J, st, t0 + 1, t1, lane);
+    role_sync<RC::THREADS>();
+    stage_next_target_row<C>(J, st, t0 + 2, t1, lane);
+    role_sync<RC::THREADS>();
+#pragma unroll 1
+    for (int t = t0; t <= t1; ++t) {
+      c_step(L, P, J, lane, st, cring + (t & 1) * RC::NCF4 * 32, t, ol, orr);
+      stage_next_target_row<C>(J, st, t + 3, t1, lane);
+      role_sync<RC::THREADS>();
+    }
+    c_reduce(L, P, J, lane);
+    return;
+  }
 #pragma unroll 1
   for (int i = 0; i < nit; ++i) {
     const int t = t0 + i - 2;
@@ -420,6 +482,18 @@ __device__ __forceinline__ void role_a2(const Params& P, const WarpJob& J, int l
       stage_a_issue2<C, false, 0, true>(L, P, J, t0 + k);
       prefetch_row2<C, false>(L, J, t0 + k + NA);
     }
+  }
+  if (NA == 1 && role_peel<C>() && !z_in_c<C, true>()) {
+#pragma unroll 1
+    for (int t = t0; t <= t1; ++t) {
+      if (!tma_in_c<C>()) stage_target_row<C>(J, st, t, lane);
+      stage_a_issue2<C, false, 1, true>(L, P, J, t);
+      stage_a_finish2<C, ST, true>(L, P, J, t, st);
+      role_sync<RoleCfg<C>::THREADS>();
+    }
+#pragma unroll 1
+    for (int p = t1 - t0 + 1; p < nit; ++p) role_sync<RoleCfg<C>::THREADS>();
+    return;
   }
 #pragma unroll 1
   for (int p = 0; p < nit; ++p) {
@@ -539,9 +613,15 @@ __device__ __forceinline__ void b_step2(Lane2<C>& L, const Params& P, const Warp
   L.tgrg = p2(tc.x, tc.y); L.tgb = tc.z;
   lf.tgrg = p2(tl.x, tl.y); lf.tgb = tl.z;
   rt.tgrg = p2(tr.x, tr.y); rt.tgb = tr.z;
-  L.pr[0] = p2(ac.x, ac.y); L.pr[1] = p2(bc_.x, bc_.y); L.pr[2] = p2(ac.z, bc_.z);
-  lf.pr[0] = p2(al.x, al.y); lf.pr[1] = p2(bl.x, bl.y); lf.pr[2] = p2(al.z, bl.z);
-  rt.pr[0] = p2(ar.x, ar.y); rt.pr[1] = p2(br.x, br.y); rt.pr[2] = p2(ar.z, br.z);
+  if (C::PAIRED) {      // fields 1 / 4 = (r0, g0, r1, g1) / (b0, b1, u0, u1): the pairs as they are
+    L.pr[0] = p2(ac.x, ac.y); L.pr[1] = p2(ac.z, ac.w); L.pr[2] = p2(bc_.x, bc_.y);
+    lf.pr[0] = p2(al.x, al.y); lf.pr[1] = p2(al.z, al.w); lf.pr[2] = p2(bl.x, bl.y);
+    rt.pr[0] = p2(ar.x, ar.y); rt.pr[1] = p2(ar.z, ar.w); rt.pr[2] = p2(br.x, br.y);
+  } else {
+    L.pr[0] = p2(ac.x, ac.y); L.pr[1] = p2(bc_.x, bc_.y); L.pr[2] = p2(ac.z, bc_.z);
+    lf.pr[0] = p2(al.x, al.y); lf.pr[1] = p2(bl.x, bl.y); lf.pr[2] = p2(al.z, bl.z);
+    rt.pr[0] = p2(ar.x, ar.y); rt.pr[1] = p2(br.x, br.y); rt.pr[2] = p2(ar.z, br.z);
+  }
   stage_b2(L, P, J, t, lane, lf, rt);
   if (C::GRAD) {
     o[0] = make_f4(L.cf[0].x, L.cf[0].y, L.cf[1].x, L.cf[1].y);
@@ -565,11 +645,22 @@ __device__ __forceinline__ void role_b2(const Params& P, const WarpJob& J, int l
     id_rows_load(L, idr, J, t0);
   } else load_identity_row2(L, J, t0);
   if (z_in_c<C, true>()) role_sync<RC::THREADS>();
+  if (role_peel<C>()) {
+    role_sync<RC::THREADS>();                                     // period 0: role A publishes row t0
 #pragma unroll 1
-  for (int i = 0; i < nit; ++i) {
-    const int t = t0 + i - 1;
-    if (i >= 1 && t <= t1) b_step2(L, P, J, lane, st, cring + (t & 1) * RC::NCF4 * 32, t, ol, orr, id_ptrs<C>() ? &idr : nullptr);
-    role_sync<RC::THREADS>();
+    for (int t = t0; t <= t1; ++t) {
+      b_step2(L, P, J, lane, st, cring + (t & 1) * RC::NCF4 * 32, t, ol, orr, id_ptrs<C>() ? &idr : nullptr);
+      role_sync<RC::THREADS>();
+    }
+#pragma unroll 1
+    for (int i = t1 - t0 + 2; i < nit; ++i) role_sync<RC::THREADS>();
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < nit; ++i) {
+      const int t = t0 + i - 1;
+      if (i >= 1 && t <= t1) b_step2(L, P, J, lane, st, cring + (t & 1) * RC::NCF4 * 32, t, ol, orr, id_ptrs<C>() ? &idr : nullptr);
+      role_sync<RC::THREADS>();
+    }
   }
   const float ls = warp_sum(L.loss);
   if (lane == 0) atomicAdd(&P.acc[acc_photo(J.s)], (double)ls);
@@ -632,6 +723,21 @@ stage_next_target_row<C>(J, st, t0, t1, lane);
   if (z_in_c<C, true>()) {
     c_publish_z(L, P, J, t0, zring);          // (lane_init put the disparity taps of row t0 in flight)
     role_sync<RC::THREADS>();
+  }
+  if (role_peel<C>() && !z_in_c<C, true>()) {
+    // periods 0 and 1: roles A / B fill the rings; this role only stages the next target rows (nit >= 3 always)
+    stage_next_target_row<C>(J, st, t0 + 1, t1, lane);
+    role_sync<RC::THREADS>();
+    stage_next_target_row<C>(J, st, t0 + 2, t1, lane);
+    role_sync<RC::THREADS>();
+#pragma unroll 1
+    for (int t = t0; t <= t1; ++t) {                               // period i = t - t0 + 2
+      c_step_from_packed(L, P, J, lane, st, cring + (t & 1) * RC::NCF4 * 32, t, ol, orr);
+      stage_next_target_row<C>(J, st, t + 3, t1, lane);
+      role_sync<RC::THREADS>();
+    }
+    c_reduce(L, P, J, lane);
+    return;
   }
 #pragma unroll 1
   for (int i = 0; i < nit; ++i) {
@@ -735,16 +841,17 @@ __global__ void MD2_ROLE_BOUNDS(C) md2_march_roles(Params P) {
     }
   }
   if constexpr (PACKED) {
+    typedef PairedOf<C> CP;
 #ifdef MD2_ROLE_A_PIPE
     if (role < RC::NA) role_a2_pipe<C>(P, J, lane, st, reinterpret_cast<P2*>(smem + RC::STASH_F4 + RC::COEF_F4 + RC::TAP_F4 + RC::BAR_F4), t0, t1, nit);
 #else
-    if (role < RC::NA) role_a2<C>(P, J, lane, role, st, zring, t0, t1, nit);
+    if (role < RC::NA) role_a2<CP>(P, J, lane, role, st, zring, t0, t1, nit);
 #endif
-    else if (role == RC::NA) role_b2<C>(P, J, lane, st, cring, t0, t1, nit);
+    else if (role == RC::NA) role_b2<CP>(P, J, lane, st, cring, t0, t1, nit);
 #ifdef MD2_ROLE_PACKED_C
     else if (C::GRAD) role_c2<C>(P, J, lane, st, cring, t0, t1, nit);
 #else
-    else if (C::GRAD) role_c_from_packed<C>(P, J, lane, st, cring, zring, t0, t1, nit);
+    else if (C::GRAD) role_c_from_packed<CP>(P, J, lane, st, cring, zring, t0, t1, nit);
 #endif
   } else {
     if (role < RC::NA) role_a<C>(P, J, lane, role, st, t0, t1, nit);
