@@ -584,6 +584,14 @@ __device__ __forceinline__ void id_rows_load(Lane2<C>& L, IdRows& R, const WarpJ
   L.nzv[0] = MD2_LDS1(R.nz0); L.nzv[1] = MD2_LDS1(R.nz1);
   const int inc = (t >= 1 && t <= J.H - 1) ? J.W : 0;
   R.id0 += inc; R.id1 += inc; R.nz0 += inc; R.nz1 += inc;
+#ifdef MD2_ROLE_ID_PREFETCH
+  // the rows the NEXT call loads are pulled into L2 now (no destination register, no scoreboard): identity loss and
+  // noise are read once per scale and come from HBM; one period is not always enough for the load itself
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(R.id0));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(R.id1));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(R.nz0));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(R.nz1));
+#endif
 }
 template <class C>
 __host__ __device__ constexpr bool id_ptrs() { return C::AUTOMASK && (MD2_ROLE_ID_PTRS != 0); }
