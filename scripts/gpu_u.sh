@@ -2,6 +2,5 @@
 cd "$(dirname "$0")/.."
 L=monodepth2_b200/lib
 for rep in 1 2; do
-for v in "" _pf; do MD2_LIB_PATH=$L/libmd2loss$v.so timeout 120 python scripts/time_loss.py 0 30 mono 2>&1 | grep -v Warn; done
-for r in 0 64 48; do MD2_LIB_PATH=$L/libmd2loss_c6.so timeout 120 python scripts/time_loss.py $r 30 mono 2>&1 | grep -v Warn; done
+for v in "" _ns; do MD2_LIB_PATH=$L/libmd2loss$v.so timeout 120 python scripts/time_loss.py 0 30 mono 2>&1 | grep -v Warn; done
 done | tee gpurun_out/u_times.log
