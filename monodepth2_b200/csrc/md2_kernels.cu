@@ -875,6 +875,7 @@ static int march_mode() {
     const char* e = getenv("MD2_MARCH");
     if (e && !strcmp(e, "warp")) return 0;
     if (e && !strcmp(e, "flow")) return 2;
+    if (e && !strcmp(e, "lockstep")) return 3;
     return 1;
   }();
   return mode;
@@ -916,6 +917,20 @@ static cudaError_t launch_march_roles(const Params& P0, cudaStream_t stream) {
   }
 #endif
   const size_t smem = (size_t)RC::SMEM_F4 * sizeof(float4);
+#ifdef MD2_WITH_MB
+  if constexpr (C::NSRC == 2 && !C::AVG && C::AUTOMASK && C::GRAD) {
+    // decoupled roles (mbarrier pipeline, md2_march_mb) for the packed two-source kernels with gradients;
+    // MD2_MARCH=lockstep keeps the one-barrier-per-row kernel
+    if (pack2_mode() != 0 && march_mode() == 1) {
+      typedef MbCfg<PairedOf<C>> MC;
+      const size_t msmem = (size_t)MC::SMEM_F4 * sizeof(float4);
+      static cudaError_t attrm = cudaFuncSetAttribute(md2_march_mb<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+      if (attrm != cudaSuccess) return attrm;
+      md2_march_mb<C><<<jobs, MC::THREADS, msmem, stream>>>(P);
+      return cudaGetLastError();
+    }
+  }
+#endif
   if constexpr (C::NSRC == 2 && !C::AVG && (C::AUTOMASK || !C::GRAD)) {
     if (pack2_mode() != 0) {          // packed-fp32 roles unless MD2_PACK2=off (--disable_automasking with
                                       // gradients: the packed form spills 16 bytes under 128 registers, scalar fits)

@@ -868,6 +868,151 @@ __global__ void MD2_ROLE_BOUNDS(C) md2_march_roles(Params P) {
   }
 }
 
+#ifdef MD2_WITH_MB
+// ------------------------------------------------------------------ decoupled roles (mbarrier pipeline)
+// md2_march_roles runs its three roles in lock step: one bar.sync per image row, so every period lasts as long as the
+// slowest role of THAT row.  Measured on the shipped kernel: roles A and B each wait 12 % of their time at the barrier
+// (C 31 %) - neither is the slowest every row, the period is E[max] instead of max E.  Here the same roles (same stage
+// functions, same rings, packed two-source kernels with gradients) hand rows over through mbarriers, the way a TMA
+// pipeline does - a "full" and an "empty" barrier per ring slot, phase = use count of the slot - and a role waits only
+// for the row it needs:
+//   A(t)  waits ringE[slot(t)] (role C is done with pixel row t - RING), publishes row t, arrives on ringF[slot(t)]
+//   B(t)  waits ringF[slot(t)] (+ the TMA barrier of the target row), waits coefE[cslot(t)], publishes the coefficients
+//         of row t, arrives on coefF[cslot(t)]
+//   C(t)  waits coefF[cslot(t)], runs the adjoint of pixel row t - 2, arrives on coefE[cslot(t)] and ringE[slot(t - 2)],
+//         stages the target row t + 3 by TMA (its slot was released by C(t + 3 - RING + 2) at the latest: RING >= 5)
+// Every barrier counts the 32 lanes of the arriving warp (each lane's arrive releases its own shared-memory writes);
+// waits are mbarrier.try_wait (the warp sleeps in hardware, no polling of shared memory, no fence).
+// Measured (profiles/r02_optimization_log.md): 0.339 ms with 8 ring / 4 coefficient slots against 0.330 ms in lock step, 0.392 ms
+// with 5 / 2 or 6 / 2 slots - the barrier waits of the lock-step kernel are not a synchronisation artefact, the roles
+// share issue slots and the LSU pipe and slow each other down whichever way they wait.  Compiled only with
+// -DMD2_WITH_MB (then the default for the packed two-source kernels with gradients; MD2_MARCH=lockstep switches back).
+#ifndef MD2_MB_RING
+#define MD2_MB_RING 8
+#endif
+#ifndef MD2_MB_CRING
+#define MD2_MB_CRING 4
+#endif
+template <class C>
+struct MbCfg {
+  static constexpr int THREADS = 96;
+  static constexpr int RING = MD2_MB_RING;                       // power of two: slot(t) is a mask
+  static constexpr int CRING = MD2_MB_CRING;
+  static constexpr int MIN_CTAS = MD2_ROLE_MIN_CTAS;
+  // 128, not the 136 that 65536 / (5 x 96) suggests: registers are allocated per warp in units of 512, a kernel that
+  // really uses 129-136 gets 4 CTAs per SM (ncu launch__occupancy_limit_registers; measured 0.43 instead of 0.33 ms)
+  static constexpr int MAXREG = RoleCfg<C>::MAXREG > 128 && RoleCfg<C>::MAXREG < 144 ? 128 : RoleCfg<C>::MAXREG;
+  static constexpr int NCF4 = RoleCfg<C>::NCF4;
+  static constexpr int STASH_F4 = RING * C::STASH4 * 32;
+  static constexpr int COEF_F4 = CRING * NCF4 * 32;
+  static constexpr int NBAR = 3 * RING + 2 * CRING;              // TMA, ring full, ring empty | coefficients full, empty
+  static constexpr int BAR_F4 = (NBAR * 8 + 15) / 16;
+  static constexpr int SMEM_F4 = STASH_F4 + COEF_F4 + BAR_F4;
+};
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+template <class C0>
+__global__ void __launch_bounds__(MbCfg<PairedOf<C0>>::THREADS) __maxnreg__(MbCfg<PairedOf<C0>>::MAXREG) md2_march_mb(Params P) {
+  typedef PairedOf<C0> C;
+  typedef MbCfg<C> MC;
+  static_assert(C::NSRC == 2 && !C::AVG && C::GRAD, "packed two-source kernels with gradients");
+  constexpr int R = MC::RING, CR = MC::CRING;
+  extern __shared__ float4 smem[];
+  const int lane = threadIdx.x & 31;
+  const int role = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
+  const int job = blockIdx.x;
+  const int per_seg = P.S * P.nband;
+  const int per_b = P.nseg * per_seg;
+  const int jb = P.B - 1 - job / per_b;
+  const int r = job - (job / per_b) * per_b;
+  const int seg = r / per_seg;
+  const int r2 = r - seg * per_seg;
+  const int js = r2 / P.nband;
+  const int jy0 = seg * P.seg_rows;
+  WarpJob J = make_job(P, js, jb, (r2 - js * P.nband) * kOwnCols, jy0, min(jy0 + P.seg_rows, P.H));
+#ifndef MD2_ROLE_NO_TMA
+  J.staged = (J.x0 - 2 >= 0) && (J.x0 + 30 <= J.W);
+#endif
+  StashT<R> st;
+  st.base = smem + lane;
+  st.bring = nullptr;
+  st.stride = 32;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + MC::STASH_F4 + MC::COEF_F4);
+  st.tbar = bars;
+  unsigned long long* ringF = bars + R;
+  unsigned long long* ringE = bars + 2 * R;
+  unsigned long long* coefF = bars + 3 * R;
+  unsigned long long* coefE = bars + 3 * R + CR;
+  F4* cring = smem + MC::STASH_F4 + lane;
+  const int t0 = J.y0 - 2, t1 = J.y1 + 1;
+  st.t0 = t0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) { mbar_init(bars + i, 1); mbar_init(ringF + i, 32); mbar_init(ringE + i, 32); }
+#pragma unroll
+    for (int i = 0; i < CR; ++i) { mbar_init(coefF + i, 32); mbar_init(coefE + i, 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int ol = (lane > 0) ? -1 : 0, orr = (lane < 31) ? 1 : 0;
+
+  if (role == 0) {
+    Lane2<C> L;
+    lane_init2(L, P, J, lane);
+#pragma unroll 1
+    for (int t = t0; t <= t1; ++t) {
+      const int n = (t - t0) / R;                                           // use count of this row's slot
+      stage_a_issue2<C, false, 1, true>(L, P, J, t);
+      if (n > 0) mbar_wait(ringE + st.slot(t), (unsigned)((n - 1) & 1));    // (after the gather is in flight)
+      stage_a_finish2<C, decltype(st), true>(L, P, J, t, st);
+      mbar_arrive(ringF + st.slot(t));
+    }
+  } else if (role == 1) {
+    Lane2<C> L;
+    lane_init2(L, P, J, lane);
+    IdRows idr;
+    if (id_ptrs<C>()) { id_rows_init(idr, L, J, t0); id_rows_load(L, idr, J, t0); }
+    else load_identity_row2(L, J, t0);
+#pragma unroll 1
+    for (int t = t0; t <= t1; ++t) {
+      const int i = t - t0, cs = i & (CR - 1), m = i / CR;
+      if (m > 0) mbar_wait(coefE + cs, (unsigned)((m - 1) & 1));
+      mbar_wait(ringF + st.slot(t), st.parity(t));
+      b_step2(L, P, J, lane, st, cring + cs * MC::NCF4 * 32, t, ol, orr, id_ptrs<C>() ? &idr : nullptr);
+      mbar_arrive(coefF + cs);
+    }
+    const float ls = warp_sum(L.loss);
+    if (lane == 0) atomicAdd(&P.acc[acc_photo(J.s)], (double)ls);
+  } else {
+    Lane<C> L;
+    lane_init(L, P, J, lane);
+    if (J.staged) {
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (t0 + k <= t1) stage_target_row<C>(J, st, t0 + k, lane);
+    }
+#pragma unroll 1
+    for (int t = t0; t <= t1; ++t) {
+      const int i = t - t0, cs = i & (CR - 1), m = i / CR;
+      mbar_wait(coefF + cs, (unsigned)(m & 1));
+      c_step_from_packed(L, P, J, lane, st, cring + cs * MC::NCF4 * 32, t, ol, orr);
+      mbar_arrive(coefE + cs);
+      if (t - 2 >= t0) mbar_arrive(ringE + st.slot(t - 2));
+      if (J.staged && t + 3 <= t1) {
+        __syncwarp();
+        stage_target_row<C>(J, st, t + 3, lane);
+      }
+    }
+    c_reduce(L, P, J, lane);
+  }
+}
+
+#endif  // MD2_WITH_MB
+
 // ------------------------------------------------------------------ free-running roles
 // md2_march_roles above runs its warps in lock step (one bar.sync per image row): every warp waits for the
 // slowest role of every row, measured at ~35 % of every warp's time.  Here the same roles are decoupled: the rings
