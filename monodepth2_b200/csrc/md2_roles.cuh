@@ -899,8 +899,8 @@ struct MbCfg {
   static constexpr int RING = MD2_MB_RING;                       // power of two: slot(t) is a mask
   static constexpr int CRING = MD2_MB_CRING;
   static constexpr int MIN_CTAS = MD2_ROLE_MIN_CTAS;
-  // 128, not the 136 that 65536 / (5 x 96) suggests: registers are allocated per warp in units of 512, a kernel that
-  // really uses 129-136 gets 4 CTAs per SM (ncu launch__occupancy_limit_registers; measured 0.43 instead of 0.33 ms)
+  // 128, not the 136 that 65536 / (5 x 96) suggests: a kernel that really uses 129-136 registers gets 4 CTAs per SM
+  // (ncu launch__occupancy_limit_registers = 4; measured 0.43 instead of 0.33 ms)
   static constexpr int MAXREG = RoleCfg<C>::MAXREG > 128 && RoleCfg<C>::MAXREG < 144 ? 128 : RoleCfg<C>::MAXREG;
   static constexpr int NCF4 = RoleCfg<C>::NCF4;
   static constexpr int STASH_F4 = RING * C::STASH4 * 32;
