@@ -1319,7 +1319,11 @@ MD2_HD void stage_c_straight(Lane<C>& L, const Params& P, const WarpJob& J, int 
     float dzsum = 0.f;
 #pragma unroll
     for (int f = 0; f < C::NSRC; ++f) {
-      const F4 sp = st.at(slot, 1 + 3 * f, C::STASH4);
+      F4 sp = st.at(slot, 1 + 3 * f, C::STASH4);
+      if (C::PAIRED) {
+        const F4 a = st.at(slot, 1, C::STASH4), b4 = st.at(slot, 4, C::STASH4);
+        sp = f == 0 ? make_f4(a.x, a.y, b4.x, b4.z) : make_f4(a.z, a.w, b4.y, b4.w);
+      }
       const F4 sdx = st.at(slot, 2 + 3 * f, C::STASH4);
       const F4 sdy = st.at(slot, 3 + 3 * f, C::STASH4);
       const float xs[3] = {sp.x, sp.y, sp.z};

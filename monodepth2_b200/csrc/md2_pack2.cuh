@@ -485,6 +485,115 @@ __device__ __forceinline__ void stage_b2(Lane2<C>& L, const Params& P, const War
   }
 }
 
+// Branch-free form of stage_b2 (MD2_B2_STRAIGHT): every lane computes the window, results are selected.
+template <class C>
+__device__ __forceinline__ void stage_b2_straight(Lane2<C>& L, const Params& P, const WarpJob& J, int t, int lane,
+                                         const Xchg1P<C>& lf, const Xchg1P<C>& rt) {
+  const int yw = t - 1;
+  P2 H0[3][3], HYrg0[2];
+  float HYb0[2];
+  HYrg0[0] = add2(add2(lf.tgrg, L.tgrg), rt.tgrg);
+  HYrg0[1] = fma2(rt.tgrg, rt.tgrg, fma2(L.tgrg, L.tgrg, mul2(lf.tgrg, lf.tgrg)));
+  HYb0[0] = lf.tgb + L.tgb + rt.tgb;
+  HYb0[1] = fmaf(rt.tgb, rt.tgb, fmaf(L.tgb, L.tgb, lf.tgb * lf.tgb));
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    const P2 yl = (s < 2) ? lf.tgrg : bc(lf.tgb), yc = (s < 2) ? L.tgrg : bc(L.tgb), yr = (s < 2) ? rt.tgrg : bc(rt.tgb);
+    const P2 xl = lf.pr[s], xc = L.pr[s], xr = rt.pr[s];
+    H0[s][0] = add2(add2(xl, xc), xr);
+    H0[s][1] = fma2(xr, xr, fma2(xc, xc, mul2(xl, xl)));
+    H0[s][2] = fma2(xr, yr, fma2(xc, yc, mul2(xl, yl)));
+  }
+  const bool win_ok = L.colok && (yw >= 0) && (yw < P.H) && (lane >= 1) && (lane <= kLanes - 2) &&
+                      (yw >= J.y0 - (C::GRAD ? 1 : 0)) && (yw < J.y1 + (C::GRAD ? 1 : 0));
+  const bool own_win = win_ok && (lane >= 2) && (lane < 2 + kOwnCols) && (yw >= J.y0) && (yw < J.y1);
+  int tag = -1;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { L.cf[i] = bc(0.f); L.cfb[i] = 0.f; }
+  {
+    P2 V[3][3], VYrg[2];
+    float VYb[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { VYrg[k] = add2(L.HYrg2[k], HYrg0[k]); VYb[k] = L.HYb2[k] + HYb0[k]; }
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) V[s][k] = add2(L.H2[s][k], H0[s][k]);
+    P2 S[3];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      S[s] = bc(0.f);
+      if (!C::NOSSIM)
+        S[s] = ssim_window2(V[s][0], V[s][1], V[s][2], (s < 2) ? VYrg[0] : bc(VYb[0]), (s < 2) ? VYrg[1] : bc(VYb[1]), nullptr);
+    }
+    const P2 e0 = sub2(L.tgrg1, L.pr1[0]), e1 = sub2(L.tgrg1, L.pr1[1]), e2 = sub2(bc(L.tgb1), L.pr1[2]);
+    float rl[2];
+    {
+      const float ss0 = ((0.f + S[0].x) + S[0].y) + S[2].x, ss1 = ((0.f + S[1].x) + S[1].y) + S[2].y;
+      const float l10 = ((0.f + fabsf(e0.x)) + fabsf(e0.y)) + fabsf(e2.x);
+      const float l11 = ((0.f + fabsf(e1.x)) + fabsf(e1.y)) + fabsf(e2.y);
+      rl[0] = C::NOSSIM ? l10 * (1.0f / 3.0f) : fmaf(0.85f / 3.0f, ss0, (0.15f / 3.0f) * l10);
+      rl[1] = C::NOSSIM ? l11 * (1.0f / 3.0f) : fmaf(0.85f / 3.0f, ss1, (0.15f / 3.0f) * l11);
+    }
+    float best = INFINITY;
+    if (C::AUTOMASK) {
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        const float cand = MD2_FADD(L.idv[f], MD2_FMUL(L.nzv[f], 0.00001f));
+        if (cand < best) best = cand;
+      }
+    }
+    const bool pm = !C::AUTOMASK && J.pm;             // --predictive_mask (see pmask_apply in md2_core.cuh)
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      const float cand = pm ? rl[f] * L.nzv[f] : rl[f];
+      if (cand < best) { best = cand; tag = f; }
+    }
+    L.loss += own_win ? best : 0.0f;
+    if (own_win) {
+      if (C::AUTOMASK && J.idsel) J.idsel[yw * J.W + L.xi] = (tag >= 0) ? 1.0f : 0.0f;
+      if (pm && C::GRAD && J.gpm) {
+#pragma unroll
+        for (int f = 0; f < 2; ++f) J.gpm[f * J.plane + yw * J.W + L.xi] = (tag == f) ? rl[f] * P.gscale : 0.0f;
+      }
+    }
+    if (!win_ok) tag = -1;
+    if (C::GRAD && !C::NOSSIM) {
+      // the winner's window sums: (r,g) pair from slot `tag`, b from that half of slot 2
+      const bool w1 = (tag == 1);
+      P2 Wrg[3];
+      float Wb[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { Wrg[k] = sel2(w1, V[1][k], V[0][k]); Wb[k] = w1 ? V[2][k].y : V[2][k].x; }
+      ssim_window2(Wrg[0], Wrg[1], Wrg[2], VYrg[0], VYrg[1], L.cf);
+      ssim_window(Wb[0], Wb[1], Wb[2], VYb[0], VYb[1], L.cfb);
+      if (pm) {
+        const float m = w1 ? L.nzv[1] : L.nzv[0];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { L.cf[k] = mul2(L.cf[k], bc(m)); L.cfb[k] *= m; }
+      }
+      // selects, not products: lanes without a window (or whose identity candidate won) may hold non-finite sums
+      const bool live = tag >= 0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { L.cf[k] = sel2(live, L.cf[k], bc(0.f)); L.cfb[k] = live ? L.cfb[k] : 0.0f; }
+    }
+  }
+  L.tag = tag;
+  // roll the forward state
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    L.HYrg2[k] = add2(L.HYrg1[k], HYrg0[k]); L.HYrg1[k] = HYrg0[k];
+    L.HYb2[k] = L.HYb1[k] + HYb0[k]; L.HYb1[k] = HYb0[k];
+  }
+  L.tgrg1 = L.tgrg; L.tgb1 = L.tgb;
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { L.H2[s][k] = add2(L.H1[s][k], H0[s][k]); L.H1[s][k] = H0[s][k]; }
+    L.pr1[s] = L.pr[s];
+  }
+}
+
 // ------------------------------------------------------------------ stage C (see stage_c_divergent)
 template <class C, class ST>
 __device__ __forceinline__ void stage_c2(Lane2<C>& L, const Params& P, const WarpJob& J, int t, int lane,

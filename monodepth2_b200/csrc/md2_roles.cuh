@@ -80,6 +80,13 @@ template <class C0>
 struct RoleOf : C0 {
   static constexpr bool BSMEM = false;
   static constexpr bool ZUP = (MD2_ROLE_ZUP != 0);      // depth planes from md2_depth_up (see Cfg::ZUP)
+  // branch-free stages B / C also under --avg_reprojection (measured at 640x192 x 12: 0.442 -> 0.413 ms; the two-source
+  // per-pixel-minimum kernels lose with it: mono 0.326 -> 0.339 ms, --disable_automasking 0.358 -> 0.375 ms)
+#ifdef MD2_ROLE_STRAIGHT
+  static constexpr bool STRAIGHT = true;
+#else
+  static constexpr bool STRAIGHT = C0::STRAIGHT || C0::AVG;
+#endif
 };
 // loops of the packed roles without a branch around the row body (the first / last periods, in which a role only
 // crosses the barrier, are peeled): with the branch ptxas may park the wait for the loads a role keeps in flight across
@@ -630,7 +637,12 @@ __device__ __forceinline__ void b_step2(Lane2<C>& L, const Params& P, const Warp
     lf.pr[0] = p2(al.x, al.y); lf.pr[1] = p2(bl.x, bl.y); lf.pr[2] = p2(al.z, bl.z);
     rt.pr[0] = p2(ar.x, ar.y); rt.pr[1] = p2(br.x, br.y); rt.pr[2] = p2(ar.z, br.z);
   }
+  // branch-free form (every lane computes its window, results are selected): 0.3257 vs 0.3295 ms with the divergent one
+#ifdef MD2_B2_DIVERGENT
   stage_b2(L, P, J, t, lane, lf, rt);
+#else
+  stage_b2_straight(L, P, J, t, lane, lf, rt);
+#endif
   if (C::GRAD) {
     o[0] = make_f4(L.cf[0].x, L.cf[0].y, L.cf[1].x, L.cf[1].y);
     o[32] = make_f4(L.cf[2].x, L.cf[2].y, L.cfb[0], L.cfb[1]);

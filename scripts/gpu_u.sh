@@ -1,7 +1,8 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-L=monodepth2_b200/lib
-for rep in 1 2; do
-for v in _m84 _m52 _m62; do MD2_LIB_PATH=$L/libmd2loss$v.so timeout 120 python scripts/time_loss.py 0 30 mono 2>&1 | grep -v Warn; done
-MD2_MARCH=lockstep MD2_LIB_PATH=$L/libmd2loss_m84.so timeout 120 python scripts/time_loss.py 0 30 mono 2>&1 | grep -v Warn
+timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -3 | tee gpurun_out/u_pytest.log
+for wl in mono_640x192_b12 mono_640x192_b12_avg_reprojection; do
+  timeout 300 python bench.py --workload $wl --no-cpu --no-train 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(d['config']['workload'], 'value %.0f'%d['value'], 'march %.4f'%d['roofline']['kernel_ms'], 'e2e %.0f'%d['e2e']['value'])"
 done | tee gpurun_out/u_times.log
