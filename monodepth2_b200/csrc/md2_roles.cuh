@@ -127,10 +127,11 @@ struct RoleCfg {
   // registers per thread such that MIN_CTAS CTAs fit an SM (64 K registers, allocation unit 8 per thread); given as
   // __maxnreg__ rather than as the min-blocks argument of __launch_bounds__, under which ptxas picks 168 registers
   // plus a few bytes of spills for the 3-source kernels although 224 would fit
-  static constexpr int MAXREG0 = ((65536 / (MIN_CTAS * THREADS)) / 8) * 8 > 255 ? 255 : ((65536 / (MIN_CTAS * THREADS)) / 8) * 8;
-  // (5 CTAs of 96 threads: the arithmetic says 136, but a kernel that really uses 129-136 registers is given 4 CTAs per
-  // SM - ncu launch__occupancy_limit_registers, measured on md2_march_mb: 0.43 instead of 0.33 ms - so the cap is 128)
-  static constexpr int MAXREG = (MAXREG0 > 128 && MAXREG0 < 144) ? 128 : MAXREG0;
+  // NOTE (5 CTAs of 96 threads): the arithmetic says 136, but a kernel that really USES 129-136 registers is given 4 CTAs
+  // per SM (ncu launch__occupancy_limit_registers, measured on md2_march_mb: 0.43 instead of 0.33 ms).  Every shipped
+  // 5-CTA instantiation uses <= 128 under this cap (tests/test_capi_symbols.py::test_register_budget reads the ptxas
+  // log); capping at 128 instead makes ptxas schedule role B 6 instructions longer (0.329 vs 0.324 ms).
+  static constexpr int MAXREG = ((65536 / (MIN_CTAS * THREADS)) / 8) * 8 > 255 ? 255 : ((65536 / (MIN_CTAS * THREADS)) / 8) * 8;
   static constexpr int NCF4 = (9 * C::NCS + 1 + 3) / 4;          // coefficient sets + winner tag, 16-byte fields
   static constexpr int STASH_F4 = RING * C::STASH4 * 32;
   static constexpr int COEF_F4 = C::GRAD ? 2 * NCF4 * 32 : 0;
