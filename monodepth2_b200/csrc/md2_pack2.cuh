@@ -85,6 +85,13 @@ struct Flight2 {                   // see Flight (md2_core.cuh)
   P2 cu, cv, cwx, cwy, cgx, cgy;   // over the two sources
   F4 ctg;
 };
+// the part of a Flight2 that does not depend on the gathered texels (role A computes it one row ahead, in the shadow of
+// the previous row's gather: stage_a_proj2 / stage_a_gather2)
+struct Proj2 {
+  float cz;
+  P2 cu, cv, cwx, cwy, cgx, cgy;
+  int toff[2], dx1[2], dy1[2];     // per source: float offset of the north-west texel, steps to the east / south tap
+};
 
 template <class C>
 struct Lane2 {
@@ -318,6 +325,60 @@ __device__ __forceinline__ void stage_a_issue2(Lane2<C>& L, Flight2& F, const Pa
 template <class C, bool WITH_ID = true, int ROW_STEP = 1, bool TG_DIRECT = false>
 __device__ __forceinline__ void stage_a_issue2(Lane2<C>& L, const Params& P, const WarpJob& J, int t) {
   stage_a_issue2<C, WITH_ID, ROW_STEP, TG_DIRECT, false>(L, L.fl, P, J, t);
+}
+
+// stage_a_issue2 in two halves (Cfg::ZUP kernels): everything up to the tap addresses of row t ...
+template <class C>
+__device__ __forceinline__ void stage_a_proj2(Lane2<C>& L, Proj2& R, const Params& P, const WarpJob& J, int t, float zrow) {
+  const int tr = reflect_clamp(t, J.H);
+  const float z = (J.s == 0) ? depth_of_disp(P, zrow) : zrow;
+  R.cz = z;
+  const float yf = (float)tr;
+  const P2 q0 = fma2(L.qb[0], bc(yf), L.qa[0]);
+  const P2 q1 = fma2(L.qb[1], bc(yf), L.qa[1]);
+  const P2 q2 = fma2(L.qb[2], bc(yf), L.qa[2]);
+  const P2 c0 = fma2(bc(z), q0, L.p4[0]);
+  const P2 c1 = fma2(bc(z), q1, L.p4[1]);
+  const P2 c2 = fma2(bc(z), q2, L.p4[2]);
+  const P2 den = add2(c2, bc(P.eps));
+  const P2 r0 = p2(rcp_fast(den.x), rcp_fast(den.y));
+  const P2 inv = fma2(r0, fma2(neg2(den), r0, bc(1.0f)), r0);      // Newton step of rcp_nr
+  const P2 u = mul2(c0, inv);
+  const P2 v = mul2(c1, inv);
+  const P2 ix = fma2(u, bc(P.sx), bc(P.ox));
+  const P2 iy = fma2(v, bc(P.sy), bc(P.oy));
+  const P2 ixc = p2(fminf(fmaxf(ix.x, 0.0f), P.wmax), fminf(fmaxf(ix.y, 0.0f), P.wmax));
+  const P2 iyc = p2(fminf(fmaxf(iy.x, 0.0f), P.hmax), fminf(fmaxf(iy.y, 0.0f), P.hmax));
+  const P2 fx0 = p2(floorf(ixc.x), floorf(ixc.y));
+  const P2 fy0 = p2(floorf(iyc.x), floorf(iyc.y));
+  const P2 gx = mul2(bc(P.sx), inv), gy = mul2(bc(P.sy), inv);
+  R.cu = u; R.cv = v;
+  R.cwx = sub2(ixc, fx0); R.cwy = sub2(iyc, fy0);
+  R.cgx = p2(((ix.x > 0.0f) && (ix.x < P.wmax)) ? gx.x : 0.0f, ((ix.y > 0.0f) && (ix.y < P.wmax)) ? gx.y : 0.0f);
+  R.cgy = p2(((iy.x > 0.0f) && (iy.x < P.hmax)) ? gy.x : 0.0f, ((iy.y > 0.0f) && (iy.y < P.hmax)) ? gy.y : 0.0f);
+#pragma unroll
+  for (int f = 0; f < 2; ++f) {
+    const int x0 = (int)(f ? fx0.y : fx0.x), y0 = (int)(f ? fy0.y : fy0.x);
+    R.toff[f] = 4 * (y0 * J.W + x0);
+    R.dx1[f] = (x0 + 1 < J.W) ? 4 : 0;
+    R.dy1[f] = (y0 + 1 < J.H) ? J.W * 4 : 0;
+  }
+}
+// ... and the gather itself (plus the target texel of bands that are not staged by TMA)
+template <class C, bool COPY = true>
+__device__ __forceinline__ void stage_a_gather2(const Lane2<C>& L, Flight2& F, const Proj2& R, const WarpJob& J, int t) {
+  if (J.staged) F.ctg = make_f4(0.f, 0.f, 0.f, 0.f);
+  else F.ctg = MD2_LDS4(J.tgt4 + 4 * (reflect_clamp(t, J.H) * J.W + L.xi));
+  if (COPY) { F.cz = R.cz; F.cu = R.cu; F.cv = R.cv; F.cwx = R.cwx; F.cwy = R.cwy; F.cgx = R.cgx; F.cgy = R.cgy; }
+#pragma unroll
+  for (int f = 0; f < 2; ++f) {
+    const int dx1 = R.dx1[f], dy1 = R.dy1[f];
+    const float* t00 = J.src4[f] + R.toff[f];
+    F.tap[f][0] = MD2_LD4(t00);
+    F.tap[f][1] = MD2_LD4(t00 + dx1);
+    F.tap[f][2] = MD2_LD4(t00 + dy1);
+    F.tap[f][3] = MD2_LD4(t00 + dy1 + dx1);
+  }
 }
 
 template <class C, class ST, bool PUBLISH = C::GRAD>

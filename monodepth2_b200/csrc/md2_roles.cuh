@@ -100,6 +100,10 @@ template <class C>
 __host__ __device__ constexpr bool role_peel() {
   return (MD2_ROLE_PEEL != 0) && !(C::NSRC == 3 && !C::AUTOMASK && C::GRAD && !C::AVG && !C::NOSSIM);
 }
+// role A of the packed kernel computes the projection of row t+1 in the shadow of row t's gather (see role_a2)
+#ifndef MD2_ROLE_A_AHEAD
+#define MD2_ROLE_A_AHEAD 2
+#endif
 // the packed two-source role kernel runs its roles over PairedOf<C>: ring layout in the register pairs role B reads
 // (see Cfg::PAIRED; the experimental packed role C and the free-running kernel keep the per-source layout)
 #ifndef MD2_ROLE_PAIRED
@@ -494,6 +498,48 @@ __device__ __forceinline__ void role_a2(const Params& P, const WarpJob& J, int l
       prefetch_row2<C, false>(L, J, t0 + k + NA);
     }
   }
+#if MD2_ROLE_A_AHEAD
+  if (NA == 1 && role_peel<C>() && !z_in_c<C, true>() && C::ZUP && tma_in_c<C>()) {
+    // projection one row ahead: the depth -> projection -> bilinear-cell chain of row t+1 (no memory access besides the
+    // depth of row t+2 put in flight) runs while the gather of row t is in flight; a period then starts with the gather
+#if MD2_ROLE_A_AHEAD == 2
+    // two records, two rows per trip: no copy of the record between its computation and its use
+    Proj2 Ra, Rb;
+    stage_a_proj2<C>(L, Ra, P, J, t0, L.nd[0]);
+    prefetch_row2<C, false>(L, J, t0 + 1);
+    auto half = [&](int t, Proj2& Rc, Proj2& Rn) {
+      stage_a_gather2<C, false>(L, L.fl, Rc, J, t);
+      const float zn = L.nd[0];
+      prefetch_row2<C, false>(L, J, t + 2);
+      stage_a_proj2<C>(L, Rn, P, J, t + 1, zn);
+      L.fl.cz = Rc.cz; L.fl.cu = Rc.cu; L.fl.cv = Rc.cv; L.fl.cwx = Rc.cwx; L.fl.cwy = Rc.cwy; L.fl.cgx = Rc.cgx; L.fl.cgy = Rc.cgy;
+      stage_a_finish2<C, ST, true>(L, P, J, t, st);
+      role_sync<RoleCfg<C>::THREADS>();
+    };
+#pragma unroll 1
+    for (int t = t0; t <= t1; t += 2) {
+      half(t, Ra, Rb);
+      if (t + 1 <= t1) half(t + 1, Rb, Ra);
+    }
+#else
+    Proj2 R;
+    stage_a_proj2<C>(L, R, P, J, t0, L.nd[0]);
+    prefetch_row2<C, false>(L, J, t0 + 1);
+#pragma unroll 1
+    for (int t = t0; t <= t1; ++t) {
+      stage_a_gather2<C>(L, L.fl, R, J, t);
+      const float zn = L.nd[0];                       // depth of row t+1 (in flight since the previous period)
+      prefetch_row2<C, false>(L, J, t + 2);
+      stage_a_proj2<C>(L, R, P, J, t + 1, zn);
+      stage_a_finish2<C, ST, true>(L, P, J, t, st);
+      role_sync<RoleCfg<C>::THREADS>();
+    }
+#endif
+#pragma unroll 1
+    for (int p = t1 - t0 + 1; p < nit; ++p) role_sync<RoleCfg<C>::THREADS>();
+    return;
+  }
+#endif
   if (NA == 1 && role_peel<C>() && !z_in_c<C, true>()) {
 #pragma unroll 1
     for (int t = t0; t <= t1; ++t) {

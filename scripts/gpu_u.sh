@@ -1,8 +1,6 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -3 | tee gpurun_out/u_pytest.log
-for wl in mono_640x192_b12 mono_640x192_b12_avg_reprojection; do
-  timeout 300 python bench.py --workload $wl --no-cpu --no-train 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print(d['config']['workload'], 'value %.0f'%d['value'], 'march %.4f'%d['roofline']['kernel_ms'], 'e2e %.0f'%d['e2e']['value'])"
-done | tee gpurun_out/u_times.log
+L=monodepth2_b200/lib
+for rep in 1 2; do for v in "" _a2; do MD2_LIB_PATH=$L/libmd2loss$v.so timeout 120 python scripts/time_loss.py 0 30 mono 2>&1 | grep -v Warn; done; done | tee gpurun_out/u_times.log
+for v in "" _a2; do for wl in hires; do MD2_LIB_PATH=$L/libmd2loss$v.so timeout 120 python scripts/time_loss.py 0 30 $wl 2>&1 | grep -v Warn; done; done | tee -a gpurun_out/u_times.log
+MD2_LIB_PATH=$L/libmd2loss_a2.so timeout 300 python -m pytest tests/test_gpu_parity.py -q -x -m gpu 2>&1 | tail -2
