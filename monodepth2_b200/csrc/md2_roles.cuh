@@ -499,7 +499,8 @@ __device__ __forceinline__ void role_a2(const Params& P, const WarpJob& J, int l
     }
   }
 #if MD2_ROLE_A_AHEAD
-  if (NA == 1 && role_peel<C>() && !z_in_c<C, true>() && C::ZUP && tma_in_c<C>()) {
+  // (--no_ssim: the kernel would land on 136 registers - the 4-CTA trap - or spill under a 128 cap; it keeps the plain form)
+  if (NA == 1 && role_peel<C>() && !z_in_c<C, true>() && C::ZUP && tma_in_c<C>() && !C::NOSSIM) {
     // projection one row ahead: the depth -> projection -> bilinear-cell chain of row t+1 (no memory access besides the
     // depth of row t+2 put in flight) runs while the gather of row t is in flight; a period then starts with the gather
 #if MD2_ROLE_A_AHEAD == 2

@@ -28,8 +28,11 @@ for n, b in enumerate(bars):
     inst = sum(f(r, "Instructions Executed") for r in rr)
     smp = sum(f(r, "# Samples") for r in rr)
     st = sorted(((s, sum(f(r, s) for r in rr)) for s in stalls), key=lambda kv: -kv[1])[:7]
+    # role A's loop holds two rows per trip since MD2_ROLE_A_AHEAD=2: four barrier-delimited bodies = A even, A odd, B, C
+    # (the per-row figures of the two A halves are per TWO rows of the launch: add them for A's instructions per row)
+    names = ["A (even rows)", "A (odd rows)", "B", "C"] if len(bars) == 4 else ["A", "B", "C"]
     print("role %s: %d static, %.0f warp-instr per row, %.1f %% of samples: %s" % (
-        "ABC"[n] if n < 3 else str(n), len(rr), inst / rows_per_launch, 100 * smp / tot,
+        names[n] if n < len(names) else str(n), len(rr), inst / rows_per_launch, 100 * smp / tot,
         " ".join("%s=%.0f%%" % (k[6:], 100 * v / max(smp, 1)) for k, v in st)))
     if topn:
         for i in sorted(sorted(range(start, end + 1), key=lambda i: -f(R[i], "# Samples"))[:topn]):
