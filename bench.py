@@ -320,6 +320,10 @@ def run_own(args, wl):
         raise RuntimeError("bench.py needs a CUDA device: the fused loss has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one process per GPU: stay on the CPUs next to this GPU, so that the pinned staging buffers of the e2e leg sit on
+    # its NUMA node (at 8 GPUs the copies otherwise share the socket interconnect: e2e efficiency 0.53)
+    from monodepth2_b200.fused_loss import bind_to_gpu_cpus
+    numa_cpus = bind_to_gpu_cpus(dev) if os.environ.get("MD2_BENCH_BIND", "1") != "0" else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -550,7 +554,7 @@ def run_own(args, wl):
             # `config` names the workload and is identical in both arms; everything about how this arm ran is in `notes`
             "config": {"workload": wl, "batch_per_gpu": BATCH, "frame_ids": [str(f) for f in frame_ids], "scales": 4,
                        "l2": L2_NOTE},
-            "notes": {"device": "cuda (B200)",
+            "notes": {"device": "cuda (B200)", "cpu_affinity": numa_cpus,
                        "rows_per_segment": plan.problem(True).rows_per_segment or "library default (wave-quantisation model)", "loss": loss_val,
                        "launch": ("eager public calls" if args.no_graph else "CUDA-graph replay of the public call") +
                                  ": view_synthesis_loss(plan, inputs, outputs) + losses['loss'].backward(); the 4 "

@@ -304,6 +304,30 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
         return tuple(out)
 
 
+def bind_to_gpu_cpus(device) -> Optional[str]:
+    """Restrict this process to the CPUs that are local to ``device`` (its PCI device's ``local_cpulist`` in sysfs), so
+    that the pinned staging buffers allocated afterwards are first-touched on the GPU's NUMA node and the per-step
+    host-to-device copy does not cross the socket interconnect.  What a one-process-per-GPU training loop does at
+    start-up; it changes the process affinity, so it is an explicit call (bench.py makes it for its e2e leg), never
+    made by the library on its own.  Returns the cpulist it bound to, or None when sysfs has nothing to say."""
+    try:
+        p = torch.cuda.get_device_properties(device)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        txt = open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if part:
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return txt
+    except Exception:
+        return None
+
+
 class _Noise(list):
     """The tie-break draws of one call; ``ready`` is the torch.cuda.Event recorded after the last draw when they were
     made on the plan's side stream (handed to the library as md2_tensors.noise_ready_event)."""
