@@ -154,47 +154,72 @@ __global__ void md2_disp_mean(Params P) {
 // zup[s](b, y, x) = disp_to_depth(bilinear_up(disp_s)(y, x))    (trainer.py:349-353, layers.py:16-25): what role A of the
 // role-specialised marching kernel used to rebuild per row and lane from four disparity taps.  The expressions are the
 // ones of prefetch_row / lane_init / stage_a_issue (md2_core.cuh), term by term, so the values are the same.
+constexpr int kDupCols = 128, kDupRows = 16;                  // fine pixels per block of md2_depth_up
 __global__ void __launch_bounds__(256) md2_depth_up(Params P) {
-  // block = 32 x 8 threads, a thread = 4 consecutive columns of one row; blockIdx.z = b * (S - 1) + s - 1, s >= 1
-  // (scale 0 is not up-sampled: its readers take the disparity plane and apply disp_to_depth themselves)
+  // block = 256 threads, tile = 128 columns x 16 rows of the full-resolution plane; blockIdx.z = b * (S - 1) + s - 1,
+  // s >= 1 (scale 0 is not up-sampled: its readers take the disparity plane and apply disp_to_depth themselves).
+  // Separable, through shared memory: pass 1 blends every coarse row the tile touches horizontally (top / bot of
+  // stage_a_issue: the same up_blend on the same operands), pass 2 blends two of those rows vertically and applies
+  // disp_to_depth - the x weights are computed once per column of the tile instead of once per pixel.
+  __shared__ __align__(16) float hrow[kDupRows / 2 + 2][kDupCols];
   const int s = 1 + blockIdx.z % (P.S - 1), b = blockIdx.z / (P.S - 1);
-  const int y = blockIdx.y * 8 + threadIdx.y;
-  const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
-  if (y >= P.H || x4 >= P.W) return;
   const int Hs = P.H >> s, Ws = P.W >> s;
+  const float rs = 1.0f / (float)(1 << s);
   const float* d = P.disp[s] + (size_t)b * Hs * Ws;
-  float* out = P.zup[s] + (size_t)b * P.H * P.W + y * P.W + x4;
-  float z[4];
-  {
-    const float rs = 1.0f / (float)(1 << s);
+  const int x_base = blockIdx.x * kDupCols, y_base = blockIdx.y * kDupRows;
+  // coarse rows touched by fine rows [y_base, y_base + kDupRows): y0 of the first row .. y1 of the last row
+  auto src_row = [&](int y, int& y0, int& y1, float& l1) {
     float syr = fmaf(rs, (float)y + 0.5f, -0.5f);
     syr = syr < 0.0f ? 0.0f : syr;
-    const int y0 = (int)syr;
-    const int y1 = y0 + ((y0 < Hs - 1) ? 1 : 0);
-    const float l1 = syr - (float)(int)syr, l0 = 1.0f - l1;
-    const float* r0 = d + y0 * Ws;
-    const float* r1 = d + y1 * Ws;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int x = min(x4 + i, P.W - 1);
-      float sxr = fmaf(rs, (float)x + 0.5f, -0.5f);
-      sxr = sxr < 0.0f ? 0.0f : sxr;
-      const int ux0 = (int)sxr;
-      const int ux1 = ux0 + ((ux0 < Ws - 1) ? 1 : 0);
-      const float ul1 = sxr - (float)ux0;
-      const float ul0 = 1.0f - ul1;
-      const float nd0 = __ldg(r0 + ux0), nd1 = __ldg(r0 + ux1), nd2 = __ldg(r1 + ux0), nd3 = __ldg(r1 + ux1);
-      const float top = up_blend(ul0, nd0, ul1, nd1);
-      const float bot = up_blend(ul0, nd2, ul1, nd3);
-      z[i] = depth_of_disp(P, up_blend(l0, top, l1, bot));
-    }
+    y0 = (int)syr;
+    y1 = y0 + ((y0 < Hs - 1) ? 1 : 0);
+    l1 = syr - (float)(int)syr;
+  };
+  int cy_lo, cy_tmp, cy_hi;
+  float ltmp;
+  src_row(y_base, cy_lo, cy_tmp, ltmp);
+  src_row(min(y_base + kDupRows, P.H) - 1, cy_tmp, cy_hi, ltmp);
+  const int ncy = cy_hi - cy_lo + 1;                          // <= kDupRows / 2 + 2 for s >= 1
+  // pass 1: thread -> (coarse row, fine column)
+  for (int i = threadIdx.x; i < ncy * kDupCols; i += 256) {
+    const int r = i / kDupCols, cx = i - r * kDupCols;
+    const int x = min(x_base + cx, P.W - 1);
+    float sxr = fmaf(rs, (float)x + 0.5f, -0.5f);
+    sxr = sxr < 0.0f ? 0.0f : sxr;
+    const int ux0 = (int)sxr;
+    const int ux1 = ux0 + ((ux0 < Ws - 1) ? 1 : 0);
+    const float ul1 = sxr - (float)ux0;
+    const float ul0 = 1.0f - ul1;
+    const float* row = d + (cy_lo + r) * Ws;
+    hrow[r][cx] = up_blend(ul0, __ldg(row + ux0), ul1, __ldg(row + ux1));
   }
-  if ((P.W & 3) == 0) {
-    *reinterpret_cast<float4*>(out) = make_float4(z[0], z[1], z[2], z[3]);
-  } else {
+  __syncthreads();
+  // pass 2: thread -> 4 consecutive columns of 2 rows (32 threads x 4 columns = 128 columns, 8 thread rows x 2)
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x4 = x_base + tx * 4;
+  if (x4 >= P.W) return;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (x4 + i < P.W) out[i] = z[i];
+  for (int k = 0; k < 2; ++k) {
+    const int y = y_base + ty * 2 + k;
+    if (y >= P.H) break;
+    int y0, y1;
+    float l1;
+    src_row(y, y0, y1, l1);
+    const float l0 = 1.0f - l1;
+    const float4 a4 = *reinterpret_cast<const float4*>(hrow[y0 - cy_lo] + tx * 4);
+    const float4 b4 = *reinterpret_cast<const float4*>(hrow[y1 - cy_lo] + tx * 4);
+    const float h0[4] = {a4.x, a4.y, a4.z, a4.w}, h1[4] = {b4.x, b4.y, b4.z, b4.w};
+    float z[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) z[i] = depth_of_disp(P, up_blend(l0, h0[i], l1, h1[i]));
+    float* out = P.zup[s] + (size_t)b * P.H * P.W + y * P.W + x4;
+    if ((P.W & 3) == 0) {
+      *reinterpret_cast<float4*>(out) = make_float4(z[0], z[1], z[2], z[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (x4 + i < P.W) out[i] = z[i];
+    }
   }
 }
 
@@ -1185,8 +1210,8 @@ static cudaError_t launch_float_entry(const Params& P, cudaStream_t stream) {
   const bool zup = (march_mode() != 0 || P.nsrc > 3) && P.S > 1;
   if (zup) {
     if ((e = cudaStreamWaitEvent(side->stream2, side->fork, 0)) != cudaSuccess) return e;
-    dim3 grid((P.W + 127) / 128, (P.H + 7) / 8, P.B * (P.S - 1)), block(32, 8);
-    md2_depth_up<<<grid, block, 0, side->stream2>>>(P);
+    dim3 grid((P.W + kDupCols - 1) / kDupCols, (P.H + kDupRows - 1) / kDupRows, P.B * (P.S - 1));
+    md2_depth_up<<<grid, 256, 0, side->stream2>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if ((e = cudaEventRecord(side->join2, side->stream2)) != cudaSuccess) return e;
   }
