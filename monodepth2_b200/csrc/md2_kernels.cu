@@ -789,7 +789,11 @@ __global__ void MD2_MARCH_BOUNDS md2_march2(Params P) {
 // with the horizontal weights.  Every fine value is read ~1.1x (the gather form read it 4x).  Block 0 also
 // writes the losses and grad_T.  Scale 0 is finished by md2_march itself.
 constexpr int kFinalThreads = 256;
-constexpr int kFinalFineRows = 16;
+// (measured at 640x192 x 12, 1 296 blocks = 1.09 waves with 16 rows: 24 rows 16.4 us, 32 rows 17.4 us, 8 rows 16.9 us, 16 rows 15.0 us)
+#ifndef MD2_FINAL_ROWS
+#define MD2_FINAL_ROWS 16
+#endif
+constexpr int kFinalFineRows = MD2_FINAL_ROWS;
 
 __host__ __device__ inline int final_tiles_x(int Ws, int K) { const int t = kFinalThreads / K - 1; return (Ws + t - 1) / t; }
 __host__ __device__ inline int final_tiles_y(int Hs, int K) { const int t = kFinalFineRows / K; return (Hs + t - 1) / t; }
