@@ -965,6 +965,12 @@ static cudaError_t launch_march_roles(const Params& P0, cudaStream_t stream) {
                                       // gradients: the packed form spills 16 bytes under 128 registers, scalar fits)
       static cudaError_t attr2 = cudaFuncSetAttribute(md2_march_roles<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (attr2 != cudaSuccess) return attr2;
+#ifdef MD2_DEV_KNOBS
+      // development knob: shared-memory carve-out in per cent of the unified L1 / shared memory (default: the driver's pick)
+      static const int carve = getenv("MD2_CARVEOUT") ? atoi(getenv("MD2_CARVEOUT")) : -1;
+      static cudaError_t attr3 = carve >= 0 ? cudaFuncSetAttribute(md2_march_roles<C, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve) : cudaSuccess;
+      if (attr3 != cudaSuccess) return attr3;
+#endif
       md2_march_roles<C, true><<<jobs, RC::THREADS, smem, stream>>>(P);
       return cudaGetLastError();
     }
