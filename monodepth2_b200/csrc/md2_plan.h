@@ -82,6 +82,9 @@ inline int default_seg_rows(const md2_problem* p) {
   // 148 SMs x 8 warps (12 for the forward-only instantiations): minimise waves x (r + 4) over r = ceil(H / n).
   // Measured on B200 (profiles/r01_optimization_log.md): 640x192 x 12: 96 rows 0.474 ms, 64 rows 0.480 ms,
   // 48 rows 0.486 ms per step; 1024x320: 160 rows 1.170 ms, 80 rows 1.185 ms, 107 rows 1.251 ms.
+  // Round 2 (role-specialised kernel, one CTA per job, 5 CTAs per SM = 740 slots with gradients): the same model with
+  // 740 slots picks the same heights (96 / 160), and the sweeps on the final kernel agree: 640x192 96 rows 0.3216 ms,
+  // 64 rows 0.3252, 48 rows 0.3334, 192 rows 0.3444; 1024x320 160 rows 0.7955 ms, 107 rows 0.7988, 80 rows 0.8015.
   if (p->rows_per_segment > 0) return p->rows_per_segment < p->height ? p->rows_per_segment : p->height;
   const long slots = 148L * (p->want_grad ? 8 : 12);
   const long nband = (p->width + kOwnCols - 1) / kOwnCols;
