@@ -37,7 +37,7 @@ typedef enum md2_status {
 typedef struct md2_problem {
   int batch;                  /* opt.batch_size                        options.py:87  */
   int height, width;          /* opt.height / opt.width                options.py:52  */
-  int num_scales;             /* len(opt.scales), scales 0..n-1        options.py:64  */
+  int num_scales;             /* len(opt.scales); levels: scale_level  options.py:64  */
   int num_src;                /* len(opt.frame_ids) - 1 (incl. "s")    options.py:80  */
   int automask;               /* !opt.disable_automasking              options.py:111 */
   int avg_reprojection;       /* opt.avg_reprojection                  options.py:108 */
@@ -52,6 +52,11 @@ typedef struct md2_problem {
                                  scale from the pose leaves with the translation multiplied by the mean inverse depth
                                  of that scale; needs axisangle / translation for every source without a fixed T */
   int predictive_mask;        /* opt.predictive_mask (options.py:114, trainer.py:447-459); needs automask == 0 */
+  int scale_level[MD2_MAX_SCALES]; /* opt.scales sorted ascending when it is not 0..n-1 (options.py:64, e.g. --scales 0 2;
+                                 trainer.py:345,413 iterate the list, the dataloader always holds levels 0..3,
+                                 trainer.py:127-135): scale slot s of every per-scale array below is pyramid level
+                                 scale_level[s], (H >> level, W >> level), smoothness weight 1 / 2^level, and
+                                 losses[1 + s] = losses["loss/<level>"].  All zero = levels 0..n-1 */
 } md2_problem;
 
 /* Tensors of one evaluation.  Names follow the reference's dict keys. */

@@ -22,6 +22,7 @@ class Md2Problem(C.Structure):
         ("min_depth", C.c_float), ("max_depth", C.c_float), ("disparity_smoothness", C.c_float),
         ("want_grad", C.c_int), ("rows_per_segment", C.c_int), ("no_ssim", C.c_int),
         ("posecnn", C.c_int), ("predictive_mask", C.c_int),
+        ("scale_level", C.c_int * MAX_SCALES),
     ]
 
 

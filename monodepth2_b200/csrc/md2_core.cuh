@@ -204,7 +204,10 @@ struct Params {
   float wmax, hmax;          // W-1, H-1
   float eps;
   float gscale;              // 1/(S*B*H*W) [* 1/nsrc under avg_reprojection]
-  float smooth_w[kMaxScales];  // disparity_smoothness / 2^s
+  float smooth_w[kMaxScales];  // disparity_smoothness / 2^lvl[s]
+  int up0;                     // first slot that is up-sampled: 1 when lvl[0] == 0, else 0
+  int lvl[kMaxScales];         // pyramid level of scale slot s: opt.scales sorted ascending (trainer.py:345,413); slot s holds
+                               // (H >> lvl[s], W >> lvl[s]) tensors.  0..S-1 for the default --scales 0 1 2 3
   int seg_rows, nseg, nband, nband_id;
   int nsm;                   // SMs of the device (role rotation of the role-specialised kernel)
   int id_rows, nseg_id;      // row segments of the (much lighter) identity pass
@@ -320,6 +323,7 @@ MD2_HD float load_px(const float* f32, const unsigned char* u8, int hwc, int b, 
 // is 32-bit index arithmetic (validate() bounds the tensors below 2^31 elements).
 struct WarpJob {
   int s, b;
+  // (slot s is at full resolution - level 0, no up-sampling - iff s < P.up0: levels ascend)
   int ps;        // pose set: s under posecnn, else 0
   const float* proj;   // projection table of (ps, b): nsrc x 12 floats
   const float* pm;     // predictive mask up-sampled to (H,W), planes [nsrc] of sample b at scale s (or null)
@@ -351,9 +355,10 @@ MD2_HD void smooth_scalars(const Params& P, int s, int b, float& inv_m, float& d
 
 MD2_HD WarpJob make_job(const Params& P, int s, int b, int x0, int y0, int y1) {
   WarpJob J;
+  const int lv = P.lvl[s];
   J.s = s; J.b = b; J.x0 = x0; J.y0 = y0; J.y1 = y1;
-  J.H = P.H; J.W = P.W; J.Hs = P.H >> s; J.Ws = P.W >> s; J.plane = P.H * P.W;
-  J.rs = 1.0f / (float)(1 << s);
+  J.H = P.H; J.W = P.W; J.Hs = P.H >> lv; J.Ws = P.W >> lv; J.plane = P.H * P.W;
+  J.rs = 1.0f / (float)(1 << lv);
   J.ps = P.posecnn ? s : 0;
   J.proj = P.proj + (size_t)((J.ps * P.B + b) * P.nsrc) * 12;
   const int boff = b * J.plane;
@@ -366,12 +371,12 @@ MD2_HD WarpJob make_job(const Params& P, int s, int b, int x0, int y0, int y1) {
   }
   J.disp = P.disp[s] + b * J.Hs * J.Ws;
   // (scale 0 needs no up-sampling: the plane is the disparity itself, turned into depth by the reader)
-  J.zup = s == 0 ? J.disp : (P.zup[s] ? P.zup[s] + boff : nullptr);
+  J.zup = lv == 0 ? J.disp : (P.zup[s] ? P.zup[s] + boff : nullptr);
   J.idl = P.idloss + P.nsrc * boff;
   J.noise = P.noise[s] ? P.noise[s] + P.nid * boff : nullptr;
   J.dD = P.dD[s] + boff;
   J.gd0 = nullptr; J.gn0 = nullptr; J.sm_inv_m = 0.f; J.sm_dterm = 0.f; J.sm_w = 0.f;
-  if (s == 0 && P.want_grad) {
+  if (lv == 0 && P.want_grad) {   // (levels ascend: level 0, when present, is slot 0)
     J.gd0 = P.grad_disp[0] + boff;
     J.gn0 = P.gn[0] + boff;
     J.sm_inv_m = MD2_LD(P.smsc + 2 * b);            // scale 0, sample b
@@ -557,7 +562,7 @@ MD2_HD void prefetch_row(Lane<C>& L, const WarpJob& J, int t) {
   if (WITH_TG) L.ntg = MD2_LDS4(J.tgt4 + 4 * (tr * J.W + L.xi));
   if (C::ZUP) {
     L.nd[0] = MD2_LD(J.zup + tr * J.W + L.xi);
-  } else if (J.s == 0) {
+  } else if (J.Hs == J.H) {
     L.nd[0] = MD2_LD(J.disp + tr * J.W + L.xi);
   } else {
     float syr = fmaf(J.rs, (float)tr + 0.5f, -0.5f);
@@ -589,7 +594,7 @@ MD2_HD void lane_init(Lane<C>& L, const Params& P, const WarpJob& J, int lane) {
     }
     L.idv[f] = 0.f; L.nzv[f] = 0.f;
   }
-  if (J.s > 0) {
+  if (J.s >= P.up0) {
     float sxr = fmaf(J.rs, (float)L.xi + 0.5f, -0.5f);
     sxr = sxr < 0.0f ? 0.0f : sxr;
     L.ux0 = (int)sxr;
@@ -715,7 +720,7 @@ MD2_HD void stage_a_issue(Lane<C>& L, Flight<C>& F, const Params& P, const WarpJ
   float D = 0.f, zpre = 0.f;
   if (C::ZUP) {
     zpre = L.nd[0];
-  } else if (J.s == 0) {
+  } else if (J.s < P.up0) {
     D = L.nd[0];
   } else {
     float syr = fmaf(J.rs, (float)tr + 0.5f, -0.5f);
@@ -727,7 +732,7 @@ MD2_HD void stage_a_issue(Lane<C>& L, Flight<C>& F, const Params& P, const WarpJ
   }
   if (ROW_STEP > 0) prefetch_row<C, !TG_DIRECT>(L, J, t + ROW_STEP);     // ROW_STEP 0: the caller prefetches
   if (WITH_ID) load_identity_row(L, J, t);
-  const float z = C::ZUP ? (J.s == 0 ? depth_of_disp(P, zpre) : zpre) : depth_of_disp(P, D);
+  const float z = C::ZUP ? (J.s < P.up0 ? depth_of_disp(P, zpre) : zpre) : depth_of_disp(P, D);
   F.cz = z;
   const float yf = (float)tr;
 #pragma unroll
@@ -1245,7 +1250,7 @@ MD2_HD void stage_c_divergent(Lane<C>& L, const Params& P, const WarpJob& J, int
     const float dD = -P.c_disp * z * z * dzsum * P.gscale;
     MD2_CHK(yp * J.W + L.xi, J.plane);
     J.dD[yp * J.W + L.xi] = dD;
-    if (J.s == 0)   // up-sampling is the identity at scale 0: finish grad_disp_0 here (A.4 + A.3)
+    if (J.s < P.up0)   // up-sampling is the identity at scale 0: finish grad_disp_0 here (A.4 + A.3)
       J.gd0[yp * J.W + L.xi] = dD + J.sm_w * (MD2_LD(J.gn0 + yp * J.W + L.xi) * J.sm_inv_m - J.sm_dterm);
   }
   if (C::BSMEM) {
@@ -1367,7 +1372,7 @@ MD2_HD void stage_c_straight(Lane<C>& L, const Params& P, const WarpJob& J, int 
     if (own) {
       MD2_CHK(yp * J.W + L.xi, J.plane);
       J.dD[yp * J.W + L.xi] = dD;
-      if (J.s == 0)   // up-sampling is the identity at scale 0: finish grad_disp_0 here (A.4 + A.3)
+      if (J.s < P.up0)   // up-sampling is the identity at scale 0: finish grad_disp_0 here (A.4 + A.3)
         J.gd0[yp * J.W + L.xi] = dD + J.sm_w * (MD2_LD(J.gn0 + yp * J.W + L.xi) * J.sm_inv_m - J.sm_dterm);
     }
   }
@@ -1632,9 +1637,9 @@ MD2_HD void pose_to_matrix_backward(const float* g, const float* v, const float*
 // proj table: M = (K T)[:3,:3] * invK[:3,:3], p4 = (K T)[:3,3], in double then rounded once.
 // value at fine pixel (y, x) of plane `d` (Hs x Ws, level s) up-sampled bilinearly to (Hs << s, Ws << s):
 // F.interpolate(..., mode="bilinear", align_corners=False) (trainer.py:350-351, 451-454), torch upsample_bilinear2d
-MD2_HD float upsample_at(const float* d, int s, int Hs, int Ws, int y, int x) {
-  if (s == 0) return MD2_LD(d + y * Ws + x);
-  const float rs = 1.0f / (float)(1 << s);
+MD2_HD float upsample_at(const float* d, int lv, int Hs, int Ws, int y, int x) {
+  if (lv == 0) return MD2_LD(d + y * Ws + x);
+  const float rs = 1.0f / (float)(1 << lv);
   float sy = fmaf(rs, (float)y + 0.5f, -0.5f);
   sy = sy < 0.0f ? 0.0f : sy;
   float sx = fmaf(rs, (float)x + 0.5f, -0.5f);
@@ -1706,7 +1711,7 @@ MD2_HD float md2_exp_neg(float g) {
 }
 MD2_HD void smooth_pixel(const Params& P, int s, int b, int y, int x, float inv_m,
                          float& ex_out, float& ey_out, float& gn_out) {
-  const int Hs = P.H >> s, Ws = P.W >> s;
+  const int Hs = P.H >> P.lvl[s], Ws = P.W >> P.lvl[s];
   const size_t plane = (size_t)Hs * Ws;
   const float* d = P.disp[s] + (size_t)b * plane;
   const size_t p = (size_t)y * Ws + x;
@@ -1739,14 +1744,14 @@ MD2_HD void smooth_pixel(const Params& P, int s, int b, int y, int x, float inv_
 
 // Per-(scale, sample) scalars of the smoothness adjoint (A.4): 1/m and (sum gn*disp)/(m^2 N).
 MD2_HD void smooth_scalars(const Params& P, int s, int b, float& inv_m, float& dterm) {
-  const int n = (P.H >> s) * (P.W >> s);
+  const int n = (P.H >> P.lvl[s]) * (P.W >> P.lvl[s]);
   const float m = (float)(P.acc[acc_dispsum(P, s, b)] / (double)n) + 1e-7f;
   inv_m = 1.0f / m;
   dterm = (float)P.acc[acc_dot(P, s, b)] / (m * m * (float)n);
 }
 // Smoothness part of d loss / d disp_s at pixel p (A.4).
 MD2_HD float final_smooth_grad(const Params& P, int s, int b, int p, float inv_m, float dterm) {
-  const int n = (P.H >> s) * (P.W >> s);
+  const int n = (P.H >> P.lvl[s]) * (P.W >> P.lvl[s]);
   const float wsm = P.smooth_w[s] / (float)P.S;
   return wsm * (MD2_LD(P.gn[s] + (size_t)b * n + p) * inv_m - dterm);
 }
@@ -1767,7 +1772,7 @@ MD2_HD float up_weight(int i, int X, int n) {
 }
 template <int K>
 MD2_HD float upsample_adjoint_part(const Params& P, int s, int b, int Y, int X, int j) {
-  const int Hs = P.H >> s, Ws = P.W >> s;
+  const int Hs = P.H >> P.lvl[s], Ws = P.W >> P.lvl[s];
   const float cst = P.posecnn ? MD2_LD(P.gmidc + s * P.B + b) : 0.0f;    // see final_pose_posecnn
   const float* dD = P.dD[s] + (size_t)b * P.H * P.W;
   const int xlo = K * X - K / 2, ylo = K * Y - K / 2;
@@ -1805,7 +1810,7 @@ MD2_HD float upsample_adjoint_part(const Params& P, int s, int b, int Y, int X, 
 MD2_HD void final_scalars(const Params& P) {
   double total = 0.0;
   for (int s = 0; s < P.S; ++s) {
-    const int Hs = P.H >> s, Ws = P.W >> s;
+    const int Hs = P.H >> P.lvl[s], Ws = P.W >> P.lvl[s];
     const double photo = P.acc[acc_photo(s)] / ((double)P.B * P.H * P.W);
     double sx = 0.0, sy = 0.0;
     for (int b = 0; b < P.B; ++b) { sx += P.acc[acc_smx(P, s, b)]; sy += P.acc[acc_smy(P, s, b)]; }
@@ -1884,8 +1889,8 @@ MD2_HD void final_pose_posecnn(const Params& P, int b) {
 // (trainer.py:451-454); stores it in the plane the marching pass reads and returns its BCE term against 1
 // (nn.BCELoss clamps log at -100, trainer.py:458)
 MD2_HD float pmask_up_pixel(const Params& P, int s, int b, int f, int y, int x) {
-  const int Hs = P.H >> s, Ws = P.W >> s;
-  const float m = upsample_at(P.pmask[s] + (size_t)(b * P.nsrc + f) * Hs * Ws, s, Hs, Ws, y, x);
+  const int Hs = P.H >> P.lvl[s], Ws = P.W >> P.lvl[s];
+  const float m = upsample_at(P.pmask[s] + (size_t)(b * P.nsrc + f) * Hs * Ws, P.lvl[s], Hs, Ws, y, x);
   P.pm[s][((size_t)(b * P.nsrc + f) * P.H + y) * P.W + x] = m;
   const float lg = logf(m);
   return -(lg < -100.0f ? -100.0f : lg);
@@ -1903,7 +1908,7 @@ MD2_HD float pmask_full_grad(const Params& P, int s, size_t i) {
 // adjoint of the up-sampling for the mask: coarse pixel (Y, X) of plane (b, f) at scale s, gather form
 template <int K>
 MD2_HD float pmask_adjoint(const Params& P, int s, int b, int f, int Y, int X) {
-  const int Hs = P.H >> s, Ws = P.W >> s;
+  const int Hs = P.H >> P.lvl[s], Ws = P.W >> P.lvl[s];
   const size_t base = (size_t)(b * P.nsrc + f) * P.H * P.W;
   if (K == 1) return pmask_full_grad(P, s, base + (size_t)Y * P.W + X);
   const int xlo = K * X - K / 2, ylo = K * Y - K / 2;
@@ -1924,13 +1929,13 @@ MD2_HD float pmask_adjoint(const Params& P, int s, int b, int f, int Y, int X) {
   return acc;
 }
 MD2_HD void pmask_grad_pixel(const Params& P, int s, int b, int f, int Y, int X) {
-  const int Hs = P.H >> s, Ws = P.W >> s;
+  const int Hs = P.H >> P.lvl[s], Ws = P.W >> P.lvl[s];
   float g;
-  switch (s) {
-    case 0: g = pmask_adjoint<1>(P, 0, b, f, Y, X); break;
-    case 1: g = pmask_adjoint<2>(P, 1, b, f, Y, X); break;
-    case 2: g = pmask_adjoint<4>(P, 2, b, f, Y, X); break;
-    default: g = pmask_adjoint<8>(P, 3, b, f, Y, X); break;
+  switch (P.lvl[s]) {
+    case 0: g = pmask_adjoint<1>(P, s, b, f, Y, X); break;
+    case 1: g = pmask_adjoint<2>(P, s, b, f, Y, X); break;
+    case 2: g = pmask_adjoint<4>(P, s, b, f, Y, X); break;
+    default: g = pmask_adjoint<8>(P, s, b, f, Y, X); break;
   }
   P.grad_pmask[s][((size_t)(b * P.nsrc + f) * Hs + Y) * Ws + X] = g;
 }

@@ -60,11 +60,11 @@ __global__ void md2_prologue(Params P) {
 // sum of the up-sampled disparity of every (scale, sample) over the full-resolution grid: one thread per fine pixel
 __global__ void __launch_bounds__(256) md2_updisp_sum(Params P) {
   const int s = blockIdx.z, b = blockIdx.y;
-  const int Hs = P.H >> s, Ws = P.W >> s, n = P.H * P.W;
+  const int lv = P.lvl[s], Hs = P.H >> lv, Ws = P.W >> lv, n = P.H * P.W;
   const float* d = P.disp[s] + (size_t)b * Hs * Ws;
   float a = 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    a += upsample_at(d, s, Hs, Ws, i / P.W, i % P.W);
+    a += upsample_at(d, lv, Hs, Ws, i / P.W, i % P.W);
   a = warp_sum(a);
   __shared__ float part[8];
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -89,6 +89,7 @@ __global__ void md2_posecnn_final(Params P) {
   const int b = blockIdx.x;
   if (threadIdx.x == 0) final_pose_posecnn(P, b);
   __syncthreads();
+  if (P.up0 == 0) return;        // no level-0 slot: every level adds its constant in the up-sampling adjoint
   const float cst = P.gmidc[b];
   float* g = P.grad_disp[0] + (size_t)b * P.H * P.W;
   for (int i = threadIdx.x; i < P.H * P.W; i += blockDim.x) g[i] += cst;
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(256) md2_pmask_up(Params P) {
 __global__ void __launch_bounds__(256) md2_pmask_grad(Params P) {
   const int s = blockIdx.z, bf = blockIdx.y;
   if (!P.grad_pmask[s]) return;
-  const int Hs = P.H >> s, Ws = P.W >> s;
+  const int Hs = P.H >> P.lvl[s], Ws = P.W >> P.lvl[s];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < Hs * Ws) pmask_grad_pixel(P, s, bf / P.nsrc, bf % P.nsrc, i / Ws, i % Ws);
 }
@@ -133,7 +134,7 @@ __global__ void md2_pack(Params P) {
 __global__ void md2_disp_mean(Params P) {
   const int s = blockIdx.z, b = blockIdx.y;
   if (s >= P.S) return;
-  const int n = (P.H >> s) * (P.W >> s);
+  const int n = (P.H >> P.lvl[s]) * (P.W >> P.lvl[s]);
   if (blockIdx.x * blockDim.x >= n) return;                      // uniform per block
   const float* d = P.disp[s] + (size_t)b * n;
   float a = 0.f;
@@ -156,15 +157,16 @@ __global__ void md2_disp_mean(Params P) {
 // ones of prefetch_row / lane_init / stage_a_issue (md2_core.cuh), term by term, so the values are the same.
 constexpr int kDupCols = 128, kDupRows = 16;                  // fine pixels per block of md2_depth_up
 __global__ void __launch_bounds__(256) md2_depth_up(Params P) {
-  // block = 256 threads, tile = 128 columns x 16 rows of the full-resolution plane; blockIdx.z = b * (S - 1) + s - 1,
-  // s >= 1 (scale 0 is not up-sampled: its readers take the disparity plane and apply disp_to_depth themselves).
+  // block = 256 threads, tile = 128 columns x 16 rows of the full-resolution plane; blockIdx.z = b * (S - up0) + s - up0,
+  // slots s >= up0, i.e. levels >= 1 (level 0 is not up-sampled: its readers take the disparity plane and apply disp_to_depth themselves).
   // Separable, through shared memory: pass 1 blends every coarse row the tile touches horizontally (top / bot of
   // stage_a_issue: the same up_blend on the same operands), pass 2 blends two of those rows vertically and applies
   // disp_to_depth - the x weights are computed once per column of the tile instead of once per pixel.
   __shared__ __align__(16) float hrow[kDupRows / 2 + 2][kDupCols];
-  const int s = 1 + blockIdx.z % (P.S - 1), b = blockIdx.z / (P.S - 1);
-  const int Hs = P.H >> s, Ws = P.W >> s;
-  const float rs = 1.0f / (float)(1 << s);
+  const int nup = P.S - P.up0;
+  const int s = P.up0 + blockIdx.z % nup, b = blockIdx.z / nup;
+  const int Hs = P.H >> P.lvl[s], Ws = P.W >> P.lvl[s];
+  const float rs = 1.0f / (float)(1 << P.lvl[s]);
   const float* d = P.disp[s] + (size_t)b * Hs * Ws;
   const int x_base = blockIdx.x * kDupCols, y_base = blockIdx.y * kDupRows;
   // coarse rows touched by fine rows [y_base, y_base + kDupRows): y0 of the first row .. y1 of the last row
@@ -493,12 +495,12 @@ __global__ void __launch_bounds__(kSmoothWarps * 32) md2_smooth(Params P) {
   int rem = blockIdx.x * kSmoothWarps + (threadIdx.x >> 5);
   int s = 0;
   for (; s < P.S; ++s) {
-    const int n = smooth_bands(P.W >> s) * smooth_segs(P.H >> s) * P.B;
+    const int n = smooth_bands(P.W >> P.lvl[s]) * smooth_segs(P.H >> P.lvl[s]) * P.B;
     if (rem < n) break;
     rem -= n;
   }
   if (s >= P.S) return;
-  const int Hs = P.H >> s, Ws = P.W >> s, plane = Hs * Ws;
+  const int Hs = P.H >> P.lvl[s], Ws = P.W >> P.lvl[s], plane = Hs * Ws;
   const int nb = smooth_bands(Ws), ns = smooth_segs(Hs);
   const int b = rem / (nb * ns);
   const int r = rem - b * nb * ns;
@@ -804,7 +806,7 @@ __device__ __forceinline__ void final_tile(const Params& P, int s, int b, int tx
   constexpr int TYC = kFinalFineRows / K;        // coarse rows per block
   constexpr int NR = (TYC + 1) * K;              // fine rows read per block
   __shared__ float sm[TYC][kFinalThreads];
-  const int Hs = P.H >> s, Ws = P.W >> s;
+  const int Hs = P.H >> P.lvl[s], Ws = P.W >> P.lvl[s];
   const int X0 = tx * TXC, Y0 = ty * TYC;
   const float* dD = P.dD[s] + (size_t)b * P.H * P.W;
   // posecnn: d loss / d (every pixel of the up-sampled disparity) through mean_inv_depth (fine indices outside the
@@ -859,18 +861,18 @@ __global__ void __launch_bounds__(kFinalThreads) md2_final(Params P) {
   if (!P.want_grad) return;
   // block -> (scale, sample, tile row, tile column), scale-major
   int rem = blockIdx.x;
-  for (int s = 1; s < P.S; ++s) {
-    const int K = 1 << s;
-    const int ntx = final_tiles_x(P.W >> s, K), nty = final_tiles_y(P.H >> s, K);
+  for (int s = P.up0; s < P.S; ++s) {
+    const int K = 1 << P.lvl[s];
+    const int ntx = final_tiles_x(P.W >> P.lvl[s], K), nty = final_tiles_y(P.H >> P.lvl[s], K);
     const int n = ntx * nty * P.B;
     if (rem < n) {
       const int b = rem / (ntx * nty);
       const int t = rem - b * ntx * nty;
       const int ty = t / ntx, tx = t - ty * ntx;
-      switch (s) {
-        case 1: final_tile<2>(P, 1, b, tx, ty); break;
-        case 2: final_tile<4>(P, 2, b, tx, ty); break;
-        default: final_tile<8>(P, 3, b, tx, ty); break;
+      switch (K) {
+        case 2: final_tile<2>(P, s, b, tx, ty); break;
+        case 4: final_tile<4>(P, s, b, tx, ty); break;
+        default: final_tile<8>(P, s, b, tx, ty); break;
       }
       return;
     }
@@ -1147,8 +1149,9 @@ static cudaError_t get_side(SideStream** out) {
 __global__ void __launch_bounds__(256) md2_u8_to_f32(Params P) {
   const int img = blockIdx.z, b = blockIdx.y;
   const int nfull = 1 + P.nsrc;
-  const int s = img < nfull ? 0 : img - nfull + 1;
-  const int plane = (P.H >> s) * (P.W >> s);
+  const int s = img < nfull ? 0 : img - nfull + P.up0;          // colour slots of level >= 1 (level 0 = the target)
+  const int lv = img < nfull ? 0 : P.lvl[s];
+  const int plane = (P.H >> lv) * (P.W >> lv);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= plane) return;
   const unsigned char* in = img == 0 ? P.tgt8 : (img < nfull ? P.src8[img - 1] : P.color8[s]);
@@ -1166,14 +1169,14 @@ cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
 #ifndef MD2_DBG_DEVICE
   static const bool cvt_on = !(getenv("MD2_U8_CONVERT") && atoi(getenv("MD2_U8_CONVERT")) == 0);
   if (P.tgt8 && cvt_on) {
-    dim3 grid((P.H * P.W + 255) / 256, P.B, 1 + P.nsrc + (P.S - 1));
+    dim3 grid((P.H * P.W + 255) / 256, P.B, 1 + P.nsrc + (P.S - P.up0));
     md2_u8_to_f32<<<grid, 256, 0, stream>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     Params Q = P;
     Q.tgt = P.cvt_img[0]; Q.tgt8 = nullptr;
     for (int f = 0; f < P.nsrc; ++f) { Q.src[f] = P.cvt_img[1 + f]; Q.src8[f] = nullptr; }
-    for (int s2 = 0; s2 < P.S; ++s2) { Q.color[s2] = s2 == 0 ? P.cvt_img[0] : P.cvt_col[s2]; Q.color8[s2] = nullptr; }
+    for (int s2 = 0; s2 < P.S; ++s2) { Q.color[s2] = P.lvl[s2] == 0 ? P.cvt_img[0] : P.cvt_col[s2]; Q.color8[s2] = nullptr; }
     return launch_float_entry(Q, stream);
   }
 #endif
@@ -1207,7 +1210,7 @@ static cudaError_t launch_float_entry(const Params& P, cudaStream_t stream) {
     md2_disp_mean<<<grid, 256, 0, side->stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     int sjobs = 0;
-    for (int s = 0; s < P.S; ++s) sjobs += smooth_bands(P.W >> s) * smooth_segs(P.H >> s) * P.B;
+    for (int s = 0; s < P.S; ++s) sjobs += smooth_bands(P.W >> P.lvl[s]) * smooth_segs(P.H >> P.lvl[s]) * P.B;
     md2_smooth<<<(sjobs + kSmoothWarps - 1) / kSmoothWarps, kSmoothWarps * 32, 0, side->stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     md2_smooth_scalars<<<(P.S * P.B + 63) / 64, 64, 0, side->stream>>>(P);
@@ -1217,10 +1220,10 @@ static cudaError_t launch_float_entry(const Params& P, cudaStream_t stream) {
   // ---- main stream: depth planes (role kernels), (identity + re-layout) or re-layout alone, then the marching kernel
   // (measured at 640x192 x 12: on the caller's stream in front of the identity pass the 12 us of md2_depth_up are
   // fully exposed; on the smoothness side stream they are too, that stream being as long as the identity pass)
-  const bool zup = (march_mode() != 0 || P.nsrc > 3) && P.S > 1;
+  const bool zup = (march_mode() != 0 || P.nsrc > 3) && P.S > P.up0;
   if (zup) {
     if ((e = cudaStreamWaitEvent(side->stream2, side->fork, 0)) != cudaSuccess) return e;
-    dim3 grid((P.W + kDupCols - 1) / kDupCols, (P.H + kDupRows - 1) / kDupRows, P.B * (P.S - 1));
+    dim3 grid((P.W + kDupCols - 1) / kDupCols, (P.H + kDupRows - 1) / kDupRows, P.B * (P.S - P.up0));
     md2_depth_up<<<grid, 256, 0, side->stream2>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if ((e = cudaEventRecord(side->join2, side->stream2)) != cudaSuccess) return e;
@@ -1269,8 +1272,8 @@ static cudaError_t launch_float_entry(const Params& P, cudaStream_t stream) {
   {
     int blocks = 0;
     if (P.want_grad)
-      for (int s = 1; s < P.S; ++s)
-        blocks += final_tiles_x(P.W >> s, 1 << s) * final_tiles_y(P.H >> s, 1 << s) * P.B;
+      for (int s = P.up0; s < P.S; ++s)
+        blocks += final_tiles_x(P.W >> P.lvl[s], 1 << P.lvl[s]) * final_tiles_y(P.H >> P.lvl[s], 1 << P.lvl[s]) * P.B;
     md2_final<<<blocks > 0 ? blocks : 1, kFinalThreads, 0, stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }

@@ -26,15 +26,31 @@ struct Layout {
   size_t total;
 };
 
+// Pyramid level of scale slot s: md2_problem::scale_level when given (strictly ascending, trainer.py:345,413 iterate
+// opt.scales; the dataloader builds levels 0..3 whatever --scales says, trainer.py:127-135), else s.
+inline bool custom_levels(const md2_problem* p) {
+  for (int s = 0; s < MD2_MAX_SCALES; ++s) if (p->scale_level[s] != 0) return true;
+  return false;
+}
+inline int level_of(const md2_problem* p, int s) { return custom_levels(p) ? p->scale_level[s] : s; }
+
 inline int validate(const md2_problem* p) {
   if (!p) return MD2_ERR_INVALID_ARGUMENT;
   if (p->batch < 1 || p->height < 4 || p->width < 4) return MD2_ERR_INVALID_ARGUMENT;
   if (p->num_scales < 1 || p->num_scales > MD2_MAX_SCALES) return MD2_ERR_INVALID_ARGUMENT;
   if (p->num_src < 1 || p->num_src > MD2_MAX_SRC) return MD2_ERR_INVALID_ARGUMENT;
-  const int div = 1 << (p->num_scales - 1);
+  for (int s = 0; s < p->num_scales; ++s) {
+    const int lv = level_of(p, s);
+    if (lv < 0 || lv >= MD2_MAX_SCALES) return MD2_ERR_INVALID_ARGUMENT;
+    if (s > 0 && lv <= level_of(p, s - 1)) return MD2_ERR_INVALID_ARGUMENT;     // ascending, no duplicates
+  }
+  // level 0 is part of every list the reference accepts: it warps at source_scale 0 with backproject_depth[0] /
+  // project_3d[0], which it builds for opt.scales only (trainer.py:151-159,377)
+  if (level_of(p, 0) != 0) return MD2_ERR_INVALID_ARGUMENT;
+  const int top = level_of(p, p->num_scales - 1);
+  const int div = 1 << top;
   if (p->height % div || p->width % div) return MD2_ERR_INVALID_ARGUMENT;
-  if ((p->height >> (p->num_scales - 1)) < 2 || (p->width >> (p->num_scales - 1)) < 2)
-    return MD2_ERR_INVALID_ARGUMENT;
+  if ((p->height >> top) < 2 || (p->width >> top) < 2) return MD2_ERR_INVALID_ARGUMENT;
   if (!(p->min_depth > 0.f) || !(p->max_depth > p->min_depth)) return MD2_ERR_INVALID_ARGUMENT;
   if ((long long)p->batch * 3 * p->height * p->width * MD2_MAX_SRC >= (1LL << 31)) return MD2_ERR_UNSUPPORTED;
   // trainer.py:90-92: "When using predictive_mask, please disable automasking with --disable_automasking"
@@ -64,7 +80,7 @@ inline Layout make_layout(const md2_problem* p) {
   for (int s = 0; s < p->num_scales; ++s) {
     L.dD_off[s] = off; off = align_up(off + B * H * W * sizeof(float), 256);
     L.zup_off[s] = off; off = align_up(off + B * H * W * sizeof(float), 256);
-    L.gn_off[s] = off; off = align_up(off + B * (H >> s) * (W >> s) * sizeof(float), 256);
+    L.gn_off[s] = off; off = align_up(off + B * (H >> level_of(p, s)) * (W >> level_of(p, s)) * sizeof(float), 256);
     if (p->predictive_mask) {
       L.pm_off[s] = off; off = align_up(off + B * p->num_src * H * W * sizeof(float), 256);
       L.gpm_off[s] = off; off = align_up(off + B * p->num_src * H * W * sizeof(float), 256);
@@ -72,7 +88,11 @@ inline Layout make_layout(const md2_problem* p) {
   }
   // (reserved whether or not the caller uses the uint8 entry: the workspace size is a function of md2_problem alone)
   for (int i = 0; i <= p->num_src; ++i) { L.cvt_img_off[i] = off; off = align_up(off + B * 3 * H * W * sizeof(float), 256); }
-  for (int s = 1; s < p->num_scales; ++s) { L.cvt_col_off[s] = off; off = align_up(off + B * 3 * (H >> s) * (W >> s) * sizeof(float), 256); }
+  for (int s = 0; s < p->num_scales; ++s) {
+    const int lv = level_of(p, s);
+    if (lv == 0) continue;                      // level 0 = the converted target frame
+    L.cvt_col_off[s] = off; off = align_up(off + B * 3 * (H >> lv) * (W >> lv) * sizeof(float), 256);
+  }
   L.total = off;
   return L;
 }
@@ -133,7 +153,11 @@ inline int fill_params(const md2_problem* p, const md2_tensors* t, void* workspa
   P->wmax = (float)(p->width - 1); P->hmax = (float)(p->height - 1);
   P->eps = 1e-7f;
   P->gscale = (float)(1.0 / ((double)p->num_scales * p->batch * H * W) / (P->avg ? (double)p->num_src : 1.0));
-  for (int s = 0; s < p->num_scales; ++s) P->smooth_w[s] = (float)((double)p->disparity_smoothness / (double)(1 << s));
+  for (int s = 0; s < p->num_scales; ++s) {
+    P->lvl[s] = level_of(p, s);
+    P->smooth_w[s] = (float)((double)p->disparity_smoothness / (double)(1 << P->lvl[s]));   // trainer.py:491: / (2 ** scale)
+  }
+  P->up0 = P->lvl[0] == 0 ? 1 : 0;
   P->noise_event = t->noise_ready_event;
   P->seg_rows = default_seg_rows(p);
   P->nseg = (p->height + P->seg_rows - 1) / P->seg_rows;
@@ -187,7 +211,7 @@ inline int fill_params(const md2_problem* p, const md2_tensors* t, void* workspa
     P->grad_T[f] = p->want_grad ? t->grad_T[f] : nullptr;
   }
   for (int s = 0; s < p->num_scales; ++s) {
-    const unsigned char* c8 = u8 ? (t->color_u8[s] ? t->color_u8[s] : (s == 0 ? t->target_u8 : nullptr)) : nullptr;
+    const unsigned char* c8 = u8 ? (t->color_u8[s] ? t->color_u8[s] : (P->lvl[s] == 0 ? t->target_u8 : nullptr)) : nullptr;
     if (!t->disp[s] || (u8 ? !c8 : !t->color[s])) return MD2_ERR_INVALID_ARGUMENT;
     if (P->automask && !t->noise[s]) return MD2_ERR_INVALID_ARGUMENT;
     if (p->want_grad && !t->grad_disp[s]) return MD2_ERR_INVALID_ARGUMENT;
@@ -213,7 +237,7 @@ inline int fill_params(const md2_problem* p, const md2_tensors* t, void* workspa
   P->idloss = (float*)(ws + L.idloss_off);
   P->smsc = (float*)(ws + L.smsc_off);
   for (int i = 0; i <= p->num_src; ++i) P->cvt_img[i] = (float*)(ws + L.cvt_img_off[i]);
-  for (int s = 1; s < p->num_scales; ++s) P->cvt_col[s] = (float*)(ws + L.cvt_col_off[s]);
+  for (int s = P->up0; s < p->num_scales; ++s) P->cvt_col[s] = (float*)(ws + L.cvt_col_off[s]);
   P->mid = (float*)(ws + L.mid_off);
   P->gmidc = (float*)(ws + L.gmidc_off);
   P->tgt4 = (float*)(ws + L.tgt4_off);

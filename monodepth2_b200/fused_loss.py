@@ -48,8 +48,17 @@ class LossPlan:
                  disable_automasking: bool = False, align_corners: bool = False,
                  rows_per_segment: int = 0, no_ssim: bool = False, v1_multiscale: bool = False,
                  posecnn: bool = False, predictive_mask: bool = False):
-        if list(scales) != list(range(len(scales))):
-            raise RuntimeError("scales must be 0..n-1, got %s" % (list(scales),))
+        # --scales (options.py:64) is any list of pyramid levels: trainer.py:345,413 iterate it, the decoder emits
+        # ("disp", s) for exactly those levels and the dataloader always holds levels 0..3 (trainer.py:127-135).  The
+        # loss is a sum over the list, so the order does not matter: the plan keeps the levels ascending
+        # (md2_problem.scale_level); slot i of every per-scale array is level self.scales[i].
+        scales = sorted(int(s) for s in scales)
+        if not scales or len(set(scales)) != len(scales) or scales[0] < 0 or scales[-1] >= MAX_SCALES:
+            raise RuntimeError("scales must be distinct pyramid levels in 0..%d, got %s" % (MAX_SCALES - 1, scales))
+        if scales[0] != 0 and not v1_multiscale:
+            # the reference warps at source_scale 0 with backproject_depth[0] / project_3d[0], which exist only when 0 is
+            # in opt.scales (trainer.py:151-159,377: KeyError otherwise)
+            raise RuntimeError("scales must contain level 0 (trainer.py:377 indexes backproject_depth[0]), got %s" % scales)
         self.batch_size, self.height, self.width = int(batch_size), int(height), int(width)
         self.frame_ids = list(frame_ids)
         self.src_ids = self.frame_ids[1:]
@@ -101,7 +110,20 @@ class LossPlan:
                           min_depth=self.min_depth, max_depth=self.max_depth,
                           disparity_smoothness=self.disparity_smoothness, want_grad=int(want_grad),
                           rows_per_segment=self.rows_per_segment, no_ssim=int(self.no_ssim),
-                          posecnn=int(self.posecnn), predictive_mask=int(self.predictive_mask))
+                          posecnn=int(self.posecnn), predictive_mask=int(self.predictive_mask),
+                          scale_level=self._levels())
+
+    def _levels(self):
+        """md2_problem.scale_level: all zero for the default 0..n-1, else the levels."""
+        lv = (C.c_int * MAX_SCALES)()
+        if self.scales != list(range(len(self.scales))):
+            for i, s in enumerate(self.scales):
+                lv[i] = s
+        return lv
+
+    def slot(self, level: int) -> int:
+        """Index of pyramid level ``level`` in the per-scale arrays of the C ABI."""
+        return self.scales.index(level)
 
     def workspace(self, device: torch.device) -> torch.Tensor:
         key = (device.type, device.index)
@@ -192,7 +214,7 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
         grad_disp = []
         grad_mask = [None] * S
         for s in range(S):
-            hs, ws = H >> s, W >> s
+            hs, ws = H >> plan.scales[s], W >> plan.scales[s]
             t.disp[s] = ptr(_check_f32_cuda(disps[s], "disp[%d]" % s, (B, 1, hs, ws)))
             if u8:
                 t.color_u8[s] = ptr(_check_u8_cuda(colors[s], "color[%d]" % s, B, hs, ws, hwc))
@@ -218,22 +240,22 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
             for s in side.get("depth_scales", []):
                 d = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
                 side[("depth", 0, s)] = d
-                t.depth[s] = ptr(d)
+                t.depth[plan.slot(s)] = ptr(d)
             for s in side.get("color_scales", []):
                 for i, f in enumerate(plan.src_ids):
                     c = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
                     side[("color", f, s)] = c
-                    t.warped[i][s] = ptr(c)
+                    t.warped[i][plan.slot(s)] = ptr(c)
             if plan.automask:
                 for s in side.get("mask_scales", []):
                     m = torch.empty((B, H, W), dtype=torch.float32, device=dev)
                     side["identity_selection/{}".format(s)] = m
-                    t.identity_selection[s] = ptr(m)
+                    t.identity_selection[plan.slot(s)] = ptr(m)
             if want_grad:
                 for s in side.get("grad_updisp_scales", []):
                     gd = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
                     side[("grad_updisp", s)] = gd
-                    t.grad_depth_dbg[s] = ptr(gd)
+                    t.grad_depth_dbg[plan.slot(s)] = ptr(gd)
             side["_cam_T_cam"] = cam_T
         losses = torch.empty(MAX_SCALES + 1, dtype=torch.float32, device=dev)
         t.losses = ptr(losses)

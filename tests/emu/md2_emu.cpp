@@ -146,9 +146,9 @@ extern "C" int md2_emu_view_synthesis_loss(const md2_problem* p, const md2_tenso
   if (P.posecnn) {
     for (int s = 0; s < P.S; ++s)
       for (int b = 0; b < P.B; ++b) {
-        const int Hs = P.H >> s, Ws = P.W >> s;
+        const int Hs = P.H >> P.lvl[s], Ws = P.W >> P.lvl[s];
         double a = 0.0;
-        for (int i = 0; i < P.H * P.W; ++i) a += upsample_at(P.disp[s] + (size_t)b * Hs * Ws, s, Hs, Ws, i / P.W, i % P.W);
+        for (int i = 0; i < P.H * P.W; ++i) a += upsample_at(P.disp[s] + (size_t)b * Hs * Ws, P.lvl[s], Hs, Ws, i / P.W, i % P.W);
         P.acc[acc_updisp(P, s, b)] = a;
         posecnn_mid(P, s, b);
       }
@@ -168,7 +168,7 @@ extern "C" int md2_emu_view_synthesis_loss(const md2_problem* p, const md2_tenso
   // 2. disparity means
   for (int s = 0; s < P.S; ++s)
     for (int b = 0; b < P.B; ++b) {
-      const int n = (P.H >> s) * (P.W >> s);
+      const int n = (P.H >> P.lvl[s]) * (P.W >> P.lvl[s]);
       double a = 0.0;
       for (int i = 0; i < n; ++i) a += P.disp[s][(size_t)b * n + i];
       P.acc[acc_dispsum(P, s, b)] = a;
@@ -181,7 +181,7 @@ extern "C" int md2_emu_view_synthesis_loss(const md2_problem* p, const md2_tenso
   // 4. smoothness
   for (int s = 0; s < P.S; ++s)
     for (int b = 0; b < P.B; ++b) {
-      const int Hs = P.H >> s, Ws = P.W >> s, n = Hs * Ws;
+      const int Hs = P.H >> P.lvl[s], Ws = P.W >> P.lvl[s], n = Hs * Ws;
       const float m = (float)(P.acc[acc_dispsum(P, s, b)] / (double)n) + 1e-7f;
       const float inv_m = 1.0f / m;
       for (int i = 0; i < n; ++i) {
@@ -203,12 +203,13 @@ extern "C" int md2_emu_view_synthesis_loss(const md2_problem* p, const md2_tenso
   if (P.want_grad && P.posecnn)
     for (int b = 0; b < P.B; ++b) {
       final_pose_posecnn(P, b);
-      for (int i = 0; i < P.H * P.W; ++i) P.grad_disp[0][(size_t)b * P.H * P.W + i] += P.gmidc[b];
+      if (P.lvl[0] == 0)   // level 0 is finished by the marching pass; the other levels add the constant in the adjoint
+        for (int i = 0; i < P.H * P.W; ++i) P.grad_disp[0][(size_t)b * P.H * P.W + i] += P.gmidc[b];
     }
   if (P.want_grad && P.pmask_on)
     for (int s = 0; s < P.S; ++s) {
       if (!P.grad_pmask[s]) continue;
-      const int Hs = P.H >> s, Ws = P.W >> s;
+      const int Hs = P.H >> P.lvl[s], Ws = P.W >> P.lvl[s];
       for (int b = 0; b < P.B; ++b)
         for (int f = 0; f < P.nsrc; ++f)
           for (int i = 0; i < Hs * Ws; ++i) pmask_grad_pixel(P, s, b, f, i / Ws, i % Ws);
@@ -218,14 +219,14 @@ extern "C" int md2_emu_view_synthesis_loss(const md2_problem* p, const md2_tenso
       for (int f = 0; f < P.nsrc; ++f) final_grad_T(P, b, f);
     for (int s = 0; s < P.S; ++s)
       for (int b = 0; b < P.B; ++b) {
-        const int Hs = P.H >> s, Ws = P.W >> s, n = Hs * Ws;
+        const int lv = P.lvl[s], Hs = P.H >> lv, Ws = P.W >> lv, n = Hs * Ws;
         const float inv_m2 = P.smsc[2 * (s * P.B + b)], dterm = P.smsc[2 * (s * P.B + b) + 1];
         for (int i = 0; i < n; ++i) {
           float up = 0.f;
           const int Y = i / Ws, X = i % Ws;
-          if (s == 0) continue;   // finished by the marching pass
-          else if (s == 1) { for (int j = 0; j < 2; ++j) up += upsample_adjoint_part<2>(P, s, b, Y, X, j); }
-          else if (s == 2) { for (int j = 0; j < 4; ++j) up += upsample_adjoint_part<4>(P, s, b, Y, X, j); }
+          if (lv == 0) continue;   // finished by the marching pass
+          else if (lv == 1) { for (int j = 0; j < 2; ++j) up += upsample_adjoint_part<2>(P, s, b, Y, X, j); }
+          else if (lv == 2) { for (int j = 0; j < 4; ++j) up += upsample_adjoint_part<4>(P, s, b, Y, X, j); }
           else { for (int j = 0; j < 8; ++j) up += upsample_adjoint_part<8>(P, s, b, Y, X, j); }
           P.grad_disp[s][(size_t)b * n + i] = up + final_smooth_grad(P, s, b, i, inv_m2, dterm);
         }

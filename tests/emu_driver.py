@@ -57,7 +57,9 @@ def run_emu(g, want_grad=True, rows_per_segment=0, align_corners=False, side_out
     z = g.z
     B, H, W = g.B, g.H, g.W
     srcs = g.frame_ids[1:]
-    p = Md2Problem(batch=B, height=H, width=W, num_scales=4, num_src=len(srcs),
+    scales = list(g.scales)          # slot i of every per-scale array = pyramid level scales[i] (md2_problem.scale_level)
+    lv = (C.c_int * 4)(*(scales + [0] * (4 - len(scales)))) if scales != list(range(len(scales))) else (C.c_int * 4)()
+    p = Md2Problem(batch=B, height=H, width=W, num_scales=len(scales), num_src=len(srcs), scale_level=lv,
                    automask=int(not g.disable_automasking), avg_reprojection=int(g.avg_reprojection),
                    align_corners=int(align_corners), min_depth=0.1, max_depth=100.0,
                    disparity_smoothness=1e-3, want_grad=int(want_grad), rows_per_segment=rows_per_segment,
@@ -115,17 +117,17 @@ def run_emu(g, want_grad=True, rows_per_segment=0, align_corners=False, side_out
     t.K = _ptr(arr(z["in__K__0"]))
     t.inv_K = _ptr(arr(z["in__inv_K__0"]))
     out["grad_disp"], out["grad_updisp"], out["idsel"], out["depth"] = [], [], [], []
-    for s in range(4):
-        t.disp[s] = _ptr(arr(z["disp__%d" % s]))
-        t.color[s], t.color_u8[s] = img("in__color__0__%d" % s)
+    for s, L in enumerate(scales):     # s: slot, L: level; the per-scale output lists are indexed by slot
+        t.disp[s] = _ptr(arr(z["disp__%d" % L]))
+        t.color[s], t.color_u8[s] = img("in__color__0__%d" % L)
         if g.n_id > 0:
-            t.noise[s] = _ptr(arr(z["noise__%d" % s][:, :g.n_id]))
-        gd = np.zeros((B, 1, H >> s, W >> s), np.float32)
+            t.noise[s] = _ptr(arr(z["noise__%d" % L][:, :g.n_id]))
+        gd = np.zeros((B, 1, H >> L, W >> L), np.float32)
         out["grad_disp"].append(gd)
         t.grad_disp[s] = _ptr(gd)
         if g.predictive_mask:
-            t.pmask[s] = _ptr(arr(z["mask__%d" % s]))
-            gm = np.zeros((B, len(srcs), H >> s, W >> s), np.float32)
+            t.pmask[s] = _ptr(arr(z["mask__%d" % L]))
+            gm = np.zeros((B, len(srcs), H >> L, W >> L), np.float32)
             out.setdefault("grad_mask", []).append(gm)
             t.grad_pmask[s] = _ptr(gm)
         if side_outputs:
@@ -140,7 +142,7 @@ def run_emu(g, want_grad=True, rows_per_segment=0, align_corners=False, side_out
             t.depth[s] = _ptr(d)
             for i, f in enumerate(srcs):
                 w = np.zeros((B, 3, H, W), np.float32)
-                out["warped"][(f, s)] = w
+                out["warped"][(f, L)] = w
                 t.warped[i][s] = _ptr(w)
     losses = np.zeros(5, np.float32)
     t.losses = _ptr(losses)
@@ -150,6 +152,7 @@ def run_emu(g, want_grad=True, rows_per_segment=0, align_corners=False, side_out
     ws = np.zeros(nbytes.value + 64, np.uint8)
     dbg = None
     if decisions:
+        assert scales == [0, 1, 2, 3], "the decision sink is laid out for the default scales"
         n_src = len(srcs)
         dbg = dict(x0=np.zeros((4, B, n_src, H, W), np.int16), y0=np.zeros((4, B, n_src, H, W), np.int16),
                    mxy=np.zeros((4, B, n_src, H, W), np.uint8), tag=np.full((4, B, H, W), -1, np.int8),

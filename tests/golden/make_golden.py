@@ -50,6 +50,16 @@ CASES = {
                             flags=["--disable_automasking", "--predictive_mask"]),
     # four source frames (options.py:80-84 takes any --frame_ids; the maximum the C ABI supports: MD2_MAX_SRC)
     "five_frames": dict(B=2, H=32, W=64, frame_ids=[0, -2, -1, 1, 2], kind="structured", seed=13, flags=[]),
+    # --scales subsets (options.py:64: any list of pyramid levels; trainer.py:345,413 iterate it, the dataloader
+    # holds levels 0..3 regardless, trainer.py:127-135): md2_problem.scale_level.  Level 0 has to be in the list: the
+    # reference builds backproject_depth / project_3d for opt.scales only and indexes [0] (trainer.py:151-159,377)
+    "scales_0_2": dict(B=2, H=48, W=80, frame_ids=[0, -1, 1], kind="structured", seed=14, flags=["--scales", "0", "2"]),
+    "scales_0_1_3_stereo": dict(B=2, H=48, W=80, frame_ids=[0, -1, 1], kind="structured", seed=15,
+                                flags=["--scales", "0", "1", "3", "--use_stereo"]),
+    "scales_0_2_posecnn": dict(B=2, H=48, W=80, frame_ids=[0, -1, 1], kind="structured", seed=16,
+                               flags=["--scales", "0", "2", "--pose_model_type", "posecnn"]),
+    "scales_0_3_predictive_mask": dict(B=2, H=48, W=80, frame_ids=[0, -1, 1], kind="structured", seed=17,
+                                       flags=["--scales", "0", "3", "--disable_automasking", "--predictive_mask"]),
     "stereo_only": dict(B=2, H=32, W=64, frame_ids=[0], kind="structured", seed=7,
                         flags=["--use_stereo", "--frame_ids", "0"]),
 }
@@ -116,7 +126,8 @@ def run_reference(T, MonodepthOptions, case, dtype=torch.float32, batch=None):
     inputs = {k: v.to(dtype) for k, v in inputs.items()}
     leaves = {}
     outs = {}
-    for s in range(4):
+    scales = list(opt.scales)
+    for s in scales:
         d = outputs[("disp", s)].to(dtype).clone().requires_grad_(True)
         leaves[("disp", s)] = d
         outs[("disp", s)] = d
@@ -137,15 +148,17 @@ def run_reference(T, MonodepthOptions, case, dtype=torch.float32, batch=None):
         gm = torch.Generator().manual_seed(1000 + case["seed"])
         outs["predictive_mask"] = {}
         for s in range(4):
+            if s not in scales:
+                continue
             m = torch.sigmoid(2.0 * torch.randn(case["B"], n_src, case["H"] >> s, case["W"] >> s, generator=gm))
             m = m.to(dtype).requires_grad_(True)
             leaves[("mask", s)] = m
             outs["predictive_mask"][("disp", s)] = m
     me = build_self(T, opt, dtype)
     me.generate_images_pred(inputs, outs)
-    for s in range(4):
+    for s in scales:
         outs[("depth", 0, s)].retain_grad()
-    draws = [n.to(dtype) for n in noise]
+    draws = [noise[s].to(dtype) for s in scales]      # one draw per entry of opt.scales, in list order
     real_randn = torch.randn
     it = iter(draws)
 
@@ -179,7 +192,10 @@ def pack(res):
     for k, v in res["inputs"].items():
         name = "in__" + "__".join(str(x) for x in (k if isinstance(k, tuple) else (k,)))
         d[name] = v.detach().numpy()
-    for s in range(4):
+    scales = list(opt.scales)
+    if scales != [0, 1, 2, 3]:
+        d["scales"] = np.array(scales)
+    for s in scales:
         d["disp__%d" % s] = res["leaves"][("disp", s)].detach().numpy()
         d["grad_disp__%d" % s] = res["leaves"][("disp", s)].grad.numpy()
         d["grad_depth__%d" % s] = res["outs"][("depth", 0, s)].grad.numpy()
@@ -193,9 +209,10 @@ def pack(res):
             d["mask__%d" % s] = res["leaves"][("mask", s)].detach().numpy()
             d["grad_mask__%d" % s] = res["leaves"][("mask", s)].grad.numpy()
     d["loss"] = res["losses"]["loss"].detach().numpy()
-    d["depth__0"] = res["outs"][("depth", 0, 0)].detach().numpy()
+    s0 = scales[0]
+    d["depth__%d" % s0] = res["outs"][("depth", 0, s0)].detach().numpy()
     for f in fids[1:]:
-        d["color__%s__0" % f] = res["outs"][("color", f, 0)].detach().numpy()
+        d["color__%s__%d" % (f, s0)] = res["outs"][("color", f, s0)].detach().numpy()
         if f != "s":
             d["axisangle__%s" % f] = res["leaves"][("axisangle", f)].detach().numpy()
             d["translation__%s" % f] = res["leaves"][("translation", f)].detach().numpy()

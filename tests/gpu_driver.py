@@ -9,10 +9,10 @@ def run_cuda(g, rows_per_segment=0, align_corners=False, want_grad=True, side_al
     plan = LossPlan(g.B, g.H, g.W, g.frame_ids, avg_reprojection=g.avg_reprojection,
                     disable_automasking=g.disable_automasking, align_corners=align_corners,
                     rows_per_segment=rows_per_segment, no_ssim=g.no_ssim, v1_multiscale=g.v1_multiscale,
-                    posecnn=g.posecnn, predictive_mask=g.predictive_mask)
+                    posecnn=g.posecnn, predictive_mask=g.predictive_mask, scales=g.scales)
     inputs = {k: v.to(dev) for k, v in g.inputs().items()}
     outs, leaves = {}, {}
-    for s in range(4):
+    for s in g.scales:
         d = g.t("disp__%d" % s).to(dev).requires_grad_(want_grad)
         outs[("disp", s)] = d
         leaves[("disp", s)] = d
@@ -41,15 +41,15 @@ def run_cuda(g, rows_per_segment=0, align_corners=False, want_grad=True, side_al
             leaves[("axisangle", f)], leaves[("translation", f)] = aa, tr
     if g.predictive_mask:      # the mask decoder's outputs (trainer.py:251-252)
         outs["predictive_mask"] = {}
-        for s in range(4):
+        for s in g.scales:
             m = g.t("mask__%d" % s).to(dev).requires_grad_(want_grad)
             outs["predictive_mask"][("disp", s)] = m
             leaves[("mask", s)] = m
     noise = [n.to(dev) for n in g.noise()] if g.n_id > 0 else None
     side = None
     if side_all:
-        side = {"depth_scales": [0, 1, 2, 3], "color_scales": [0, 1, 2, 3], "mask_scales": [0, 1, 2, 3],
-                "grad_updisp_scales": [0, 1, 2, 3]}
+        side = {"depth_scales": list(g.scales), "color_scales": list(g.scales), "mask_scales": list(g.scales),
+                "grad_updisp_scales": list(g.scales)}
     if want_grad:
         losses = view_synthesis_loss(plan, inputs, outs, noise, side)
         losses["loss"].backward()

@@ -33,13 +33,15 @@ class Golden:
         self.B, _, self.H, self.W = z["in__color__0__0"].shape
         self.n_src = len(self.frame_ids) - 1
         self.n_id = 0 if self.disable_automasking else (1 if self.avg_reprojection else self.n_src)
+        # --scales (options.py:64): the fixtures of the default 0 1 2 3 carry no "scales" entry
+        self.scales = [int(s) for s in z["scales"]] if "scales" in z.files else [0, 1, 2, 3]
 
     def cfg(self, **kw):
         return O.OracleConfig(height=self.H, width=self.W, frame_ids=tuple(self.frame_ids),
                               avg_reprojection=self.avg_reprojection,
                               disable_automasking=self.disable_automasking, no_ssim=self.no_ssim,
                               v1_multiscale=self.v1_multiscale, posecnn=self.posecnn,
-                              predictive_mask=self.predictive_mask, **kw)
+                              predictive_mask=self.predictive_mask, scales=tuple(self.scales), **kw)
 
     def t(self, key, dtype=torch.float32):
         return torch.from_numpy(np.asarray(self.z[key])).to(dtype)
@@ -60,15 +62,15 @@ class Golden:
         return d
 
     def noise(self, dtype=torch.float32):
-        return [self.t("noise__%d" % s, dtype)[:, :max(self.n_id, 1)] for s in range(4)]
+        return [self.t("noise__%d" % s, dtype)[:, :max(self.n_id, 1)] for s in self.scales]
 
     def leaves(self, dtype=torch.float32):
         """disp_s and (axisangle, translation) leaves with requires_grad."""
         lv = {}
-        for s in range(4):
+        for s in self.scales:
             lv[("disp", s)] = self.t("disp__%d" % s, dtype).requires_grad_(True)
         if self.predictive_mask:
-            for s in range(4):
+            for s in self.scales:
                 lv[("mask", s)] = self.t("mask__%d" % s, dtype).requires_grad_(True)
         for f in self.frame_ids[1:]:
             if f == "s":
@@ -84,7 +86,7 @@ def run_oracle(g: Golden, dtype=torch.float32, **cfgkw):
     inputs = g.inputs(dtype)
     lv = g.leaves(dtype)
     outs = {}
-    for s in range(4):
+    for s in g.scales:
         outs[("disp", s)] = lv[("disp", s)]
     for f in g.frame_ids[1:]:
         if f == "s":
@@ -95,9 +97,9 @@ def run_oracle(g: Golden, dtype=torch.float32, **cfgkw):
         outs[("axisangle", 0, f)] = lv[("axisangle", f)].reshape(-1, 1, 1, 3)
         outs[("translation", 0, f)] = lv[("translation", f)].reshape(-1, 1, 1, 3)
     if g.predictive_mask:
-        outs["predictive_mask"] = {("disp", s): lv[("mask", s)] for s in range(4)}
+        outs["predictive_mask"] = {("disp", s): lv[("mask", s)] for s in g.scales}
     O.generate_images_pred(inputs, outs, cfg)
-    for s in range(4):
+    for s in g.scales:
         outs[("depth", 0, s)].retain_grad()
     losses = O.compute_losses(inputs, outs, cfg, g.noise(dtype))
     losses["loss"].backward()

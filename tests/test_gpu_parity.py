@@ -26,20 +26,20 @@ def test_cuda_matches_reference_golden(name, rows):
     z = g.z
     r = run_cuda(g, rows_per_segment=rows)
     assert abs(float(r["losses"]["loss"]) - float(z["loss"])) <= LOSS_RTOL * abs(float(z["loss"]))
-    for s in range(4):
+    for s in g.scales:
         assert abs(float(r["losses"]["loss/%d" % s]) - float(z["loss__%d" % s])) <= LOSS_RTOL * abs(float(z["loss__%d" % s]))
     np.testing.assert_allclose(r["side"][("depth", 0, 0)].cpu().numpy(), z["depth__0"], rtol=2e-6)
     for f in g.frame_ids[1:]:
         np.testing.assert_allclose(r["side"][("color", f, 0)].cpu().numpy(), z["color__%s__0" % f], atol=5e-5, rtol=0)
     if g.n_id > 0:
-        for s in range(4):
+        for s in g.scales:
             m = r["side"]["identity_selection/%d" % s].cpu().numpy().astype(np.uint8)
             assert (m != z["idsel__%d" % s]).mean() <= 5e-4     # tiny fixtures: 1 flip of 7680 px = 1.3e-4
     # per-pixel (pre-aggregation) gradient, protocol P2
     a, c = 0.01, 9.99
     # (under posecnn the disparity also acts through the per-scale T: that part is a per-(scale, sample) constant added
     # by the final pass, outside the per-pixel map exported here)
-    for s in range(4) if not g.posecnn else []:
+    for s in g.scales if not g.posecnn else []:
         gd = r["side"][("grad_updisp", s)].cpu().numpy()
         d_s = g.t("disp__%d" % s)
         if not g.v1_multiscale:
@@ -48,7 +48,7 @@ def test_cuda_matches_reference_golden(name, rows):
         ref = z["grad_depth__%d" % s] * (-c * depth * depth)       # d loss / d upsampled disp
         assert frac_within(gd, ref, P2_TOL) >= 0.995, (name, s)    # small fixture: a few flips weigh more
     # aggregated gradients: relL2 bounded (flips allowed, see test_full_size for the P3 protocol)
-    for s in range(4):
+    for s in g.scales:
         assert rel_l2(r["leaves"][("disp", s)].grad.cpu(), z["grad_disp__%d" % s]) < 8e-2
         if g.predictive_mask:
             assert rel_l2(r["leaves"][("mask", s)].grad.cpu(), z["grad_mask__%d" % s]) < 1e-3
@@ -81,12 +81,12 @@ def test_cuda_matches_host_emulator_of_the_same_source(name):
     e = run_emu(g, rows_per_segment=16)
     r = run_cuda(g, rows_per_segment=16)
     assert abs(float(r["losses"]["loss"]) - float(e["losses"][0])) <= 2e-6 * abs(float(e["losses"][0]))
-    for s in range(4):
+    for i, s in enumerate(g.scales):
         got = r["side"][("grad_updisp", s)].cpu().numpy()
-        assert frac_within(got, e["grad_updisp"][s], 1e-5) >= 0.999, (name, s)
+        assert frac_within(got, e["grad_updisp"][i], 1e-5) >= 0.999, (name, s)
         if g.n_id > 0:
             m = r["side"]["identity_selection/%d" % s].cpu().numpy()
-            assert (m != e["idsel"][s]).mean() <= 5e-4
+            assert (m != e["idsel"][i]).mean() <= 5e-4
 
 
 def test_packed_and_scalar_two_source_kernels_agree(tmp_path):

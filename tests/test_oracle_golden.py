@@ -13,7 +13,7 @@ def test_oracle_matches_reference_golden(name):
     z = g.z
     # losses: the oracle calls the same library kernels in the same order -> ~bit-equal
     assert abs(float(r["losses"]["loss"]) - float(z["loss"])) <= 1e-6 * abs(float(z["loss"]))
-    for s in range(4):
+    for s in g.scales:
         assert abs(float(r["losses"]["loss/%d" % s]) - float(z["loss__%d" % s])) <= 1e-6 * abs(float(z["loss__%d" % s]))
     # side outputs
     np.testing.assert_allclose(r["outs"][("depth", 0, 0)].detach().numpy(), z["depth__0"], rtol=1e-6, atol=0)
@@ -21,15 +21,15 @@ def test_oracle_matches_reference_golden(name):
         np.testing.assert_allclose(r["outs"][("color", f, 0)].detach().numpy(), z["color__%s__0" % f],
                                    rtol=0, atol=2e-6)
     if not g.disable_automasking:
-        for s in range(4):
+        for s in g.scales:
             m = r["outs"]["identity_selection/%d" % s].numpy().astype(np.uint8)
             assert (m != z["idsel__%d" % s]).mean() <= 1e-4
     # gradients (fp32 vs fp32, same kernels: tight)
-    for s in range(4):
+    for s in g.scales:
         assert rel_l2(r["leaves"][("disp", s)].grad, z["grad_disp__%d" % s]) < 1e-4
         assert rel_l2(r["outs"][("depth", 0, s)].grad, z["grad_depth__%d" % s]) < 1e-4
     if g.predictive_mask:
-        for s in range(4):
+        for s in g.scales:
             assert rel_l2(r["leaves"][("mask", s)].grad, z["grad_mask__%d" % s]) < 1e-4
     for f in g.frame_ids[1:]:
         if f == "s":

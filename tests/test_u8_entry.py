@@ -10,14 +10,14 @@ from helpers import Golden
 from emu_driver import run_emu, quantise_u8
 
 
-@pytest.mark.parametrize("case", ["mono_structured", "stereo_iid", "disable_automasking"])
+@pytest.mark.parametrize("case", ["mono_structured", "stereo_iid", "disable_automasking", "scales_0_2"])
 @pytest.mark.parametrize("layout", ["hwc", "chw"])
 def test_emulator_u8_entry_is_bit_identical_to_float_entry(case, layout):
     g = Golden(case)
     ref = run_emu(g, u8="f32")
     got = run_emu(g, u8=layout)
     assert np.array_equal(ref["losses"], got["losses"])
-    for s in range(4):
+    for s in range(len(g.scales)):
         assert np.array_equal(ref["grad_disp"][s], got["grad_disp"][s])
         assert np.array_equal(ref["idsel"][s], got["idsel"][s])
     for f in ref["grad_T"]:
@@ -27,7 +27,7 @@ def test_emulator_u8_entry_is_bit_identical_to_float_entry(case, layout):
 def _cuda_run(g, mode, dev="cuda:0"):
     from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
     plan = LossPlan(g.B, g.H, g.W, g.frame_ids, avg_reprojection=g.avg_reprojection,
-                    disable_automasking=g.disable_automasking, no_ssim=g.no_ssim)
+                    disable_automasking=g.disable_automasking, no_ssim=g.no_ssim, scales=g.scales)
     inputs = {}
     for k, v in g.inputs().items():
         if isinstance(k, tuple) and k[0] == "color":
@@ -40,13 +40,13 @@ def _cuda_run(g, mode, dev="cuda:0"):
                 v = q
         inputs[k] = v.to(dev)
     outs = {}
-    for s in range(4):
+    for s in g.scales:
         outs[("disp", s)] = g.t("disp__%d" % s).to(dev).requires_grad_(True)
     for f in g.frame_ids[1:]:
         if f != "s":
             outs[("cam_T_cam", 0, f)] = g.t("cam_T_cam__%s" % f).to(dev).requires_grad_(True)
     noise = [n.to(dev) for n in g.noise()] if g.n_id > 0 else None
-    side = {"mask_scales": [0, 1, 2, 3]} if g.n_id > 0 else None
+    side = {"mask_scales": list(g.scales)} if g.n_id > 0 else None
     losses = view_synthesis_loss(plan, inputs, outs, noise, side)
     losses["loss"].backward()
     torch.cuda.synchronize()
@@ -54,7 +54,8 @@ def _cuda_run(g, mode, dev="cuda:0"):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["mono_iid", "mono_structured", "stereo_iid", "avg_reprojection", "disable_automasking"])
+@pytest.mark.parametrize("case", ["mono_iid", "mono_structured", "stereo_iid", "avg_reprojection", "disable_automasking",
+                                  "scales_0_2"])
 @pytest.mark.parametrize("layout", ["hwc", "chw"])
 def test_cuda_u8_entry_is_bit_identical_to_float_entry(case, layout):
     g = Golden(case)
@@ -63,10 +64,10 @@ def test_cuda_u8_entry_is_bit_identical_to_float_entry(case, layout):
     for k in l0:
         assert torch.equal(l0[k], l1[k]), k
     if s0 is not None:
-        for s in range(4):
+        for s in g.scales:
             assert torch.equal(s0["identity_selection/%d" % s], s1["identity_selection/%d" % s])
     # the scalar sums are accumulated with fp64 atomics (order varies run to run): per-pixel gradients are exact
-    for s in range(4):
+    for s in g.scales:
         assert torch.equal(o0[("disp", s)].grad, o1[("disp", s)].grad), s
 
 
