@@ -205,9 +205,6 @@ struct Params {
   float eps;
   float gscale;              // 1/(S*B*H*W) [* 1/nsrc under avg_reprojection]
   float smooth_w[kMaxScales];  // disparity_smoothness / 2^lvl[s]
-  int up0;                     // first slot that is up-sampled: 1 when lvl[0] == 0, else 0
-  int lvl[kMaxScales];         // pyramid level of scale slot s: opt.scales sorted ascending (trainer.py:345,413); slot s holds
-                               // (H >> lvl[s], W >> lvl[s]) tensors.  0..S-1 for the default --scales 0 1 2 3
   int seg_rows, nseg, nband, nband_id;
   int nsm;                   // SMs of the device (role rotation of the role-specialised kernel)
   int id_rows, nseg_id;      // row segments of the (much lighter) identity pass
@@ -263,6 +260,15 @@ struct Params {
   float* depth[kMaxScales];
   float* warped[kMaxSrc][kMaxScales];
   float* idsel[kMaxScales];
+  // --scales subsets (options.py:64).  At the end of the struct: the constant-bank offsets of every field above are
+  // the ones the marching kernels were tuned with.
+  int lvl[kMaxScales];         // pyramid level of scale slot s: opt.scales sorted ascending (trainer.py:345,413); slot s holds
+                               // (H >> lvl[s], W >> lvl[s]) tensors.  0..S-1 for the default --scales 0 1 2 3.  lvl[0] == 0
+                               // always (validate(): the reference needs level 0, trainer.py:377), so "slot 0" and
+                               // "full resolution, no up-sampling" are the same thing in every kernel
+  int up0;                     // first slot that is up-sampled (= 1)
+  int lvl4;                    // the same levels, 4 bits per slot: level of slot s = (lvl4 >> 4 s) & 15 (make_job: plain shifts
+                               // of one kernel parameter instead of an indexed constant load - same code as `>> s` had)
 };
 
 // accumulator layout (doubles)
@@ -323,7 +329,7 @@ MD2_HD float load_px(const float* f32, const unsigned char* u8, int hwc, int b, 
 // is 32-bit index arithmetic (validate() bounds the tensors below 2^31 elements).
 struct WarpJob {
   int s, b;
-  // (slot s is at full resolution - level 0, no up-sampling - iff s < P.up0: levels ascend)
+  // (slot s is at full resolution - level 0, no up-sampling - iff s == 0: validate() requires level 0 in the list)
   int ps;        // pose set: s under posecnn, else 0
   const float* proj;   // projection table of (ps, b): nsrc x 12 floats
   const float* pm;     // predictive mask up-sampled to (H,W), planes [nsrc] of sample b at scale s (or null)
@@ -355,7 +361,7 @@ MD2_HD void smooth_scalars(const Params& P, int s, int b, float& inv_m, float& d
 
 MD2_HD WarpJob make_job(const Params& P, int s, int b, int x0, int y0, int y1) {
   WarpJob J;
-  const int lv = P.lvl[s];
+  const int lv = (P.lvl4 >> (4 * s)) & 15;
   J.s = s; J.b = b; J.x0 = x0; J.y0 = y0; J.y1 = y1;
   J.H = P.H; J.W = P.W; J.Hs = P.H >> lv; J.Ws = P.W >> lv; J.plane = P.H * P.W;
   J.rs = 1.0f / (float)(1 << lv);
@@ -371,12 +377,12 @@ MD2_HD WarpJob make_job(const Params& P, int s, int b, int x0, int y0, int y1) {
   }
   J.disp = P.disp[s] + b * J.Hs * J.Ws;
   // (scale 0 needs no up-sampling: the plane is the disparity itself, turned into depth by the reader)
-  J.zup = lv == 0 ? J.disp : (P.zup[s] ? P.zup[s] + boff : nullptr);
+  J.zup = s == 0 ? J.disp : (P.zup[s] ? P.zup[s] + boff : nullptr);
   J.idl = P.idloss + P.nsrc * boff;
   J.noise = P.noise[s] ? P.noise[s] + P.nid * boff : nullptr;
   J.dD = P.dD[s] + boff;
   J.gd0 = nullptr; J.gn0 = nullptr; J.sm_inv_m = 0.f; J.sm_dterm = 0.f; J.sm_w = 0.f;
-  if (lv == 0 && P.want_grad) {   // (levels ascend: level 0, when present, is slot 0)
+  if (s == 0 && P.want_grad) {
     J.gd0 = P.grad_disp[0] + boff;
     J.gn0 = P.gn[0] + boff;
     J.sm_inv_m = MD2_LD(P.smsc + 2 * b);            // scale 0, sample b
@@ -562,7 +568,7 @@ MD2_HD void prefetch_row(Lane<C>& L, const WarpJob& J, int t) {
   if (WITH_TG) L.ntg = MD2_LDS4(J.tgt4 + 4 * (tr * J.W + L.xi));
   if (C::ZUP) {
     L.nd[0] = MD2_LD(J.zup + tr * J.W + L.xi);
-  } else if (J.Hs == J.H) {
+  } else if (J.s == 0) {
     L.nd[0] = MD2_LD(J.disp + tr * J.W + L.xi);
   } else {
     float syr = fmaf(J.rs, (float)tr + 0.5f, -0.5f);
@@ -594,7 +600,7 @@ MD2_HD void lane_init(Lane<C>& L, const Params& P, const WarpJob& J, int lane) {
     }
     L.idv[f] = 0.f; L.nzv[f] = 0.f;
   }
-  if (J.s >= P.up0) {
+  if (J.s > 0) {
     float sxr = fmaf(J.rs, (float)L.xi + 0.5f, -0.5f);
     sxr = sxr < 0.0f ? 0.0f : sxr;
     L.ux0 = (int)sxr;
@@ -720,7 +726,7 @@ MD2_HD void stage_a_issue(Lane<C>& L, Flight<C>& F, const Params& P, const WarpJ
   float D = 0.f, zpre = 0.f;
   if (C::ZUP) {
     zpre = L.nd[0];
-  } else if (J.s < P.up0) {
+  } else if (J.s == 0) {
     D = L.nd[0];
   } else {
     float syr = fmaf(J.rs, (float)tr + 0.5f, -0.5f);
@@ -732,7 +738,7 @@ MD2_HD void stage_a_issue(Lane<C>& L, Flight<C>& F, const Params& P, const WarpJ
   }
   if (ROW_STEP > 0) prefetch_row<C, !TG_DIRECT>(L, J, t + ROW_STEP);     // ROW_STEP 0: the caller prefetches
   if (WITH_ID) load_identity_row(L, J, t);
-  const float z = C::ZUP ? (J.s < P.up0 ? depth_of_disp(P, zpre) : zpre) : depth_of_disp(P, D);
+  const float z = C::ZUP ? (J.s == 0 ? depth_of_disp(P, zpre) : zpre) : depth_of_disp(P, D);
   F.cz = z;
   const float yf = (float)tr;
 #pragma unroll
@@ -1250,7 +1256,7 @@ MD2_HD void stage_c_divergent(Lane<C>& L, const Params& P, const WarpJob& J, int
     const float dD = -P.c_disp * z * z * dzsum * P.gscale;
     MD2_CHK(yp * J.W + L.xi, J.plane);
     J.dD[yp * J.W + L.xi] = dD;
-    if (J.s < P.up0)   // up-sampling is the identity at scale 0: finish grad_disp_0 here (A.4 + A.3)
+    if (J.s == 0)   // up-sampling is the identity at scale 0: finish grad_disp_0 here (A.4 + A.3)
       J.gd0[yp * J.W + L.xi] = dD + J.sm_w * (MD2_LD(J.gn0 + yp * J.W + L.xi) * J.sm_inv_m - J.sm_dterm);
   }
   if (C::BSMEM) {
@@ -1372,7 +1378,7 @@ MD2_HD void stage_c_straight(Lane<C>& L, const Params& P, const WarpJob& J, int 
     if (own) {
       MD2_CHK(yp * J.W + L.xi, J.plane);
       J.dD[yp * J.W + L.xi] = dD;
-      if (J.s < P.up0)   // up-sampling is the identity at scale 0: finish grad_disp_0 here (A.4 + A.3)
+      if (J.s == 0)   // up-sampling is the identity at scale 0: finish grad_disp_0 here (A.4 + A.3)
         J.gd0[yp * J.W + L.xi] = dD + J.sm_w * (MD2_LD(J.gn0 + yp * J.W + L.xi) * J.sm_inv_m - J.sm_dterm);
     }
   }
@@ -1929,9 +1935,10 @@ MD2_HD float pmask_adjoint(const Params& P, int s, int b, int f, int Y, int X) {
   return acc;
 }
 MD2_HD void pmask_grad_pixel(const Params& P, int s, int b, int f, int Y, int X) {
-  const int Hs = P.H >> P.lvl[s], Ws = P.W >> P.lvl[s];
+  const int lv = (P.lvl4 >> (4 * s)) & 15;
+  const int Hs = P.H >> lv, Ws = P.W >> lv;
   float g;
-  switch (P.lvl[s]) {
+  switch (lv) {
     case 0: g = pmask_adjoint<1>(P, s, b, f, Y, X); break;
     case 1: g = pmask_adjoint<2>(P, s, b, f, Y, X); break;
     case 2: g = pmask_adjoint<4>(P, s, b, f, Y, X); break;

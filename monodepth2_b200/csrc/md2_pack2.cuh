@@ -142,7 +142,7 @@ __device__ __forceinline__ void prefetch_row2(Lane2<C>& L, const WarpJob& J, int
   if (WITH_TG) L.ntg = MD2_LDS4(J.tgt4 + 4 * (tr * J.W + L.xi));
   if (C::ZUP) {
     L.nd[0] = MD2_LD(J.zup + tr * J.W + L.xi);
-  } else if (J.Hs == J.H) {
+  } else if (J.s == 0) {
     L.nd[0] = MD2_LD(J.disp + tr * J.W + L.xi);
   } else {
     float syr = fmaf(J.rs, (float)tr + 0.5f, -0.5f);
@@ -172,7 +172,7 @@ __device__ __forceinline__ void lane_init2(Lane2<C>& L, const Params& P, const W
     L.p4[i] = p2(MD2_LD(m0 + 9 + i), MD2_LD(m1 + 9 + i));
   }
   L.idv[0] = L.idv[1] = L.nzv[0] = L.nzv[1] = 0.f;
-  if (J.s >= P.up0) {
+  if (J.s > 0) {
     float sxr = fmaf(J.rs, (float)L.xi + 0.5f, -0.5f);
     sxr = sxr < 0.0f ? 0.0f : sxr;
     L.ux0 = (int)sxr;
@@ -244,7 +244,7 @@ __device__ __forceinline__ void stage_a_issue2(Lane2<C>& L, Flight2& F, const Pa
     float D = 0.f, zpre = 0.f;
     if (C::ZUP) {
       zpre = L.nd[0];
-    } else if (J.s < P.up0) {
+    } else if (J.s == 0) {
       D = L.nd[0];
     } else {
       float syr = fmaf(J.rs, (float)tr + 0.5f, -0.5f);
@@ -256,7 +256,7 @@ __device__ __forceinline__ void stage_a_issue2(Lane2<C>& L, Flight2& F, const Pa
     }
     if (ROW_STEP > 0) prefetch_row2<C, !TG_DIRECT>(L, J, t + ROW_STEP);
     if (WITH_ID) load_identity_row2(L, J, t);
-    z = C::ZUP ? (J.s < P.up0 ? depth_of_disp(P, zpre) : zpre) : depth_of_disp(P, D);
+    z = C::ZUP ? (J.s == 0 ? depth_of_disp(P, zpre) : zpre) : depth_of_disp(P, D);
   }
   F.cz = z;
   const float yf = (float)tr;
@@ -331,7 +331,7 @@ __device__ __forceinline__ void stage_a_issue2(Lane2<C>& L, const Params& P, con
 template <class C>
 __device__ __forceinline__ void stage_a_proj2(Lane2<C>& L, Proj2& R, const Params& P, const WarpJob& J, int t, float zrow) {
   const int tr = reflect_clamp(t, J.H);
-  const float z = (J.s < P.up0) ? depth_of_disp(P, zrow) : zrow;
+  const float z = (J.s == 0) ? depth_of_disp(P, zrow) : zrow;
   R.cz = z;
   const float yf = (float)tr;
   const P2 q0 = fma2(L.qb[0], bc(yf), L.qa[0]);
@@ -732,7 +732,7 @@ __device__ __forceinline__ void stage_c2(Lane2<C>& L, const Params& P, const War
     L.S3[0] = add2(L.S3[0], d0); L.S3[1] = add2(L.S3[1], d1); L.S3[2] = add2(L.S3[2], d2);
     const float dD = -P.c_disp * z * z * dzsum * P.gscale;
     J.dD[yp * J.W + L.xi] = dD;
-    if (J.s < P.up0)
+    if (J.s == 0)
       J.gd0[yp * J.W + L.xi] = dD + J.sm_w * (MD2_LD(J.gn0 + yp * J.W + L.xi) * J.sm_inv_m - J.sm_dterm);
   }
 #pragma unroll

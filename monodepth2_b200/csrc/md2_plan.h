@@ -158,6 +158,7 @@ inline int fill_params(const md2_problem* p, const md2_tensors* t, void* workspa
     P->smooth_w[s] = (float)((double)p->disparity_smoothness / (double)(1 << P->lvl[s]));   // trainer.py:491: / (2 ** scale)
   }
   P->up0 = P->lvl[0] == 0 ? 1 : 0;
+  for (int s = 0; s < p->num_scales; ++s) P->lvl4 |= P->lvl[s] << (4 * s);
   P->noise_event = t->noise_ready_event;
   P->seg_rows = default_seg_rows(p);
   P->nseg = (p->height + P->seg_rows - 1) / P->seg_rows;

@@ -175,7 +175,7 @@ template <class C>
 __device__ __forceinline__ void c_publish_z(Lane<C>& L, const Params& P, const WarpJob& J, int t, float* zdst) {
   const int tr = reflect_clamp(t, J.H);
   float D;
-  if (J.s < P.up0) {
+  if (J.s == 0) {
     D = L.nd[0];
   } else {
     float syr = fmaf(J.rs, (float)tr + 0.5f, -0.5f);
