@@ -59,7 +59,9 @@ typedef struct md2_problem {
                                  losses[1 + s] = losses["loss/<level>"].  All zero = levels 0..n-1 */
 } md2_problem;
 
-/* Tensors of one evaluation.  Names follow the reference's dict keys. */
+/* Tensors of one evaluation.  Names follow the reference's dict keys.  Per-scale arrays are indexed by scale SLOT
+ * s = 0..num_scales-1; slot s is pyramid level md2_problem.scale_level[s] (= s for the default --scales 0 1 2 3), and
+ * "H>>s" below reads H >> level. */
 typedef struct md2_tensors {
   /* ---- inputs ---- */
   const float *target;                  /* inputs[("color",0,0)]         (B,3,H,W)      */
