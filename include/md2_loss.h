@@ -129,9 +129,10 @@ int md2_loss_workspace_bytes(const md2_problem *p, size_t *bytes);
  * losses["loss"].backward() (trainer.py:208) propagates to disp_s and cam_T_cam.
  * Threading: the library keeps one internal side stream and event pair per device (the small smoothness
  * kernels overlap the identity pass on it; fork/join by events, so the caller's stream order and CUDA-graph
- * capture of `stream` are preserved).  Calls for the same device must not be issued concurrently from several
- * host threads; one process per GPU (the reference's model, and DDP's) needs no locking.  `workspace` may be
- * reused by successive calls on the same stream; two calls in flight on different streams need two workspaces. */
+ * capture of `stream` are preserved).  The enqueue of a call runs under a library lock, so calls may be issued from
+ * several host threads (their side-stream work is then ordered one call after the other; the work on the callers'
+ * streams is not).  `workspace` may be reused by successive calls on the same stream; two calls in flight on
+ * different streams need two workspaces. */
 int md2_view_synthesis_loss(const md2_problem *p, const md2_tensors *t,
                             void *workspace, size_t workspace_bytes, void *stream);
 

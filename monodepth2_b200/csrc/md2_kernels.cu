@@ -1165,7 +1165,13 @@ __global__ void __launch_bounds__(256) md2_u8_to_f32(Params P) {
 
 static cudaError_t launch_float_entry(const Params& P, cudaStream_t stream);
 
+// The fork / join events and the side streams are shared by every call on a device: the enqueue of one call (a few
+// dozen microseconds of host time) runs under a lock, so that calls issued from several host threads - on the same or on
+// different streams - cannot interleave their event records and waits.  The GPU work itself is not serialised by this.
+static std::mutex g_enqueue_mu;
+
 cudaError_t launch_view_synthesis_loss(const Params& P, cudaStream_t stream) {
+  std::lock_guard<std::mutex> enqueue_lock(g_enqueue_mu);
 #ifndef MD2_DBG_DEVICE
   static const bool cvt_on = !(getenv("MD2_U8_CONVERT") && atoi(getenv("MD2_U8_CONVERT")) == 0);
   if (P.tgt8 && cvt_on) {

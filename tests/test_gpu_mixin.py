@@ -220,3 +220,49 @@ def test_mixin_compute_depth_losses_runs_the_fused_metrics():
     for i, k in enumerate(T.depth_metric_names):
         assert isinstance(losses[k], np.ndarray)
         assert abs(float(losses[k]) - float(ref[i])) <= 2e-5 * abs(float(ref[i])) + 1e-7, k
+
+
+def test_calls_from_two_host_threads_on_two_streams():
+    """The library's side streams and fork / join events are shared per device; the enqueue of a call runs under a
+    lock (md2_kernels.cu: g_enqueue_mu), so two host threads, each with its own stream, plan and workspace, may call
+    concurrently (ctypes drops the GIL during the call).  Same results as the serial run: per-pixel gradients bit for
+    bit, losses up to the order of the fp64 atomic sums."""
+    import threading
+    from monodepth2_b200.fused_loss import LossPlan, view_synthesis_loss
+    from monodepth2_b200.synthetic import make_batch
+    dev = "cuda:0"
+    fids = [0, -1, 1]
+    jobs = []
+    for seed in (41, 42):
+        inputs, outputs, _pose, noise = make_batch(4, 96, 320, fids, 4, seed, "structured", n_id=2)
+        jobs.append(dict(plan=LossPlan(4, 96, 320, fids), ins={k: v.to(dev) for k, v in inputs.items()},
+                         outs={k: v.to(dev).requires_grad_(True) for k, v in outputs.items()},
+                         noise=[n.to(dev) for n in noise], stream=torch.cuda.Stream(device=dev)))
+
+    def run(j, reps):
+        with torch.cuda.stream(j["stream"]):
+            for _ in range(reps):
+                for v in j["outs"].values():
+                    v.grad = None
+                ls = view_synthesis_loss(j["plan"], j["ins"], j["outs"], j["noise"])
+                ls["loss"].backward()
+            j["stream"].synchronize()
+        return float(ls["loss"]), {k: v.grad.clone() for k, v in j["outs"].items()}
+
+    torch.cuda.synchronize()
+    serial = [run(j, 1) for j in jobs]
+    got = [None, None]
+
+    def worker(i):
+        got[i] = run(jobs[i], 25)
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    torch.cuda.synchronize()
+    for (l0, g0), (l1, g1) in zip(serial, got):
+        assert abs(l0 - l1) <= 2e-6 * abs(l0)
+        for k in g0:
+            if k[0] == "disp":
+                assert torch.equal(g0[k], g1[k]), k
+            else:
+                assert float((g0[k] - g1[k]).abs().max()) <= 1e-5 * float(g0[k].abs().max()), k
