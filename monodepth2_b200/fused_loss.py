@@ -52,7 +52,8 @@ class LossPlan:
         # ("disp", s) for exactly those levels and the dataloader always holds levels 0..3 (trainer.py:127-135).  The
         # loss is a sum over the list, so the order does not matter: the plan keeps the levels ascending
         # (md2_problem.scale_level); slot i of every per-scale array is level self.scales[i].
-        scales = sorted(int(s) for s in scales)
+        self.scales_given = [int(s) for s in scales]     # the order trainer.py:413 iterates (and draws the noise in)
+        scales = sorted(self.scales_given)
         if not scales or len(set(scales)) != len(scales) or scales[0] < 0 or scales[-1] >= MAX_SCALES:
             raise RuntimeError("scales must be distinct pyramid levels in 0..%d, got %s" % (MAX_SCALES - 1, scales))
         if scales[0] != 0 and not v1_multiscale:
@@ -350,6 +351,17 @@ def bind_to_gpu_cpus(device) -> Optional[str]:
         return None
 
 
+def _in_slot_order(plan: "LossPlan", drawn: list) -> list:
+    """``drawn[i]`` belongs to ``plan.scales_given[i]`` (trainer.py:413,468-469: one draw per entry of opt.scales, in list
+    order); the C ABI wants slot order = ascending levels.  The identity for a list given in ascending order."""
+    if plan.scales_given == plan.scales:
+        return drawn
+    out = [None] * len(drawn)
+    for i, s in enumerate(plan.scales_given):
+        out[plan.slot(s)] = drawn[i]
+    return out
+
+
 class _Noise(list):
     """The tie-break draws of one call; ``ready`` is the torch.cuda.Event recorded after the last draw when they were
     made on the plan's side stream (handed to the library as md2_tensors.noise_ready_event)."""
@@ -367,7 +379,7 @@ def _draw_noise(plan: LossPlan, dev) -> "_Noise":
     first kernel that reads them.  MD2_NOISE_STREAM=0: draw on the current stream."""
     shape = (plan.batch_size, plan.n_id, plan.height, plan.width)
     if os.environ.get("MD2_NOISE_STREAM", "1") == "0":
-        return _Noise(torch.randn(shape, device=dev) for _ in plan.scales)
+        return _Noise(_in_slot_order(plan, [torch.randn(shape, device=dev) for _ in plan.scales]))
     main = torch.cuda.current_stream(dev)
     key = (dev.index if dev.index is not None else torch.cuda.current_device())
     side_stream = _NOISE_STREAMS.get(key)
@@ -377,7 +389,7 @@ def _draw_noise(plan: LossPlan, dev) -> "_Noise":
     # last reader of the previous draws, whose memory the allocator may hand out again - comes first
     side_stream.wait_stream(main)
     with torch.cuda.stream(side_stream):
-        noise = _Noise(torch.randn(shape, device=dev) for _ in plan.scales)
+        noise = _Noise(_in_slot_order(plan, [torch.randn(shape, device=dev) for _ in plan.scales]))
         noise.ready = torch.cuda.Event()
         noise.ready.record(side_stream)
     return noise
@@ -627,7 +639,7 @@ class FusedLossMixin:
             # drawn here exactly as view_synthesis_loss would (one torch.randn per scale, in scale order,
             # trainer.py:468-469) and kept so that a later on-demand side-output call sees the same masks
             shape = (plan.batch_size, plan.n_id, plan.height, plan.width)
-            noise = [torch.randn(shape, device=inputs[("color", 0, 0)].device) for _ in plan.scales]
+            noise = _in_slot_order(plan, [torch.randn(shape, device=inputs[("color", 0, 0)].device) for _ in plan.scales])
             outputs["_md2_noise"] = noise
         outputs["_md2_losses"] = view_synthesis_loss(plan, inputs, outputs, noise=noise, side=side)
 

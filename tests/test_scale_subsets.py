@@ -16,6 +16,13 @@ def test_plan_keeps_levels_ascending_and_rejects_bad_lists():
     from monodepth2_b200.fused_loss import LossPlan
     p = LossPlan(2, 48, 80, [0, -1, 1], scales=[2, 0])
     assert p.scales == [0, 2] and p.slot(2) == 1
+    # the reference draws the tie-break noise in the order of the list (trainer.py:413,468-469): the host side draws in
+    # that order and hands the draws over in slot order, so a seeded run sees the reference's values per scale
+    from monodepth2_b200.fused_loss import _in_slot_order
+    assert p.scales_given == [2, 0] and _in_slot_order(p, ["first draw", "second draw"]) == ["second draw", "first draw"]
+    q = LossPlan(2, 48, 80, [0, -1, 1], scales=[0, 1, 3])
+    drawn = ["a", "b", "c"]
+    assert _in_slot_order(q, drawn) is drawn
     assert list(p.problem(True).scale_level) == [0, 2, 0, 0] and p.problem(True).num_scales == 2
     d = LossPlan(2, 48, 80, [0, -1, 1])
     assert list(d.problem(True).scale_level) == [0, 0, 0, 0] and d.problem(True).num_scales == 4
